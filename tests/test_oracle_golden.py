@@ -1,0 +1,100 @@
+"""The oracle port (oracle/caption_hn_oracle.py) against vectors produced by the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import caption_hn_oracle as O
+from golden_util import load_case, params_of, rel_err, grad_close
+
+TOL = 2e-6  # same torch CPU kernels in the same order; observed <= 1e-6
+
+
+def _leafify(p):
+    return {k: v.clone().requires_grad_(v.dtype.is_floating_point) for k, v in p.items()}
+
+
+@pytest.mark.parametrize("name", ["attn_flickr", "attn_cc"])
+def test_attention_variant_matches_reference(name):
+    c = load_case(name)
+    p = _leafify(params_of(c))
+    rng = np.random.RandomState(0)
+    logits, att, theta, gw = O.path_attention(p, c["style"], c["features"], c["captions"], 0.0, rng, flow=False)
+    for k, w in zip(("weight_ih", "weight_hh", "bias_ih", "bias_hh"), gw):
+        assert rel_err(w, c["gen/" + k]) < TOL, k
+    assert rel_err(logits, c["tf/logits"]) < TOL
+    assert rel_err(att, c["tf/attn"]) < TOL
+    loss = O.caption_loss(logits, c["captions"], 0)
+    assert abs(loss.item() - c["tf/loss"].item()) < 1e-6 * abs(c["tf/loss"].item()) + 1e-7
+    loss.backward()
+    for k, w in zip(("weight_ih", "weight_hh", "bias_ih", "bias_hh"), gw):
+        assert grad_close(w.grad, c["tf/grad/captioner.gru." + k], 1e-5), k
+    nograd = set(c["tf/nograd"].tolist())
+    for k, v in p.items():
+        if "tf/grad/" + k in c:
+            assert grad_close(v.grad, c["tf/grad/" + k], 1e-5), k
+        elif k in nograd:  # reference graph cut: hypernet params get no gradient in literal mode
+            assert v.grad is None or float(v.grad.abs().max()) == 0.0, k
+
+
+@pytest.mark.parametrize("name", ["attn_flickr", "attn_cc"])
+def test_attention_variant_flow_grads(name):
+    c = load_case(name)
+    p = _leafify(params_of(c))
+    logits, _, _, _ = O.path_attention(p, c["style"], c["features"], c["captions"], 0.0,
+                                       np.random.RandomState(0), flow=True)
+    O.caption_loss(logits, c["captions"], 0).backward()
+    n = 0
+    for k, v in c.items():
+        if k.startswith("flow/grad/"):
+            assert grad_close(p[k[10:]].grad, v, 1e-5), k
+            n += 1
+    assert n >= 12
+
+
+@pytest.mark.parametrize("name", ["attn_flickr", "attn_cc"])
+def test_attention_variant_greedy_token_exact(name):
+    c = load_case(name)
+    p = params_of(c)
+    with torch.no_grad():
+        logits, att, _, _ = O.path_attention(p, c["style"], c["features"], c["captions"], 1.0,
+                                             np.random.RandomState(0))
+    assert torch.equal(logits.argmax(-1), c["greedy/logits"].argmax(-1))
+    assert rel_err(logits, c["greedy/logits"]) < TOL
+    assert rel_err(att, c["greedy/attn"]) < TOL
+
+
+@pytest.mark.parametrize("name,L", [("pooled_l1", 1), ("pooled_l2", 2)])
+def test_pooled_variant_matches_reference(name, L):
+    c = load_case(name)
+    p = _leafify(params_of(c))
+    logits, theta, cells = O.path_pooled(p, c["style"], c["pooled"], c["captions"], c["h0"], L=L, flow=False)
+    for ci, cell in enumerate(cells):
+        for k, w in zip(("weight_ih", "weight_hh", "bias_ih", "bias_hh"), cell):
+            assert rel_err(w, c[f"gen/{ci}/{k}"]) < TOL, (ci, k)
+    assert rel_err(logits, c["tf/logits"]) < TOL
+    loss = O.caption_loss(logits, c["captions"], None)
+    assert abs(loss.item() - c["tf/loss"].item()) < 1e-6 * abs(c["tf/loss"].item())
+    loss.backward()
+    for ci, cell in enumerate(cells):
+        for k, w in zip(("weight_ih", "weight_hh", "bias_ih", "bias_hh"), cell):
+            assert grad_close(w.grad, c[f"tf/grad/gen/{ci}/{k}"], 1e-5), (ci, k)
+    for k in ("image_encoder.fc.weight", "captioner.embed.weight", "captioner.fc_out.weight", "captioner.fc_out.bias"):
+        assert grad_close(p[k].grad, c["tf/grad/" + k], 1e-5), k
+    with torch.no_grad():
+        probs, _, _ = O.path_pooled(p, c["style"], c["pooled"], None, c["h0"], L=L, infer_len=c["infer/probs"].shape[1])
+    assert torch.equal(probs.argmax(-1), c["infer/probs"].argmax(-1))
+    assert rel_err(probs, c["infer/probs"]) < TOL
+
+
+@pytest.mark.parametrize("name,L", [("pooled_l1", 1), ("pooled_l2", 2)])
+def test_pooled_variant_flow_grads(name, L):
+    c = load_case(name)
+    p = _leafify(params_of(c))
+    logits, _, _ = O.path_pooled(p, c["style"], c["pooled"], c["captions"], c["h0"], L=L, flow=True)
+    O.caption_loss(logits, c["captions"], None).backward()
+    n = 0
+    for k, v in c.items():
+        if k.startswith("flow/grad/"):
+            assert grad_close(p[k[10:]].grad, v, 1e-5), k
+            n += 1
+    assert n >= 12
