@@ -1,0 +1,79 @@
+"""ctypes binding of libcaphn_b200.so -- the C-ABI boundary (include/caphn_b200.h).
+
+Every entry point takes raw device pointers, sizes and a cudaStream_t (as void*), and returns an int
+(0 = ok, -1 = invalid argument, otherwise a cudaError_t).  There is no CPU fallback: if the library is missing or a
+call fails, this module raises.
+"""
+import ctypes
+import os
+from ctypes import c_float, c_int, c_long, c_longlong, c_void_p
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libcaphn_b200.so")
+
+P = c_void_p  # every pointer argument
+I = c_int
+L = c_long
+LL = c_longlong
+F = c_float
+
+# name -> argtypes (mirrors include/caphn_b200.h)
+SIGNATURES = {
+    "caphn_rows_linear_fwd": [P, P, P, L, P, L, I, L, L, I, F, P],
+    "caphn_rows_linear_bwd": [P, P, L, P, L, P, L, P, P, P, P, L, I, L, L, I, F, P],
+    "caphn_gemm_f32": [P, L, I, P, L, I, P, L, P, I, I, I, I, I, I, P],
+    "caphn_transpose_pad": [P, L, P, L, I, I, P],
+    "caphn_copy_pad": [P, L, P, L, L, I, P],
+    "caphn_gru_seq_fwd": [P, P, I, P, P, P, P, P, P, P, I, I, I, P],
+    "caphn_gru_seq_bwd": [P, P, P, P, P, P, P, I, P, P, P, I, I, I, P],
+    "caphn_ce_fwd": [P, L, P, L, I, I, LL, P, P, P, P],
+    "caphn_ce_bwd": [P, L, P, L, I, I, LL, P, P, P, P, L, P],
+    "caphn_softmax_argmax": [P, L, L, I, P, L, P, P],
+    "caphn_gather_rows": [P, P, L, I, P, L, P],
+    "caphn_build_inputs": [P, P, P, I, I, I, I, P, P],
+    "caphn_embed_scatter_add": [P, P, I, I, I, I, P, P],
+    "caphn_colsum": [P, L, L, I, P, P],
+    "caphn_mean_pos": [P, I, I, I, P, P],
+    "caphn_mean_pos_bwd": [P, I, I, I, P, P],
+    "caphn_relu_mask": [P, P, L, P],
+}
+
+_lib = None
+_launches = 0  # number of C-ABI calls made (bench.py reports kernel launches from the per-call launch counts below)
+
+
+class CaphnError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (building it first if nvcc is available and the sources changed)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:  # no silent fallback: the product path needs the CUDA library
+            raise CaphnError(f"libcaphn_b200.so is missing and could not be built: {e}") from e
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch; must be loud
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    global _launches
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    _launches += 1
+    if rc != 0:
+        raise CaphnError(f"{name} failed with status {rc}" + (" (invalid argument)" if rc == -1 else " (cudaError_t)"))
+
+
+def launches():
+    return _launches

@@ -1,0 +1,317 @@
+// Memory-bound pieces of the decoder: softmax cross-entropy over the vocabulary (forward + backward), row softmax /
+// argmax for greedy decode, embedding gather / scatter-add, column sums (bias gradients), mean over image positions.
+//
+// Reference call sites: F.cross_entropy(..., ignore_index=<pad>) cc_train_hypernet.py:153 / hypernet.py:145;
+// nn.Embedding lookups models/decoderlstm.py:62,96, later.py:400,473; softmax+argmax later.py:472,479 and
+// log_softmax+topk models/decoderlstm.py:94-95; torch.mean(features, dim=1) models/decoderlstm.py:133.
+#include "common.cuh"
+#include <math.h>
+
+namespace caphn {
+
+constexpr int CE_THREADS = 256;
+
+__device__ __forceinline__ float block_reduce_sum(float v, float* sh) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    float r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.f;
+    if (w == 0) r = warp_sum(r);
+    if (threadIdx.x == 0) sh[0] = r;
+    __syncthreads();
+    return sh[0];
+}
+__device__ __forceinline__ float block_reduce_max(float v, float* sh) {
+    v = warp_max(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    float r = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : -INFINITY;
+    if (w == 0) r = warp_max(r);
+    if (threadIdx.x == 0) sh[0] = r;
+    __syncthreads();
+    return sh[0];
+}
+
+// One CTA per row: lse[m], row_loss[m] = valid ? lse - x[target] : 0, row_valid[m].
+__global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const float* __restrict__ X, long ld,
+                                                            const long long* __restrict__ tgt, int V, int has_ignore,
+                                                            long long ignore, float* __restrict__ lse,
+                                                            float* __restrict__ row_loss, float* __restrict__ row_valid) {
+    __shared__ float sh[32];
+    const long m = blockIdx.x;
+    const float* x = X + m * ld;
+    const bool vec = ((ld & 3) == 0) && ((V & 3) == 0) && (((uintptr_t)X & 15) == 0);
+    float mx = -INFINITY;
+    if (vec) {
+        for (int i = threadIdx.x * 4; i < V; i += CE_THREADS * 4) {
+            const float4 v = *reinterpret_cast<const float4*>(x + i);
+            mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        }
+    } else {
+        for (int i = threadIdx.x; i < V; i += CE_THREADS) mx = fmaxf(mx, x[i]);
+    }
+    mx = block_reduce_max(mx, sh);
+    float s = 0.f;
+    if (vec) {
+        for (int i = threadIdx.x * 4; i < V; i += CE_THREADS * 4) {
+            const float4 v = *reinterpret_cast<const float4*>(x + i);
+            s += expf(v.x - mx) + expf(v.y - mx) + expf(v.z - mx) + expf(v.w - mx);
+        }
+    } else {
+        for (int i = threadIdx.x; i < V; i += CE_THREADS) s += expf(x[i] - mx);
+    }
+    s = block_reduce_sum(s, sh);
+    if (threadIdx.x == 0) {
+        const float l = mx + logf(s);
+        lse[m] = l;
+        const long long t = tgt[m];
+        const bool valid = !(has_ignore && t == ignore);
+        row_valid[m] = valid ? 1.f : 0.f;
+        row_loss[m] = valid ? (l - x[t]) : 0.f;
+    }
+}
+
+// out[0] = sum(row_loss) / max(sum(row_valid), 1)   out[1] = sum(row_valid)        (single CTA; deterministic)
+__global__ void __launch_bounds__(1024) ce_finish_kernel(const float* __restrict__ row_loss,
+                                                         const float* __restrict__ row_valid, long M,
+                                                         float* __restrict__ out) {
+    __shared__ float sh[32];
+    float a = 0.f, c = 0.f;
+    for (long i = threadIdx.x; i < M; i += 1024) { a += row_loss[i]; c += row_valid[i]; }
+    a = block_reduce_sum(a, sh);
+    c = block_reduce_sum(c, sh);
+    if (threadIdx.x == 0) { out[0] = a / fmaxf(c, 1.f); out[1] = c; }
+}
+
+// dX[m,v] = (exp(x - lse[m]) - [v == tgt[m]]) * gscale[0] / count   for valid rows, 0 otherwise.
+__global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restrict__ X, long ld,
+                                                            const long long* __restrict__ tgt, int V, int has_ignore,
+                                                            long long ignore, const float* __restrict__ lse,
+                                                            const float* __restrict__ gscale,
+                                                            const float* __restrict__ lossbuf, float* __restrict__ dX,
+                                                            long lddx) {
+    const long m = blockIdx.x;
+    const float* x = X + m * ld;
+    float* dx = dX + m * lddx;
+    const long long t = tgt[m];
+    const bool valid = !(has_ignore && t == ignore);
+    const float sc = valid ? gscale[0] / fmaxf(lossbuf[1], 1.f) : 0.f;
+    const float l = lse[m];
+    const bool vec = ((ld & 3) == 0) && ((lddx & 3) == 0) && ((V & 3) == 0) && (((uintptr_t)X & 15) == 0) &&
+                     (((uintptr_t)dX & 15) == 0);
+    if (vec) {
+        for (int i = threadIdx.x * 4; i < V; i += CE_THREADS * 4) {
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) {
+                const float4 v = *reinterpret_cast<const float4*>(x + i);
+                o.x = (expf(v.x - l) - (i == t ? 1.f : 0.f)) * sc;
+                o.y = (expf(v.y - l) - (i + 1 == t ? 1.f : 0.f)) * sc;
+                o.z = (expf(v.z - l) - (i + 2 == t ? 1.f : 0.f)) * sc;
+                o.w = (expf(v.w - l) - (i + 3 == t ? 1.f : 0.f)) * sc;
+            }
+            *reinterpret_cast<float4*>(dx + i) = o;
+        }
+    } else {
+        for (int i = threadIdx.x; i < V; i += CE_THREADS)
+            dx[i] = valid ? (expf(x[i] - l) - (i == t ? 1.f : 0.f)) * sc : 0.f;
+    }
+}
+
+// Row softmax (optional, Y may be null) and first-max argmax (matches torch.argmax / topk(1) tie-breaking: lowest index).
+__global__ void __launch_bounds__(CE_THREADS) softmax_argmax_kernel(const float* __restrict__ X, long ld, int V,
+                                                                    float* __restrict__ Y, long ldy,
+                                                                    long long* __restrict__ amax) {
+    __shared__ float sh[32];
+    __shared__ int shi[32];
+    const long m = blockIdx.x;
+    const float* x = X + m * ld;
+    float mx = -INFINITY;
+    int mi = 0x7fffffff;
+    for (int i = threadIdx.x; i < V; i += CE_THREADS) {
+        const float v = x[i];
+        if (v > mx || (v == mx && i < mi)) { mx = v; mi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[w] = mx; shi[w] = mi; }
+    __syncthreads();
+    if (w == 0) {
+        float v = l < (CE_THREADS >> 5) ? sh[l] : -INFINITY;
+        int vi = l < (CE_THREADS >> 5) ? shi[l] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+            if (ov > v || (ov == v && oi < vi)) { v = ov; vi = oi; }
+        }
+        if (l == 0) { sh[0] = v; shi[0] = vi; }
+    }
+    __syncthreads();
+    mx = sh[0];
+    if (threadIdx.x == 0 && amax) amax[m] = shi[0];
+    if (!Y) return;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < V; i += CE_THREADS) s += expf(x[i] - mx);
+    s = block_reduce_sum(s, sh);
+    const float inv = 1.f / s;
+    float* y = Y + m * ldy;
+    for (int i = threadIdx.x; i < V; i += CE_THREADS) y[i] = expf(x[i] - mx) * inv;
+}
+
+// out[i,:] = idx[i] >= 0 ? table[idx[i],:] : 0      (i < n, row length E)
+__global__ void gather_rows_kernel(const float* __restrict__ table, const long long* __restrict__ idx, long n, int E,
+                                   float* __restrict__ out, long ldo) {
+    const long i = blockIdx.x;
+    const long long r = idx[i];
+    for (int e = threadIdx.x; e < E; e += blockDim.x) out[i * ldo + e] = r >= 0 ? table[r * E + e] : 0.f;
+}
+
+// Decoder inputs, time-major X[t,b,:]:  mode 0 (DecoderGRU, later.py:411,418): X[0,b] = feat[b], X[t,b] = Emb[caps[b,t-1]]
+//                                       mode 1 (AttentionGru, decoderlstm.py:82-88): X[0] = X[1] = 0, X[t] = Emb[caps[b,t-1]]
+__global__ void build_inputs_kernel(const float* __restrict__ feat, const float* __restrict__ emb,
+                                    const long long* __restrict__ caps, int B, int T, int E, int mode,
+                                    float* __restrict__ X) {
+    const int t = blockIdx.x / B, b = blockIdx.x - t * B;
+    float* x = X + ((long)t * B + b) * E;
+    const float* src = nullptr;
+    if (mode == 0) src = (t == 0) ? feat + (long)b * E : emb + caps[(long)b * T + t - 1] * E;
+    else if (t >= 2) src = emb + caps[(long)b * T + t - 1] * E;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) x[e] = src ? src[e] : 0.f;
+}
+
+// dEmb[caps[b,t-1],:] += dX[t,b,:]  for t >= t0 (t0 = 1 pooled, 2 attention).
+__global__ void embed_scatter_add_kernel(const float* __restrict__ dX, const long long* __restrict__ caps, int B, int T,
+                                         int E, int t0, float* __restrict__ dEmb) {
+    const int t = t0 + blockIdx.x / B, b = blockIdx.x % B;
+    if (t >= T) return;
+    const long long r = caps[(long)b * T + t - 1];
+    const float* d = dX + ((long)t * B + b) * E;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(dEmb + r * E + e, d[e]);
+}
+
+// out[n] (+)= sum_m X[m*ld + n]
+__global__ void colsum_kernel(const float* __restrict__ X, long ld, long M, int N, long rows_per_block,
+                              float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const long m0 = (long)blockIdx.y * rows_per_block;
+    const long m1 = min(M, m0 + rows_per_block);
+    if (n >= N) return;
+    float s = 0.f;
+    for (long m = m0; m < m1; ++m) s += X[m * ld + n];
+    atomicAdd(out + n, s);
+}
+
+// out[b,f] = mean_p X[b,p,f]
+__global__ void mean_pos_kernel(const float* __restrict__ X, int P, int Fd, float* __restrict__ out) {
+    const long b = blockIdx.x;
+    for (int f = threadIdx.x; f < Fd; f += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < P; ++p) s += X[(b * P + p) * Fd + f];
+        out[b * Fd + f] = s / (float)P;
+    }
+}
+// dX[b,p,f] += g[b,f] / P
+__global__ void mean_pos_bwd_kernel(const float* __restrict__ g, int P, int Fd, float* __restrict__ dX) {
+    const long b = blockIdx.x;
+    const float inv = 1.f / (float)P;
+    for (int i = threadIdx.x; i < P * Fd; i += blockDim.x) dX[b * P * Fd + i] += g[b * Fd + (i % Fd)] * inv;
+}
+
+// y = relu'(ref) * y   (in place on y): y[i] = ref[i] > 0 ? y[i] : 0
+__global__ void relu_mask_kernel(const float* __restrict__ ref, float* __restrict__ y, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && !(ref[i] > 0.f)) y[i] = 0.f;
+}
+
+}  // namespace caphn
+
+using namespace caphn;
+
+extern "C" {
+
+// Cross-entropy over rows of X [M,V] (row stride ld).  ignore_index is honoured when has_ignore != 0.
+// Outputs: lse [M]; scratch [2*M]; lossbuf[0] = mean loss over valid rows, lossbuf[1] = number of valid rows.
+int caphn_ce_fwd(const float* X, long ld, const long long* tgt, long M, int V, int has_ignore, long long ignore,
+                 float* lse, float* scratch, float* lossbuf, void* stream) {
+    if (M <= 0 || V <= 0) return CAPHN_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    ce_fwd_kernel<<<(unsigned)M, CE_THREADS, 0, st>>>(X, ld, tgt, V, has_ignore, ignore, lse, scratch, scratch + M);
+    CAPHN_CHECK(cudaGetLastError());
+    ce_finish_kernel<<<1, 1024, 0, st>>>(scratch, scratch + M, M, lossbuf);
+    CAPHN_RETURN_LAST();
+}
+
+// dX = d(mean loss)/dX * gscale[0];  lossbuf as produced by caphn_ce_fwd (valid-row count read on device: no sync).
+int caphn_ce_bwd(const float* X, long ld, const long long* tgt, long M, int V, int has_ignore, long long ignore,
+                 const float* lse, const float* gscale, const float* lossbuf, float* dX, long lddx, void* stream) {
+    if (M <= 0 || V <= 0) return CAPHN_EINVAL;
+    ce_bwd_kernel<<<(unsigned)M, CE_THREADS, 0, (cudaStream_t)stream>>>(X, ld, tgt, V, has_ignore, ignore, lse, gscale,
+                                                                        lossbuf, dX, lddx);
+    CAPHN_RETURN_LAST();
+}
+
+// Y (optional) = softmax rows of X; amax (optional) = argmax per row (lowest index on ties).
+int caphn_softmax_argmax(const float* X, long ld, long M, int V, float* Y, long ldy, long long* amax, void* stream) {
+    if (M <= 0 || V <= 0) return CAPHN_EINVAL;
+    softmax_argmax_kernel<<<(unsigned)M, CE_THREADS, 0, (cudaStream_t)stream>>>(X, ld, V, Y, ldy, amax);
+    CAPHN_RETURN_LAST();
+}
+
+int caphn_gather_rows(const float* table, const long long* idx, long n, int E, float* out, long ldo, void* stream) {
+    if (n <= 0 || E <= 0) return CAPHN_EINVAL;
+    gather_rows_kernel<<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(table, idx, n, E, out, ldo);
+    CAPHN_RETURN_LAST();
+}
+
+int caphn_build_inputs(const float* feat, const float* emb, const long long* caps, int B, int T, int E, int mode,
+                       float* X, void* stream) {
+    if (B <= 0 || T <= 0 || E <= 0) return CAPHN_EINVAL;
+    build_inputs_kernel<<<(unsigned)(B * T), 128, 0, (cudaStream_t)stream>>>(feat, emb, caps, B, T, E, mode, X);
+    CAPHN_RETURN_LAST();
+}
+
+int caphn_embed_scatter_add(const float* dX, const long long* caps, int B, int T, int E, int t0, float* dEmb,
+                            void* stream) {
+    if (B <= 0 || T <= 0 || E <= 0 || t0 < 1) return CAPHN_EINVAL;
+    if (T - t0 <= 0) return CAPHN_OK;
+    embed_scatter_add_kernel<<<(unsigned)(B * (T - t0)), 128, 0, (cudaStream_t)stream>>>(dX, caps, B, T, E, t0, dEmb);
+    CAPHN_RETURN_LAST();
+}
+
+// out[n] += sum_m X[m,n]   (caller zeroes out for a plain sum)
+int caphn_colsum(const float* X, long ld, long M, int N, float* out, void* stream) {
+    if (M <= 0 || N <= 0) return CAPHN_EINVAL;
+    long rpb = 256;
+    dim3 grid(ceil_div(N, 128), ceil_div(M, rpb));
+    colsum_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(X, ld, M, N, rpb, out);
+    CAPHN_RETURN_LAST();
+}
+
+int caphn_mean_pos(const float* X, int B, int P, int Fd, float* out, void* stream) {
+    if (B <= 0 || P <= 0 || Fd <= 0) return CAPHN_EINVAL;
+    mean_pos_kernel<<<(unsigned)B, 128, 0, (cudaStream_t)stream>>>(X, P, Fd, out);
+    CAPHN_RETURN_LAST();
+}
+
+int caphn_mean_pos_bwd(const float* g, int B, int P, int Fd, float* dX, void* stream) {
+    if (B <= 0 || P <= 0 || Fd <= 0) return CAPHN_EINVAL;
+    mean_pos_bwd_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(g, P, Fd, dX);
+    CAPHN_RETURN_LAST();
+}
+
+int caphn_relu_mask(const float* ref, float* y, long n, void* stream) {
+    if (n <= 0) return CAPHN_EINVAL;
+    relu_mask_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(ref, y, n);
+    CAPHN_RETURN_LAST();
+}
+
+}  // extern "C"

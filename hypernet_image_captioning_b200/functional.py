@@ -1,0 +1,174 @@
+"""autograd.Function wrappers: forward and backward both run the hand-written CUDA kernels (no torch math)."""
+from typing import List, Optional, Sequence
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+from .ops import ACT_LEAKY, ACT_NONE
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# hypernetwork: X[G,he] -> Theta[G,theta]      (reference hypernet_attention.py:111-118 / hypernet.py:104-111)
+# ----------------------------------------------------------------------------------------------------------------------
+class HyperNetThetaFn(Function):
+    """params = [base0.W, base0.b, base2.W, base2.b, (head_i.0.W, head_i.0.b, head_i.2.W, head_i.2.b) * n_heads]."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        nh = (len(params) - 4) // 4
+        b0 = ops.rows_linear_fwd(params[0], params[1], x, ACT_LEAKY)
+        b1 = ops.rows_linear_fwd(params[2], params[3], b0, ACT_LEAKY)
+        sizes = [params[4 + 4 * i + 2].shape[0] for i in range(nh)]
+        theta = torch.empty(x.shape[0], sum(sizes), device=x.device, dtype=torch.float32)
+        mids, off = [], 0
+        for i in range(nh):
+            W1, c1, W2, c2 = params[4 + 4 * i: 8 + 4 * i]
+            a = ops.rows_linear_fwd(W1, c1, b1, ACT_LEAKY)
+            ops.rows_linear_fwd(W2, c2, a, ACT_NONE, out=theta[:, off:off + sizes[i]])
+            mids.append(a)
+            off += sizes[i]
+        ctx.save_for_backward(x, b0, b1, *mids, *params)
+        ctx.nh = nh
+        ctx.sizes = sizes
+        return theta
+
+    @staticmethod
+    def backward(ctx, dtheta):
+        nh, sizes = ctx.nh, ctx.sizes
+        sv = ctx.saved_tensors
+        x, b0, b1 = sv[0], sv[1], sv[2]
+        mids = sv[3:3 + nh]
+        params = sv[3 + nh:]
+        need = ctx.needs_input_grad  # [x, *params]
+        dtheta = dtheta.contiguous()
+        grads: List[Optional[torch.Tensor]] = [None] * len(params)
+        db1 = torch.zeros_like(b1)
+        off = 0
+        for i in range(nh):
+            W1, c1, W2, c2 = params[4 + 4 * i: 8 + 4 * i]
+            pi = 4 + 4 * i
+            dW2, dc2, da = ops.rows_linear_bwd(W2, mids[i], None, dtheta[:, off:off + sizes[i]], ACT_NONE,
+                                               need_dW=need[1 + pi + 2])
+            dW1, dc1, _ = ops.rows_linear_bwd(W1, b1, mids[i], da, ACT_LEAKY, need_dW=need[1 + pi], dA=db1)
+            grads[pi], grads[pi + 1], grads[pi + 2], grads[pi + 3] = dW1, dc1, dW2, dc2
+            off += sizes[i]
+        dWb1, dcb1, db0 = ops.rows_linear_bwd(params[2], b0, b1, db1, ACT_LEAKY, need_dW=need[3])
+        dWb0, dcb0, dx = ops.rows_linear_bwd(params[0], x, b0, db0, ACT_LEAKY, need_dW=need[1], need_dA=need[0])
+        grads[0], grads[1], grads[2], grads[3] = dWb0, dcb0, dWb1, dcb1
+        for j in range(len(grads)):
+            if not need[1 + j]:
+                grads[j] = None
+        return (dx if need[0] else None, *grads)
+
+
+def hypernet_theta(x2d: torch.Tensor, params: Sequence[torch.Tensor]) -> torch.Tensor:
+    return HyperNetThetaFn.apply(x2d, *params)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# y = x W^T + b (ReLU optional)        -- nn.Linear replacement (image_encoder.fc hypernet.py:46, feature_fc, init_h ...)
+# ----------------------------------------------------------------------------------------------------------------------
+class LinearFn(Function):
+    @staticmethod
+    def forward(ctx, x, W, b, relu):
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        y = ops.linear(x2, W.contiguous(), b, relu=relu)
+        ctx.save_for_backward(x2, W, y if relu else None)
+        ctx.relu = relu
+        ctx.xshape = x.shape
+        return y.reshape(*x.shape[:-1], W.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W, y = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        if ctx.relu:
+            dy2 = dy2.clone()
+            ops._cabi.call("caphn_relu_mask", y.data_ptr(), dy2.data_ptr(), dy2.numel(), ops._stream())
+        dx = ops.matmul_nn(dy2, W.contiguous()).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
+        dW = ops.matmul_tn(dy2, x2) if ctx.needs_input_grad[1] else None
+        db = ops.colsum(dy2) if ctx.needs_input_grad[2] else None
+        return dx, dW, db, None
+
+
+def linear(x, W, b, relu=False):
+    return LinearFn.apply(x, W, b, relu)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fused softmax cross-entropy (mean over non-ignored rows)      -- F.cross_entropy at cc_train_hypernet.py:153
+# ----------------------------------------------------------------------------------------------------------------------
+class CrossEntropyFn(Function):
+    @staticmethod
+    def forward(ctx, logits, targets, ignore_index):
+        l2 = logits.reshape(-1, logits.shape[-1])
+        if l2.stride(1) != 1:
+            l2 = l2.contiguous()
+        t = targets.reshape(-1).contiguous()
+        lossbuf, lse = ops.ce_fwd(l2, t, ignore_index)
+        ctx.save_for_backward(l2, t, lse, lossbuf)
+        ctx.ignore_index = ignore_index
+        ctx.shape = logits.shape
+        return lossbuf[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        l2, t, lse, lossbuf = ctx.saved_tensors
+        g = g.reshape(1).to(torch.float32).contiguous()
+        dX = ops.ce_bwd(l2, t, ctx.ignore_index, lse, lossbuf, g)
+        return dX.reshape(ctx.shape), None, None
+
+
+def cross_entropy(logits, targets, ignore_index: Optional[int] = None):
+    """Mean CE over rows whose target != ignore_index (None = no masking, hypernet.py:145)."""
+    return CrossEntropyFn.apply(logits, targets, ignore_index)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Variant A decoder: teacher-forced DecoderGRU.forward  (reference later.py:389-457), single GRUCell
+# ----------------------------------------------------------------------------------------------------------------------
+class DecoderGRUSeqFn(Function):
+    @staticmethod
+    def forward(ctx, feats, captions, h0, emb_w, W_ih, W_hh, b_ih, b_hh, fc_w, fc_b):
+        B, T = captions.shape
+        H = W_hh.shape[1]
+        caps = captions.contiguous()
+        feats = feats.contiguous()
+        emb_w = emb_w.contiguous()
+        X = ops.build_inputs(feats, emb_w, caps, 0)                       # [T*B, E]
+        GI = ops.linear(X, W_ih.contiguous(), b_ih.contiguous())          # [T*B, 3H]
+        WhhT = ops.transpose_pad(W_hh.contiguous(), ops.round4(3 * H))    # [H, ld3]
+        Hall, Hbm, saved = ops.gru_seq_fwd(GI, WhhT, b_hh.contiguous(), h0.contiguous(), T, save=True)
+        logits = ops.linear(Hbm.view(B * T, H), fc_w.contiguous(), fc_b)
+        ctx.save_for_backward(caps, X, Hall, Hbm, saved, emb_w, W_ih, W_hh, fc_w)
+        return logits.view(B, T, -1)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        caps, X, Hall, Hbm, saved, emb_w, W_ih, W_hh, fc_w = ctx.saved_tensors
+        B, T = caps.shape
+        H = W_hh.shape[1]
+        E = X.shape[1]
+        need = ctx.needs_input_grad
+        dl = dlogits.reshape(B * T, -1).contiguous()
+        Hbm2 = Hbm.view(B * T, H)
+        dfc_w = ops.matmul_tn(dl, Hbm2) if need[8] else None
+        dfc_b = ops.colsum(dl) if need[9] else None
+        dHbm = ops.matmul_nn(dl, fc_w.contiguous())                        # [B*T, H]
+        Whh_p = ops.copy_pad(W_hh.contiguous(), ops.round4(H))
+        dGI, dGH, dh0 = ops.gru_seq_bwd(dHbm.view(B, T, H), saved, Hall, Whh_p)
+        Hprev = Hall[:-1].reshape(T * B, H)
+        dW_hh = ops.matmul_tn(dGH, Hprev) if need[5] else None
+        db_hh = ops.colsum(dGH) if need[7] else None
+        dW_ih = ops.matmul_tn(dGI, X) if need[4] else None
+        db_ih = ops.colsum(dGI) if need[6] else None
+        dfeats = demb = None
+        if need[0] or need[3]:
+            dX = ops.matmul_nn(dGI, W_ih.contiguous())                     # [T*B, E]
+            if need[0]:
+                dfeats = dX[:B].clone()
+            if need[3]:
+                demb = torch.zeros_like(emb_w)
+                ops.embed_scatter_add(dX, caps, demb, 1)
+        return dfeats, None, (dh0 if need[2] else None), demb, dW_ih, dW_hh, db_ih, db_hh, dfc_w, dfc_b

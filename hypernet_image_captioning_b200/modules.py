@@ -1,0 +1,194 @@
+"""Host-side mirror of the reference module API (constructor / forward signatures and state_dict layout unchanged).
+
+  reference class                                   ->  class here
+  hypernet.HyperNet              (hypernet.py:26)    ->  HyperNetPooled  (alias ``hypernet.HyperNet`` in dropin/)
+  later.DecoderGRU               (later.py:362)      ->  DecoderGRU
+  hypernet_attention.HyperNet    (hypernet_attention.py:32) -> HyperNetAttention   (modules_attention.py)
+  models.decoderlstm.AttentionGru (models/decoderlstm.py:11) -> AttentionGru       (modules_attention.py)
+
+All arithmetic runs in the CUDA kernels behind the C-ABI; the nn.Module objects here only own parameters.
+``grad_mode``: "flow" (default) lets the caption loss reach the hypernet heads through the generated weights (the
+intended semantics, BASELINE.json north_star); "literal" reproduces the reference's graph cut (utils.py:57): the
+generated weights become leaves and their gradient lands on ``captioner.<cell>.weight_*.grad``.
+"""
+from typing import List
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import functional as Fn
+from . import ops
+
+try:  # the reference classes are LightningModules; use the real base when it exists
+    import pytorch_lightning as _pl
+    _Base = _pl.LightningModule
+except Exception:  # noqa: BLE001
+    class _Base(nn.Module):
+        def __init__(self):
+            super().__init__()
+            object.__setattr__(self, "hparams", {})
+
+        def log(self, *a, **k):
+            pass
+
+        @property
+        def device(self):
+            return next(self.parameters()).device
+
+
+def _hn_params(hn) -> List[torch.Tensor]:
+    ps = [hn.hn_base[0].weight, hn.hn_base[0].bias, hn.hn_base[2].weight, hn.hn_base[2].bias]
+    for head in hn.hn_heads:
+        ps += [head[0].weight, head[0].bias, head[2].weight, head[2].bias]
+    return ps
+
+
+class _HyperNetMixin:
+    """theta generation + injection shared by both variants (reference utils.py:24-69 flip/set_all_parameters)."""
+
+    grad_mode = "flow"
+
+    def generate_theta(self, x: torch.Tensor) -> torch.Tensor:
+        x2 = x.reshape(1, -1) if x.dim() == 1 else x
+        x2 = x2.to(torch.float32).contiguous()
+        if self.grad_mode == "literal":
+            with torch.no_grad():
+                return Fn.hypernet_theta(x2, _hn_params(self))
+        return Fn.hypernet_theta(x2, _hn_params(self))
+
+
+class PooledFeatureEncoder(nn.Module):
+    """Stands in for the frozen ResNet-101 + trainable fc of hypernet.py:40-48: the CNN trunk is out of scope
+    (BASELINE.json), so ``forward`` takes the precomputed pooled 2048-d feature and applies ``fc``."""
+
+    def __init__(self, num_ftrs, embed_size):
+        super().__init__()
+        self.fc = nn.Linear(num_ftrs, embed_size)
+
+    def forward(self, pooled):
+        return Fn.linear(pooled, self.fc.weight, self.fc.bias)
+
+
+class DecoderGRU(nn.Module):
+    """Drop-in for later.py:362 DecoderGRU (constructor signature, forward/infer signatures, state_dict keys).
+
+    ``data/vocab.pkl`` is *not* opened (reference later.py:372 loads it only for the discarded per-token text loop at
+    :451-452); the hard-coded V = 9684 of :449 is likewise not required."""
+
+    def __init__(self, embed_size, hidden_size, vocab_size, num_layers=1, dropout=False):
+        super().__init__()
+        self.embed_size, self.hidden_size, self.vocab_size = embed_size, hidden_size, vocab_size
+        self.dropout, self.num_layers = dropout, num_layers
+        self.lstm_cell = nn.GRUCell(input_size=embed_size, hidden_size=hidden_size)
+        self.layers = None
+        if num_layers > 1:
+            self.layers = nn.ModuleList([nn.GRUCell(hidden_size, hidden_size) for _ in range(num_layers - 1)])
+        self.fc_out = nn.Linear(hidden_size, vocab_size)
+        self.embed = nn.Embedding(vocab_size, embed_size)
+        self._generated = None  # per-cell (W_ih, W_hh, b_ih, b_hh) carrying the hypernet graph (flow mode)
+
+    def _cells(self):
+        if self._generated is not None:
+            return self._generated
+        cells = [self.lstm_cell] + (list(self.layers) if self.layers else [])
+        return [(c.weight_ih, c.weight_hh, c.bias_ih, c.bias_hh) for c in cells]
+
+    def _h0(self, features):
+        # reference later.py:393-394: global CPU RNG, then type_as(features)
+        return torch.rand(size=(features.size(0), self.hidden_size)).to(features.device, features.dtype)
+
+    def forward(self, features, captions, teacher_forcing=True, h0=None):
+        if not teacher_forcing:
+            raise NotImplementedError("multinomial-sampled decoding (later.py:424-434) is outside the hot path")
+        cells = self._cells()
+        if len(cells) != 1:
+            raise NotImplementedError("num_layers > 1 runs through forward_multilayer (see DESIGN.md)")
+        if h0 is None:
+            h0 = self._h0(features)
+        W_ih, W_hh, b_ih, b_hh = cells[0]
+        return Fn.DecoderGRUSeqFn.apply(features, captions, h0, self.embed.weight, W_ih, W_hh, b_ih, b_hh,
+                                        self.fc_out.weight, self.fc_out.bias)
+
+    @torch.no_grad()
+    def infer(self, features, max_len=50, h0=None):
+        """Greedy decode, reference later.py:459-490: argmax feedback, first cell only, returns softmax probs."""
+        W_ih, W_hh, b_ih, b_hh = [t.detach().contiguous() for t in self._cells()[0]]
+        B, H = features.size(0), self.hidden_size
+        if h0 is None:
+            h0 = self._h0(features)
+        emb, fc_w, fc_b = self.embed.weight.detach(), self.fc_out.weight.detach(), self.fc_out.bias.detach()
+        WhhT = ops.transpose_pad(W_hh, ops.round4(3 * H))
+        outputs = torch.empty(B, max_len, self.vocab_size, device=features.device, dtype=torch.float32)
+        h = h0.contiguous()
+        x = features.contiguous()
+        logits = torch.empty(B, self.vocab_size, device=features.device, dtype=torch.float32)
+        for t in range(max_len):
+            GI = ops.linear(x, W_ih, b_ih)
+            Hall, _, _ = ops.gru_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False)
+            h = Hall[1]
+            ops.linear(h, fc_w, fc_b, out=logits)
+            _, words = ops.softmax_argmax(logits, want_probs=True, probs_out=outputs[:, t, :])
+            if t + 1 < max_len:
+                x = ops.gather_rows(emb, words)
+        return outputs
+
+
+class HyperNetPooled(_HyperNetMixin, _Base):
+    """Drop-in for hypernet.py:26 HyperNet (pooled-feature variant)."""
+
+    def __init__(self, embed_size, hidden_size, vocab_size, vocab, num_layers=1, type='gru', lr=1e-6):
+        super().__init__()
+        if type != 'gru':
+            raise NotImplementedError("LSTM captioner (hypernet.py:53) is outside the hot path")
+        self.hparams['vocab_size'] = vocab_size
+        self.hparams['embed_size'] = embed_size
+        self.hparams['hidden_size'] = hidden_size
+        self.vocab = vocab
+        self.hparams['lr'] = lr
+        self.hparams['num_layers'] = num_layers
+        self.teacher_forcing_proba = 1.0
+        self.image_encoder = PooledFeatureEncoder(2048, embed_size)
+        self.captioner = DecoderGRU(embed_size, hidden_size, vocab_size, num_layers=num_layers, dropout=False)
+        E = embed_size
+        self.hn_base = nn.Sequential(nn.Linear(E, 4 * E), nn.LeakyReLU(), nn.Linear(4 * E, 8 * E), nn.LeakyReLU())
+        heads = []
+        for name, W in self.captioner.named_parameters():  # hypernet.py:62-89
+            if name in ('embed.weight', 'fc_out.weight', 'fc_out.bias'):
+                continue
+            w = W.numel()
+            if w < 8 * E:
+                dims = (8 * E, w, w)
+            elif w // 8 < 8 * E:
+                dims = (8 * E, 8 * E, 8 * E)
+            else:
+                dims = (8 * E, w // 8, w // 8)
+            heads.append(nn.Sequential(nn.Linear(dims[0], dims[1]), nn.LeakyReLU(), nn.Linear(dims[2], w)))
+        self.hn_heads = nn.ModuleList(heads)
+
+    def forward(self, x):
+        """theta = heads(base(x)); inject into the captioner's GRU cells; returns self.captioner (hypernet.py:104-114)."""
+        theta = self.generate_theta(x)[0]
+        E, H = self.hparams['embed_size'], self.hparams['hidden_size']
+        cells_mod = [self.captioner.lstm_cell] + (list(self.captioner.layers) if self.captioner.layers else [])
+        gen = []
+        for ci, cell in enumerate(cells_mod):
+            a = 0  # utils.py:45 -- every recursive call restarts at offset 0, so extra layers alias theta[0:...]
+            ws = []
+            for name in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                p = getattr(cell, name)
+                w = theta[a:a + p.numel()].reshape(p.shape)
+                a += p.numel()
+                with torch.no_grad():
+                    p.copy_(w)  # state_dict keeps the last generated weights, as the reference does
+                ws.append(w)
+            gen.append(tuple(ws))
+        self.captioner._generated = gen if self.grad_mode == "flow" else None
+        return self.captioner
+
+    def configure_optimizers(self):  # hypernet.py:116-124
+        params = list(self.hn_heads.parameters()) + list(self.hn_base.parameters())
+        params += list(self.captioner.embed.parameters()) + list(self.image_encoder.fc.parameters())
+        opt = torch.optim.Adam(params, lr=self.hparams['lr'])
+        sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, cooldown=2)
+        return [opt], [{'scheduler': sch, 'monitor': 'val_loss'}]

@@ -1,0 +1,264 @@
+"""Tensor-level wrappers over the C-ABI (device pointers in, nothing computed on the host).
+
+torch is used here for memory (allocation, views) and the current CUDA stream only.
+"""
+from typing import Optional
+
+import torch
+
+from . import _cabi
+
+LEAKY_SLOPE = 0.01
+ACT_NONE, ACT_LEAKY = 0, 1
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype=torch.float32):
+    if not t.is_cuda:
+        raise _cabi.CaphnError("caphn ops need CUDA tensors (there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise _cabi.CaphnError(f"expected {dtype}, got {t.dtype}")
+    return t
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _aligned16(t: torch.Tensor) -> torch.Tensor:
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# hypernet linear layers (weight streaming)
+# ----------------------------------------------------------------------------------------------------------------------
+def rows_linear_fwd(W, bias, A, act=ACT_NONE, out=None, slope=LEAKY_SLOPE):
+    """Y[g,n] = act(A[g,:] . W[n,:] + bias[n]).  A [G,K] (row stride may exceed K), W [N,K] contiguous.
+    ``out`` may be a column slice of a wider matrix (e.g. theta[:, a:b])."""
+    _chk(W), _chk(A)
+    W = _aligned16(W)
+    N, K = W.shape
+    G = A.shape[0]
+    assert A.shape[1] == K and A.stride(1) == 1
+    if out is None:
+        out = torch.empty(G, N, device=W.device, dtype=torch.float32)
+    assert out.shape == (G, N) and out.stride(1) == 1
+    for g0 in range(0, G, 8):
+        g1 = min(G, g0 + 8)
+        _cabi.call("caphn_rows_linear_fwd", W.data_ptr(), _p(bias), A[g0:g1].data_ptr(), A.stride(0),
+                   out[g0:g1].data_ptr(), out.stride(0), g1 - g0, N, K, act, slope, _stream())
+    return out
+
+
+def rows_linear_bwd(W, A, Y, dY, act=ACT_NONE, need_dW=True, need_dA=True, dA=None, slope=LEAKY_SLOPE):
+    """Backward of rows_linear_fwd.  Returns (dW [N,K] or None, dbias [N], dA [G,K] or None).
+    When ``dA`` is given the input gradient is accumulated into it (atomics)."""
+    _chk(W), _chk(A), _chk(dY)
+    W = _aligned16(W)
+    N, K = W.shape
+    G = A.shape[0]
+    assert dY.shape == (G, N) and dY.stride(1) == 1 and A.stride(1) == 1
+    if act != ACT_NONE:
+        assert Y is not None and Y.shape == (G, N) and Y.stride(1) == 1
+    dev = W.device
+    dP = torch.empty(G, N, device=dev, dtype=torch.float32)
+    dbias = torch.empty(N, device=dev, dtype=torch.float32)
+    dW = torch.empty(N, K, device=dev, dtype=torch.float32) if (need_dW or need_dA) else None
+    if need_dA and dA is None:
+        dA = torch.zeros(G, K, device=dev, dtype=torch.float32)
+    if not need_dA:
+        dA = None
+    _cabi.call("caphn_rows_linear_bwd", W.data_ptr(), A.data_ptr(), A.stride(0), _p(Y), Y.stride(0) if Y is not None else 0,
+               dY.data_ptr(), dY.stride(0), dP.data_ptr(), _p(dW), dbias.data_ptr(), _p(dA),
+               dA.stride(0) if dA is not None else 0, G, N, K, act, slope, _stream())
+    return (dW if need_dW else None), dbias, dA
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# dense fp32 GEMMs
+# ----------------------------------------------------------------------------------------------------------------------
+def _gemm(A, lda, a_k, Bm, ldb, b_k, M, N, K, bias=None, relu=False, out=None, splitk=1, accumulate=False):
+    if out is None:
+        if splitk > 1 or accumulate:
+            out = torch.zeros(M, N, device=A.device, dtype=torch.float32)
+        else:
+            out = torch.empty(M, N, device=A.device, dtype=torch.float32)
+    assert out.stride(-1) == 1
+    _cabi.call("caphn_gemm_f32", A.data_ptr(), lda, int(a_k), Bm.data_ptr(), ldb, int(b_k), out.data_ptr(),
+               out.stride(0), _p(bias), M, N, K, int(relu), splitk, int(accumulate), _stream())
+    return out
+
+
+def _auto_splitk(M, N, K):
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    if tiles >= 148 or K <= 512:
+        return 1
+    return max(1, min((K + 255) // 256, (2 * 148 + tiles - 1) // tiles))
+
+
+def linear(X, W, bias=None, relu=False, out=None):
+    """out[M,N] = X[M,K] @ W[N,K]^T + bias (optional ReLU)."""
+    _chk(X), _chk(W)
+    assert X.dim() == 2 and X.stride(1) == 1 and W.stride(1) == 1 and X.shape[1] == W.shape[1]
+    return _gemm(X, X.stride(0), 1, W, W.stride(0), 1, X.shape[0], W.shape[0], X.shape[1], bias, relu, out)
+
+
+def matmul_nn(A, Bm, out=None, accumulate=False):
+    """out[M,N] = A[M,K] @ B[K,N]."""
+    _chk(A), _chk(Bm)
+    assert A.stride(1) == 1 and Bm.stride(1) == 1 and A.shape[1] == Bm.shape[0]
+    return _gemm(A, A.stride(0), 1, Bm, Bm.stride(0), 0, A.shape[0], Bm.shape[1], A.shape[1], out=out,
+                 accumulate=accumulate)
+
+
+def matmul_tn(A, Bm, out=None, accumulate=False):
+    """out[M,N] = A[K,M]^T @ B[K,N]   (weight gradients: dW = dY^T X); split-K when the output is small."""
+    _chk(A), _chk(Bm)
+    assert A.stride(1) == 1 and Bm.stride(1) == 1 and A.shape[0] == Bm.shape[0]
+    K, M = A.shape
+    N = Bm.shape[1]
+    sk = _auto_splitk(M, N, K)
+    if out is not None and sk > 1 and not accumulate:
+        out.zero_()
+    return _gemm(A, A.stride(0), 0, Bm, Bm.stride(0), 0, M, N, K, out=out, splitk=sk, accumulate=accumulate)
+
+
+def colsum(X, out=None):
+    """out[n] (+)= sum_m X[m,n]."""
+    _chk(X)
+    assert X.dim() == 2 and X.stride(1) == 1
+    if out is None:
+        out = torch.zeros(X.shape[1], device=X.device, dtype=torch.float32)
+    _cabi.call("caphn_colsum", X.data_ptr(), X.stride(0), X.shape[0], X.shape[1], out.data_ptr(), _stream())
+    return out
+
+
+def transpose_pad(src, ldd):
+    """dst [C, ldd] with dst[c, r] = src[r, c], zero padded."""
+    _chk(src)
+    R, C = src.shape
+    assert src.stride(1) == 1
+    dst = torch.empty(C, ldd, device=src.device, dtype=torch.float32)
+    _cabi.call("caphn_transpose_pad", src.data_ptr(), src.stride(0), dst.data_ptr(), ldd, R, C, _stream())
+    return dst
+
+
+def copy_pad(src, ldd):
+    _chk(src)
+    R, C = src.shape
+    assert src.stride(1) == 1
+    if ldd == C and src.is_contiguous() and src.data_ptr() % 16 == 0:
+        return src
+    dst = torch.empty(R, ldd, device=src.device, dtype=torch.float32)
+    _cabi.call("caphn_copy_pad", src.data_ptr(), src.stride(0), dst.data_ptr(), ldd, R, C, _stream())
+    return dst
+
+
+def round4(n):
+    return (n + 3) // 4 * 4
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# recurrences
+# ----------------------------------------------------------------------------------------------------------------------
+def gru_seq_fwd(GI, WhhT, bhh, h0, T, save=True, want_bm=True):
+    """GI [T*B,3H] time-major, WhhT [H,ld3]; returns Hall [T+1,B,H], Hbm [B,T,H] | None, saved gates | None."""
+    B, H = h0.shape
+    dev = GI.device
+    Hall = torch.empty(T + 1, B, H, device=dev, dtype=torch.float32)
+    Hall[0].copy_(h0)
+    Hbm = torch.empty(B, T, H, device=dev, dtype=torch.float32) if want_bm else None
+    saved = torch.empty(4, T, B, H, device=dev, dtype=torch.float32) if save else None
+    sp = [saved[i].data_ptr() for i in range(4)] if save else [None] * 4
+    _cabi.call("caphn_gru_seq_fwd", GI.data_ptr(), WhhT.data_ptr(), WhhT.stride(0), bhh.data_ptr(), Hall.data_ptr(),
+               _p(Hbm), sp[0], sp[1], sp[2], sp[3], B, T, H, _stream())
+    return Hall, Hbm, saved
+
+
+def gru_seq_bwd(dHbm, saved, Hall, Whh_p):
+    """Returns dGI, dGH [T*B,3H] (time-major) and dh0 [B,H]."""
+    Tp1, B, H = Hall.shape
+    T = Tp1 - 1
+    dev = Hall.device
+    dGI = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+    dGH = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+    dh0 = torch.empty(B, H, device=dev, dtype=torch.float32)
+    assert dHbm.is_contiguous()
+    _cabi.call("caphn_gru_seq_bwd", dHbm.data_ptr(), saved[0].data_ptr(), saved[1].data_ptr(), saved[2].data_ptr(),
+               saved[3].data_ptr(), Hall.data_ptr(), Whh_p.data_ptr(), Whh_p.stride(0), dGI.data_ptr(), dGH.data_ptr(),
+               dh0.data_ptr(), B, T, H, _stream())
+    return dGI, dGH, dh0
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# cross-entropy, softmax/argmax, embedding
+# ----------------------------------------------------------------------------------------------------------------------
+def ce_fwd(logits2d, targets, ignore_index):
+    """Returns (lossbuf [2] = (mean loss, #valid rows), lse [M])."""
+    _chk(logits2d), _chk(targets, torch.int64)
+    M, V = logits2d.shape
+    assert logits2d.stride(1) == 1 and targets.is_contiguous() and targets.numel() == M
+    dev = logits2d.device
+    lse = torch.empty(M, device=dev, dtype=torch.float32)
+    scratch = torch.empty(2 * M, device=dev, dtype=torch.float32)
+    lossbuf = torch.empty(2, device=dev, dtype=torch.float32)
+    has = ignore_index is not None
+    _cabi.call("caphn_ce_fwd", logits2d.data_ptr(), logits2d.stride(0), targets.data_ptr(), M, V, int(has),
+               int(ignore_index) if has else 0, lse.data_ptr(), scratch.data_ptr(), lossbuf.data_ptr(), _stream())
+    return lossbuf, lse
+
+
+def ce_bwd(logits2d, targets, ignore_index, lse, lossbuf, gscale):
+    M, V = logits2d.shape
+    dX = torch.empty(M, V, device=logits2d.device, dtype=torch.float32)
+    has = ignore_index is not None
+    _cabi.call("caphn_ce_bwd", logits2d.data_ptr(), logits2d.stride(0), targets.data_ptr(), M, V, int(has),
+               int(ignore_index) if has else 0, lse.data_ptr(), gscale.data_ptr(), lossbuf.data_ptr(), dX.data_ptr(),
+               dX.stride(0), _stream())
+    return dX
+
+
+def softmax_argmax(X, want_probs=True, probs_out=None, want_argmax=True):
+    _chk(X)
+    M, V = X.shape
+    assert X.stride(1) == 1
+    Y = None
+    if want_probs:
+        Y = probs_out if probs_out is not None else torch.empty(M, V, device=X.device, dtype=torch.float32)
+        assert Y.stride(1) == 1
+    am = torch.empty(M, device=X.device, dtype=torch.int64) if want_argmax else None
+    _cabi.call("caphn_softmax_argmax", X.data_ptr(), X.stride(0), M, V, _p(Y), Y.stride(0) if Y is not None else 0,
+               _p(am), _stream())
+    return Y, am
+
+
+def gather_rows(table, idx):
+    _chk(table), _chk(idx, torch.int64)
+    idx = idx.contiguous()
+    n, E = idx.numel(), table.shape[1]
+    out = torch.empty(n, E, device=table.device, dtype=torch.float32)
+    _cabi.call("caphn_gather_rows", table.data_ptr(), idx.data_ptr(), n, E, out.data_ptr(), E, _stream())
+    return out
+
+
+def build_inputs(feat, emb, caps, mode):
+    """Time-major decoder inputs X [T*B, E]; mode 0 = pooled decoder (x_0 = feat), 1 = attention decoder (x_0 = x_1 = 0)."""
+    _chk(emb), _chk(caps, torch.int64)
+    B, T = caps.shape
+    E = emb.shape[1]
+    X = torch.empty(T * B, E, device=emb.device, dtype=torch.float32)
+    _cabi.call("caphn_build_inputs", _p(feat), emb.data_ptr(), caps.data_ptr(), B, T, E, mode, X.data_ptr(), _stream())
+    return X
+
+
+def embed_scatter_add(dX, caps, dEmb, t0):
+    B, T = caps.shape
+    E = dEmb.shape[1]
+    _cabi.call("caphn_embed_scatter_add", dX.data_ptr(), caps.data_ptr(), B, T, E, t0, dEmb.data_ptr(), _stream())
+    return dEmb

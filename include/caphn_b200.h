@@ -1,0 +1,91 @@
+/* caphn_b200.h -- C-ABI of libcaphn_b200.so: the B200 (sm_100a) hot path of Caption-HN.
+ *
+ * The reference (zacharie12/Hypernet-image-captioning) is pure Python: it has no FFI/plugin boundary of its own, its
+ * "kernels" are torch.nn calls.  This header is therefore the boundary a reference maintainer would bind (ctypes
+ * stub in INTEGRATION.md); every entry point names the reference lines whose torch calls it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers (fp32 unless noted; token ids are int64 = torch.long), caller-allocated;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it (no sync, no allocation);
+ *   - return value: 0 = ok, -1 = invalid argument, otherwise the cudaError_t of the failed launch;
+ *   - "time-major" sequence tensors have row index t*B + b; "batch-major" b*T + t;
+ *   - `long` is 64-bit (LP64).
+ */
+#ifndef CAPHN_B200_H
+#define CAPHN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- hypernetwork layers (hypernet_attention.py:111-118, hypernet.py:104-111; nn.Linear + nn.LeakyReLU) ----------- */
+
+/* Y[g*ldy+n] = act(sum_k A[g*lda+k] * W[n*K+k] + bias[n]), g < G <= 8.  act: 0 none, 1 LeakyReLU(slope).
+ * W is streamed exactly once (HBM-bound); Y may be a column slice of theta (ldy = theta length).  W 16-byte aligned. */
+int caphn_rows_linear_fwd(const float* W, const float* bias, const float* A, long lda, float* Y, long ldy, int G,
+                          long N, long K, int act, float slope, void* stream);
+
+/* Backward of the above (autograd of the same reference lines).  dP: scratch [G,N].  dW[N,K], dbias[N] are written;
+ * dA[g*ldda+k] is accumulated with atomics (caller zero-initialises; NULL skips it).  Y only read when act == 1.
+ * One pass: reads W once, writes dW once.  G <= 64. */
+int caphn_rows_linear_bwd(const float* W, const float* A, long lda, const float* Y, long ldy, const float* dY,
+                          long lddy, float* dP, float* dW, float* dbias, float* dA, long ldda, int G, long N, long K,
+                          int act, float slope, void* stream);
+
+/* ---- dense fp32 GEMM (addmm behind nn.Linear / nn.GRUCell: models/decoderlstm.py:61,100,105; later.py:411,418,442) -- */
+
+/* C[m*ldc+n] = sum_k A(m,k) B(n,k) (+bias[n]) (ReLU).  A(m,k) = a_kmajor ? A[m*lda+k] : A[k*lda+m]; same for B.
+ * splitk > 1 or accumulate != 0: result is atomically added into C. */
+int caphn_gemm_f32(const float* A, long lda, int a_kmajor, const float* B, long ldb, int b_kmajor, float* C, long ldc,
+                   const float* bias, int M, int N, int K, int relu, int splitk, int accumulate, void* stream);
+
+/* dst[c*ldd+r] = src[r*lds+c] (zero padded to ldd) / dst[r*ldd+c] = src[r*lds+c] (zero padded): lay generated
+ * weights out with 16-byte rows for the recurrence kernels. */
+int caphn_transpose_pad(const float* src, long lds, float* dst, long ldd, int R, int C, void* stream);
+int caphn_copy_pad(const float* src, long lds, float* dst, long ldd, long R, int C, void* stream);
+
+/* ---- pooled-feature decoder recurrence (later.py:389-490 DecoderGRU; torch GRUCell gates r,z,n) -------------------- */
+
+/* All T steps in one launch.  GI [T,B,3H] = x_t W_ih^T + b_ih (time-major); WhhT [H,ld3] (= W_hh^T, ld3 % 4 == 0);
+ * Hall [T+1,B,H] with Hall[0] = h0 on entry, Hall[t+1] = h_t on exit; Hbm [B,T,H] (optional batch-major copy);
+ * R,Z,Nn,GHN [T,B,H] saved gate values for the backward (all four or none). */
+int caphn_gru_seq_fwd(const float* GI, const float* WhhT, int ld3, const float* bhh, float* Hall, float* Hbm, float* R,
+                      float* Z, float* Nn, float* GHN, int B, int T, int H, void* stream);
+
+/* BPTT.  dHbm [B,T,H] = dL/dh_t from the vocabulary projection; Whh [3H,ldh]; outputs dGI,dGH [T,B,3H], dh0 [B,H]. */
+int caphn_gru_seq_bwd(const float* dHbm, const float* R, const float* Z, const float* Nn, const float* GHN,
+                      const float* Hall, const float* Whh, int ldh, float* dGI, float* dGH, float* dh0, int B, int T,
+                      int H, void* stream);
+
+/* ---- loss / sampling / embedding (cc_train_hypernet.py:153, hypernet.py:145; decoderlstm.py:62,91-96; later.py:472-479) */
+
+/* Mean softmax cross-entropy over rows of X[M,V] whose target != ignore (when has_ignore).  lse [M]; scratch [2M];
+ * lossbuf[0] = mean loss, lossbuf[1] = number of counted rows. */
+int caphn_ce_fwd(const float* X, long ld, const long long* tgt, long M, int V, int has_ignore, long long ignore,
+                 float* lse, float* scratch, float* lossbuf, void* stream);
+/* dX = gscale[0] * d(mean loss)/dX, using lse / lossbuf from caphn_ce_fwd (no host sync). */
+int caphn_ce_bwd(const float* X, long ld, const long long* tgt, long M, int V, int has_ignore, long long ignore,
+                 const float* lse, const float* gscale, const float* lossbuf, float* dX, long lddx, void* stream);
+/* Y (optional) = row softmax of X[M,V]; amax (optional, int64) = row argmax, lowest index on ties. */
+int caphn_softmax_argmax(const float* X, long ld, long M, int V, float* Y, long ldy, long long* amax, void* stream);
+/* out[i,:] = table[idx[i],:]  (idx int64; negative idx -> zero row). */
+int caphn_gather_rows(const float* table, const long long* idx, long n, int E, float* out, long ldo, void* stream);
+/* Time-major decoder inputs X[T,B,E].  mode 0 (later.py:411,418): X[0]=feat, X[t]=Emb[caps[:,t-1]];
+ * mode 1 (models/decoderlstm.py:82-88): X[0]=X[1]=0, X[t]=Emb[caps[:,t-1]]. */
+int caphn_build_inputs(const float* feat, const float* emb, const long long* caps, int B, int T, int E, int mode,
+                       float* X, void* stream);
+/* dEmb[caps[b,t-1],:] += dX[t,b,:] for t >= t0  (embedding_dense_backward). */
+int caphn_embed_scatter_add(const float* dX, const long long* caps, int B, int T, int E, int t0, float* dEmb,
+                            void* stream);
+/* out[n] += sum_m X[m*ld+n]  (bias gradients). */
+int caphn_colsum(const float* X, long ld, long M, int N, float* out, void* stream);
+/* out[b,f] = mean_p X[b,p,f] (models/decoderlstm.py:133) and its backward dX[b,p,f] += g[b,f]/P. */
+int caphn_mean_pos(const float* X, int B, int P, int Fd, float* out, void* stream);
+int caphn_mean_pos_bwd(const float* g, int B, int P, int Fd, float* dX, void* stream);
+/* y[i] = ref[i] > 0 ? y[i] : 0  (ReLU backward, in place). */
+int caphn_relu_mask(const float* ref, float* y, long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAPHN_B200_H */

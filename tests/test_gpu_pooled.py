@@ -1,0 +1,119 @@
+"""Module-level parity of the pooled-feature path (HyperNetPooled + DecoderGRU) through the drop-in API:
+against the golden vectors of the unmodified reference (tests/golden/pooled_l1.npz) and against the oracle port
+on larger seeded inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from golden_util import load_case, params_of, rel_err, grad_close
+from oracle import caption_hn_oracle as O
+
+TOL_LOGITS = 1e-4   # BASELINE.json north_star: fp32 mode within 1e-4 relative on logits and loss
+TOL_GRAD = 1e-3     # gradients <= 1e-3 relative
+
+
+def _model_from(p, E, H, V, L=1, mode="flow"):
+    import hypernet_image_captioning_b200 as C
+    m = C.HyperNetPooled(E, H, V, None, num_layers=L)
+    sd = m.state_dict()
+    missing = [k for k in p if k not in sd]
+    assert not missing, missing
+    for k, v in p.items():
+        sd[k] = v
+    m.load_state_dict(sd)
+    m.grad_mode = mode
+    return m.cuda()
+
+
+def test_state_dict_layout_matches_reference():
+    c = load_case("pooled_l1")
+    p = params_of(c)
+    import hypernet_image_captioning_b200 as C
+    m = C.HyperNetPooled(8, 6, 9684, None)
+    sd = m.state_dict()
+    gen = {"captioner.lstm_cell." + k for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")}
+    assert set(sd.keys()) == set(p.keys()) | gen
+    for k, v in p.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+
+
+@pytest.mark.parametrize("mode", ["literal", "flow"])
+def test_pooled_golden(mode):
+    c = load_case("pooled_l1")
+    p = params_of(c)
+    m = _model_from(p, 8, 6, 9684, mode=mode)
+    import hypernet_image_captioning_b200 as C
+    captioner = m.forward(c["style"].cuda())
+    for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+        assert rel_err(getattr(captioner.lstm_cell, k), c["gen/0/" + k]) < 1e-5, k
+    feats = m.image_encoder(c["pooled"].cuda())
+    logits = captioner(feats, c["captions"].cuda(), True, h0=c["h0"].cuda())
+    assert rel_err(logits, c["tf/logits"]) < TOL_LOGITS
+    loss = C.cross_entropy(logits, c["captions"].cuda(), None)
+    assert abs(loss.item() - c["tf/loss"].item()) < TOL_LOGITS * abs(c["tf/loss"].item())
+    loss.backward()
+    named = dict(m.named_parameters())
+    for k in ("image_encoder.fc.weight", "image_encoder.fc.bias", "captioner.embed.weight",
+              "captioner.fc_out.weight", "captioner.fc_out.bias"):
+        assert grad_close(named[k].grad, c["tf/grad/" + k], TOL_GRAD), k
+    if mode == "literal":
+        for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+            assert grad_close(getattr(captioner.lstm_cell, k).grad, c["tf/grad/gen/0/" + k], TOL_GRAD), k
+        assert all(v.grad is None for k, v in named.items() if k.startswith("hn_"))
+    else:
+        n = 0
+        for k, v in c.items():
+            if k.startswith("flow/grad/"):
+                assert grad_close(named[k[10:]].grad, v, TOL_GRAD), k
+                n += 1
+        assert n >= 12
+
+
+def test_pooled_infer_golden_token_exact():
+    c = load_case("pooled_l1")
+    m = _model_from(params_of(c), 8, 6, 9684)
+    with torch.no_grad():
+        captioner = m.forward(c["style"].cuda())
+        probs = captioner.infer(m.image_encoder(c["pooled"].cuda()), max_len=c["infer/probs"].shape[1],
+                                h0=c["h0"].cuda())
+    assert torch.equal(probs.argmax(-1).cpu(), c["infer/probs"].argmax(-1))
+    assert rel_err(probs, c["infer/probs"]) < TOL_LOGITS
+
+
+def test_pooled_rng_consumption_matches_reference():
+    """DecoderGRU.forward draws torch.rand(B,H) from the global CPU generator (later.py:393)."""
+    c = load_case("pooled_l1")
+    m = _model_from(params_of(c), 8, 6, 9684)
+    captioner = m.forward(c["style"].cuda())
+    feats = m.image_encoder(c["pooled"].cuda())
+    torch.manual_seed(1)
+    logits = captioner(feats, c["captions"].cuda(), True)
+    assert rel_err(logits, c["tf/logits"]) < TOL_LOGITS
+
+
+@pytest.mark.parametrize("B,T,E,H,V", [(37, 9, 24, 30, 311), (64, 20, 200, 150, 2000)])
+def test_pooled_vs_oracle_medium(B, T, E, H, V):
+    import hypernet_image_captioning_b200 as C
+    p = O.init_params_pooled(2048, E, H, V, L=1, seed=5)
+    g = torch.Generator().manual_seed(99)
+    pooled = torch.relu(torch.randn(B, 2048, generator=g))
+    caps = O.synth_captions(B, T, V, g)
+    style = torch.randn(1, E, generator=g)
+    h0 = torch.rand(B, H, generator=g)
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    logits_ref, theta_ref, _ = O.path_pooled(pl, style, pooled, caps, h0, L=1, flow=True)
+    loss_ref = O.caption_loss(logits_ref, caps, None)
+    loss_ref.backward()
+
+    m = _model_from(p, E, H, V)
+    captioner = m.forward(style.cuda())
+    logits = captioner(m.image_encoder(pooled.cuda()), caps.cuda(), True, h0=h0.cuda())
+    loss = C.cross_entropy(logits, caps.cuda(), None)
+    loss.backward()
+    assert rel_err(logits, logits_ref) < TOL_LOGITS
+    assert abs(loss.item() - loss_ref.item()) < TOL_LOGITS * abs(loss_ref.item())
+    for k, v in m.named_parameters():
+        if k.startswith("captioner.lstm_cell."):
+            continue
+        assert grad_close(v.grad, pl[k].grad, TOL_GRAD), k
