@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py -- captions/s of the Caption-HN hot path on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                      # our CUDA path (default N=1)
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]     # the reference's CPU path (oracle port)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N # N > 1 (one rank per GPU, NCCL)
+
+Workload (BASELINE.json configs[1]): pooled-feature hypernet-GRU (hypernet.py HyperNet + DecoderGRU), batch 512 per
+GPU, T=20, E=200, H=150, V=9684, L=1, fp32, teacher-forced forward + backward with the gradient flowing through the
+generated weights into the hypernet heads ("flow"), hypernet forward included, no optimizer step.
+A "step" = hypernet -> theta -> image_encoder.fc -> decoder -> cross-entropy -> full backward on one batch.
+Synthetic data, default-init weights.  Weak scaling: the per-GPU batch is fixed.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(B=512, T=20, E=200, H=150, V=9684, L=1, D=2048)
+CPU_SAMPLE_B = 512  # same batch as the GPU arm: the per-step hypernet cost amortises over the batch, so a smaller sample would understate the CPU
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=CFG["B"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        load = [s for s, p in zip(sm, power) if p > 250] or sm
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle port of the reference's PyTorch path on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_arm(steps, warmup, B=CPU_SAMPLE_B):
+    """Times hypernet fwd + image_encoder.fc + DecoderGRU fwd + CE + backward (flow) on the CPU, all host threads."""
+    from oracle import caption_hn_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = CFG
+    p = O.init_params_pooled(c["D"], c["E"], c["H"], c["V"], L=c["L"], seed=0)
+    p = {k: v.requires_grad_(True) for k, v in p.items()}
+    g = torch.Generator().manual_seed(1234)
+    pooled = torch.relu(torch.randn(B, c["D"], generator=g))
+    caps = O.synth_captions(B, c["T"], c["V"], g)
+    h0 = torch.rand(B, c["H"], generator=g)
+
+    def step():
+        for v in p.values():
+            v.grad = None
+        style = p["captioner.embed.weight"][4:5]
+        logits, _, _ = O.path_pooled(p, style, pooled, caps, h0, L=c["L"], flow=True)
+        loss = O.caption_loss(logits, caps, None)
+        loss.backward()
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": B * steps / dt, "unit": "captions/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"oracle port (torch CPU fp32) of the same workload at batch {B} x {steps} steps "
+                      f"(+{warmup} warm-up), flow-mode fwd+bwd incl. hypernet", "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    r = cpu_reference_arm(steps, warmup)
+    line = {
+        "impl": "reference", "metric": "hypernet-GRU train captions/s", "value": r["value"], "unit": "captions/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    c = CFG
+    return {
+        "workload": (f"BASELINE configs[1]: pooled-feature hypernet-GRU (hypernet.py HyperNet + DecoderGRU) teacher-forced "
+                     f"fwd+bwd, flow mode, hypernet fwd included, no optimizer; B={args.batch}/GPU T={c['T']} E={c['E']} "
+                     f"H={c['H']} V={c['V']} L={c['L']} D={c['D']}"),
+        "global_batch": args.batch * world, "seq_len": c["T"], "parallelism": f"dp{world}",
+        "l2": "inputs larger than L2: 6.46 GB of hypernet head weights are streamed every step",
+    }
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import hypernet_image_captioning_b200 as C
+    from hypernet_image_captioning_b200 import _cabi, ops, parallel
+    from oracle import caption_hn_oracle as O  # synthetic-input generators + cpu_baseline leg only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.load()
+
+    c = CFG
+    B, T = args.batch, c["T"]
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = C.HyperNetPooled(c["E"], c["H"], c["V"], None, num_layers=c["L"])
+    model.grad_mode = "flow"
+    model.dp_enabled = world > 1
+    shared = parallel.shared_parameters(model)
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    pooled_h = torch.relu(torch.randn(B, c["D"], generator=g)).pin_memory()
+    caps_h = O.synth_captions(B, T, c["V"], g).pin_memory()
+    pooled_d, caps_d = pooled_h.to(dev), caps_h.to(dev)
+    h0_d = torch.rand(B, c["H"], generator=g).to(dev)
+    loss_h = torch.empty(1, pin_memory=True)
+    inv_world = 1.0 / world
+
+    def step(pooled, caps, h0):
+        model.zero_grad(set_to_none=True)
+        style = model.captioner.embed.weight[4:5]          # 'factual' row, hypernet_attention.py:139-142 idiom
+        captioner = model.forward(style)
+        feats = model.image_encoder(pooled)
+        logits = captioner(feats, caps, True, h0=h0)
+        loss = C.cross_entropy(logits, caps, None)
+        (loss * inv_world if world > 1 else loss).backward()
+        if world > 1:
+            parallel.allreduce_shared_grads(shared)
+        return loss
+
+    def step_e2e():
+        pooled = pooled_h.to(dev, non_blocking=True)
+        caps = caps_h.to(dev, non_blocking=True)
+        loss = step(pooled, caps, None)                    # h0 drawn on the host like the reference (later.py:393)
+        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return loss_h
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        step(pooled_d, caps_d, h0_d)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _cabi.launches()
+    ms = timed(lambda: step(pooled_d, caps_d, h0_d), args.steps)
+    launches = _cabi.launches() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * world * args.steps / (ms * 1e-3)
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
+    h2d = pooled_h.numel() * 4 + caps_h.numel() * 8 + B * c["H"] * 4
+    final_loss = float(loss_h.item())
+
+    # ---- roofline of the dominant kernel: the fused head backward (reads W2 once, writes dW2 once), timed alone ----
+    head = model.hn_heads[0]
+    W2 = head[2].weight.detach()
+    N, K = W2.shape
+    a1 = torch.randn(1, K, device=dev)
+    dY = torch.randn(1, N, device=dev)
+    for _ in range(2):
+        ops.rows_linear_bwd(W2, a1, None, dY, ops.ACT_NONE)
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(5):
+        dWs = torch.empty(N, K, device=dev)
+        dP, db, dA = torch.empty(1, N, device=dev), torch.empty(N, device=dev), torch.zeros(1, K, device=dev)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        _cabi.call("caphn_rows_linear_bwd", W2.data_ptr(), a1.data_ptr(), K, None, 0, dY.data_ptr(), N, dP.data_ptr(),
+                   dWs.data_ptr(), db.data_ptr(), dA.data_ptr(), K, 1, N, K, 0, 0.01,
+                   torch.cuda.current_stream().cuda_stream)
+        e.record()
+        evs.append((s, e))
+        del dWs
+    torch.cuda.synchronize()
+    k_ms = statistics.mean(s.elapsed_time(e) for s, e in evs)
+    alg_bytes = 2.0 * N * K * 4
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("rows_bwd_kernel")
+    except Exception:  # noqa: BLE001
+        pass
+    roofline = {"kernel": "rows_bwd_kernel<1> (hn_heads.0.2 backward: dW2 + dA1 in one pass)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650 GB/s",
+                "alg_bytes_per_launch": alg_bytes, "ms_per_launch": k_ms}
+
+    extras = {}
+    if not args.no_extras:
+        # literal mode (the reference's actual behaviour: graph cut at utils.py:57, no head backward)
+        model.grad_mode = "literal"
+        for _ in range(3):
+            step(pooled_d, caps_d, h0_d)
+        ms_lit = timed(lambda: step(pooled_d, caps_d, h0_d), args.steps)
+        model.grad_mode = "flow"
+        extras["literal_mode_captions_per_s"] = B * world * args.steps / (ms_lit * 1e-3)
+        # greedy decode (DecoderGRU.infer, max_len = T), hypernet forward included
+        def decode():
+            with torch.no_grad():
+                cap = model.forward(model.captioner.embed.weight[4:5])
+                return cap.infer(model.image_encoder(pooled_d), max_len=T, h0=h0_d)
+        for _ in range(3):
+            decode()
+        ms_dec = timed(decode, args.steps)
+        extras["greedy_decode_captions_per_s"] = B * world * args.steps / (ms_dec * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del model
+        torch.cuda.empty_cache()
+        cpu = cpu_reference_arm(steps=3, warmup=1)
+
+    if rank == 0:
+        line = {
+            "metric": "hypernet-GRU train captions/s", "value": value, "unit": "captions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+            "loss": final_loss, "extras": extras,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

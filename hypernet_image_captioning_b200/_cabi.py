@@ -36,6 +36,8 @@ SIGNATURES = {
     "caphn_mean_pos": [P, I, I, I, P, P],
     "caphn_mean_pos_bwd": [P, I, I, I, P, P],
     "caphn_relu_mask": [P, P, L, P],
+    "caphn_launch_count": [P],
+    "caphn_build_arch": [P],
 }
 
 _lib = None
@@ -76,4 +78,7 @@ def call(name, *args):
 
 
 def launches():
-    return _launches
+    """Number of CUDA kernels the library has launched since load (counted inside the library)."""
+    out = ctypes.c_ulonglong(0)
+    call("caphn_launch_count", ctypes.byref(out))
+    return int(out.value)

@@ -245,7 +245,7 @@ int caphn_ce_fwd(const float* X, long ld, const long long* tgt, long M, int V, i
     if (M <= 0 || V <= 0) return CAPHN_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     ce_fwd_kernel<<<(unsigned)M, CE_THREADS, 0, st>>>(X, ld, tgt, V, has_ignore, ignore, lse, scratch, scratch + M);
-    CAPHN_CHECK(cudaGetLastError());
+    CAPHN_LAUNCH_CHECK();
     ce_finish_kernel<<<1, 1024, 0, st>>>(scratch, scratch + M, M, lossbuf);
     CAPHN_RETURN_LAST();
 }

@@ -6,11 +6,23 @@
 #define CAPHN_OK 0
 #define CAPHN_EINVAL (-1)
 
-// Launch-error check used by every extern "C" entry point: returns the cudaError_t as int (0 == ok).
+// Number of kernels this library has launched (bench.py reports it as gpu_launches); defined in api_misc.cu.
+extern unsigned long long caphn_launch_counter;
+
+// After a kernel launch at the end of an entry point: count it and return the cudaError_t as int (0 == ok).
 #define CAPHN_RETURN_LAST()                    \
     do {                                       \
+        ++caphn_launch_counter;                \
         cudaError_t e__ = cudaGetLastError();  \
         return (int)e__;                       \
+    } while (0)
+
+// After a kernel launch in the middle of an entry point.
+#define CAPHN_LAUNCH_CHECK()                       \
+    do {                                           \
+        ++caphn_launch_counter;                    \
+        cudaError_t e__ = cudaGetLastError();      \
+        if (e__ != cudaSuccess) return (int)e__;   \
     } while (0)
 
 #define CAPHN_CHECK(expr)                          \

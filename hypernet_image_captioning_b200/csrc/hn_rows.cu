@@ -280,7 +280,7 @@ int caphn_rows_linear_bwd(const float* W, const float* A, long lda, const float*
     if (N <= 0 || K <= 0 || G <= 0 || G > 64 || ((uintptr_t)W & 15) || (dW && ((uintptr_t)dW & 15)) || K > (1 << 28))
         return CAPHN_EINVAL;
     rows_bwd_prep_kernel<<<ceil_div(N, 256), 256, 0, st>>>(Y, ldy, dY, lddy, dP, N, dbias, G, N, act, slope, 0);
-    CAPHN_CHECK(cudaGetLastError());
+    CAPHN_LAUNCH_CHECK();
     if (!dW && !dA) return CAPHN_OK;
     // dW == NULL (only dA wanted): the same kernel is used with a dummy store target avoided by host: require dW.
     if (!dW) return CAPHN_EINVAL;

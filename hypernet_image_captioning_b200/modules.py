@@ -48,6 +48,8 @@ class _HyperNetMixin:
     """theta generation + injection shared by both variants (reference utils.py:24-69 flip/set_all_parameters)."""
 
     grad_mode = "flow"
+    dp_group = None      # set dp_enabled = True under torch.distributed to all-reduce d(theta) (parallel.py)
+    dp_enabled = False
 
     def generate_theta(self, x: torch.Tensor) -> torch.Tensor:
         x2 = x.reshape(1, -1) if x.dim() == 1 else x
@@ -55,7 +57,11 @@ class _HyperNetMixin:
         if self.grad_mode == "literal":
             with torch.no_grad():
                 return Fn.hypernet_theta(x2, _hn_params(self))
-        return Fn.hypernet_theta(x2, _hn_params(self))
+        theta = Fn.hypernet_theta(x2, _hn_params(self))
+        if self.dp_enabled:
+            from .parallel import allreduce_grad
+            theta = allreduce_grad(theta, self.dp_group)
+        return theta
 
 
 class PooledFeatureEncoder(nn.Module):

@@ -85,6 +85,12 @@ int caphn_mean_pos_bwd(const float* g, int B, int P, int Fd, float* dX, void* st
 /* y[i] = ref[i] > 0 ? y[i] : 0  (ReLU backward, in place). */
 int caphn_relu_mask(const float* ref, float* y, long n, void* stream);
 
+/* ---- bookkeeping -------------------------------------------------------------------------------------------------- */
+/* *out = number of CUDA kernels launched by this library so far (host-side counter). */
+int caphn_launch_count(unsigned long long* out);
+/* *out = 100 (library compiled for sm_100a). */
+int caphn_build_arch(int* out);
+
 #ifdef __cplusplus
 }
 #endif
