@@ -6,5 +6,7 @@ C-ABI declared in include/caphn_b200.h.  Importing the package does not need a G
 from . import _cabi, ops, functional  # noqa: F401
 from .functional import cross_entropy, linear, hypernet_theta  # noqa: F401
 from .modules import DecoderGRU, HyperNetPooled, PooledFeatureEncoder  # noqa: F401
+from .modules_attention import AttentionGru, BahdanauAttention, HyperNetAttention, SpatialFeatureEncoder  # noqa: F401
 
-__all__ = ["DecoderGRU", "HyperNetPooled", "PooledFeatureEncoder", "cross_entropy", "linear", "hypernet_theta"]
+__all__ = ["AttentionGru", "BahdanauAttention", "HyperNetAttention", "SpatialFeatureEncoder",
+           "DecoderGRU", "HyperNetPooled", "PooledFeatureEncoder", "cross_entropy", "linear", "hypernet_theta"]

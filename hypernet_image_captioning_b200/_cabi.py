@@ -32,7 +32,11 @@ SIGNATURES = {
     "caphn_gather_rows": [P, P, L, I, P, L, P],
     "caphn_build_inputs": [P, P, P, I, I, I, I, P, P],
     "caphn_embed_scatter_add": [P, P, I, I, I, I, P, P],
+    "caphn_scatter_add_rows": [P, L, P, L, I, P, P],
     "caphn_colsum": [P, L, L, I, P, P],
+    "caphn_attgru_seq_fwd": [P] * 14 + [L] + [P] * 5 + [I] * 9 + [P],
+    "caphn_attgru_seq_bwd": [P] * 23 + [I] * 7 + [P],
+    "caphn_attn_df": [P, P, P, I, I, I, I, P],
     "caphn_mean_pos": [P, I, I, I, P, P],
     "caphn_mean_pos_bwd": [P, I, I, I, P, P],
     "caphn_relu_mask": [P, P, L, P],

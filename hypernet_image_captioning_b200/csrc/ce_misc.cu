@@ -198,6 +198,15 @@ __global__ void embed_scatter_add_kernel(const float* __restrict__ dX, const lon
     for (int e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(dEmb + r * E + e, d[e]);
 }
 
+// table[idx[i],:] += dX[i,:]   (rows with idx < 0 are skipped)
+__global__ void scatter_add_rows_kernel(const float* __restrict__ dX, long ldx, const long long* __restrict__ idx,
+                                        int E, float* __restrict__ table) {
+    const long i = blockIdx.x;
+    const long long r = idx[i];
+    if (r < 0) return;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(table + r * E + e, dX[i * ldx + e]);
+}
+
 // out[n] (+)= sum_m X[m*ld + n]
 __global__ void colsum_kernel(const float* __restrict__ X, long ld, long M, int N, long rows_per_block,
                               float* __restrict__ out) {
@@ -284,6 +293,12 @@ int caphn_embed_scatter_add(const float* dX, const long long* caps, int B, int T
     if (B <= 0 || T <= 0 || E <= 0 || t0 < 1) return CAPHN_EINVAL;
     if (T - t0 <= 0) return CAPHN_OK;
     embed_scatter_add_kernel<<<(unsigned)(B * (T - t0)), 128, 0, (cudaStream_t)stream>>>(dX, caps, B, T, E, t0, dEmb);
+    CAPHN_RETURN_LAST();
+}
+
+int caphn_scatter_add_rows(const float* dX, long ldx, const long long* idx, long n, int E, float* table, void* stream) {
+    if (n <= 0 || E <= 0) return CAPHN_EINVAL;
+    scatter_add_rows_kernel<<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(dX, ldx, idx, E, table);
     CAPHN_RETURN_LAST();
 }
 

@@ -1,0 +1,267 @@
+"""Attention variant ("Variant B"): hypernet_attention.HyperNet + models.decoderlstm.AttentionGru, drop-in API.
+
+Reference: hypernet_attention.py:32-131 (HyperNet), models/decoderlstm.py:11-135 (AttentionGru),
+models/attention.py:5-46 (BahdanauAttention).  The CNN trunk (models/encoder.py EncoderCNN) is out of scope: features are
+the precomputed 7x7x2048 ResNet maps ``[B, 49, 2048]``.
+"""
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+from torch.autograd import Function
+
+from . import functional as Fn
+from . import ops
+from .modules import _Base, _HyperNetMixin
+
+
+class AttentionGruFn(Function):
+    """Whole AttentionGru.forward (models/decoderlstm.py:49-120) as one autograd node.
+
+    ``use_sampling[t]`` are the host-side scheduled-sampling decisions of :79-80 (already drawn by the caller from
+    NumPy's global RNG, one per step).  All-False = teacher forcing: one persistent launch covers every step and the
+    vocabulary projection is a single GEMM.  Otherwise the recurrence runs step by step with the argmax feedback of
+    :91-96 between steps (greedy decode = all True after t = 0, the test_hn.py path).
+    """
+
+    @staticmethod
+    def forward(ctx, features, captions, use_sampling, fc0_w, fc0_b, fc2_w, fc2_b, emb_w, W_ih, W_hh, b_ih, b_hh,
+                fc_w, fc_b, Wa_w, Wa_b, Ua_w, Ua_b, va_w, va_b, init_w, init_b):
+        B, P, D = features.shape
+        T = captions.shape[1]
+        E = emb_w.shape[1]
+        H = W_hh.shape[1]
+        Fd = fc2_w.shape[0]
+        V = fc_w.shape[0]
+        dev = features.device
+        caps = captions.contiguous()
+        feats2 = features.reshape(B * P, D)
+        if not feats2.is_contiguous():
+            feats2 = feats2.contiguous()
+        emb_w = emb_w.contiguous()
+        W_ih, W_hh = W_ih.contiguous(), W_hh.contiguous()
+        # ---- loop-invariant part: feature_fc (:61), keys W_a f (attention.py:34, hoisted), h0 (:63,133-134) ----
+        f1 = ops.linear(feats2, fc0_w, fc0_b, relu=True)                  # [B*P, F]
+        f = ops.linear(f1, fc2_w, fc2_b)                                  # [B*P, F]
+        Kp = ops.linear(f, Wa_w, Wa_b)                                    # [B*P, H]
+        fmean = ops.mean_pos(f.view(B, P, Fd))                            # [B, F]
+        h0 = ops.linear(fmean, init_w, init_b)                            # [B, H]
+        lw = ops.AttGruWeights(W_ih, W_hh, Ua_w.contiguous(), E)
+        va = va_w.reshape(-1).contiguous()
+        bv = va_b.reshape(1).contiguous()
+        Ua_b = Ua_b.contiguous()
+        b_hh = b_hh.contiguous()
+        Hall = torch.empty(T + 1, B, H, device=dev, dtype=torch.float32)
+        Hall[0].copy_(h0)
+        Hbm = torch.empty(B, T, H, device=dev, dtype=torch.float32)
+        attn = torch.empty(B, T, P, device=dev, dtype=torch.float32)
+        XC = torch.empty(T * B, E + Fd, device=dev, dtype=torch.float32)   # [x_word | ctx] per (t,b)
+        need_grad = any(ctx.needs_input_grad)
+        saved = torch.empty(5, T, B, H, device=dev, dtype=torch.float32) if need_grad else None
+        logits = torch.empty(B, T, V, device=dev, dtype=torch.float32)
+        f3, K3 = f.view(B, P, Fd), Kp.view(B, P, H)
+        W_ih_w = W_ih[:, :E]
+        fed = torch.full((T, B), -1, device=dev, dtype=torch.int64)        # token whose embedding was fed at (t,b)
+
+        if not any(use_sampling):
+            # x_0 = x_1 = 0 (in-place aliasing, :83-88), x_t = Emb[caps[:, t-1]] for t >= 2
+            if T > 2:
+                fed[2:] = caps[:, 1:T - 1].t()
+            Xw = ops.build_inputs(None, emb_w, caps, 1)                    # [T*B, E]
+            XC[:, :E].copy_(Xw)
+            GIw = ops.linear(Xw, W_ih_w, b_ih.contiguous())                # [T*B, 3H]
+            ops.attgru_seq_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, 0, T)
+            ops.linear(Hbm.view(B * T, H), fc_w, fc_b, out=logits.view(B * T, V))
+        else:
+            GIw = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+            for t in range(T):
+                if use_sampling[t]:
+                    # :91-96  argmax of log_softmax(logits/0.5) == argmax of logits (lowest index on ties)
+                    _, top = ops.softmax_argmax(logits[:, t - 1, :], want_probs=False)
+                    fed[t].copy_(top)
+                elif t >= 2:
+                    fed[t].copy_(caps[:, t - 1])
+                xw = ops.gather_rows(emb_w, fed[t])                        # zeros where fed == -1
+                XC[t * B:(t + 1) * B, :E].copy_(xw)
+                ops.linear(xw, W_ih_w, b_ih.contiguous(), out=GIw[t * B:(t + 1) * B])
+                ops.attgru_seq_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, t, t + 1)
+                ops.linear(Hall[t + 1], fc_w, fc_b, out=logits[:, t, :])
+        if need_grad:
+            ctx.save_for_backward(feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih,
+                                  W_hh, fc_w, Wa_w, Ua_w, va, init_w)
+            ctx.dims = (B, T, P, D, E, H, Fd, V)
+        return logits, attn
+
+    @staticmethod
+    def backward(ctx, dlogits, dattn):
+        (feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih, W_hh, fc_w, Wa_w, Ua_w,
+         va, init_w) = ctx.saved_tensors
+        B, T, P, D, E, H, Fd, V = ctx.dims
+        dev = f.device
+        dl = dlogits.reshape(B * T, V).contiguous()
+        dfc_w = ops.matmul_tn(dl, Hbm.view(B * T, H))
+        dfc_b = ops.colsum(dl)
+        dHbm = ops.matmul_nn(dl, fc_w.contiguous())
+        if dattn is not None:
+            dattn = dattn.contiguous()
+        f3, K3 = f.view(B, P, Fd), Kp.view(B, P, H)
+        dGI, dGH, dU, dCTX, dK, dva, dbv, dh0 = ops.attgru_seq_bwd(
+            dHbm.view(B, T, H), dattn, K3, f3, attn, saved, Hall, Ua_w.contiguous(), va, W_ih, W_hh, E)
+        Hprev = Hall[:-1].reshape(T * B, H)
+        dW_ih = ops.matmul_tn(dGI, XC)                                     # [3H, E+F]
+        db_ih = ops.colsum(dGI)
+        dW_hh = ops.matmul_tn(dGH, Hprev)
+        db_hh = ops.colsum(dGH)
+        dUa_w = ops.matmul_tn(dU, Hprev)                                   # [H, H]
+        dUa_b = ops.colsum(dU)
+        # word embeddings (t >= 2 teacher-forced rows, or the fed-back argmax rows)
+        dXw = ops.matmul_nn(dGI, W_ih[:, :E])                              # [T*B, E]
+        demb = torch.zeros_like(emb_w)
+        ops.scatter_add_rows(dXw, fed.reshape(-1), demb)
+        # attention keys / features
+        dK2 = dK.view(B * P, H)
+        dWa_w = ops.matmul_tn(dK2, f)                                      # [H, F]
+        dWa_b = ops.colsum(dK2)
+        df = ops.matmul_nn(dK2, Wa_w.contiguous())                         # [B*P, F]
+        ops.attn_df(attn, dCTX, df.view(B, P, Fd))
+        # init_h
+        dinit_w = ops.matmul_tn(dh0, fmean)                                # [H, F]
+        dinit_b = ops.colsum(dh0)
+        dfmean = ops.matmul_nn(dh0, init_w.contiguous())                   # [B, F]
+        ops.mean_pos_bwd(dfmean, df.view(B, P, Fd))
+        # feature_fc (no gradient w.r.t. the image features: they are a leaf input)
+        dfc2_w = ops.matmul_tn(df, f1)
+        dfc2_b = ops.colsum(df)
+        df1 = ops.matmul_nn(df, fc2_w.contiguous())
+        ops.relu_mask_(f1, df1)
+        dfc0_w = ops.matmul_tn(df1, feats2)                                # [F, D]
+        dfc0_b = ops.colsum(df1)
+        return (None, None, None, dfc0_w, dfc0_b, dfc2_w, dfc2_b, demb, dW_ih, dW_hh, db_ih, db_hh, dfc_w, dfc_b,
+                dWa_w, dWa_b, dUa_w, dUa_b, dva.view(1, H), dbv.view(1), dinit_w, dinit_b)
+
+
+class BahdanauAttention(nn.Module):
+    """Parameter holder with the reference layout (models/attention.py:9-19); the math runs inside the recurrence."""
+
+    def __init__(self, num_features, hidden_dim, output_dim=1):
+        super().__init__()
+        self.num_features, self.hidden_dim, self.output_dim = num_features, hidden_dim, output_dim
+        self.W_a = nn.Linear(num_features, hidden_dim)
+        self.U_a = nn.Linear(hidden_dim, hidden_dim)
+        self.v_a = nn.Linear(hidden_dim, output_dim)
+
+
+class AttentionGru(nn.Module):
+    """Drop-in for models/decoderlstm.py:11 AttentionGru (num_layers = 1, dropout p = 0 as in every hypernet launcher)."""
+
+    def __init__(self, num_features, feature_out, embedding_dim, hidden_dim, vocab_size, num_layers=1, p=0.0):
+        super().__init__()
+        if num_layers != 1:
+            raise NotImplementedError("AttentionGru with extra GRU layers is not used by any hypernet launcher")
+        if p != 0.0:
+            raise NotImplementedError("dropout p > 0 is outside the hot path (HyperNet passes p=0.0)")
+        self.num_features, self.embedding_dim, self.hidden_dim = num_features, embedding_dim, hidden_dim
+        self.vocab_size, self.num_layers, self.sample_temp = vocab_size, num_layers, 0.5
+        self.feature_fc = nn.Sequential(nn.Linear(num_features, feature_out), nn.ReLU(),
+                                        nn.Linear(feature_out, feature_out))
+        self.embed = nn.Embedding(vocab_size, embedding_dim)
+        self.gru = nn.GRUCell(embedding_dim + feature_out, hidden_dim)
+        self.layers = None
+        self.fc = nn.Linear(hidden_dim, vocab_size)
+        self.attention = BahdanauAttention(feature_out, hidden_dim)
+        self.drop = nn.Dropout(p=p)
+        self.init_h = nn.Linear(feature_out, hidden_dim)
+        self._generated = None
+
+    def _gru_weights(self):
+        if self._generated is not None:
+            return self._generated
+        g = self.gru
+        return (g.weight_ih, g.weight_hh, g.bias_ih, g.bias_hh)
+
+    def forward(self, features, captions, sample_prob=0.0):
+        """Returns (outputs [B,T,V], atten_weights [B,T,P]) -- models/decoderlstm.py:49-120.
+        Consumes one np.random.random() per time step from NumPy's global RNG exactly like the reference (:79-80)."""
+        T = captions.size(1)
+        use = []
+        for t in range(T):
+            sp = 0.0 if t == 0 else sample_prob
+            use.append(bool(np.random.random() < sp))
+        W_ih, W_hh, b_ih, b_hh = self._gru_weights()
+        a = self.attention
+        return AttentionGruFn.apply(
+            features, captions, tuple(use), self.feature_fc[0].weight, self.feature_fc[0].bias,
+            self.feature_fc[2].weight, self.feature_fc[2].bias, self.embed.weight, W_ih, W_hh, b_ih, b_hh,
+            self.fc.weight, self.fc.bias, a.W_a.weight, a.W_a.bias, a.U_a.weight, a.U_a.bias, a.v_a.weight, a.v_a.bias,
+            self.init_h.weight, self.init_h.bias)
+
+    def init_hidden(self, features):
+        """h0 = init_h(mean over positions) -- models/decoderlstm.py:122-135 (features already through feature_fc)."""
+        B, P, Fd = features.shape
+        return Fn.linear(ops.mean_pos(features.contiguous()), self.init_h.weight, self.init_h.bias)
+
+
+class SpatialFeatureEncoder(nn.Module):
+    """Stands in for models/encoder.py EncoderCNN (ResNet-152 trunk, out of scope): passes precomputed [B,49,2048]
+    feature maps through unchanged."""
+
+    def forward(self, feats):
+        return feats
+
+
+class HyperNetAttention(_HyperNetMixin, _Base):
+    """Drop-in for hypernet_attention.py:32 HyperNet."""
+
+    def __init__(self, feature_size, embed_size, hidden_size, vocab_size, vocab, num_layers=1, lr=1e-6, mixup=False,
+                 alpha=0.3, cc=False, hyper_emb=10):
+        super().__init__()
+        self.hparams['feature_size'] = feature_size
+        self.hparams['vocab_size'] = vocab_size
+        self.hparams['embed_size'] = embed_size
+        self.hparams['hidden_size'] = hidden_size
+        self.vocab = vocab
+        self.hparams['lr'] = lr
+        self.hparams['num_layers'] = num_layers
+        self.teacher_forcing_proba = 0.0
+        self.beam_size = 3
+        self.mixup, self.alpha = mixup, alpha
+        self.image_encoder = SpatialFeatureEncoder()
+        self.captioner = AttentionGru(2048, feature_size, embed_size, hidden_size, vocab_size, p=0.0)
+        N, M = 1, 500
+        he = hyper_emb if cc else embed_size
+        self.hn_base = nn.Sequential(nn.Linear(he, N * he), nn.LeakyReLU(), nn.Linear(N * he, N * he), nn.LeakyReLU())
+        heads = []
+        for name, W in self.captioner.gru.named_parameters():  # hypernet_attention.py:69-96
+            w = W.numel()
+            if w < N * he:
+                heads.append(nn.Sequential(nn.Linear(N * he, N), nn.LeakyReLU(), nn.Linear(w, w)))
+            elif w // M < N * he:
+                heads.append(nn.Sequential(nn.Linear(N * he, N * he), nn.LeakyReLU(), nn.Linear(N * he, w)))
+            else:
+                heads.append(nn.Sequential(nn.Linear(N * he, w // M), nn.LeakyReLU(), nn.Linear(w // M, w)))
+        self.hn_heads = nn.ModuleList(heads)
+
+    def forward(self, x):
+        """theta -> captioner.gru weights; returns self.captioner (hypernet_attention.py:111-121)."""
+        theta = self.generate_theta(x)[0]
+        gru = self.captioner.gru
+        a, ws = 0, []
+        for name in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+            p = getattr(gru, name)
+            w = theta[a:a + p.numel()].reshape(p.shape)
+            a += p.numel()
+            with torch.no_grad():
+                p.copy_(w)
+            ws.append(w)
+        self.captioner._generated = tuple(ws) if self.grad_mode == "flow" else None
+        return self.captioner
+
+    def configure_optimizers(self):  # hypernet_attention.py:123-134
+        c = self.captioner
+        params = list(self.hn_heads.parameters()) + list(self.hn_base.parameters())
+        for m in (c.feature_fc, c.embed, c.fc, c.attention, c.init_h):
+            params += list(m.parameters())
+        opt = torch.optim.Adam(params, lr=self.hparams['lr'])
+        sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, cooldown=2, factor=0.5)
+        return [opt], [{'scheduler': sch, 'monitor': 'val_loss with TF', 'interval': 'epoch'}]

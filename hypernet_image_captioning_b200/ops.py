@@ -153,7 +153,7 @@ def copy_pad(src, ldd):
     _chk(src)
     R, C = src.shape
     assert src.stride(1) == 1
-    if ldd == C and src.is_contiguous() and src.data_ptr() % 16 == 0:
+    if ldd == C and src.is_contiguous() and src.stride(0) == C and src.data_ptr() % 16 == 0:
         return src
     dst = torch.empty(R, ldd, device=src.device, dtype=torch.float32)
     _cabi.call("caphn_copy_pad", src.data_ptr(), src.stride(0), dst.data_ptr(), ldd, R, C, _stream())
@@ -262,3 +262,88 @@ def embed_scatter_add(dX, caps, dEmb, t0):
     E = dEmb.shape[1]
     _cabi.call("caphn_embed_scatter_add", dX.data_ptr(), caps.data_ptr(), B, T, E, t0, dEmb.data_ptr(), _stream())
     return dEmb
+
+
+def scatter_add_rows(dX, idx, table):
+    """table[idx[i], :] += dX[i, :] for idx[i] >= 0."""
+    _chk(dX), _chk(idx, torch.int64)
+    idx = idx.contiguous()
+    assert dX.stride(1) == 1 and dX.shape[0] == idx.numel()
+    _cabi.call("caphn_scatter_add_rows", dX.data_ptr(), dX.stride(0), idx.data_ptr(), idx.numel(), table.shape[1],
+               table.data_ptr(), _stream())
+    return table
+
+
+def mean_pos(X):
+    """X [B,P,F] -> mean over P."""
+    B, P, Fd = X.shape
+    out = torch.empty(B, Fd, device=X.device, dtype=torch.float32)
+    _cabi.call("caphn_mean_pos", X.data_ptr(), B, P, Fd, out.data_ptr(), _stream())
+    return out
+
+
+def mean_pos_bwd(g, dX):
+    B, P, Fd = dX.shape
+    _cabi.call("caphn_mean_pos_bwd", g.data_ptr(), B, P, Fd, dX.data_ptr(), _stream())
+    return dX
+
+
+def relu_mask_(ref, y):
+    _cabi.call("caphn_relu_mask", ref.data_ptr(), y.data_ptr(), y.numel(), _stream())
+    return y
+
+
+class AttGruWeights:
+    """Generated / attention weights laid out for the recurrence kernels (16-byte rows)."""
+
+    def __init__(self, W_ih, W_hh, U_a, E):
+        H = W_hh.shape[1]
+        Fd = W_ih.shape[1] - E
+        self.ldh, self.ld3, self.ldf = round4(H), round4(3 * H), round4(Fd)
+        self.UaT = transpose_pad(U_a, self.ldh)
+        self.WhhT = transpose_pad(W_hh, self.ld3)
+        self.WihcT = transpose_pad(W_ih[:, E:], self.ld3)
+
+
+def attgru_seq_fwd(Kp, f, GIw, lw, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, saved, t0, t1):
+    """Runs steps [t0,t1).  Kp [B,P,H], f [B,P,F], GIw [T*B,3H], XC [T*B,E+F] (ctx written into columns E:),
+    saved = tensor [5,T,B,H] (Upre,R,Z,Nn,GHN) or None."""
+    B, P, H = Kp.shape
+    Fd = f.shape[2]
+    T = Hall.shape[0] - 1
+    sp = [saved[i].data_ptr() for i in range(5)] if saved is not None else [None] * 5
+    ctx_ptr = XC.data_ptr() + 4 * E
+    _cabi.call("caphn_attgru_seq_fwd", Kp.data_ptr(), f.data_ptr(), GIw.data_ptr(), lw.UaT.data_ptr(), bu.data_ptr(),
+               va.data_ptr(), bv.data_ptr(), lw.WihcT.data_ptr(), lw.WhhT.data_ptr(), bhh.data_ptr(), Hall.data_ptr(),
+               _p(Hbm), attn.data_ptr(), ctx_ptr, XC.stride(0), sp[0], sp[1], sp[2], sp[3], sp[4],
+               B, T, P, H, Fd, lw.ldh, lw.ld3, t0, t1, _stream())
+
+
+def attgru_seq_bwd(dHbm, dattn, Kp, f, attn, saved, Hall, U_a, va, W_ih, W_hh, E):
+    B, P, H = Kp.shape
+    Fd = f.shape[2]
+    T = Hall.shape[0] - 1
+    dev = Kp.device
+    ldh, ldf = round4(H), round4(Fd)
+    Ua_p = copy_pad(U_a, ldh)
+    Whh_p = copy_pad(W_hh, ldh)
+    Wihc_p = copy_pad(W_ih[:, E:], ldf)
+    if Wihc_p.data_ptr() % 16 or Wihc_p.stride(0) != ldf:
+        Wihc_p = Wihc_p.contiguous().clone()
+    z = lambda *s: torch.zeros(*s, device=dev, dtype=torch.float32)
+    e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    dGI, dGH, dU, dCTX = e(T * B, 3 * H), e(T * B, 3 * H), e(T * B, H), e(T * B, Fd)
+    dK, dva, dbv, dh0 = z(B, P, H), z(H), z(1), e(B, H)
+    _cabi.call("caphn_attgru_seq_bwd", dHbm.data_ptr(), _p(dattn), Kp.data_ptr(), f.data_ptr(), attn.data_ptr(),
+               saved[0].data_ptr(), saved[1].data_ptr(), saved[2].data_ptr(), saved[3].data_ptr(), saved[4].data_ptr(),
+               Hall.data_ptr(), Ua_p.data_ptr(), va.data_ptr(), Wihc_p.data_ptr(), Whh_p.data_ptr(), dGI.data_ptr(),
+               dGH.data_ptr(), dU.data_ptr(), dCTX.data_ptr(), dK.data_ptr(), dva.data_ptr(), dbv.data_ptr(),
+               dh0.data_ptr(), B, T, P, H, Fd, ldh, ldf, _stream())
+    return dGI, dGH, dU, dCTX, dK, dva, dbv, dh0
+
+
+def attn_df(attn, dCTX, df):
+    B, T, P = attn.shape
+    Fd = df.shape[-1]
+    _cabi.call("caphn_attn_df", attn.data_ptr(), dCTX.data_ptr(), df.data_ptr(), B, T, P, Fd, _stream())
+    return df

@@ -57,6 +57,29 @@ int caphn_gru_seq_bwd(const float* dHbm, const float* R, const float* Z, const f
                       const float* Hall, const float* Whh, int ldh, float* dGI, float* dGH, float* dh0, int B, int T,
                       int H, void* stream);
 
+/* ---- attention decoder recurrence (models/decoderlstm.py:78-108 AttentionGru loop; models/attention.py:21-46) ------- */
+
+/* Steps [t0,t1) of: u = U_a h + b_u; s_p = v_a.tanh(K_p + u) + b_v; alpha = softmax_p s; ctx = sum_p alpha_p f_p;
+ * h' = GRUCell([x_w, ctx], h) with the word half of the input projection precomputed (GIw [T,B,3H], incl. b_ih).
+ * Kp [B,P,H] = W_a f + b_a (hoisted, attention.py:34); f [B,P,F]; UaT [H,ldh] = U_a^T; WihcT [F,ld3] = W_ih[:,E:]^T;
+ * WhhT [H,ld3] = W_hh^T.  Hall [T+1,B,H] (Hall[t0] = previous state on entry); Hbm [B,T,H] optional; attn [B,T,P];
+ * ctx rows at ctx + (t*B+b)*ldctx; Upre,R,Z,Nn,GHN [T,B,H] saved for the backward (all or none). */
+int caphn_attgru_seq_fwd(const float* Kp, const float* f, const float* GIw, const float* UaT, const float* bu,
+                         const float* va, const float* bv, const float* WihcT, const float* WhhT, const float* bhh,
+                         float* Hall, float* Hbm, float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z,
+                         float* Nn, float* GHN, int B, int T, int P, int H, int F, int ldh, int ld3, int t0, int t1,
+                         void* stream);
+/* BPTT of the above over all T steps.  Ua [H,ldh], Wihc [3H,ldf] = W_ih[:,E:], Whh [3H,ldh].
+ * Outputs dGI,dGH [T,B,3H], dU [T,B,H], dCTX [T,B,F], dh0 [B,H]; dK [B,P,H], dva [H], dbv [1] are accumulated
+ * (zero-initialised by the caller).  dattn [B,T,P] (gradient of the returned attention weights) may be NULL. */
+int caphn_attgru_seq_bwd(const float* dHbm, const float* dattn, const float* Kp, const float* f, const float* attn,
+                         const float* Upre, const float* R, const float* Z, const float* Nn, const float* GHN,
+                         const float* Hall, const float* Ua, const float* va, const float* Wihc, const float* Whh,
+                         float* dGI, float* dGH, float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0,
+                         int B, int T, int P, int H, int F, int ldh, int ldf, void* stream);
+/* df[b,p,:] += sum_t attn[b,t,p] * dCTX[t,b,:]  (context-vector backward, deferred out of the BPTT loop). */
+int caphn_attn_df(const float* attn, const float* dCTX, float* df, int B, int T, int P, int F, void* stream);
+
 /* ---- loss / sampling / embedding (cc_train_hypernet.py:153, hypernet.py:145; decoderlstm.py:62,91-96; later.py:472-479) */
 
 /* Mean softmax cross-entropy over rows of X[M,V] whose target != ignore (when has_ignore).  lse [M]; scratch [2M];
@@ -77,6 +100,8 @@ int caphn_build_inputs(const float* feat, const float* emb, const long long* cap
 /* dEmb[caps[b,t-1],:] += dX[t,b,:] for t >= t0  (embedding_dense_backward). */
 int caphn_embed_scatter_add(const float* dX, const long long* caps, int B, int T, int E, int t0, float* dEmb,
                             void* stream);
+/* table[idx[i],:] += dX[i*ldx + :]  for idx[i] >= 0  (embedding backward for arbitrary fed-back tokens). */
+int caphn_scatter_add_rows(const float* dX, long ldx, const long long* idx, long n, int E, float* table, void* stream);
 /* out[n] += sum_m X[m*ld+n]  (bias gradients). */
 int caphn_colsum(const float* X, long ld, long M, int N, float* out, void* stream);
 /* out[b,f] = mean_p X[b,p,f] (models/decoderlstm.py:133) and its backward dX[b,p,f] += g[b,f]/P. */

@@ -1,0 +1,162 @@
+"""Module-level parity of the attention path (HyperNetAttention + AttentionGru) through the drop-in API: golden vectors
+of the unmodified reference (tests/golden/attn_*.npz) and the oracle port on larger seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from golden_util import load_case, params_of, rel_err, grad_close
+from oracle import caption_hn_oracle as O
+
+TOL_LOGITS = 1e-4   # BASELINE.json north_star: fp32 mode within 1e-4 relative on logits and loss
+TOL_GRAD = 1e-3
+
+
+def _model_from(p, Fo, E, H, V, cc, he, mode="flow"):
+    import hypernet_image_captioning_b200 as C
+    m = C.HyperNetAttention(Fo, E, H, V, None, cc=cc, hyper_emb=he)
+    sd = m.state_dict()
+    missing = [k for k in p if k not in sd]
+    assert not missing, missing
+    sd.update(p)
+    m.load_state_dict(sd)
+    m.grad_mode = mode
+    return m.cuda()
+
+
+CASES = [("attn_flickr", False, 10), ("attn_cc", True, 10)]
+
+
+@pytest.mark.parametrize("name,cc,he", CASES)
+def test_state_dict_layout_matches_reference(name, cc, he):
+    import hypernet_image_captioning_b200 as C
+    c = load_case(name)
+    p = params_of(c)
+    m = C.HyperNetAttention(16, 12, 20, 50, None, cc=cc, hyper_emb=he)
+    sd = m.state_dict()
+    gen = {"captioner.gru." + k for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")}
+    assert set(sd.keys()) == set(p.keys()) | gen
+    for k, v in p.items():
+        assert tuple(sd[k].shape) == tuple(v.shape), k
+
+
+@pytest.mark.parametrize("name,cc,he", CASES)
+@pytest.mark.parametrize("mode", ["literal", "flow"])
+def test_attention_golden_teacher_forced(name, cc, he, mode):
+    import hypernet_image_captioning_b200 as C
+    c = load_case(name)
+    m = _model_from(params_of(c), 16, 12, 20, 50, cc, he, mode)
+    captioner = m.forward(c["style"].cuda())
+    for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+        assert rel_err(getattr(captioner.gru, k), c["gen/" + k]) < 1e-5, k
+    np.random.seed(0)
+    logits, att = captioner(c["features"].cuda(), c["captions"].cuda(), 0.0)
+    assert rel_err(logits, c["tf/logits"]) < TOL_LOGITS
+    assert rel_err(att, c["tf/attn"]) < TOL_LOGITS
+    loss = C.cross_entropy(logits, c["captions"].cuda(), 0)
+    assert abs(loss.item() - c["tf/loss"].item()) < TOL_LOGITS * abs(c["tf/loss"].item())
+    loss.backward()
+    named = dict(m.named_parameters())
+    for k, v in c.items():
+        if not k.startswith("tf/grad/") or k.startswith("tf/grad/captioner.gru."):
+            continue
+        assert grad_close(named[k[8:]].grad, v, TOL_GRAD), k
+    if mode == "literal":
+        for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+            assert grad_close(getattr(captioner.gru, k).grad, c["tf/grad/captioner.gru." + k], TOL_GRAD), k
+        assert all(v.grad is None for k, v in named.items() if k.startswith("hn_"))
+    else:
+        n = 0
+        for k, v in c.items():
+            if k.startswith("flow/grad/"):
+                assert grad_close(named[k[10:]].grad, v, TOL_GRAD), k
+                n += 1
+        assert n >= 12
+
+
+@pytest.mark.parametrize("name,cc,he", CASES)
+def test_attention_golden_greedy_token_exact(name, cc, he):
+    c = load_case(name)
+    m = _model_from(params_of(c), 16, 12, 20, 50, cc, he)
+    np.random.seed(0)
+    with torch.no_grad():
+        captioner = m.forward(c["style"].cuda())
+        logits, att = captioner(c["features"].cuda(), c["captions"].cuda(), 1.0)
+    assert torch.equal(logits.argmax(-1).cpu(), c["greedy/logits"].argmax(-1))
+    assert rel_err(logits, c["greedy/logits"]) < TOL_LOGITS
+    assert rel_err(att, c["greedy/attn"]) < TOL_LOGITS
+
+
+def test_numpy_rng_consumption_matches_reference():
+    """One np.random.random() per step, also at t = 0 (models/decoderlstm.py:79-80)."""
+    c = load_case("attn_flickr")
+    m = _model_from(params_of(c), 16, 12, 20, 50, False, 10)
+    T = c["captions"].shape[1]
+    np.random.seed(123)
+    with torch.no_grad():
+        m.forward(c["style"].cuda())(c["features"].cuda(), c["captions"].cuda(), 0.0)
+    after = np.random.random()
+    np.random.seed(123)
+    for _ in range(T):
+        np.random.random()
+    assert after == np.random.random()
+
+
+@pytest.mark.parametrize("B,T,Fo,E,H,V,he,cc", [(13, 7, 24, 20, 28, 211, 20, False), (32, 20, 200, 200, 200, 1500, 100, True)])
+def test_attention_vs_oracle_medium(B, T, Fo, E, H, V, he, cc):
+    import hypernet_image_captioning_b200 as C
+    p = O.init_params_attention(2048, Fo, E, H, V, he if cc else E, seed=7)
+    g = torch.Generator().manual_seed(17)
+    feats = torch.randn(B, 49, 2048, generator=g)
+    caps = O.synth_captions(B, T, V, g)
+    if cc:
+        style = torch.zeros(he); style[5] = 1.0
+    else:
+        style = torch.randn(1, E, generator=g)
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    logits_ref, att_ref, _, _ = O.path_attention(pl, style, feats, caps, 0.0, np.random.RandomState(0), flow=True)
+    loss_ref = O.caption_loss(logits_ref, caps, 0)
+    loss_ref.backward()
+
+    m = _model_from(p, Fo, E, H, V, cc, he)
+    captioner = m.forward(style.cuda())
+    logits, att = captioner(feats.cuda(), caps.cuda(), 0.0)
+    loss = C.cross_entropy(logits, caps.cuda(), 0)
+    loss.backward()
+    assert rel_err(logits, logits_ref) < TOL_LOGITS
+    assert rel_err(att, att_ref) < TOL_LOGITS
+    assert abs(loss.item() - loss_ref.item()) < TOL_LOGITS * abs(loss_ref.item())
+    for k, v in m.named_parameters():
+        if k.startswith("captioner.gru."):
+            continue
+        assert grad_close(v.grad, pl[k].grad, TOL_GRAD), k
+
+    # greedy decode on the same model: token-exact against the oracle
+    with torch.no_grad():
+        gl_ref, _, _, _ = O.path_attention(p, style, feats, caps, 1.0, np.random.RandomState(0))
+        gl, _ = m.forward(style.cuda())(feats.cuda(), caps.cuda(), 1.0)
+    match = (gl.argmax(-1).cpu() == gl_ref.argmax(-1)).float().mean().item()
+    assert match == 1.0, f"greedy token match {match}"
+    assert rel_err(gl, gl_ref) < TOL_LOGITS
+
+
+def test_attention_scheduled_sampling_mixed_matches_oracle():
+    """0 < sample_prob < 1: per-step host decisions from NumPy's RNG, gradient still flows through fed embeddings."""
+    import hypernet_image_captioning_b200 as C
+    B, T, Fo, E, H, V = 6, 8, 16, 12, 20, 60
+    p = O.init_params_attention(2048, Fo, E, H, V, E, seed=9)
+    g = torch.Generator().manual_seed(3)
+    feats = torch.randn(B, 49, 2048, generator=g)
+    caps = O.synth_captions(B, T, V, g)
+    style = torch.randn(1, E, generator=g)
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    lr, _, _, _ = O.path_attention(pl, style, feats, caps, 0.5, np.random.RandomState(4), flow=True)
+    O.caption_loss(lr, caps, 0).backward()
+    m = _model_from(p, Fo, E, H, V, False, 10)
+    np.random.seed(4)
+    logits, _ = m.forward(style.cuda())(feats.cuda(), caps.cuda(), 0.5)
+    C.cross_entropy(logits, caps.cuda(), 0).backward()
+    assert rel_err(logits, lr) < TOL_LOGITS
+    for k in ("captioner.embed.weight", "hn_heads.0.2.weight", "captioner.attention.U_a.weight"):
+        assert grad_close(dict(m.named_parameters())[k].grad, pl[k].grad, TOL_GRAD), k
