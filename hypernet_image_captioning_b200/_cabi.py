@@ -22,6 +22,9 @@ SIGNATURES = {
     "caphn_rows_linear_fwd": [P, P, P, L, P, L, I, L, L, I, F, P],
     "caphn_rows_linear_bwd": [P, P, L, P, L, P, L, P, P, P, P, L, I, L, L, I, F, P],
     "caphn_gemm_f32": [P, L, I, P, L, I, P, L, P, I, I, I, I, I, I, P],
+    "caphn_split_bf16": [P, L, L, I, P, P, L, P],
+    "caphn_split_bf16_t": [P, L, I, I, P, P, L, P],
+    "caphn_gemm_tc": [P, P, P, P, L, P, L, P, I, I, I, P],
     "caphn_transpose_pad": [P, L, P, L, I, I, P],
     "caphn_copy_pad": [P, L, P, L, L, I, P],
     "caphn_gru_seq_fwd": [P, P, I, P, P, P, P, P, P, P, I, I, I, P],

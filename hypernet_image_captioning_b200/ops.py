@@ -347,3 +347,53 @@ def attn_df(attn, dCTX, df):
     Fd = df.shape[-1]
     _cabi.call("caphn_attn_df", attn.data_ptr(), dCTX.data_ptr(), df.data_ptr(), B, T, P, Fd, _stream())
     return df
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# tensor-core GEMM (tcgen05/TMEM/TMA) on bf16x3-split operands
+# ----------------------------------------------------------------------------------------------------------------------
+def round64(n):
+    return (n + 63) // 64 * 64
+
+
+class SplitOperand:
+    """fp32 matrix [R, C] in the bf16x3 operand format: hi, lo [R, Kp] bf16 (lo None in plain-bf16 mode)."""
+    __slots__ = ("hi", "lo", "rows", "Kp")
+
+    def __init__(self, hi, lo, rows, Kp):
+        self.hi, self.lo, self.rows, self.Kp = hi, lo, rows, Kp
+
+
+def split_bf16(src, want_lo=True):
+    _chk(src)
+    assert src.dim() == 2 and src.stride(1) == 1
+    R, C = src.shape
+    Kp = round64(C)
+    hi = torch.empty(R, Kp, device=src.device, dtype=torch.bfloat16)
+    lo = torch.empty(R, Kp, device=src.device, dtype=torch.bfloat16) if want_lo else None
+    _cabi.call("caphn_split_bf16", src.data_ptr(), src.stride(0), R, C, hi.data_ptr(), _p(lo), Kp, _stream())
+    return SplitOperand(hi, lo, R, Kp)
+
+
+def split_bf16_t(src, want_lo=True):
+    """src [R, C] -> operand for src^T: hi, lo [C, Rp]."""
+    _chk(src)
+    assert src.dim() == 2 and src.stride(1) == 1
+    R, C = src.shape
+    Rp = round64(R)
+    hi = torch.empty(C, Rp, device=src.device, dtype=torch.bfloat16)
+    lo = torch.empty(C, Rp, device=src.device, dtype=torch.bfloat16) if want_lo else None
+    _cabi.call("caphn_split_bf16_t", src.data_ptr(), src.stride(0), R, C, hi.data_ptr(), _p(lo), Rp, _stream())
+    return SplitOperand(hi, lo, C, Rp)
+
+
+def gemm_tc(A: SplitOperand, Bm: SplitOperand, bias=None, relu=False, out=None):
+    """out[M,N] = A B^T (+bias) on the tensor cores; A [M,Kp], B [N,Kp] split operands with equal Kp."""
+    assert A.Kp == Bm.Kp and (A.lo is None) == (Bm.lo is None)
+    M, N = A.rows, Bm.rows
+    if out is None:
+        out = torch.empty(M, N, device=A.hi.device, dtype=torch.float32)
+    assert out.stride(1) == 1
+    _cabi.call("caphn_gemm_tc", A.hi.data_ptr(), _p(A.lo), Bm.hi.data_ptr(), _p(Bm.lo), A.Kp, out.data_ptr(),
+               out.stride(0), _p(bias), M, N, int(relu), _stream())
+    return out

@@ -39,6 +39,18 @@ int caphn_rows_linear_bwd(const float* W, const float* A, long lda, const float*
 int caphn_gemm_f32(const float* A, long lda, int a_kmajor, const float* B, long ldb, int b_kmajor, float* C, long ldc,
                    const float* bias, int M, int N, int K, int relu, int splitk, int accumulate, void* stream);
 
+/* ---- tensor-core GEMM (tcgen05 + TMEM + TMA), same reference call sites as caphn_gemm_f32 for the large products --- */
+
+/* Split fp32 into the bf16x3 operand format: hi = rn(x), lo = rn(x - hi), both [R, Kp] bf16 row-major, Kp % 64 == 0,
+ * columns [C, Kp) zero.  lo == NULL: hi only (plain bf16 mode).  The _t variant transposes: src [R,C] -> hi/lo [C, Rp]. */
+int caphn_split_bf16(const float* src, long lds, long R, int C, void* hi, void* lo, long Kp, void* stream);
+int caphn_split_bf16_t(const float* src, long lds, int R, int C, void* hi, void* lo, long Rp, void* stream);
+/* C[M,N] (fp32, ldc) = A B^T (+bias[n]) (ReLU); A = (Ahi, Alo) [M,Kp], B = (Bhi, Blo) [N,Kp] in the split format.
+ * Three MMAs per k-slice (hi*hi + hi*lo + lo*hi) with fp32 accumulation in TMEM: ~1e-5 relative, fp32-class.
+ * Alo == Blo == NULL: single bf16 MMA per k-slice. */
+int caphn_gemm_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, long Kp, float* C, long ldc,
+                  const float* bias, int M, int N, int relu, void* stream);
+
 /* dst[c*ldd+r] = src[r*lds+c] (zero padded to ldd) / dst[r*ldd+c] = src[r*lds+c] (zero padded): lay generated
  * weights out with 16-byte rows for the recurrence kernels. */
 int caphn_transpose_pad(const float* src, long lds, float* dst, long ldd, int R, int C, void* stream);

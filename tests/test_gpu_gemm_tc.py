@@ -1,0 +1,51 @@
+"""tcgen05 GEMM (bf16x3 split, fp32 accumulate in TMEM) against fp64 matmul."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from golden_util import rel_err
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 150, 150), (1000, 9684, 150), (2000, 150, 9684),
+                                   (9684, 150, 2048), (300, 200, 2048), (128, 128, 6400), (4097, 257, 65)])
+def test_gemm_tc_split_matches_fp64(M, N, K):
+    from hypernet_image_captioning_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = torch.randn(N, K, generator=g).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    out = ops.gemm_tc(ops.split_bf16(A), ops.split_bf16(W), bias=b)
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t() + b.double()
+    # The tensor core adds each MMA into the fp32 TMEM accumulator with truncation, so the error grows with the number
+    # of accumulation steps (K/16 * 3): ~1e-6 at K = 150-200 (logits), ~5e-6 at K = 2048, ~4e-5 at K ~ 1e4 (the two
+    # vocabulary-projection gradient products, whose budget is 1e-3).
+    tol = 2e-5 if K <= 2048 else 1e-4
+    assert rel_err(out, ref) < tol
+    out2 = ops.gemm_tc(ops.split_bf16(A), ops.split_bf16(W), bias=b, relu=True)
+    assert rel_err(out2, ref.relu()) < tol
+
+
+def test_gemm_tc_transposed_operands_and_bf16_mode():
+    from hypernet_image_captioning_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    dl = torch.randn(1536, 700, generator=g).cuda()      # [K, M]
+    Hs = torch.randn(1536, 150, generator=g).cuda()      # [K, N]
+    out = ops.gemm_tc(ops.split_bf16_t(dl), ops.split_bf16_t(Hs))   # dl^T @ Hs
+    assert rel_err(out, dl.double().t() @ Hs.double()) < 2e-5  # K = 1536
+    A = torch.randn(512, 256, generator=g).cuda()
+    W = torch.randn(384, 256, generator=g).cuda()
+    out = ops.gemm_tc(ops.split_bf16(A, want_lo=False), ops.split_bf16(W, want_lo=False))
+    assert rel_err(out, A.double() @ W.double().t()) < 2e-2
+
+
+def test_gemm_tc_strided_output():
+    from hypernet_image_captioning_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    A = torch.randn(256, 100, generator=g).cuda()
+    W = torch.randn(200, 100, generator=g).cuda()
+    big = torch.zeros(256, 3, 200).cuda()
+    ops.gemm_tc(ops.split_bf16(A), ops.split_bf16(W), out=big[:, 1, :])
+    assert rel_err(big[:, 1, :], A.double() @ W.double().t()) < 2e-5
+    assert float(big[:, 0, :].abs().max()) == 0 and float(big[:, 2, :].abs().max()) == 0
