@@ -102,10 +102,20 @@ def _auto_splitk(M, N, K):
     return max(1, min((K + 255) // 256, (2 * 148 + tiles - 1) // tiles))
 
 
+TC_ENABLED = True   # route the large dense contractions to the tcgen05 kernel (bf16x3, fp32-class accuracy)
+TC_MIN_WORK = 1 << 24
+
+
+def _tc_ok(M, N, K, accumulate=False):
+    return TC_ENABLED and not accumulate and M >= 128 and N >= 128 and K >= 32 and M * N * K >= TC_MIN_WORK
+
+
 def linear(X, W, bias=None, relu=False, out=None):
     """out[M,N] = X[M,K] @ W[N,K]^T + bias (optional ReLU)."""
     _chk(X), _chk(W)
     assert X.dim() == 2 and X.stride(1) == 1 and W.stride(1) == 1 and X.shape[1] == W.shape[1]
+    if _tc_ok(X.shape[0], W.shape[0], X.shape[1]):
+        return gemm_tc(split_bf16(X), split_bf16(W), bias=bias, relu=relu, out=out)
     return _gemm(X, X.stride(0), 1, W, W.stride(0), 1, X.shape[0], W.shape[0], X.shape[1], bias, relu, out)
 
 
@@ -113,6 +123,8 @@ def matmul_nn(A, Bm, out=None, accumulate=False):
     """out[M,N] = A[M,K] @ B[K,N]."""
     _chk(A), _chk(Bm)
     assert A.stride(1) == 1 and Bm.stride(1) == 1 and A.shape[1] == Bm.shape[0]
+    if _tc_ok(A.shape[0], Bm.shape[1], A.shape[1], accumulate):
+        return gemm_tc(split_bf16(A), split_bf16_t(Bm), out=out)
     return _gemm(A, A.stride(0), 1, Bm, Bm.stride(0), 0, A.shape[0], Bm.shape[1], A.shape[1], out=out,
                  accumulate=accumulate)
 
@@ -123,6 +135,8 @@ def matmul_tn(A, Bm, out=None, accumulate=False):
     assert A.stride(1) == 1 and Bm.stride(1) == 1 and A.shape[0] == Bm.shape[0]
     K, M = A.shape
     N = Bm.shape[1]
+    if _tc_ok(M, N, K, accumulate):
+        return gemm_tc(split_bf16_t(A), split_bf16_t(Bm), out=out)
     sk = _auto_splitk(M, N, K)
     if out is not None and sk > 1 and not accumulate:
         out.zero_()

@@ -74,12 +74,19 @@ def test_gemm_variants(M, N, K):
     W = torch.randn(N, K, generator=g).cuda()
     b = torch.randn(N, generator=g).cuda()
     ref = F.linear(X.double(), W.double(), b.double())
-    assert rel_err(ops.linear(X, W, b), ref) < 2e-6
-    assert rel_err(ops.linear(X, W, b, relu=True), ref.relu()) < 2e-6
+    # large shapes are routed to the tcgen05 bf16x3 kernel (~1e-5), small ones to the exact-fp32 CUDA-core kernel
+    tol = 2e-5 if ops._tc_ok(M, N, K) else 2e-6
+    assert rel_err(ops.linear(X, W, b), ref) < tol
+    assert rel_err(ops.linear(X, W, b, relu=True), ref.relu()) < tol
     Bm = torch.randn(K, N, generator=g).cuda()
-    assert rel_err(ops.matmul_nn(X, Bm), X.double() @ Bm.double()) < 2e-6
+    assert rel_err(ops.matmul_nn(X, Bm), X.double() @ Bm.double()) < tol
     At = torch.randn(K, M, generator=g).cuda()
-    assert rel_err(ops.matmul_tn(At, Bm), At.double().t() @ Bm.double()) < 2e-6
+    assert rel_err(ops.matmul_tn(At, Bm), At.double().t() @ Bm.double()) < tol
+    ops.TC_ENABLED = False
+    try:
+        assert rel_err(ops.linear(X, W, b), ref) < 2e-6
+    finally:
+        ops.TC_ENABLED = True
 
 
 def test_gemm_splitk_and_colsum():
