@@ -109,9 +109,11 @@ __global__ void rows_bwd_prep_kernel(const float* __restrict__ Y, long ldy, cons
 }
 
 // One pass over W: dW[n,k] (=|+=) sum_g dP[g,n] A[g,k]   and   dA[g,k] += sum_n dP[g,n] W[n,k]  (atomics, dA pre-zeroed).
-// Work item = (block of RB rows) x (strip of 32 aligned quads).  Rows are visited class by class (n & 3 == cls) so that
-// a lane sees the same k for every row of the class and can keep its dA partial sums in registers.
-template <int GC>
+// Work item = (block of RB rows) x (strip of 32*QPL aligned quads): a warp touches QPL*512 contiguous bytes of a row per
+// load/store batch (the access shape that reaches ~95 % of copy bandwidth in the forward kernel).  Rows are visited class
+// by class (n & 3 == cls) so that a lane sees the same k for every row of the class and keeps its dA partial sums in
+// registers; RU rows are in flight per lane (RU*QPL 128-bit loads).
+template <int GC, int QPL, int RU>
 __global__ void __launch_bounds__(ROWS_BWD_THREADS) rows_bwd_kernel(
     const float* __restrict__ W, const float* __restrict__ A, long lda, const float* __restrict__ dP, long ldp,
     float* __restrict__ dW, float* __restrict__ dA, long ldda, long N, int K, int RB, int S, long items, int accum_dw,
@@ -125,59 +127,67 @@ __global__ void __launch_bounds__(ROWS_BWD_THREADS) rows_bwd_kernel(
         const int s = (int)(item - rb * S);
         const long row0 = rb * RB;
         const long row1 = (row0 + RB < N) ? row0 + RB : N;
-        const int q = s * 32 + lane;
         for (int cls = 0; cls < ncls; ++cls) {
             const int m = (cls * (K & 3)) & 3;
-            const int k0 = 4 * q - m;
-            bool valid[4];
+            int k0[QPL];
+            bool full[QPL], any = false;
+            float a[GC][QPL][4], acc[GC][QPL][4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) valid[c] = (k0 + c >= 0) && (k0 + c < K);
-            const bool any = valid[0] || valid[1] || valid[2] || valid[3];
-            const bool full = valid[0] && valid[3];
-            float a[GC][4], acc[GC][4];
+            for (int u = 0; u < QPL; ++u) {
+                k0[u] = 4 * ((s * QPL + u) * 32 + lane) - m;
+                full[u] = (k0[u] >= 0) && (k0[u] + 3 < K);
+                any = any || (k0[u] + 3 >= 0 && k0[u] < K);
 #pragma unroll
-            for (int g = 0; g < GC; ++g)
+                for (int g = 0; g < GC; ++g)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    a[g][c] = valid[c] ? A[(long)g * lda + k0 + c] : 0.f;
-                    acc[g][c] = 0.f;
-                }
-            if (any) {
-                for (long nb = row0 + cls; nb < row1; nb += 4 * ncls) {
-                    float wv[4][4];
+                    for (int c = 0; c < 4; ++c) {
+                        const int k = k0[u] + c;
+                        a[g][u][c] = (k >= 0 && k < K) ? A[(long)g * lda + k] : 0.f;
+                        acc[g][u][c] = 0.f;
+                    }
+            }
+            if (!any) continue;
+            for (long nb = row0 + cls; nb < row1; nb += (long)RU * ncls) {
+                float wv[RU][QPL][4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const long n = nb + (long)u * ncls;
+                for (int r = 0; r < RU; ++r) {
+                    const long n = nb + (long)r * ncls;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) wv[u][c] = 0.f;
+                    for (int u = 0; u < QPL; ++u) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) wv[r][u][c] = 0.f;
                         if (n < row1) {
-                            const float* p = W + n * (long)K + k0;
-                            if (full) {
+                            const float* p = W + n * (long)K + k0[u];
+                            if (full[u]) {
                                 const float4 t = ldg_stream4(p);
-                                wv[u][0] = t.x; wv[u][1] = t.y; wv[u][2] = t.z; wv[u][3] = t.w;
+                                wv[r][u][0] = t.x; wv[r][u][1] = t.y; wv[r][u][2] = t.z; wv[r][u][3] = t.w;
                             } else {
 #pragma unroll
                                 for (int c = 0; c < 4; ++c)
-                                    if (valid[c]) wv[u][c] = ldg_stream1(p + c);
+                                    if (k0[u] + c >= 0 && k0[u] + c < K) wv[r][u][c] = ldg_stream1(p + c);
                             }
                         }
                     }
+                }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const long n = nb + (long)u * ncls;
-                        if (n < row1) {
+                for (int r = 0; r < RU; ++r) {
+                    const long n = nb + (long)r * ncls;
+                    if (n < row1) {
+                        float dp[GC];
+#pragma unroll
+                        for (int g = 0; g < GC; ++g) dp[g] = __ldg(dP + (long)g * ldp + n);
+#pragma unroll
+                        for (int u = 0; u < QPL; ++u) {
                             float dw[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                            for (int g = 0; g < GC; ++g) {
-                                const float dp = __ldg(dP + (long)g * ldp + n);
+                            for (int g = 0; g < GC; ++g)
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) {
-                                    acc[g][c] = fmaf(dp, wv[u][c], acc[g][c]);
-                                    dw[c] = fmaf(dp, a[g][c], dw[c]);
+                                    acc[g][u][c] = fmaf(dp[g], wv[r][u][c], acc[g][u][c]);
+                                    dw[c] = fmaf(dp[g], a[g][u][c], dw[c]);
                                 }
-                            }
-                            float* o = dW + n * (long)K + k0;
-                            if (full) {
+                            float* o = dW + n * (long)K + k0[u];
+                            if (full[u]) {
                                 float4 t = make_float4(dw[0], dw[1], dw[2], dw[3]);
                                 if (accum_dw) {
                                     const float4 old = *reinterpret_cast<const float4*>(o);
@@ -187,18 +197,22 @@ __global__ void __launch_bounds__(ROWS_BWD_THREADS) rows_bwd_kernel(
                             } else {
 #pragma unroll
                                 for (int c = 0; c < 4; ++c)
-                                    if (valid[c]) o[c] = accum_dw ? o[c] + dw[c] : dw[c];
+                                    if (k0[u] + c >= 0 && k0[u] + c < K) o[c] = accum_dw ? o[c] + dw[c] : dw[c];
                             }
                         }
                     }
                 }
-                if (need_da) {
+            }
+            if (need_da) {
 #pragma unroll
-                    for (int g = 0; g < GC; ++g)
+                for (int g = 0; g < GC; ++g)
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            if (valid[c]) atomicAdd(dA + (long)g * ldda + k0 + c, acc[g][c]);
-                }
+                    for (int u = 0; u < QPL; ++u)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int k = k0[u] + c;
+                            if (k >= 0 && k < K) atomicAdd(dA + (long)g * ldda + k, acc[g][u][c]);
+                        }
             }
         }
     }
@@ -222,18 +236,18 @@ static int launch_rows_fwd(const float* W, const float* bias, const float* A, lo
     CAPHN_RETURN_LAST();
 }
 
-template <int GC>
+template <int GC, int QPL, int RU>
 static int launch_rows_bwd(const float* W, const float* A, long lda, const float* dP, long ldp, float* dW, float* dA,
                            long ldda, long N, int K, int accum_dw, int need_da, cudaStream_t st) {
-    const int S = ((K + 6) / 4 + 31) / 32;
+    const int S = ((K + 6) / 4 + 32 * QPL - 1) / (32 * QPL);
     int RB = 128;
     while (RB > 16 && ((N + RB - 1) / RB) * S < 8L * kNumSMs * (ROWS_BWD_THREADS / 32)) RB >>= 1;
     const long items = ((N + RB - 1) / RB) * S;
     long blocks = (items + (ROWS_BWD_THREADS / 32) - 1) / (ROWS_BWD_THREADS / 32);
     const long cap = (long)kNumSMs * 64;
     if (blocks > cap) blocks = cap;
-    rows_bwd_kernel<GC><<<(unsigned)blocks, ROWS_BWD_THREADS, 0, st>>>(W, A, lda, dP, ldp, dW, dA, ldda, N, K, RB, S,
-                                                                       items, accum_dw, need_da);
+    rows_bwd_kernel<GC, QPL, RU><<<(unsigned)blocks, ROWS_BWD_THREADS, 0, st>>>(W, A, lda, dP, ldp, dW, dA, ldda, N, K,
+                                                                                RB, S, items, accum_dw, need_da);
     CAPHN_RETURN_LAST();
 }
 
@@ -292,9 +306,9 @@ int caphn_rows_linear_bwd(const float* W, const float* A, long lda, const float*
         float* dAg = dA ? dA + (long)g0 * ldda : nullptr;
         int rc;
         switch (gc) {
-            case 4: rc = launch_rows_bwd<4>(W, Ag, lda, dPg, N, dW, dAg, ldda, N, (int)K, g0 > 0, dA != nullptr, st); break;
-            case 2: rc = launch_rows_bwd<2>(W, Ag, lda, dPg, N, dW, dAg, ldda, N, (int)K, g0 > 0, dA != nullptr, st); break;
-            default: rc = launch_rows_bwd<1>(W, Ag, lda, dPg, N, dW, dAg, ldda, N, (int)K, g0 > 0, dA != nullptr, st); break;
+            case 4: rc = launch_rows_bwd<4, 1, 4>(W, Ag, lda, dPg, N, dW, dAg, ldda, N, (int)K, g0 > 0, dA != nullptr, st); break;
+            case 2: rc = launch_rows_bwd<2, 2, 2>(W, Ag, lda, dPg, N, dW, dAg, ldda, N, (int)K, g0 > 0, dA != nullptr, st); break;
+            default: rc = launch_rows_bwd<1, 4, 2>(W, Ag, lda, dPg, N, dW, dAg, ldda, N, (int)K, g0 > 0, dA != nullptr, st); break;
         }
         if (rc) return rc;
         g0 += gc;
