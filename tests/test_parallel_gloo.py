@@ -1,0 +1,66 @@
+"""Data-parallel plumbing on CPU (gloo, world_size 2): the d(theta) all-reduce hook and the flat shared-gradient bucket
+reproduce the single-process global-batch gradients."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _toy(theta_src, W, xb, scale):
+    """theta = theta_src**2 (stands in for the replicated hypernet); per-rank loss = scale * sum((xb @ W) * theta)."""
+    from hypernet_image_captioning_b200.parallel import allreduce_grad
+    theta = theta_src * theta_src
+    theta = allreduce_grad(theta)
+    return scale * ((xb @ W) * theta).sum()
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hypernet_image_captioning_b200.parallel import allreduce_shared_grads
+    g = torch.Generator().manual_seed(0)
+    theta_src = torch.randn(5, generator=g).requires_grad_(True)
+    W = torch.nn.Parameter(torch.randn(3, 5, generator=g))
+    x = torch.randn(8, 3, generator=g)
+    xb = x[rank * 4:(rank + 1) * 4]
+    loss = _toy(theta_src, W, xb, 1.0 / world)
+    loss.backward()
+    cnt = torch.tensor([float(xb.shape[0])])
+    allreduce_shared_grads([W], extra=cnt)
+    torch.save({"theta_grad": theta_src.grad, "W_grad": W.grad, "cnt": cnt}, os.path.join(out, f"r{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_dp_gradients_match_single_process(tmp_path):
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(0)
+    theta_src = torch.randn(5, generator=g).requires_grad_(True)
+    W = torch.nn.Parameter(torch.randn(3, 5, generator=g))
+    x = torch.randn(8, 3, generator=g)
+    theta = theta_src * theta_src
+    loss = (1.0 / world) * ((x @ W) * theta).sum()
+    loss.backward()
+    for r in range(world):
+        d = torch.load(os.path.join(str(tmp_path), f"r{r}.pt"))
+        # the hypernet-side gradient is identical on every rank after the d(theta) all-reduce ...
+        assert torch.allclose(d["theta_grad"], theta_src.grad, atol=1e-6)
+        # ... and the shared-parameter bucket sums the per-rank contributions
+        assert torch.allclose(d["W_grad"], W.grad, atol=1e-6)
+        assert d["cnt"].item() == 8.0
+
+
+def test_shared_parameter_selection():
+    import hypernet_image_captioning_b200 as C
+    from hypernet_image_captioning_b200.parallel import shared_parameters
+    m = C.HyperNetPooled(8, 6, 50, None)
+    names = {n for n, p in m.named_parameters() if any(p is q for q in shared_parameters(m))}
+    assert all(not n.startswith("hn_") for n in names)
+    assert {"captioner.embed.weight", "captioner.fc_out.weight", "image_encoder.fc.weight"} <= names
