@@ -27,8 +27,8 @@ SIGNATURES = {
     "caphn_gemm_tc": [P, P, P, P, L, P, L, P, I, I, I, P],
     "caphn_transpose_pad": [P, L, P, L, I, I, P],
     "caphn_copy_pad": [P, L, P, L, L, I, P],
-    "caphn_gru_seq_fwd": [P, P, I, P, P, P, P, P, P, P, I, I, I, P],
-    "caphn_gru_seq_bwd": [P, P, P, P, P, P, P, I, P, P, P, I, I, I, P],
+    "caphn_gru_seq_fwd": [P, P, I, P, P, P, P, P, P, I, I, I, I, P],
+    "caphn_gru_seq_bwd": [P, P, P, P, P, I, P, P, P, P, P, P, I, I, I, I, P],
     "caphn_ce_fwd": [P, L, P, L, I, I, LL, P, P, P, P],
     "caphn_ce_bwd": [P, L, P, L, I, I, LL, P, P, P, P, L, P],
     "caphn_softmax_argmax": [P, L, L, I, P, L, P, P],

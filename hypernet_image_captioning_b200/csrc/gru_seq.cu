@@ -11,196 +11,188 @@
 //
 // Sequence tensors are time-major: row index = t*B + b.  Hall is [T+1, B, H] with Hall[0] = h0, so that
 // Hall[1:] = h_t and Hall[:-1] = h_{t-1} are both plain [T*B, H] matrices for the dW_hh GEMM.
-#include "common.cuh"
+#include "seq_common.cuh"
 
 namespace caphn {
 
-constexpr int SEQ_THREADS = 512;
+constexpr int GRU_MAX_EXTRA = 3;  // DecoderGRU(num_layers <= 4)
 
-__host__ __device__ inline int pow2_ceil(int v) {
-    int p = 1;
-    while (p < v) p <<= 1;
-    return p;
-}
+struct GruFwdArgs {
+    const float* GI;     // [T,B,3H] layer-0 input projection (+ b_ih)
+    const float* WhhT;   // [H, ld3] layer 0
+    const float* bhh;    // [3H]
+    float* Hall;         // [T+1,B,H]: Hall[0] = h0, Hall[t+1] = output of the LAST layer at step t
+    float* Hbm;          // [B,T,H] or null
+    float* saved;        // [NL][4][T,B,H] (R,Z,N,GHN per layer) or null
+    float* Hmid;         // [NL-1][T,B,H] outputs of layers 0..NL-2 (needed for NL > 1 when saving)
+    const float* xWihT[GRU_MAX_EXTRA];  // extra layers: [H, ld3] each (input = state = previous layer's output)
+    const float* xWhhT[GRU_MAX_EXTRA];
+    const float* xbih[GRU_MAX_EXTRA];
+    const float* xbhh[GRU_MAX_EXTRA];
+    int NL, B, T, H, ld3;
+};
 
-template <int BT>
-__global__ void __launch_bounds__(SEQ_THREADS) gru_seq_fwd_kernel(
-    const float* __restrict__ GI,    // [T,B,3H]
-    const float* __restrict__ WhhT,  // [H, ld3]
-    int ld3, const float* __restrict__ bhh, float* __restrict__ Hall,  // [T+1,B,H], Hall[0] = h0 on entry
-    float* __restrict__ Hbm,   // [B,T,H] batch-major copy (may be null)
-    float* __restrict__ R, float* __restrict__ Z, float* __restrict__ Nn, float* __restrict__ GHN,  // [T,B,H] or null
-    int B, int T, int H, int CQT) {
+__global__ void __launch_bounds__(AT_THREADS) gru_seq_fwd_kernel(const GruFwdArgs a) {
+    constexpr int BT = AT_BT;
     extern __shared__ __align__(16) float smem[];
-    float* hs = smem;                 // [H][BT]
-    float* part = smem + H * BT;      // [KG][BT][ld3]   (H*BT is a multiple of 4 floats because BT % 4 == 0)
+    const int H = a.H, B = a.B, T = a.T, ld3 = a.ld3, H3 = 3 * a.H;
+    const int CQT3 = at_cqt(ld3), KG3 = AT_THREADS / CQT3;
+    float* hs = smem;                           // [H][BT]
+    float* part_gh = smem + H * BT;             // [KG3][BT][ld3]
+    float* part_gi = part_gh + KG3 * BT * ld3;  // [KG3][BT][ld3]   (extra layers only)
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * BT;
-    const int NCQ = ld3 >> 2;
-    const int KG = SEQ_THREADS / CQT;
-    const int kg = tid / CQT, cq0 = tid - kg * CQT;
-    const int kchunk = (H + KG - 1) / KG;
-    const int k0 = kg * kchunk, k1 = min(H, k0 + kchunk);
-    const int H3 = 3 * H;
+    const long TBH = (long)T * B * H;
 
-    for (int i = tid; i < H * BT; i += SEQ_THREADS) {
+    for (int i = tid; i < H * BT; i += AT_THREADS) {
         const int k = i / BT, b = i - k * BT;
-        hs[i] = (b0 + b < B) ? Hall[(long)(b0 + b) * H + k] : 0.f;
+        hs[i] = (b0 + b < B) ? a.Hall[(long)(b0 + b) * H + k] : 0.f;
     }
     __syncthreads();
 
     for (int t = 0; t < T; ++t) {
-        // ---- phase 1: partial products over this thread group's k range ----
-        for (int cq = cq0; cq < NCQ; cq += CQT) {
-            float acc[BT][4];
-#pragma unroll
-            for (int b = 0; b < BT; ++b)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[b][c] = 0.f;
-            const float* wp = WhhT + (long)k0 * ld3 + 4 * cq;
-#pragma unroll 4
-            for (int k = k0; k < k1; ++k, wp += ld3) {
-                const float4 w = *reinterpret_cast<const float4*>(wp);
-                float hv[BT];
-#pragma unroll
-                for (int b4 = 0; b4 < BT; b4 += 4) {
-                    const float4 h4 = *reinterpret_cast<const float4*>(hs + k * BT + b4);
-                    hv[b4] = h4.x; hv[b4 + 1] = h4.y; hv[b4 + 2] = h4.z; hv[b4 + 3] = h4.w;
-                }
-#pragma unroll
-                for (int b = 0; b < BT; ++b) {
-                    acc[b][0] = fmaf(w.x, hv[b], acc[b][0]);
-                    acc[b][1] = fmaf(w.y, hv[b], acc[b][1]);
-                    acc[b][2] = fmaf(w.z, hv[b], acc[b][2]);
-                    acc[b][3] = fmaf(w.w, hv[b], acc[b][3]);
+        for (int l = 0; l < a.NL; ++l) {
+            const bool last = (l == a.NL - 1);
+            if (l == 0) {
+                block_matvec<BT, false>(a.WhhT, ld3, H, hs, part_gh, CQT3, tid);
+            } else {
+                block_matvec<BT, false>(a.xWihT[l - 1], ld3, H, hs, part_gi, CQT3, tid);
+                block_matvec<BT, false>(a.xWhhT[l - 1], ld3, H, hs, part_gh, CQT3, tid);
+            }
+            __syncthreads();
+            const float* bhh = (l == 0) ? a.bhh : a.xbhh[l - 1];
+            for (int i = tid; i < BT * H; i += AT_THREADS) {
+                const int b = i / H, j = i - b * H;
+                const int gb = b0 + b;
+                if (gb < B) {
+                    const float ghr = bhh[j] + part_sum(part_gh, KG3, BT, ld3, b, j);
+                    const float ghz = bhh[H + j] + part_sum(part_gh, KG3, BT, ld3, b, H + j);
+                    const float ghn = bhh[2 * H + j] + part_sum(part_gh, KG3, BT, ld3, b, 2 * H + j);
+                    float gir, giz, gin;
+                    if (l == 0) {
+                        const float* gi = a.GI + ((long)t * B + gb) * H3;
+                        gir = gi[j]; giz = gi[H + j]; gin = gi[2 * H + j];
+                    } else {
+                        const float* bih = a.xbih[l - 1];
+                        gir = bih[j] + part_sum(part_gi, KG3, BT, ld3, b, j);
+                        giz = bih[H + j] + part_sum(part_gi, KG3, BT, ld3, b, H + j);
+                        gin = bih[2 * H + j] + part_sum(part_gi, KG3, BT, ld3, b, 2 * H + j);
+                    }
+                    const float r = sigmoidf_acc(gir + ghr);
+                    const float z = sigmoidf_acc(giz + ghz);
+                    const float n = tanhf(gin + r * ghn);
+                    const float hp = hs[j * BT + b];
+                    const float hn = (1.f - z) * n + z * hp;
+                    hs[j * BT + b] = hn;
+                    const long o = ((long)t * B + gb) * H + j;
+                    if (last) {
+                        a.Hall[o + (long)B * H] = hn;
+                        if (a.Hbm) a.Hbm[((long)gb * T + t) * H + j] = hn;
+                    } else if (a.Hmid) {
+                        a.Hmid[(long)l * TBH + o] = hn;
+                    }
+                    if (a.saved) {
+                        float* sv = a.saved + (long)l * 4 * TBH + o;
+                        sv[0] = r; sv[TBH] = z; sv[2 * TBH] = n; sv[3 * TBH] = ghn;
+                    }
                 }
             }
-#pragma unroll
-            for (int b = 0; b < BT; ++b)
-                *reinterpret_cast<float4*>(part + ((long)(kg * BT + b)) * ld3 + 4 * cq) =
-                    make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+            __syncthreads();
         }
-        __syncthreads();
-        // ---- phase 2: gates + state update, one (row, unit) per thread-iteration ----
-        for (int i = tid; i < BT * H; i += SEQ_THREADS) {
-            const int b = i / H, j = i - b * H;
-            const int gb = b0 + b;
-            if (gb < B) {
-                float ghr = bhh[j], ghz = bhh[H + j], ghn = bhh[2 * H + j];
-                for (int g = 0; g < KG; ++g) {
-                    const float* pp = part + ((long)(g * BT + b)) * ld3;
-                    ghr += pp[j]; ghz += pp[H + j]; ghn += pp[2 * H + j];
-                }
-                const float* gi = GI + ((long)t * B + gb) * H3;
-                const float r = sigmoidf_acc(gi[j] + ghr);
-                const float z = sigmoidf_acc(gi[H + j] + ghz);
-                const float n = tanhf(gi[2 * H + j] + r * ghn);
-                const float hp = hs[j * BT + b];
-                const float hn = (1.f - z) * n + z * hp;
-                hs[j * BT + b] = hn;
-                const long o = ((long)t * B + gb) * H + j;
-                Hall[o + (long)B * H] = hn;
-                if (Hbm) Hbm[((long)gb * T + t) * H + j] = hn;
-                if (R) { R[o] = r; Z[o] = z; Nn[o] = n; GHN[o] = ghn; }
-            }
-        }
-        __syncthreads();
     }
 }
 
-// BPTT.  dHbm[b,t,:] is the gradient flowing into h_t from the vocabulary projection (batch-major);
-// outputs dGI/dGH (time-major [T,B,3H]) feed the time-batched dW_ih / dW_hh / dx GEMMs; dh0 [B,H].
-template <int BT>
-__global__ void __launch_bounds__(SEQ_THREADS) gru_seq_bwd_kernel(
-    const float* __restrict__ dHbm, const float* __restrict__ R, const float* __restrict__ Z,
-    const float* __restrict__ Nn, const float* __restrict__ GHN, const float* __restrict__ Hall,
-    const float* __restrict__ Whh,  // [3H, ldh]
-    int ldh, float* __restrict__ dGI, float* __restrict__ dGH, float* __restrict__ dh0, int B, int T, int H,
-    int CQT) {
+struct GruBwdArgs {
+    const float* dHbm;   // [B,T,H] gradient w.r.t. the last layer's output at every step
+    const float* saved;  // [NL][4][T,B,H]
+    const float* Hall;   // [T+1,B,H]
+    const float* Hmid;   // [NL-1][T,B,H]
+    const float* Whh;    // [3H, ldh] layer 0
+    const float* xWih[GRU_MAX_EXTRA];  // [3H, ldh]
+    const float* xWhh[GRU_MAX_EXTRA];
+    float* dGI;          // [T,B,3H] layer 0
+    float* dGH;          // [T,B,3H] layer 0
+    float* xdGI;         // [NL-1][T,B,3H]
+    float* xdGH;         // [NL-1][T,B,3H]
+    float* dh0;          // [B,H]
+    int NL, B, T, H, ldh;
+};
+
+// One GRU cell backward for the (row, unit) items of this CTA.  dht = total gradient w.r.t. the cell output.
+__device__ __forceinline__ void gru_gate_bwd(float dht, float r, float z, float n, float ghn, float hp, float& dar,
+                                             float& daz, float& dan, float& danr, float& keep) {
+    const float dn = dht * (1.f - z);
+    const float dz = dht * (hp - n);
+    dan = dn * (1.f - n * n);
+    dar = dan * ghn * r * (1.f - r);
+    daz = dz * z * (1.f - z);
+    danr = dan * r;
+    keep = dht * z;
+}
+
+__global__ void __launch_bounds__(AT_THREADS) gru_seq_bwd_kernel(const GruBwdArgs a) {
+    constexpr int BT = AT_BT;
     extern __shared__ __align__(16) float smem[];
-    const int H3 = 3 * H;
-    float* dg = smem;                     // [3H][BT]
-    float* dhd = dg + H3 * BT;            // [BT][H]   direct term dh_t * z
-    float* part = dhd + ((BT * H + 3) & ~3);  // [JG][BT][ldh]
+    const int H = a.H, B = a.B, T = a.T, ldh = a.ldh, H3 = 3 * a.H;
+    const int CQTh = at_cqt(ldh), KGh = AT_THREADS / CQTh;
+    float* dgi = smem;                               // [3H][BT]
+    float* dgh = dgi + H3 * BT;                      // [3H][BT]
+    float* dhd = dgh + H3 * BT;                      // [BT][H] carried direct term (layer 0: dh_t * z)
+    float* dhin = dhd + ((BT * H + 3) & ~3);         // [BT][H] gradient handed from layer l to layer l-1
+    float* part_dh = dhin + ((BT * H + 3) & ~3);     // [KGh][BT][ldh]  dgh . W_hh
+    float* part_di = part_dh + KGh * BT * ldh;       // [KGh][BT][ldh]  dgi . W_ih (extra layers)
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * BT;
-    const int NCQ = ldh >> 2;
-    const int JG = SEQ_THREADS / CQT;
-    const int jg = tid / CQT, cq0 = tid - jg * CQT;
-    const int jchunk = (H3 + JG - 1) / JG;
-    const int j0 = jg * jchunk, j1 = min(H3, j0 + jchunk);
+    const long TBH = (long)T * B * H, TB3 = (long)T * B * H3;
 
-    for (int i = tid; i < BT * H; i += SEQ_THREADS) dhd[i] = 0.f;
-    for (int i = tid; i < JG * BT * ldh; i += SEQ_THREADS) part[i] = 0.f;
+    for (int i = tid; i < BT * H; i += AT_THREADS) dhd[i] = 0.f;
+    for (int i = tid; i < KGh * BT * ldh; i += AT_THREADS) part_dh[i] = 0.f;
     __syncthreads();
 
     for (int t = T - 1; t >= 0; --t) {
-        for (int i = tid; i < BT * H; i += SEQ_THREADS) {
-            const int b = i / H, j = i - b * H;
-            const int gb = b0 + b;
-            float dar = 0.f, daz = 0.f, dan = 0.f, danr = 0.f, keep = 0.f;
-            if (gb < B) {
-                float dht = dhd[i] + dHbm[((long)gb * T + t) * H + j];
-                for (int g = 0; g < JG; ++g) dht += part[((long)(g * BT + b)) * ldh + j];
-                const long o = ((long)t * B + gb) * H + j;
-                const float r = R[o], z = Z[o], n = Nn[o], ghn = GHN[o];
-                const float hp = Hall[o];  // Hall[t] = h_{t-1}
-                const float dn = dht * (1.f - z);
-                const float dz = dht * (hp - n);
-                dan = dn * (1.f - n * n);
-                dar = dan * ghn * r * (1.f - r);
-                daz = dz * z * (1.f - z);
-                danr = dan * r;
-                keep = dht * z;
-                float* gi = dGI + ((long)t * B + gb) * H3;
-                float* gh = dGH + ((long)t * B + gb) * H3;
-                gi[j] = dar; gi[H + j] = daz; gi[2 * H + j] = dan;
-                gh[j] = dar; gh[H + j] = daz; gh[2 * H + j] = danr;
-            }
-            dhd[i] = keep;
-            dg[j * BT + b] = dar;
-            dg[(H + j) * BT + b] = daz;
-            dg[(2 * H + j) * BT + b] = danr;
-        }
-        __syncthreads();
-        for (int cq = cq0; cq < NCQ; cq += CQT) {
-            float acc[BT][4];
-#pragma unroll
-            for (int b = 0; b < BT; ++b)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[b][c] = 0.f;
-            const float* wp = Whh + (long)j0 * ldh + 4 * cq;
-#pragma unroll 4
-            for (int j = j0; j < j1; ++j, wp += ldh) {
-                const float4 w = *reinterpret_cast<const float4*>(wp);
-                float dv[BT];
-#pragma unroll
-                for (int b4 = 0; b4 < BT; b4 += 4) {
-                    const float4 d4 = *reinterpret_cast<const float4*>(dg + j * BT + b4);
-                    dv[b4] = d4.x; dv[b4 + 1] = d4.y; dv[b4 + 2] = d4.z; dv[b4 + 3] = d4.w;
+        for (int l = a.NL - 1; l >= 0; --l) {
+            const bool top = (l == a.NL - 1);
+            for (int i = tid; i < BT * H; i += AT_THREADS) {
+                const int b = i / H, j = i - b * H;
+                const int gb = b0 + b;
+                float dar = 0.f, daz = 0.f, dan = 0.f, danr = 0.f, keep = 0.f;
+                if (gb < B) {
+                    float dht;
+                    if (top) dht = dhd[i] + a.dHbm[((long)gb * T + t) * H + j] + part_sum(part_dh, KGh, BT, ldh, b, j);
+                    else dht = dhin[i];
+                    const long o = ((long)t * B + gb) * H + j;
+                    const float* sv = a.saved + (long)l * 4 * TBH + o;
+                    const float hp = (l == 0) ? a.Hall[o] : a.Hmid[(long)(l - 1) * TBH + o];
+                    gru_gate_bwd(dht, sv[0], sv[TBH], sv[2 * TBH], sv[3 * TBH], hp, dar, daz, dan, danr, keep);
+                    float* gi = ((l == 0) ? a.dGI : a.xdGI + (long)(l - 1) * TB3) + ((long)t * B + gb) * H3;
+                    float* gh = ((l == 0) ? a.dGH : a.xdGH + (long)(l - 1) * TB3) + ((long)t * B + gb) * H3;
+                    gi[j] = dar; gi[H + j] = daz; gi[2 * H + j] = dan;
+                    gh[j] = dar; gh[H + j] = daz; gh[2 * H + j] = danr;
                 }
-#pragma unroll
-                for (int b = 0; b < BT; ++b) {
-                    acc[b][0] = fmaf(w.x, dv[b], acc[b][0]);
-                    acc[b][1] = fmaf(w.y, dv[b], acc[b][1]);
-                    acc[b][2] = fmaf(w.z, dv[b], acc[b][2]);
-                    acc[b][3] = fmaf(w.w, dv[b], acc[b][3]);
-                }
+                if (l == 0) dhd[i] = keep; else dhin[i] = keep;
+                dgh[j * BT + b] = dar; dgh[(H + j) * BT + b] = daz; dgh[(2 * H + j) * BT + b] = danr;
+                if (l > 0) { dgi[j * BT + b] = dar; dgi[(H + j) * BT + b] = daz; dgi[(2 * H + j) * BT + b] = dan; }
             }
-#pragma unroll
-            for (int b = 0; b < BT; ++b)
-                *reinterpret_cast<float4*>(part + ((long)(jg * BT + b)) * ldh + 4 * cq) =
-                    make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+            __syncthreads();
+            if (l == 0) {
+                block_matvec<BT, false>(a.Whh, ldh, H3, dgh, part_dh, CQTh, tid);
+                __syncthreads();
+            } else {
+                // input and state of an extra layer are the same vector: both paths flow into the layer below
+                block_matvec<BT, false>(a.xWhh[l - 1], ldh, H3, dgh, part_di, CQTh, tid);
+                block_matvec<BT, true>(a.xWih[l - 1], ldh, H3, dgi, part_di, CQTh, tid);
+                __syncthreads();
+                for (int i = tid; i < BT * H; i += AT_THREADS) {
+                    const int b = i / H, j = i - b * H;
+                    dhin[i] += part_sum(part_di, KGh, BT, ldh, b, j);
+                }
+                __syncthreads();
+            }
         }
-        __syncthreads();
     }
-    for (int i = tid; i < BT * H; i += SEQ_THREADS) {
+    for (int i = tid; i < BT * H; i += AT_THREADS) {
         const int b = i / H, j = i - b * H;
-        if (b0 + b < B) {
-            float v = dhd[i];
-            for (int g = 0; g < JG; ++g) v += part[((long)(g * BT + b)) * ldh + j];
-            dh0[(long)(b0 + b) * H + j] = v;
-        }
+        if (b0 + b < B) a.dh0[(long)(b0 + b) * H + j] = dhd[i] + part_sum(part_dh, KGh, BT, ldh, b, j);
     }
 }
 
@@ -249,40 +241,50 @@ int caphn_copy_pad(const float* src, long lds, float* dst, long ldd, long R, int
     CAPHN_RETURN_LAST();
 }
 
-// GRU recurrence over T steps.  GI [T,B,3H] (x-projection incl. b_ih); WhhT [H, ld3] (ld3 % 4 == 0, 16B aligned);
-// Hall [T+1,B,H] with Hall[0] = h0 filled by the caller; optional Hbm [B,T,H]; optional saved gates R,Z,Nn,GHN [T,B,H].
-int caphn_gru_seq_fwd(const float* GI, const float* WhhT, int ld3, const float* bhh, float* Hall, float* Hbm, float* R,
-                      float* Z, float* Nn, float* GHN, int B, int T, int H, void* stream) {
+// GRU recurrence over T steps (all layers).  GI [T,B,3H] (layer-0 x-projection incl. b_ih); WhhT [H, ld3] (ld3 % 4 == 0,
+// 16B aligned); Hall [T+1,B,H] with Hall[0] = h0 filled by the caller; optional Hbm [B,T,H].  Extra layers (DecoderGRU
+// num_layers > 1, later.py:413-414: h = layer(h, h)): `extra` is a HOST array of 4*(NL-1) device pointers
+// {WihT_l, WhhT_l, bih_l, bhh_l}.  saved [NL][4][T,B,H] and Hmid [NL-1][T,B,H] are needed for the backward (or NULL).
+int caphn_gru_seq_fwd(const float* GI, const float* WhhT, int ld3, const float* bhh, float* Hall, float* Hbm,
+                      float* saved, float* Hmid, const void* const* extra, int NL, int B, int T, int H, void* stream) {
     if (B <= 0 || T <= 0 || H <= 0 || (ld3 & 3) || ld3 < 3 * H || ((uintptr_t)WhhT & 15)) return CAPHN_EINVAL;
-    if (R && !(Z && Nn && GHN)) return CAPHN_EINVAL;
-    constexpr int BT = 4;
-    int CQT = pow2_ceil(ld3 >> 2);
-    if (CQT > SEQ_THREADS) CQT = SEQ_THREADS;
-    if (CQT < 32) CQT = 32;
-    const int KG = SEQ_THREADS / CQT;
-    const size_t smem = ((size_t)H * BT + (size_t)KG * BT * ld3) * sizeof(float);
+    if (NL < 1 || NL > 1 + GRU_MAX_EXTRA || (NL > 1 && !extra) || (NL > 1 && saved && !Hmid)) return CAPHN_EINVAL;
+    GruFwdArgs a{};
+    a.GI = GI; a.WhhT = WhhT; a.bhh = bhh; a.Hall = Hall; a.Hbm = Hbm; a.saved = saved; a.Hmid = Hmid;
+    a.NL = NL; a.B = B; a.T = T; a.H = H; a.ld3 = ld3;
+    for (int l = 0; l < NL - 1; ++l) {
+        a.xWihT[l] = (const float*)extra[4 * l]; a.xWhhT[l] = (const float*)extra[4 * l + 1];
+        a.xbih[l] = (const float*)extra[4 * l + 2]; a.xbhh[l] = (const float*)extra[4 * l + 3];
+        if (((uintptr_t)a.xWihT[l] & 15) || ((uintptr_t)a.xWhhT[l] & 15)) return CAPHN_EINVAL;
+    }
+    const int KG3 = AT_THREADS / at_cqt(ld3);
+    const size_t smem = ((size_t)H * AT_BT + 2 * (size_t)KG3 * AT_BT * ld3) * sizeof(float);
     if (smem > 227 * 1024) return CAPHN_EINVAL;
-    CAPHN_CHECK(cudaFuncSetAttribute(gru_seq_fwd_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gru_seq_fwd_kernel<BT><<<ceil_div(B, BT), SEQ_THREADS, smem, (cudaStream_t)stream>>>(
-        GI, WhhT, ld3, bhh, Hall, Hbm, R, Z, Nn, GHN, B, T, H, CQT);
+    CAPHN_CHECK(cudaFuncSetAttribute(gru_seq_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gru_seq_fwd_kernel<<<ceil_div(B, AT_BT), AT_THREADS, smem, (cudaStream_t)stream>>>(a);
     CAPHN_RETURN_LAST();
 }
 
-// BPTT of caphn_gru_seq_fwd.  Whh [3H, ldh] (ldh % 4 == 0).  dGI, dGH [T,B,3H]; dh0 [B,H].
-int caphn_gru_seq_bwd(const float* dHbm, const float* R, const float* Z, const float* Nn, const float* GHN,
-                      const float* Hall, const float* Whh, int ldh, float* dGI, float* dGH, float* dh0, int B, int T,
-                      int H, void* stream) {
+// BPTT of caphn_gru_seq_fwd.  Whh [3H, ldh] (ldh % 4 == 0); `extra` = HOST array of 2*(NL-1) device pointers
+// {Wih_l, Whh_l} ([3H, ldh] each).  Outputs: dGI, dGH [T,B,3H] (layer 0), xdGI, xdGH [NL-1][T,B,3H], dh0 [B,H].
+int caphn_gru_seq_bwd(const float* dHbm, const float* saved, const float* Hall, const float* Hmid, const float* Whh,
+                      int ldh, const void* const* extra, float* dGI, float* dGH, float* xdGI, float* xdGH, float* dh0,
+                      int NL, int B, int T, int H, void* stream) {
     if (B <= 0 || T <= 0 || H <= 0 || (ldh & 3) || ldh < H || ((uintptr_t)Whh & 15)) return CAPHN_EINVAL;
-    constexpr int BT = 4;
-    int CQT = pow2_ceil(ldh >> 2);
-    if (CQT > SEQ_THREADS) CQT = SEQ_THREADS;
-    if (CQT < 32) CQT = 32;
-    const int JG = SEQ_THREADS / CQT;
-    const size_t smem = ((size_t)3 * H * BT + (size_t)((BT * H + 3) & ~3) + (size_t)JG * BT * ldh) * sizeof(float);
+    if (NL < 1 || NL > 1 + GRU_MAX_EXTRA || (NL > 1 && !(extra && Hmid && xdGI && xdGH))) return CAPHN_EINVAL;
+    GruBwdArgs a{};
+    a.dHbm = dHbm; a.saved = saved; a.Hall = Hall; a.Hmid = Hmid; a.Whh = Whh; a.dGI = dGI; a.dGH = dGH;
+    a.xdGI = xdGI; a.xdGH = xdGH; a.dh0 = dh0; a.NL = NL; a.B = B; a.T = T; a.H = H; a.ldh = ldh;
+    for (int l = 0; l < NL - 1; ++l) {
+        a.xWih[l] = (const float*)extra[2 * l]; a.xWhh[l] = (const float*)extra[2 * l + 1];
+        if (((uintptr_t)a.xWih[l] & 15) || ((uintptr_t)a.xWhh[l] & 15)) return CAPHN_EINVAL;
+    }
+    const int KGh = AT_THREADS / at_cqt(ldh);
+    const size_t smem = (2 * (size_t)3 * H * AT_BT + 2 * (size_t)((AT_BT * H + 3) & ~3) +
+                         2 * (size_t)KGh * AT_BT * ldh) * sizeof(float);
     if (smem > 227 * 1024) return CAPHN_EINVAL;
-    CAPHN_CHECK(cudaFuncSetAttribute(gru_seq_bwd_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    gru_seq_bwd_kernel<BT><<<ceil_div(B, BT), SEQ_THREADS, smem, (cudaStream_t)stream>>>(
-        dHbm, R, Z, Nn, GHN, Hall, Whh, ldh, dGI, dGH, dh0, B, T, H, CQT);
+    CAPHN_CHECK(cudaFuncSetAttribute(gru_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gru_seq_bwd_kernel<<<ceil_div(B, AT_BT), AT_THREADS, smem, (cudaStream_t)stream>>>(a);
     CAPHN_RETURN_LAST();
 }
 

@@ -129,40 +129,62 @@ def cross_entropy(logits, targets, ignore_index: Optional[int] = None):
 # Variant A decoder: teacher-forced DecoderGRU.forward  (reference later.py:389-457), single GRUCell
 # ----------------------------------------------------------------------------------------------------------------------
 class DecoderGRUSeqFn(Function):
+    """inputs: feats, captions, h0, emb_w, fc_w, fc_b, then (W_ih, W_hh, b_ih, b_hh) for every GRU cell (layer 0 first).
+    Extra layers are applied as h = cell_l(h, h) at every step (later.py:413-414, 420-421)."""
+
     @staticmethod
-    def forward(ctx, feats, captions, h0, emb_w, W_ih, W_hh, b_ih, b_hh, fc_w, fc_b):
+    def forward(ctx, feats, captions, h0, emb_w, fc_w, fc_b, *cells):
         B, T = captions.shape
+        NL = len(cells) // 4
+        W_ih, W_hh, b_ih, b_hh = cells[0:4]
         H = W_hh.shape[1]
         caps = captions.contiguous()
         feats = feats.contiguous()
         emb_w = emb_w.contiguous()
         X = ops.build_inputs(feats, emb_w, caps, 0)                       # [T*B, E]
         GI = ops.linear(X, W_ih.contiguous(), b_ih.contiguous())          # [T*B, 3H]
-        WhhT = ops.transpose_pad(W_hh.contiguous(), ops.round4(3 * H))    # [H, ld3]
-        Hall, Hbm, saved = ops.gru_seq_fwd(GI, WhhT, b_hh.contiguous(), h0.contiguous(), T, save=True)
+        ld3 = ops.round4(3 * H)
+        WhhT = ops.transpose_pad(W_hh.contiguous(), ld3)                  # [H, ld3]
+        extra = []
+        for l in range(1, NL):
+            Wi, Wh, bi, bh = cells[4 * l: 4 * l + 4]
+            extra.append((ops.transpose_pad(Wi.contiguous(), ld3), ops.transpose_pad(Wh.contiguous(), ld3),
+                          bi.contiguous(), bh.contiguous()))
+        Hall, Hbm, saved, Hmid = ops.gru_seq_fwd(GI, WhhT, b_hh.contiguous(), h0.contiguous(), T, save=True, extra=extra)
         logits = ops.linear(Hbm.view(B * T, H), fc_w.contiguous(), fc_b)
-        ctx.save_for_backward(caps, X, Hall, Hbm, saved, emb_w, W_ih, W_hh, fc_w)
+        ctx.save_for_backward(caps, X, Hall, Hbm, saved, Hmid, emb_w, fc_w, *cells)
+        ctx.NL = NL
         return logits.view(B, T, -1)
 
     @staticmethod
     def backward(ctx, dlogits):
-        caps, X, Hall, Hbm, saved, emb_w, W_ih, W_hh, fc_w = ctx.saved_tensors
+        caps, X, Hall, Hbm, saved, Hmid, emb_w, fc_w = ctx.saved_tensors[:8]
+        cells = ctx.saved_tensors[8:]
+        NL = ctx.NL
+        W_ih, W_hh = cells[0], cells[1]
         B, T = caps.shape
         H = W_hh.shape[1]
-        E = X.shape[1]
         need = ctx.needs_input_grad
         dl = dlogits.reshape(B * T, -1).contiguous()
         Hbm2 = Hbm.view(B * T, H)
-        dfc_w = ops.matmul_tn(dl, Hbm2) if need[8] else None
-        dfc_b = ops.colsum(dl) if need[9] else None
+        dfc_w = ops.matmul_tn(dl, Hbm2) if need[4] else None
+        dfc_b = ops.colsum(dl) if need[5] else None
         dHbm = ops.matmul_nn(dl, fc_w.contiguous())                        # [B*T, H]
-        Whh_p = ops.copy_pad(W_hh.contiguous(), ops.round4(H))
-        dGI, dGH, dh0 = ops.gru_seq_bwd(dHbm.view(B, T, H), saved, Hall, Whh_p)
+        ldh = ops.round4(H)
+        Whh_p = ops.copy_pad(W_hh.contiguous(), ldh)
+        extra = [(ops.copy_pad(cells[4 * l].contiguous(), ldh), ops.copy_pad(cells[4 * l + 1].contiguous(), ldh))
+                 for l in range(1, NL)]
+        dGI, dGH, xdGI, xdGH, dh0 = ops.gru_seq_bwd(dHbm.view(B, T, H), saved, Hall, Hmid, Whh_p, extra=extra)
         Hprev = Hall[:-1].reshape(T * B, H)
-        dW_hh = ops.matmul_tn(dGH, Hprev) if need[5] else None
-        db_hh = ops.colsum(dGH) if need[7] else None
-        dW_ih = ops.matmul_tn(dGI, X) if need[4] else None
-        db_ih = ops.colsum(dGI) if need[6] else None
+        cell_grads = [ops.matmul_tn(dGI, X) if need[6] else None, ops.matmul_tn(dGH, Hprev) if need[7] else None,
+                      ops.colsum(dGI) if need[8] else None, ops.colsum(dGH) if need[9] else None]
+        for l in range(1, NL):
+            Hin = Hmid[l - 1].reshape(T * B, H)                            # input == state of layer l
+            n0 = 6 + 4 * l
+            cell_grads += [ops.matmul_tn(xdGI[l - 1], Hin) if need[n0] else None,
+                           ops.matmul_tn(xdGH[l - 1], Hin) if need[n0 + 1] else None,
+                           ops.colsum(xdGI[l - 1]) if need[n0 + 2] else None,
+                           ops.colsum(xdGH[l - 1]) if need[n0 + 3] else None]
         dfeats = demb = None
         if need[0] or need[3]:
             dX = ops.matmul_nn(dGI, W_ih.contiguous())                     # [T*B, E]
@@ -171,4 +193,4 @@ class DecoderGRUSeqFn(Function):
             if need[3]:
                 demb = torch.zeros_like(emb_w)
                 ops.embed_scatter_add(dX, caps, demb, 1)
-        return dfeats, None, (dh0 if need[2] else None), demb, dW_ih, dW_hh, db_ih, db_hh, dfc_w, dfc_b
+        return (dfeats, None, (dh0 if need[2] else None), demb, dfc_w, dfc_b, *cell_grads)

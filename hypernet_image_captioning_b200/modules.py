@@ -108,13 +108,13 @@ class DecoderGRU(nn.Module):
         if not teacher_forcing:
             raise NotImplementedError("multinomial-sampled decoding (later.py:424-434) is outside the hot path")
         cells = self._cells()
-        if len(cells) != 1:
-            raise NotImplementedError("num_layers > 1 runs through forward_multilayer (see DESIGN.md)")
+        if len(cells) > 4:
+            raise NotImplementedError("DecoderGRU with more than 4 layers")
         if h0 is None:
             h0 = self._h0(features)
-        W_ih, W_hh, b_ih, b_hh = cells[0]
-        return Fn.DecoderGRUSeqFn.apply(features, captions, h0, self.embed.weight, W_ih, W_hh, b_ih, b_hh,
-                                        self.fc_out.weight, self.fc_out.bias)
+        flat = [w for cell in cells for w in cell]
+        return Fn.DecoderGRUSeqFn.apply(features, captions, h0, self.embed.weight, self.fc_out.weight,
+                                        self.fc_out.bias, *flat)
 
     @torch.no_grad()
     def infer(self, features, max_len=50, h0=None):
@@ -131,7 +131,7 @@ class DecoderGRU(nn.Module):
         logits = torch.empty(B, self.vocab_size, device=features.device, dtype=torch.float32)
         for t in range(max_len):
             GI = ops.linear(x, W_ih, b_ih)
-            Hall, _, _ = ops.gru_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False)
+            Hall, _, _, _ = ops.gru_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False)
             h = Hall[1]
             ops.linear(h, fc_w, fc_b, out=logits)
             _, words = ops.softmax_argmax(logits, want_probs=True, probs_out=outputs[:, t, :])

@@ -181,33 +181,48 @@ def round4(n):
 # ----------------------------------------------------------------------------------------------------------------------
 # recurrences
 # ----------------------------------------------------------------------------------------------------------------------
-def gru_seq_fwd(GI, WhhT, bhh, h0, T, save=True, want_bm=True):
-    """GI [T*B,3H] time-major, WhhT [H,ld3]; returns Hall [T+1,B,H], Hbm [B,T,H] | None, saved gates | None."""
+def _ptr_array(tensors):
+    import ctypes
+    arr = (ctypes.c_void_p * max(1, len(tensors)))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def gru_seq_fwd(GI, WhhT, bhh, h0, T, save=True, want_bm=True, extra=()):
+    """GI [T*B,3H] time-major, WhhT [H,ld3]; ``extra`` = [(WihT_l, WhhT_l, bih_l, bhh_l), ...] for layers 1..NL-1.
+    Returns Hall [T+1,B,H], Hbm [B,T,H] | None, saved [NL,4,T,B,H] | None, Hmid [NL-1,T,B,H] | None."""
     B, H = h0.shape
+    NL = 1 + len(extra)
     dev = GI.device
     Hall = torch.empty(T + 1, B, H, device=dev, dtype=torch.float32)
     Hall[0].copy_(h0)
     Hbm = torch.empty(B, T, H, device=dev, dtype=torch.float32) if want_bm else None
-    saved = torch.empty(4, T, B, H, device=dev, dtype=torch.float32) if save else None
-    sp = [saved[i].data_ptr() for i in range(4)] if save else [None] * 4
+    saved = torch.empty(NL, 4, T, B, H, device=dev, dtype=torch.float32) if save else None
+    Hmid = torch.empty(NL - 1, T, B, H, device=dev, dtype=torch.float32) if (save and NL > 1) else None
+    flat = [t for cell in extra for t in cell]
+    arr = _ptr_array(flat)
     _cabi.call("caphn_gru_seq_fwd", GI.data_ptr(), WhhT.data_ptr(), WhhT.stride(0), bhh.data_ptr(), Hall.data_ptr(),
-               _p(Hbm), sp[0], sp[1], sp[2], sp[3], B, T, H, _stream())
-    return Hall, Hbm, saved
+               _p(Hbm), _p(saved), _p(Hmid), arr if NL > 1 else None, NL, B, T, H, _stream())
+    return Hall, Hbm, saved, Hmid
 
 
-def gru_seq_bwd(dHbm, saved, Hall, Whh_p):
-    """Returns dGI, dGH [T*B,3H] (time-major) and dh0 [B,H]."""
+def gru_seq_bwd(dHbm, saved, Hall, Hmid, Whh_p, extra=()):
+    """``extra`` = [(Wih_l, Whh_l) padded [3H,ldh], ...].  Returns dGI, dGH [T*B,3H], xdGI, xdGH [NL-1,T*B,3H] | None, dh0."""
     Tp1, B, H = Hall.shape
     T = Tp1 - 1
+    NL = 1 + len(extra)
     dev = Hall.device
     dGI = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
     dGH = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+    xdGI = torch.empty(NL - 1, T * B, 3 * H, device=dev, dtype=torch.float32) if NL > 1 else None
+    xdGH = torch.empty(NL - 1, T * B, 3 * H, device=dev, dtype=torch.float32) if NL > 1 else None
     dh0 = torch.empty(B, H, device=dev, dtype=torch.float32)
     assert dHbm.is_contiguous()
-    _cabi.call("caphn_gru_seq_bwd", dHbm.data_ptr(), saved[0].data_ptr(), saved[1].data_ptr(), saved[2].data_ptr(),
-               saved[3].data_ptr(), Hall.data_ptr(), Whh_p.data_ptr(), Whh_p.stride(0), dGI.data_ptr(), dGH.data_ptr(),
-               dh0.data_ptr(), B, T, H, _stream())
-    return dGI, dGH, dh0
+    flat = [t for cell in extra for t in cell]
+    arr = _ptr_array(flat)
+    _cabi.call("caphn_gru_seq_bwd", dHbm.data_ptr(), saved.data_ptr(), Hall.data_ptr(), _p(Hmid), Whh_p.data_ptr(),
+               Whh_p.stride(0), arr if NL > 1 else None, dGI.data_ptr(), dGH.data_ptr(), _p(xdGI), _p(xdGH),
+               dh0.data_ptr(), NL, B, T, H, _stream())
+    return dGI, dGH, xdGI, xdGH, dh0
 
 
 # ----------------------------------------------------------------------------------------------------------------------

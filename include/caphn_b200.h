@@ -58,16 +58,19 @@ int caphn_copy_pad(const float* src, long lds, float* dst, long ldd, long R, int
 
 /* ---- pooled-feature decoder recurrence (later.py:389-490 DecoderGRU; torch GRUCell gates r,z,n) -------------------- */
 
-/* All T steps in one launch.  GI [T,B,3H] = x_t W_ih^T + b_ih (time-major); WhhT [H,ld3] (= W_hh^T, ld3 % 4 == 0);
- * Hall [T+1,B,H] with Hall[0] = h0 on entry, Hall[t+1] = h_t on exit; Hbm [B,T,H] (optional batch-major copy);
- * R,Z,Nn,GHN [T,B,H] saved gate values for the backward (all four or none). */
-int caphn_gru_seq_fwd(const float* GI, const float* WhhT, int ld3, const float* bhh, float* Hall, float* Hbm, float* R,
-                      float* Z, float* Nn, float* GHN, int B, int T, int H, void* stream);
+/* All T steps (and all layers) in one launch.  GI [T,B,3H] = x_t W_ih^T + b_ih of layer 0 (time-major); WhhT [H,ld3]
+ * (= W_hh^T, ld3 % 4 == 0); Hall [T+1,B,H] with Hall[0] = h0 on entry, Hall[t+1] = h_t (last layer) on exit; Hbm [B,T,H]
+ * optional batch-major copy.  Extra layers (num_layers > 1, later.py:413-414 `h = layer(h, h)`): `extra` is a HOST array
+ * of 4*(NL-1) device pointers {WihT_l, WhhT_l, bih_l, bhh_l}.  saved [NL][4][T,B,H] (R,Z,N,GHN) and Hmid [NL-1][T,B,H]
+ * (outputs of the lower layers) are written for the backward when non-NULL. */
+int caphn_gru_seq_fwd(const float* GI, const float* WhhT, int ld3, const float* bhh, float* Hall, float* Hbm,
+                      float* saved, float* Hmid, const void* const* extra, int NL, int B, int T, int H, void* stream);
 
-/* BPTT.  dHbm [B,T,H] = dL/dh_t from the vocabulary projection; Whh [3H,ldh]; outputs dGI,dGH [T,B,3H], dh0 [B,H]. */
-int caphn_gru_seq_bwd(const float* dHbm, const float* R, const float* Z, const float* Nn, const float* GHN,
-                      const float* Hall, const float* Whh, int ldh, float* dGI, float* dGH, float* dh0, int B, int T,
-                      int H, void* stream);
+/* BPTT.  dHbm [B,T,H] = dL/dh_t from the vocabulary projection; Whh [3H,ldh]; `extra` = HOST array of 2*(NL-1) device
+ * pointers {Wih_l, Whh_l} ([3H,ldh]).  Outputs dGI,dGH [T,B,3H] (layer 0), xdGI,xdGH [NL-1][T,B,3H], dh0 [B,H]. */
+int caphn_gru_seq_bwd(const float* dHbm, const float* saved, const float* Hall, const float* Hmid, const float* Whh,
+                      int ldh, const void* const* extra, float* dGI, float* dGH, float* xdGI, float* xdGH, float* dh0,
+                      int NL, int B, int T, int H, void* stream);
 
 /* ---- attention decoder recurrence (models/decoderlstm.py:78-108 AttentionGru loop; models/attention.py:21-46) ------- */
 

@@ -122,10 +122,10 @@ def test_gru_seq_fwd_bwd(B, T, H):
     GIc = GI.detach().float().cuda().reshape(T * B, 3 * H).contiguous()
     Wc = W_hh.detach().float().cuda()
     WhhT = ops.transpose_pad(Wc, ops.round4(3 * H))
-    Hall, Hbm, saved = ops.gru_seq_fwd(GIc, WhhT, b_hh.detach().float().cuda(), h0.detach().float().cuda(), T)
+    Hall, Hbm, saved, _ = ops.gru_seq_fwd(GIc, WhhT, b_hh.detach().float().cuda(), h0.detach().float().cuda(), T)
     assert rel_err(Hall[1:], Href) < 5e-6
     assert rel_err(Hbm, Href.permute(1, 0, 2)) < 5e-6
-    dGI, dGH, dh0 = ops.gru_seq_bwd(dH.float().cuda().contiguous(), saved, Hall, ops.copy_pad(Wc, ops.round4(H)))
+    dGI, dGH, _, _, dh0 = ops.gru_seq_bwd(dH.float().cuda().contiguous(), saved, Hall, None, ops.copy_pad(Wc, ops.round4(H)))
     assert rel_err(dGI.view(T, B, 3 * H), GI.grad) < 2e-5
     assert rel_err(dh0, h0.grad) < 2e-5
     dW = ops.matmul_tn(dGH, Hall[:-1].reshape(T * B, H))

@@ -26,27 +26,33 @@ def _model_from(p, E, H, V, L=1, mode="flow"):
     return m.cuda()
 
 
-def test_state_dict_layout_matches_reference():
-    c = load_case("pooled_l1")
+@pytest.mark.parametrize("name,L", [("pooled_l1", 1), ("pooled_l2", 2)])
+def test_state_dict_layout_matches_reference(name, L):
+    c = load_case(name)
     p = params_of(c)
     import hypernet_image_captioning_b200 as C
-    m = C.HyperNetPooled(8, 6, 9684, None)
+    m = C.HyperNetPooled(8, 6, 9684, None, num_layers=L)
     sd = m.state_dict()
     gen = {"captioner.lstm_cell." + k for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")}
+    gen |= {f"captioner.layers.{l}.{k}" for l in range(L - 1) for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")}
     assert set(sd.keys()) == set(p.keys()) | gen
     for k, v in p.items():
         assert tuple(sd[k].shape) == tuple(v.shape), k
 
 
+@pytest.mark.parametrize("name,L", [("pooled_l1", 1), ("pooled_l2", 2)])
 @pytest.mark.parametrize("mode", ["literal", "flow"])
-def test_pooled_golden(mode):
-    c = load_case("pooled_l1")
+def test_pooled_golden(name, L, mode):
+    """L = 2 exercises the offset-0 aliasing of utils.py:45,68 (layer 2 reads theta[0:...]) and `h = layer(h, h)`."""
+    c = load_case(name)
     p = params_of(c)
-    m = _model_from(p, 8, 6, 9684, mode=mode)
+    m = _model_from(p, 8, 6, 9684, L=L, mode=mode)
     import hypernet_image_captioning_b200 as C
     captioner = m.forward(c["style"].cuda())
-    for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
-        assert rel_err(getattr(captioner.lstm_cell, k), c["gen/0/" + k]) < 1e-5, k
+    cells_mod = [captioner.lstm_cell] + (list(captioner.layers) if captioner.layers else [])
+    for ci, cell in enumerate(cells_mod):
+        for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+            assert rel_err(getattr(cell, k), c[f"gen/{ci}/{k}"]) < 1e-5, (ci, k)
     feats = m.image_encoder(c["pooled"].cuda())
     logits = captioner(feats, c["captions"].cuda(), True, h0=c["h0"].cuda())
     assert rel_err(logits, c["tf/logits"]) < TOL_LOGITS
@@ -58,8 +64,9 @@ def test_pooled_golden(mode):
               "captioner.fc_out.weight", "captioner.fc_out.bias"):
         assert grad_close(named[k].grad, c["tf/grad/" + k], TOL_GRAD), k
     if mode == "literal":
-        for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
-            assert grad_close(getattr(captioner.lstm_cell, k).grad, c["tf/grad/gen/0/" + k], TOL_GRAD), k
+        for ci, cell in enumerate(cells_mod):
+            for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                assert grad_close(getattr(cell, k).grad, c[f"tf/grad/gen/{ci}/{k}"], TOL_GRAD), (ci, k)
         assert all(v.grad is None for k, v in named.items() if k.startswith("hn_"))
     else:
         n = 0
@@ -70,9 +77,10 @@ def test_pooled_golden(mode):
         assert n >= 12
 
 
-def test_pooled_infer_golden_token_exact():
-    c = load_case("pooled_l1")
-    m = _model_from(params_of(c), 8, 6, 9684)
+@pytest.mark.parametrize("name,L", [("pooled_l1", 1), ("pooled_l2", 2)])
+def test_pooled_infer_golden_token_exact(name, L):
+    c = load_case(name)
+    m = _model_from(params_of(c), 8, 6, 9684, L=L)
     with torch.no_grad():
         captioner = m.forward(c["style"].cuda())
         probs = captioner.infer(m.image_encoder(c["pooled"].cuda()), max_len=c["infer/probs"].shape[1],
@@ -92,21 +100,22 @@ def test_pooled_rng_consumption_matches_reference():
     assert rel_err(logits, c["tf/logits"]) < TOL_LOGITS
 
 
-@pytest.mark.parametrize("B,T,E,H,V", [(37, 9, 24, 30, 311), (64, 20, 200, 150, 2000)])
-def test_pooled_vs_oracle_medium(B, T, E, H, V):
+@pytest.mark.parametrize("B,T,E,H,V,L", [(37, 9, 24, 30, 311, 1), (64, 20, 200, 150, 2000, 1), (21, 6, 24, 30, 211, 2),
+                                         (10, 5, 16, 12, 97, 3)])
+def test_pooled_vs_oracle_medium(B, T, E, H, V, L):
     import hypernet_image_captioning_b200 as C
-    p = O.init_params_pooled(2048, E, H, V, L=1, seed=5)
+    p = O.init_params_pooled(2048, E, H, V, L=L, seed=5)
     g = torch.Generator().manual_seed(99)
     pooled = torch.relu(torch.randn(B, 2048, generator=g))
     caps = O.synth_captions(B, T, V, g)
     style = torch.randn(1, E, generator=g)
     h0 = torch.rand(B, H, generator=g)
     pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-    logits_ref, theta_ref, _ = O.path_pooled(pl, style, pooled, caps, h0, L=1, flow=True)
+    logits_ref, theta_ref, _ = O.path_pooled(pl, style, pooled, caps, h0, L=L, flow=True)
     loss_ref = O.caption_loss(logits_ref, caps, None)
     loss_ref.backward()
 
-    m = _model_from(p, E, H, V)
+    m = _model_from(p, E, H, V, L=L)
     captioner = m.forward(style.cuda())
     logits = captioner(m.image_encoder(pooled.cuda()), caps.cuda(), True, h0=h0.cuda())
     loss = C.cross_entropy(logits, caps.cuda(), None)
@@ -114,6 +123,6 @@ def test_pooled_vs_oracle_medium(B, T, E, H, V):
     assert rel_err(logits, logits_ref) < TOL_LOGITS
     assert abs(loss.item() - loss_ref.item()) < TOL_LOGITS * abs(loss_ref.item())
     for k, v in m.named_parameters():
-        if k.startswith("captioner.lstm_cell."):
+        if k.startswith("captioner.lstm_cell.") or k.startswith("captioner.layers."):
             continue
         assert grad_close(v.grad, pl[k].grad, TOL_GRAD), k
