@@ -63,6 +63,34 @@ class _HyperNetMixin:
             theta = allreduce_grad(theta, self.dp_group)
         return theta
 
+    def forward_grouped(self, X: torch.Tensor):
+        """Grouped generalisation (BASELINE.json north_star "per-style grouped"): ``X`` = [G, he] style/domain vectors.
+        One pass over the hypernet weights generates all G weight sets (the reference would stream them G times, one
+        ``forward`` per style); the captioner then decodes every batch row with the weights of its group:
+        ``captioner(features, captions, ..., groups=group_ids)``.  Oracle = one reference call per group, concatenated."""
+        Theta = self.generate_theta(X)
+        self.captioner._generated_groups = [self._split_theta(Theta[g]) for g in range(Theta.shape[0])]
+        return self.captioner
+
+
+def _run_grouped(fn, groups: torch.Tensor, tensors, n_groups: int):
+    """Apply ``fn(g, *row_subsets)`` per group and put the rows back in their original order (differentiable glue)."""
+    groups = groups.to(tensors[0].device)
+    order = torch.argsort(groups, stable=True)
+    counts = torch.bincount(groups, minlength=n_groups).tolist()
+    outs, start = None, 0
+    for g, n in enumerate(counts):
+        if n == 0:
+            continue
+        idx = order[start:start + n]
+        start += n
+        res = fn(g, *[t.index_select(0, idx) for t in tensors])
+        res = res if isinstance(res, tuple) else (res,)
+        outs = [[r] for r in res] if outs is None else [o + [r] for o, r in zip(outs, res)]
+    inv = torch.empty_like(order)
+    inv[order] = torch.arange(order.numel(), device=order.device)
+    return tuple(torch.cat(o, 0).index_select(0, inv) for o in outs)
+
 
 class PooledFeatureEncoder(nn.Module):
     """Stands in for the frozen ResNet-101 + trainable fc of hypernet.py:40-48: the CNN trunk is out of scope
@@ -93,8 +121,11 @@ class DecoderGRU(nn.Module):
         self.fc_out = nn.Linear(hidden_size, vocab_size)
         self.embed = nn.Embedding(vocab_size, embed_size)
         self._generated = None  # per-cell (W_ih, W_hh, b_ih, b_hh) carrying the hypernet graph (flow mode)
+        self._generated_groups = None  # list over style groups of the above (forward_grouped)
 
-    def _cells(self):
+    def _cells(self, group=None):
+        if group is not None:
+            return self._generated_groups[group]
         if self._generated is not None:
             return self._generated
         cells = [self.lstm_cell] + (list(self.layers) if self.layers else [])
@@ -104,14 +135,21 @@ class DecoderGRU(nn.Module):
         # reference later.py:393-394: global CPU RNG, then type_as(features)
         return torch.rand(size=(features.size(0), self.hidden_size)).to(features.device, features.dtype)
 
-    def forward(self, features, captions, teacher_forcing=True, h0=None):
+    def forward(self, features, captions, teacher_forcing=True, h0=None, groups=None):
         if not teacher_forcing:
             raise NotImplementedError("multinomial-sampled decoding (later.py:424-434) is outside the hot path")
-        cells = self._cells()
-        if len(cells) > 4:
-            raise NotImplementedError("DecoderGRU with more than 4 layers")
+        if groups is not None:
+            if h0 is None:
+                h0 = self._h0(features)
+            return _run_grouped(lambda g, f, c, h: self._forward_one(f, c, h, self._cells(g)), groups,
+                                [features, captions, h0], len(self._generated_groups))[0]
         if h0 is None:
             h0 = self._h0(features)
+        return self._forward_one(features, captions, h0, self._cells())
+
+    def _forward_one(self, features, captions, h0, cells):
+        if len(cells) > 4:
+            raise NotImplementedError("DecoderGRU with more than 4 layers")
         flat = [w for cell in cells for w in cell]
         return Fn.DecoderGRUSeqFn.apply(features, captions, h0, self.embed.weight, self.fc_out.weight,
                                         self.fc_out.bias, *flat)
@@ -175,7 +213,12 @@ class HyperNetPooled(_HyperNetMixin, _Base):
     def forward(self, x):
         """theta = heads(base(x)); inject into the captioner's GRU cells; returns self.captioner (hypernet.py:104-114)."""
         theta = self.generate_theta(x)[0]
-        E, H = self.hparams['embed_size'], self.hparams['hidden_size']
+        gen = self._split_theta(theta, write_params=True)
+        self.captioner._generated = gen if self.grad_mode == "flow" else None
+        self.captioner._generated_groups = None
+        return self.captioner
+
+    def _split_theta(self, theta, write_params=False):
         cells_mod = [self.captioner.lstm_cell] + (list(self.captioner.layers) if self.captioner.layers else [])
         gen = []
         for ci, cell in enumerate(cells_mod):
@@ -185,12 +228,12 @@ class HyperNetPooled(_HyperNetMixin, _Base):
                 p = getattr(cell, name)
                 w = theta[a:a + p.numel()].reshape(p.shape)
                 a += p.numel()
-                with torch.no_grad():
-                    p.copy_(w)  # state_dict keeps the last generated weights, as the reference does
+                if write_params:
+                    with torch.no_grad():
+                        p.copy_(w)  # state_dict keeps the last generated weights, as the reference does
                 ws.append(w)
             gen.append(tuple(ws))
-        self.captioner._generated = gen if self.grad_mode == "flow" else None
-        return self.captioner
+        return gen
 
     def configure_optimizers(self):  # hypernet.py:116-124
         params = list(self.hn_heads.parameters()) + list(self.hn_base.parameters())

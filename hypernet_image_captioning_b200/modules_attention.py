@@ -13,7 +13,7 @@ from torch.autograd import Function
 
 from . import functional as Fn
 from . import ops
-from .modules import _Base, _HyperNetMixin
+from .modules import _Base, _HyperNetMixin, _run_grouped
 
 
 class AttentionGruFn(Function):
@@ -173,25 +173,36 @@ class AttentionGru(nn.Module):
         self.drop = nn.Dropout(p=p)
         self.init_h = nn.Linear(feature_out, hidden_dim)
         self._generated = None
+        self._generated_groups = None
 
-    def _gru_weights(self):
+    def _gru_weights(self, group=None):
+        if group is not None:
+            return self._generated_groups[group]
         if self._generated is not None:
             return self._generated
         g = self.gru
         return (g.weight_ih, g.weight_hh, g.bias_ih, g.bias_hh)
 
-    def forward(self, features, captions, sample_prob=0.0):
+    def forward(self, features, captions, sample_prob=0.0, groups=None):
         """Returns (outputs [B,T,V], atten_weights [B,T,P]) -- models/decoderlstm.py:49-120.
-        Consumes one np.random.random() per time step from NumPy's global RNG exactly like the reference (:79-80)."""
+        Consumes one np.random.random() per time step from NumPy's global RNG exactly like the reference (:79-80).
+        ``groups`` ([B] int64 group id per row, after ``HyperNet.forward_grouped``) decodes every row with the generated
+        weights of its style group; the scheduled-sampling draws are shared by all groups of the call."""
         T = captions.size(1)
         use = []
         for t in range(T):
             sp = 0.0 if t == 0 else sample_prob
             use.append(bool(np.random.random() < sp))
-        W_ih, W_hh, b_ih, b_hh = self._gru_weights()
+        if groups is not None:
+            return _run_grouped(lambda g, f, c: self._forward_one(f, c, tuple(use), self._gru_weights(g)), groups,
+                                [features, captions], len(self._generated_groups))
+        return self._forward_one(features, captions, tuple(use), self._gru_weights())
+
+    def _forward_one(self, features, captions, use, gru_w):
+        W_ih, W_hh, b_ih, b_hh = gru_w
         a = self.attention
         return AttentionGruFn.apply(
-            features, captions, tuple(use), self.feature_fc[0].weight, self.feature_fc[0].bias,
+            features, captions, use, self.feature_fc[0].weight, self.feature_fc[0].bias,
             self.feature_fc[2].weight, self.feature_fc[2].bias, self.embed.weight, W_ih, W_hh, b_ih, b_hh,
             self.fc.weight, self.fc.bias, a.W_a.weight, a.W_a.bias, a.U_a.weight, a.U_a.bias, a.v_a.weight, a.v_a.bias,
             self.init_h.weight, self.init_h.bias)
@@ -245,17 +256,23 @@ class HyperNetAttention(_HyperNetMixin, _Base):
     def forward(self, x):
         """theta -> captioner.gru weights; returns self.captioner (hypernet_attention.py:111-121)."""
         theta = self.generate_theta(x)[0]
+        ws = self._split_theta(theta, write_params=True)
+        self.captioner._generated = ws if self.grad_mode == "flow" else None
+        self.captioner._generated_groups = None
+        return self.captioner
+
+    def _split_theta(self, theta, write_params=False):
         gru = self.captioner.gru
         a, ws = 0, []
         for name in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
             p = getattr(gru, name)
             w = theta[a:a + p.numel()].reshape(p.shape)
             a += p.numel()
-            with torch.no_grad():
-                p.copy_(w)
+            if write_params:
+                with torch.no_grad():
+                    p.copy_(w)
             ws.append(w)
-        self.captioner._generated = tuple(ws) if self.grad_mode == "flow" else None
-        return self.captioner
+        return tuple(ws)
 
     def configure_optimizers(self):  # hypernet_attention.py:123-134
         c = self.captioner
