@@ -9,9 +9,11 @@
 // Replaces the large addmm calls behind nn.Linear in the reference: vocabulary projection self.fc / fc_out
 // (models/decoderlstm.py:105, later.py:442) forward and both backward products, feature_fc (models/decoderlstm.py:61).
 //
-// Warp roles (256 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (tcgen05.ld -> smem transpose -> coalesced global stores).  Two TMEM accumulator
-// stages (2 x 128 columns) let the MMAs of tile i+1 overlap the epilogue of tile i.
+// Warp roles (384 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
+// allocator, warps 4-11 = epilogue (tcgen05.ld -> swizzled smem transpose -> 128-bit coalesced global stores, or fp32
+// atomics under split-K).  Two TMEM accumulator stages (2 x BN columns) let the MMAs of work unit i+1 overlap the
+// epilogue of unit i.  The N tile is chosen at run time (one tile of N rounded to 16 when N <= 256, e.g. 160 for
+// H = 150), and long-K / few-tile products are split along K so that ~148 CTAs are busy.
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -19,11 +21,8 @@
 namespace caphn {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int BM = 128, BK = 64;
 constexpr int TILE_BYTES = BM * BK * 2;  // 16 KiB: one 128 x 64 bf16 operand tile (128-byte rows, SWIZZLE_128B)
-constexpr int THREADS = 256;
-constexpr int STG_FLOATS = 4 * 32 * 33;
-constexpr uint32_t TMEM_COLS = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -105,42 +104,55 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <bool SPLIT>
-struct Cfg {
-    static constexpr int NT = SPLIT ? 4 : 2;          // operand tiles per pipeline stage
-    static constexpr int STAGES = SPLIT ? 3 : 6;
-    static constexpr int STAGE_BYTES = NT * TILE_BYTES;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STG_FLOATS * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
+// Shared-memory plan (dynamic, 1024-byte aligned): [stage 0 | stage 1 | ...][epilogue staging][mbarriers][tmem slot].
+// A stage holds A_hi, (A_lo), B_hi, (B_lo); A tiles are 128 x 64 bf16 (16 KiB), B tiles BN x 64 bf16 (BN * 128 B).
+constexpr int EPI_WARPS = 8;
+constexpr int STG_STRIDE = 32;                              // floats per staged row; float4 slots XOR-swizzled by (row & 7)
+constexpr int STG_FLOATS_V2 = EPI_WARPS * 32 * STG_STRIDE;  // 32 KiB
+constexpr int THREADS_V2 = 128 + EPI_WARPS * 32;            // warps 0-3: TMA / MMA / TMEM alloc / idle; 4-11: epilogue
+constexpr int MAX_STAGES = 6;
+constexpr size_t SMEM_BUDGET = 227 * 1024;
+
+struct TcParams {
+    float* C; long ldc; const float* bias;
+    int M, N, num_kb, relu;
+    int BN;          // N tile (multiple of 16, <= 256)
+    int splitk;      // K split factor; > 1 => epilogue adds atomically into a zero-initialised C
+    int kb_per;      // k-blocks per split
+    int stages, stage_bytes, b_bytes;
+    uint32_t tmem_cols;
 };
 
 template <bool SPLIT>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS_V2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
-               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-               float* __restrict__ C, long ldc, const float* __restrict__ bias, int M, int N, int num_kb, int relu) {
-    using G = Cfg<SPLIT>;
+               const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;
-    float* stg = reinterpret_cast<float*>(smem + (size_t)G::STAGES * G::STAGE_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(stg + STG_FLOATS);
-    uint64_t* empty = full + G::STAGES;
-    uint64_t* tfull = empty + G::STAGES;
+    float* stg = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(stg + STG_FLOATS_V2);
+    uint64_t* empty = full + MAX_STAGES;
+    uint64_t* tfull = empty + MAX_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
-    const int num_tiles = tiles_m * tiles_n;
+    const int BN = p.BN;
+    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    const int num_units = tiles_m * tiles_n * p.splitk;
+    // operand offsets inside a stage
+    const int offAh = 0, offBh = TILE_BYTES;
+    const int offAl = TILE_BYTES + p.b_bytes, offBl = 2 * TILE_BYTES + p.b_bytes;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < G::STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, 4); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(TMEM_COLS)
+                     "r"(p.tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -153,19 +165,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int ks = unit % p.splitk, tile = unit / p.splitk;
                 const int mb = tile % tiles_m, nb = tile / tiles_m;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb0 = ks * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty + stage, phase ^ 1);
-                    mbar_expect_tx(full + stage, G::STAGE_BYTES);
-                    uint8_t* st = tiles + (size_t)stage * G::STAGE_BYTES;
-                    tma_load_2d(st, &tmAh, full + stage, kb * BK, mb * BM);
-                    tma_load_2d(st + TILE_BYTES, &tmBh, full + stage, kb * BK, nb * BN);
+                    mbar_expect_tx(full + stage, (uint32_t)p.stage_bytes);
+                    uint8_t* st = tiles + (size_t)stage * p.stage_bytes;
+                    tma_load_2d(st + offAh, &tmAh, full + stage, kb * BK, mb * BM);
+                    tma_load_2d(st + offBh, &tmBh, full + stage, kb * BK, nb * BN);
                     if (SPLIT) {
-                        tma_load_2d(st + 2 * TILE_BYTES, &tmAl, full + stage, kb * BK, mb * BM);
-                        tma_load_2d(st + 3 * TILE_BYTES, &tmBl, full + stage, kb * BK, nb * BN);
+                        tma_load_2d(st + offAl, &tmAl, full + stage, kb * BK, mb * BM);
+                        tma_load_2d(st + offBl, &tmBl, full + stage, kb * BK, nb * BN);
                     }
-                    if (++stage == G::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -175,67 +189,120 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+                const int ks = unit % p.splitk;
+                const int kb0 = ks * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
                 const int as = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
                 mbar_wait(tempty + as, aph ^ 1);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full + stage, phase);
                     tcgen05_fence_after();
-                    const uint32_t sbase = smem_u32(tiles + (size_t)stage * G::STAGE_BYTES);
-                    const uint64_t dAh = make_desc(sbase), dBh = make_desc(sbase + TILE_BYTES);
-                    const uint64_t dAl = make_desc(sbase + 2 * TILE_BYTES), dBl = make_desc(sbase + 3 * TILE_BYTES);
+                    const uint32_t sbase = smem_u32(tiles + (size_t)stage * p.stage_bytes);
+                    const uint64_t dAh = make_desc(sbase + offAh), dBh = make_desc(sbase + offBh);
+                    const uint64_t dAl = make_desc(sbase + offAl), dBl = make_desc(sbase + offBl);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t ko = (uint64_t)((k * 16 * 2) >> 4);  // advance 32 bytes along K inside the swizzle atom
-                        umma_f16(tmem_d, dAh + ko, dBh + ko, idesc, (kb | k) ? 1u : 0u);
+                        const uint64_t ko = (uint64_t)((k * 16 * 2) >> 4);  // +32 bytes along K inside the swizzle atom
+                        umma_f16(tmem_d, dAh + ko, dBh + ko, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                         if (SPLIT) {
                             umma_f16(tmem_d, dAh + ko, dBl + ko, idesc, 1u);
                             umma_f16(tmem_d, dAl + ko, dBh + ko, idesc, 1u);
                         }
                     }
                     umma_commit(empty + stage);   // frees this smem stage once the MMAs above have read it
-                    if (++stage == G::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tfull + as);          // accumulator complete -> epilogue
             }
         }
     } else if (warp >= 4) {
-        const int q = warp - 4;                   // TMEM lane quadrant this warp may access
-        float* st = stg + q * (32 * 33);
+        const int ew = warp - 4;
+        const int q = warp & 3;                   // TMEM lane quadrant this warp may access (warp id % 4)
+        const int half = ew >> 2;                 // two warps per quadrant split the 32-column chunks
+        float* st = stg + ew * (32 * STG_STRIDE);
+        const int nchunks = (BN + 31) / 32;
+        const bool atomic = p.splitk > 1;
+        const bool vec = !atomic && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+            const int ks = unit % p.splitk, tile = unit / p.splitk;
             const int mb = tile % tiles_m, nb = tile / tiles_m;
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             mbar_wait(tfull + as, aph);
             tcgen05_fence_after();
             const int row0 = mb * BM + q * 32;
+            const bool add_bias = p.bias != nullptr && ks == 0;
+            int last_c = half;
+            while (last_c + 2 < nchunks) last_c += 2;
+            if (half >= nchunks) {                 // nothing to read for this warp: release the stage immediately
+                tcgen05_fence_before();
+                if (lane == 0) mbar_arrive(tempty + as);
+            }
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = half; c < nchunks; c += 2) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
                 tmem_ld_wait();
-                if (c == BN / 32 - 1) {
+                if (c == last_c) {
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty + as);   // TMEM stage drained (4 warps -> count 4)
+                    if (lane == 0) mbar_arrive(tempty + as);   // this warp no longer needs the TMEM stage
                 }
+                const int colbase = nb * BN + c * 32;
+                const int cvalid = min(32, min(BN - c * 32, p.N - colbase));   // valid columns of this chunk
 #pragma unroll
-                for (int j = 0; j < 32; ++j) st[lane * 33 + j] = __uint_as_float(r[j]);
+                for (int j4 = 0; j4 < 8; ++j4)   // row = lane; float4 slot j4 lives at (j4 ^ (row & 7)): conflict-free
+                    *reinterpret_cast<float4*>(st + lane * STG_STRIDE + ((j4 ^ (lane & 7)) << 2)) =
+                        make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
+                                    __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
                 __syncwarp();
-                const int col = nb * BN + c * 32 + lane;
-                const bool colok = col < N;
-                const float bv = (bias != nullptr && colok) ? bias[col] : 0.f;
+                if (vec) {
+                    const int cl = (lane & 7) * 4;             // 4 consecutive columns per lane, 8 lanes per row
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (add_bias) {
+                        if (cl + 0 < cvalid) bv.x = p.bias[colbase + cl + 0];
+                        if (cl + 1 < cvalid) bv.y = p.bias[colbase + cl + 1];
+                        if (cl + 2 < cvalid) bv.z = p.bias[colbase + cl + 2];
+                        if (cl + 3 < cvalid) bv.w = p.bias[colbase + cl + 3];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = (lane >> 3) + 4 * i;
+                        const int row = row0 + rr;
+                        float4 v = *reinterpret_cast<const float4*>(st + rr * STG_STRIDE + (((lane & 7) ^ (rr & 7)) << 2));
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (row < p.M) {
+                            float* o = p.C + (long)row * p.ldc + colbase + cl;
+                            if (cl + 3 < cvalid) {
+                                *reinterpret_cast<float4*>(o) = v;
+                            } else {
+                                if (cl + 0 < cvalid) o[0] = v.x;
+                                if (cl + 1 < cvalid) o[1] = v.y;
+                                if (cl + 2 < cvalid) o[2] = v.z;
+                            }
+                        }
+                    }
+                } else {
+                    const bool colok = lane < cvalid;
+                    const float bv = (add_bias && colok) ? p.bias[colbase + lane] : 0.f;
 #pragma unroll 8
-                for (int rr = 0; rr < 32; ++rr) {
-                    const int row = row0 + rr;
-                    if (row < M && colok) {
-                        float v = st[rr * 33 + lane] + bv;
-                        if (relu) v = fmaxf(v, 0.f);
-                        C[(long)row * ldc + col] = v;
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = row0 + rr;
+                        if (row < p.M && colok) {
+                            float v = st[rr * STG_STRIDE + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))] + bv;
+                            float* o = p.C + (long)row * p.ldc + colbase + lane;
+                            if (atomic) {
+                                atomicAdd(o, v);
+                            } else {
+                                if (p.relu) v = fmaxf(v, 0.f);
+                                *o = v;
+                            }
+                        }
                     }
                 }
                 __syncwarp();
@@ -246,7 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     __syncthreads();
     if (warp == 2) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
     }
 }
 
@@ -309,13 +376,13 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D map over a row-major bf16 matrix [rows, Kp]: box = 64 (K) x 128 (rows), 128-byte swizzle, zero fill out of bounds.
-static int make_map(CUtensorMap* m, const void* base, long rows, long Kp) {
+// 2-D map over a row-major bf16 matrix [rows, Kp]: box = 64 (K) x box_rows, 128-byte swizzle, zero fill out of bounds.
+static int make_map(CUtensorMap* m, const void* base, long rows, long Kp, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return CAPHN_EINVAL;
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -350,32 +417,67 @@ int caphn_split_bf16_t(const float* src, long lds, int R, int C, void* hi, void*
 
 // C[M,N] (fp32, row stride ldc) = A B^T (+bias[n]) (ReLU) on the tensor cores.  A = (Ahi, Alo) [M, Kp], B = (Bhi, Blo)
 // [N, Kp] in the split format above (16-byte aligned, Kp % 64 == 0).  Alo == Blo == NULL selects plain bf16.
+// splitk: 0 = choose automatically, 1 = none, > 1 = split the K loop and add partial tiles atomically (C is zeroed here).
 int caphn_gemm_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, long Kp, float* C, long ldc,
-                  const float* bias, int M, int N, int relu, void* stream) {
+                  const float* bias, int M, int N, int relu, int splitk, void* stream) {
     if (M <= 0 || N <= 0 || Kp <= 0 || (Kp & 63) || ((Alo == nullptr) != (Blo == nullptr))) return CAPHN_EINVAL;
     if (((uintptr_t)Ahi & 15) || ((uintptr_t)Bhi & 15) || ((uintptr_t)Alo & 15) || ((uintptr_t)Blo & 15))
         return CAPHN_EINVAL;
     const bool split = Alo != nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    tc::TcParams p{};
+    p.C = C; p.ldc = ldc; p.bias = bias; p.M = M; p.N = N; p.relu = relu;
+    p.num_kb = (int)(Kp / tc::BK);
+    // N tile: one tile when N <= 256 (rounded up to 16), otherwise 128-wide tiles
+    p.BN = (N <= 256) ? ((N + 15) / 16) * 16 : 128;
+    const int tiles = ceil_div(M, tc::BM) * ceil_div(N, p.BN);
+    if (splitk <= 0) {
+        // smallest split whose unit count fills the 148 SMs to >= 90 % (or the best available), >= 4 k-blocks per unit
+        splitk = 1;
+        if (!relu && tiles < 3 * kNumSMs) {
+            double best = 0.0;
+            const int smax = p.num_kb / 4 > 32 ? 32 : (p.num_kb / 4 < 1 ? 1 : p.num_kb / 4);
+            for (int s = 1; s <= smax; ++s) {
+                const long units = (long)tiles * s;
+                const double eff = (double)units / (double)(((units + kNumSMs - 1) / kNumSMs) * kNumSMs);
+                if (eff > best + 0.02) { best = eff; splitk = s; }
+                if (eff >= 0.9) break;
+            }
+        }
+    }
+    if (splitk > 1 && relu) return CAPHN_EINVAL;
+    p.kb_per = (p.num_kb + splitk - 1) / splitk;
+    p.splitk = (p.num_kb + p.kb_per - 1) / p.kb_per;
+    p.b_bytes = p.BN * tc::BK * 2;
+    p.stage_bytes = (split ? 2 : 1) * (tc::TILE_BYTES + p.b_bytes);
+    const size_t fixed = (size_t)tc::STG_FLOATS_V2 * 4 + (2 * tc::MAX_STAGES + 4) * 8 + 16 + 1024;
+    int stages = (int)((tc::SMEM_BUDGET - fixed) / p.stage_bytes);
+    if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
+    if (stages < 2) return CAPHN_EINVAL;
+    p.stages = stages;
+    p.tmem_cols = (2 * p.BN <= 256) ? 256u : 512u;
+    const size_t smem = (size_t)stages * p.stage_bytes + fixed;
+    if (p.splitk > 1) {
+        if (ldc == N) {
+            CAPHN_CHECK(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st));
+        } else {
+            CAPHN_CHECK(cudaMemset2DAsync(C, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, st));
+        }
+    }
     CUtensorMap mAh, mAl, mBh, mBl;
     int rc;
-    if ((rc = tc::make_map(&mAh, Ahi, M, Kp))) return rc;
-    if ((rc = tc::make_map(&mBh, Bhi, N, Kp))) return rc;
-    if ((rc = tc::make_map(&mAl, split ? Alo : Ahi, M, Kp))) return rc;
-    if ((rc = tc::make_map(&mBl, split ? Blo : Bhi, N, Kp))) return rc;
-    const int tiles = ceil_div(M, tc::BM) * ceil_div(N, tc::BN);
-    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-    const int num_kb = (int)(Kp / tc::BK);
-    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = tc::make_map(&mAh, Ahi, M, Kp, tc::BM))) return rc;
+    if ((rc = tc::make_map(&mBh, Bhi, N, Kp, p.BN))) return rc;
+    if ((rc = tc::make_map(&mAl, split ? Alo : Ahi, M, Kp, tc::BM))) return rc;
+    if ((rc = tc::make_map(&mBl, split ? Blo : Bhi, N, Kp, p.BN))) return rc;
+    const long units = (long)tiles * p.splitk;
+    const int grid = units < kNumSMs ? (int)units : kNumSMs;
     if (split) {
-        CAPHN_CHECK(cudaFuncSetAttribute(tc::gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)tc::Cfg<true>::SMEM));
-        tc::gemm_tc_kernel<true><<<grid, tc::THREADS, tc::Cfg<true>::SMEM, st>>>(mAh, mAl, mBh, mBl, C, ldc, bias, M, N,
-                                                                                 num_kb, relu);
+        CAPHN_CHECK(cudaFuncSetAttribute(tc::gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::gemm_tc_kernel<true><<<grid, tc::THREADS_V2, smem, st>>>(mAh, mAl, mBh, mBl, p);
     } else {
-        CAPHN_CHECK(cudaFuncSetAttribute(tc::gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)tc::Cfg<false>::SMEM));
-        tc::gemm_tc_kernel<false><<<grid, tc::THREADS, tc::Cfg<false>::SMEM, st>>>(mAh, mAl, mBh, mBl, C, ldc, bias, M, N,
-                                                                                  num_kb, relu);
+        CAPHN_CHECK(cudaFuncSetAttribute(tc::gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::gemm_tc_kernel<false><<<grid, tc::THREADS_V2, smem, st>>>(mAh, mAl, mBh, mBl, p);
     }
     CAPHN_RETURN_LAST();
 }

@@ -107,7 +107,7 @@ TC_MIN_WORK = 1 << 24
 
 
 def _tc_ok(M, N, K, accumulate=False):
-    return TC_ENABLED and not accumulate and M >= 128 and N >= 128 and K >= 32 and M * N * K >= TC_MIN_WORK
+    return TC_ENABLED and not accumulate and M >= 128 and N >= 16 and K >= 32 and M * N * K >= TC_MIN_WORK
 
 
 def linear(X, W, bias=None, relu=False, out=None):
@@ -416,7 +416,7 @@ def split_bf16_t(src, want_lo=True):
     return SplitOperand(hi, lo, C, Rp)
 
 
-def gemm_tc(A: SplitOperand, Bm: SplitOperand, bias=None, relu=False, out=None):
+def gemm_tc(A: SplitOperand, Bm: SplitOperand, bias=None, relu=False, out=None, splitk=0):
     """out[M,N] = A B^T (+bias) on the tensor cores; A [M,Kp], B [N,Kp] split operands with equal Kp."""
     assert A.Kp == Bm.Kp and (A.lo is None) == (Bm.lo is None)
     M, N = A.rows, Bm.rows
@@ -424,5 +424,5 @@ def gemm_tc(A: SplitOperand, Bm: SplitOperand, bias=None, relu=False, out=None):
         out = torch.empty(M, N, device=A.hi.device, dtype=torch.float32)
     assert out.stride(1) == 1
     _cabi.call("caphn_gemm_tc", A.hi.data_ptr(), _p(A.lo), Bm.hi.data_ptr(), _p(Bm.lo), A.Kp, out.data_ptr(),
-               out.stride(0), _p(bias), M, N, int(relu), _stream())
+               out.stride(0), _p(bias), M, N, int(relu), 1 if relu else splitk, _stream())
     return out

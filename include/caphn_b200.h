@@ -47,9 +47,10 @@ int caphn_split_bf16(const float* src, long lds, long R, int C, void* hi, void* 
 int caphn_split_bf16_t(const float* src, long lds, int R, int C, void* hi, void* lo, long Rp, void* stream);
 /* C[M,N] (fp32, ldc) = A B^T (+bias[n]) (ReLU); A = (Ahi, Alo) [M,Kp], B = (Bhi, Blo) [N,Kp] in the split format.
  * Three MMAs per k-slice (hi*hi + hi*lo + lo*hi) with fp32 accumulation in TMEM: ~1e-5 relative, fp32-class.
- * Alo == Blo == NULL: single bf16 MMA per k-slice. */
+ * Alo == Blo == NULL: single bf16 MMA per k-slice.  splitk: 0 = automatic, 1 = none, > 1 = split the K loop over more
+ * CTAs and add the partial tiles atomically (C is zeroed by the call; not combinable with ReLU). */
 int caphn_gemm_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, long Kp, float* C, long ldc,
-                  const float* bias, int M, int N, int relu, void* stream);
+                  const float* bias, int M, int N, int relu, int splitk, void* stream);
 
 /* dst[c*ldd+r] = src[r*lds+c] (zero padded to ldd) / dst[r*ldd+c] = src[r*lds+c] (zero padded): lay generated
  * weights out with 16-byte rows for the recurrence kernels. */

@@ -49,3 +49,17 @@ def test_gemm_tc_strided_output():
     ops.gemm_tc(ops.split_bf16(A), ops.split_bf16(W), out=big[:, 1, :])
     assert rel_err(big[:, 1, :], A.double() @ W.double().t()) < 2e-5
     assert float(big[:, 0, :].abs().max()) == 0 and float(big[:, 2, :].abs().max()) == 0
+
+
+@pytest.mark.parametrize("M,N,K,splitk", [(512, 150, 9684, 0), (450, 150, 10240, 0), (450, 200, 4096, 7), (9684, 150, 4096, 0),
+                                          (256, 208, 640, 3), (300, 16, 128, 1), (130, 250, 200, 0), (1024, 600, 200, 0)])
+def test_gemm_tc_tile_shapes_and_splitk(M, N, K, splitk):
+    """Run-time N tile (N <= 256 -> one tile rounded to 16) and split-K with atomic accumulation."""
+    from hypernet_image_captioning_b200 import ops
+    g = torch.Generator().manual_seed(M * 3 + N * 5 + K)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = torch.randn(N, K, generator=g).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    out = ops.gemm_tc(ops.split_bf16(A), ops.split_bf16(W), bias=b, splitk=splitk)
+    ref = A.double() @ W.double().t() + b.double()
+    assert rel_err(out, ref) < (2e-5 if K <= 2048 else 1e-4)
