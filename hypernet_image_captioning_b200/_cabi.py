@@ -31,6 +31,7 @@ SIGNATURES = {
     "caphn_gru_seq_bwd": [P, P, P, P, P, I, P, P, P, P, P, P, I, I, I, I, P],
     "caphn_ce_fwd": [P, L, P, L, I, I, LL, P, P, P, P],
     "caphn_ce_bwd": [P, L, P, L, I, I, LL, P, P, P, P, L, P],
+    "caphn_ce_bwd_split": [P, L, P, L, I, I, LL, P, P, P, P, P, L, P, P, L, P, P],
     "caphn_softmax_argmax": [P, L, L, I, P, L, P, P],
     "caphn_gather_rows": [P, P, L, I, P, L, P],
     "caphn_build_inputs": [P, P, P, I, I, I, I, P, P],

@@ -5,6 +5,7 @@
 // nn.Embedding lookups models/decoderlstm.py:62,96, later.py:400,473; softmax+argmax later.py:472,479 and
 // log_softmax+topk models/decoderlstm.py:94-95; torch.mean(features, dim=1) models/decoderlstm.py:133.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <math.h>
 
 namespace caphn {
@@ -118,6 +119,101 @@ __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restr
     } else {
         for (int i = threadIdx.x; i < V; i += CE_THREADS)
             dx[i] = valid ? (expf(x[i] - l) - (i == t ? 1.f : 0.f)) * sc : 0.f;
+    }
+}
+
+// Cross-entropy backward emitted directly in the tensor-core operand format (no fp32 dlogits round trip):
+//   d[m,v] = (exp(x - lse[m]) - [v == tgt[m]]) * gscale / count   (0 for ignored rows)
+//   hi/lo  [M, Vp]  bf16 split of d        (operand of dH  = d  . W_out,  K = V)
+//   hiT/loT [V, Mp] bf16 split of d^T      (operand of dW  = d^T . H,     K = M)
+//   dbias[v] += sum_m d[m,v]
+// One CTA per 64 x 64 tile: coalesced row-major writes, shared-memory transpose for the [V, Mp] copy.
+__global__ void __launch_bounds__(256) ce_bwd_split_kernel(
+    const float* __restrict__ X, long ld, const long long* __restrict__ tgt, int M, int V, int has_ignore,
+    long long ignore, const float* __restrict__ lse, const float* __restrict__ gscale,
+    const float* __restrict__ lossbuf, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long Vp,
+    __nv_bfloat16* __restrict__ hiT, __nv_bfloat16* __restrict__ loT, long Mp, float* __restrict__ dbias) {
+    __shared__ float tile[64][65];
+    __shared__ float csum[16][64];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * 64, v0 = blockIdx.x * 64;
+    const float sc0 = gscale[0] / fmaxf(lossbuf[1], 1.f);
+    const int c4 = (tid & 15) * 4;
+    const bool vecx = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && (v0 + c4 + 3 < V);
+    float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = (tid >> 4) + 16 * i;
+        const int m = m0 + r;
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        if (m < M) {
+            const long long t = tgt[m];
+            const bool valid = !(has_ignore && t == ignore);
+            if (valid) {
+                const float l = lse[m];
+                const float* xp = X + (long)m * ld + v0 + c4;
+                float x[4] = {0.f, 0.f, 0.f, 0.f};
+                if (vecx) {
+                    const float4 xv = *reinterpret_cast<const float4*>(xp);
+                    x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (v0 + c4 + c < V) x[c] = xp[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int v = v0 + c4 + c;
+                    if (v < V) d[c] = (expf(x[c] - l) - (v == t ? 1.f : 0.f)) * sc0;
+                }
+            }
+            __nv_bfloat16 h[4], lw[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                h[c] = __float2bfloat16_rn(d[c]);
+                lw[c] = __float2bfloat16_rn(d[c] - __bfloat162float(h[c]));
+            }
+            // 4 bf16 = one 8-byte store per array (row offsets are multiples of 4 elements: Vp % 64 == 0)
+            uint2 ph, pl;
+            ph.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+            ph.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+            pl.x = (uint32_t)__bfloat16_as_ushort(lw[0]) | ((uint32_t)__bfloat16_as_ushort(lw[1]) << 16);
+            pl.y = (uint32_t)__bfloat16_as_ushort(lw[2]) | ((uint32_t)__bfloat16_as_ushort(lw[3]) << 16);
+            *reinterpret_cast<uint2*>(hi + (long)m * Vp + v0 + c4) = ph;
+            *reinterpret_cast<uint2*>(lo + (long)m * Vp + v0 + c4) = pl;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { tile[r][c4 + c] = d[c]; cs[c] += d[c]; }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) csum[tid >> 4][c4 + c] = cs[c];
+    __syncthreads();
+    if (tid < 64 && dbias != nullptr && v0 + tid < V) {
+        float s = 0.f;
+#pragma unroll
+        for (int g = 0; g < 16; ++g) s += csum[g][tid];
+        atomicAdd(dbias + v0 + tid, s);
+    }
+    // transposed copy: item = (column c, group of 8 rows); 8 consecutive lanes cover the 64 rows of one column = 128 B
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const int item = tid + it * 256;
+        const int c = item >> 3, r8 = (item & 7) * 8;
+        const int v = v0 + c;
+        if (v < V) {
+            uint32_t wh[4], wl[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float x0 = tile[r8 + 2 * k][c], x1 = tile[r8 + 2 * k + 1][c];
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                wh[k] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                wl[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            *reinterpret_cast<uint4*>(hiT + (long)v * Mp + m0 + r8) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+            *reinterpret_cast<uint4*>(loT + (long)v * Mp + m0 + r8) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        }
     }
 }
 
@@ -265,6 +361,19 @@ int caphn_ce_bwd(const float* X, long ld, const long long* tgt, long M, int V, i
     if (M <= 0 || V <= 0) return CAPHN_EINVAL;
     ce_bwd_kernel<<<(unsigned)M, CE_THREADS, 0, (cudaStream_t)stream>>>(X, ld, tgt, V, has_ignore, ignore, lse, gscale,
                                                                         lossbuf, dX, lddx);
+    CAPHN_RETURN_LAST();
+}
+
+// Cross-entropy backward written straight into the bf16x3 operand formats of caphn_gemm_tc (see kernel comment):
+// hi/lo [M, Vp], hiT/loT [V, Mp] (Vp, Mp multiples of 64, >= V, M), dbias [V] accumulated (zero-initialised by caller).
+int caphn_ce_bwd_split(const float* X, long ld, const long long* tgt, long M, int V, int has_ignore, long long ignore,
+                       const float* lse, const float* gscale, const float* lossbuf, void* hi, void* lo, long Vp,
+                       void* hiT, void* loT, long Mp, float* dbias, void* stream) {
+    if (M <= 0 || V <= 0 || Vp < V || (Vp & 63) || Mp < M || (Mp & 63) || M > (1L << 30)) return CAPHN_EINVAL;
+    dim3 grid((unsigned)(Vp / 64), (unsigned)(Mp / 64));
+    ce_bwd_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        X, ld, tgt, (int)M, V, has_ignore, ignore, lse, gscale, lossbuf, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Vp,
+        (__nv_bfloat16*)hiT, (__nv_bfloat16*)loT, Mp, dbias);
     CAPHN_RETURN_LAST();
 }
 

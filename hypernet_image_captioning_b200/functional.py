@@ -126,71 +126,138 @@ def cross_entropy(logits, targets, ignore_index: Optional[int] = None):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# Variant A decoder: teacher-forced DecoderGRU.forward  (reference later.py:389-457), single GRUCell
+# vocabulary projection backward, shared by both decoders
 # ----------------------------------------------------------------------------------------------------------------------
+def vocab_bwd_from_dlogits(dl, Hbm2, fc_w, need_w=True, need_b=True):
+    """dl [B*T, V] fp32 (as handed over by autograd).  Returns (dfc_w, dfc_b, dHbm)."""
+    dfc_w = ops.matmul_tn(dl, Hbm2) if need_w else None
+    dfc_b = ops.colsum(dl) if need_b else None
+    dHbm = ops.matmul_nn(dl, fc_w.contiguous())
+    return dfc_w, dfc_b, dHbm
+
+
+def vocab_bwd_fused(logits2d, targets, ignore_index, lse, lossbuf, gscale, Hbm2, fc_w):
+    """Loss fused with the projection: the cross-entropy gradient is written directly as bf16x3 tensor-core operands
+    (row-major for dH = d W_out, transposed for dW_out = d^T H) and the bias gradient is reduced in the same pass, so
+    the fp32 dlogits tensor never exists."""
+    M, V = logits2d.shape
+    H = Hbm2.shape[1]
+    if not (ops._tc_ok(M, H, V) and ops._tc_ok(V, H, M)):
+        dl = ops.ce_bwd(logits2d, targets, ignore_index, lse, lossbuf, gscale)
+        return vocab_bwd_from_dlogits(dl, Hbm2, fc_w)
+    d, dT, dfc_b = ops.ce_bwd_split(logits2d, targets, ignore_index, lse, lossbuf, gscale)
+    dHbm = ops.gemm_tc(d, ops.split_bf16_t(fc_w.contiguous()))            # [B*T, H]   (K = V)
+    dfc_w = ops.gemm_tc(dT, ops.split_bf16_t(Hbm2))                       # [V, H]     (K = B*T)
+    return dfc_w, dfc_b, dHbm
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Variant A decoder: teacher-forced DecoderGRU.forward  (reference later.py:389-457)
+# ----------------------------------------------------------------------------------------------------------------------
+def _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells):
+    B, T = captions.shape
+    NL = len(cells) // 4
+    W_ih, W_hh, b_ih, b_hh = cells[0:4]
+    H = W_hh.shape[1]
+    caps = captions.contiguous()
+    feats = feats.contiguous()
+    emb_w = emb_w.contiguous()
+    X = ops.build_inputs(feats, emb_w, caps, 0)                       # [T*B, E]
+    GI = ops.linear(X, W_ih.contiguous(), b_ih.contiguous())          # [T*B, 3H]
+    ld3 = ops.round4(3 * H)
+    WhhT = ops.transpose_pad(W_hh.contiguous(), ld3)                  # [H, ld3]
+    extra = []
+    for l in range(1, NL):
+        Wi, Wh, bi, bh = cells[4 * l: 4 * l + 4]
+        extra.append((ops.transpose_pad(Wi.contiguous(), ld3), ops.transpose_pad(Wh.contiguous(), ld3),
+                      bi.contiguous(), bh.contiguous()))
+    Hall, Hbm, saved, Hmid = ops.gru_seq_fwd(GI, WhhT, b_hh.contiguous(), h0.contiguous(), T, save=True, extra=extra)
+    logits = ops.linear(Hbm.view(B * T, H), fc_w.contiguous(), fc_b)
+    return logits.view(B, T, -1), (caps, X, Hall, Hbm, saved, Hmid, emb_w, fc_w)
+
+
+def _gru_decoder_backward(saved_tensors, NL, need, vocab):
+    """need = needs_input_grad of (feats, captions, h0, emb_w, fc_w, fc_b, *cells); vocab = (dfc_w, dfc_b, dHbm)."""
+    caps, X, Hall, Hbm, saved, Hmid, emb_w, fc_w = saved_tensors[:8]
+    cells = saved_tensors[8:]
+    W_ih, W_hh = cells[0], cells[1]
+    B, T = caps.shape
+    H = W_hh.shape[1]
+    dfc_w, dfc_b, dHbm = vocab
+    ldh = ops.round4(H)
+    Whh_p = ops.copy_pad(W_hh.contiguous(), ldh)
+    extra = [(ops.copy_pad(cells[4 * l].contiguous(), ldh), ops.copy_pad(cells[4 * l + 1].contiguous(), ldh))
+             for l in range(1, NL)]
+    dGI, dGH, xdGI, xdGH, dh0 = ops.gru_seq_bwd(dHbm.view(B, T, H), saved, Hall, Hmid, Whh_p, extra=extra)
+    Hprev = Hall[:-1].reshape(T * B, H)
+    cell_grads = [ops.matmul_tn(dGI, X) if need[6] else None, ops.matmul_tn(dGH, Hprev) if need[7] else None,
+                  ops.colsum(dGI) if need[8] else None, ops.colsum(dGH) if need[9] else None]
+    for l in range(1, NL):
+        Hin = Hmid[l - 1].reshape(T * B, H)                            # input == state of layer l
+        n0 = 6 + 4 * l
+        cell_grads += [ops.matmul_tn(xdGI[l - 1], Hin) if need[n0] else None,
+                       ops.matmul_tn(xdGH[l - 1], Hin) if need[n0 + 1] else None,
+                       ops.colsum(xdGI[l - 1]) if need[n0 + 2] else None,
+                       ops.colsum(xdGH[l - 1]) if need[n0 + 3] else None]
+    dfeats = demb = None
+    if need[0] or need[3]:
+        dX = ops.matmul_nn(dGI, W_ih.contiguous())                     # [T*B, E]
+        if need[0]:
+            dfeats = dX[:B].clone()
+        if need[3]:
+            demb = torch.zeros_like(emb_w)
+            ops.embed_scatter_add(dX, caps, demb, 1)
+    return (dfeats, None, (dh0 if need[2] else None), demb, dfc_w if need[4] else None,
+            dfc_b if need[5] else None, *cell_grads)
+
+
 class DecoderGRUSeqFn(Function):
     """inputs: feats, captions, h0, emb_w, fc_w, fc_b, then (W_ih, W_hh, b_ih, b_hh) for every GRU cell (layer 0 first).
-    Extra layers are applied as h = cell_l(h, h) at every step (later.py:413-414, 420-421)."""
+    Extra layers are applied as h = cell_l(h, h) at every step (later.py:413-414, 420-421).  Returns logits [B,T,V]."""
 
     @staticmethod
     def forward(ctx, feats, captions, h0, emb_w, fc_w, fc_b, *cells):
-        B, T = captions.shape
-        NL = len(cells) // 4
-        W_ih, W_hh, b_ih, b_hh = cells[0:4]
-        H = W_hh.shape[1]
-        caps = captions.contiguous()
-        feats = feats.contiguous()
-        emb_w = emb_w.contiguous()
-        X = ops.build_inputs(feats, emb_w, caps, 0)                       # [T*B, E]
-        GI = ops.linear(X, W_ih.contiguous(), b_ih.contiguous())          # [T*B, 3H]
-        ld3 = ops.round4(3 * H)
-        WhhT = ops.transpose_pad(W_hh.contiguous(), ld3)                  # [H, ld3]
-        extra = []
-        for l in range(1, NL):
-            Wi, Wh, bi, bh = cells[4 * l: 4 * l + 4]
-            extra.append((ops.transpose_pad(Wi.contiguous(), ld3), ops.transpose_pad(Wh.contiguous(), ld3),
-                          bi.contiguous(), bh.contiguous()))
-        Hall, Hbm, saved, Hmid = ops.gru_seq_fwd(GI, WhhT, b_hh.contiguous(), h0.contiguous(), T, save=True, extra=extra)
-        logits = ops.linear(Hbm.view(B * T, H), fc_w.contiguous(), fc_b)
-        ctx.save_for_backward(caps, X, Hall, Hbm, saved, Hmid, emb_w, fc_w, *cells)
-        ctx.NL = NL
-        return logits.view(B, T, -1)
+        logits, sv = _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells)
+        ctx.save_for_backward(*sv, *cells)
+        ctx.NL = len(cells) // 4
+        return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        caps, X, Hall, Hbm, saved, Hmid, emb_w, fc_w = ctx.saved_tensors[:8]
-        cells = ctx.saved_tensors[8:]
-        NL = ctx.NL
-        W_ih, W_hh = cells[0], cells[1]
-        B, T = caps.shape
-        H = W_hh.shape[1]
+        sv = ctx.saved_tensors
+        Hbm, fc_w = sv[3], sv[7]
+        B, T, H = Hbm.shape
         need = ctx.needs_input_grad
         dl = dlogits.reshape(B * T, -1).contiguous()
-        Hbm2 = Hbm.view(B * T, H)
-        dfc_w = ops.matmul_tn(dl, Hbm2) if need[4] else None
-        dfc_b = ops.colsum(dl) if need[5] else None
-        dHbm = ops.matmul_nn(dl, fc_w.contiguous())                        # [B*T, H]
-        ldh = ops.round4(H)
-        Whh_p = ops.copy_pad(W_hh.contiguous(), ldh)
-        extra = [(ops.copy_pad(cells[4 * l].contiguous(), ldh), ops.copy_pad(cells[4 * l + 1].contiguous(), ldh))
-                 for l in range(1, NL)]
-        dGI, dGH, xdGI, xdGH, dh0 = ops.gru_seq_bwd(dHbm.view(B, T, H), saved, Hall, Hmid, Whh_p, extra=extra)
-        Hprev = Hall[:-1].reshape(T * B, H)
-        cell_grads = [ops.matmul_tn(dGI, X) if need[6] else None, ops.matmul_tn(dGH, Hprev) if need[7] else None,
-                      ops.colsum(dGI) if need[8] else None, ops.colsum(dGH) if need[9] else None]
-        for l in range(1, NL):
-            Hin = Hmid[l - 1].reshape(T * B, H)                            # input == state of layer l
-            n0 = 6 + 4 * l
-            cell_grads += [ops.matmul_tn(xdGI[l - 1], Hin) if need[n0] else None,
-                           ops.matmul_tn(xdGH[l - 1], Hin) if need[n0 + 1] else None,
-                           ops.colsum(xdGI[l - 1]) if need[n0 + 2] else None,
-                           ops.colsum(xdGH[l - 1]) if need[n0 + 3] else None]
-        dfeats = demb = None
-        if need[0] or need[3]:
-            dX = ops.matmul_nn(dGI, W_ih.contiguous())                     # [T*B, E]
-            if need[0]:
-                dfeats = dX[:B].clone()
-            if need[3]:
-                demb = torch.zeros_like(emb_w)
-                ops.embed_scatter_add(dX, caps, demb, 1)
-        return (dfeats, None, (dh0 if need[2] else None), demb, dfc_w, dfc_b, *cell_grads)
+        vocab = vocab_bwd_from_dlogits(dl, Hbm.view(B * T, H), fc_w, need[4], need[5])
+        return _gru_decoder_backward(sv, ctx.NL, need, vocab)
+
+
+class DecoderGRULossFn(Function):
+    """Decoder + mean cross-entropy as ONE autograd node (hypernet.py:139-145 computes exactly this pair): returns
+    (loss, logits) with logits non-differentiable; the backward never materialises fp32 dlogits."""
+
+    @staticmethod
+    def forward(ctx, ignore_index, feats, captions, h0, emb_w, fc_w, fc_b, *cells):
+        logits, sv = _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells)
+        B, T, V = logits.shape
+        targets = captions.reshape(-1).contiguous()
+        lossbuf, lse = ops.ce_fwd(logits.view(B * T, V), targets, ignore_index)
+        ctx.save_for_backward(*sv, *cells, logits, targets, lse, lossbuf)
+        ctx.NL = len(cells) // 4
+        ctx.ignore_index = ignore_index
+        ctx.mark_non_differentiable(logits)
+        ctx.set_materialize_grads(False)   # do not zero-fill a [B,T,V] gradient for the unused logits output
+        return lossbuf[0].clone(), logits
+
+    @staticmethod
+    def backward(ctx, g, _unused):
+        allsv = ctx.saved_tensors
+        sv, (logits, targets, lse, lossbuf) = allsv[:-4], allsv[-4:]
+        Hbm, fc_w = sv[3], sv[7]
+        B, T, H = Hbm.shape
+        need = ctx.needs_input_grad[1:]
+        g = g.reshape(1).to(torch.float32).contiguous()
+        vocab = vocab_bwd_fused(logits.view(B * T, -1), targets, ctx.ignore_index, lse, lossbuf, g,
+                                Hbm.view(B * T, H), fc_w)
+        return (None, *_gru_decoder_backward(sv, ctx.NL, need, vocab))

@@ -147,6 +147,16 @@ class DecoderGRU(nn.Module):
             h0 = self._h0(features)
         return self._forward_one(features, captions, h0, self._cells())
 
+    def forward_loss(self, features, captions, h0=None, ignore_index=None):
+        """Teacher-forced forward fused with the mean cross-entropy of hypernet.py:145 (``ignore_index=None``: no
+        masking): returns ``(loss, logits)``.  Same numbers as ``cross_entropy(self(features, captions), captions)``
+        but one autograd node whose backward writes the softmax gradient straight into tensor-core operands."""
+        if h0 is None:
+            h0 = self._h0(features)
+        flat = [w for cell in self._cells() for w in cell]
+        return Fn.DecoderGRULossFn.apply(ignore_index, features, captions, h0, self.embed.weight, self.fc_out.weight,
+                                         self.fc_out.bias, *flat)
+
     def _forward_one(self, features, captions, h0, cells):
         if len(cells) > 4:
             raise NotImplementedError("DecoderGRU with more than 4 layers")

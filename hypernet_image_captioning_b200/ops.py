@@ -253,6 +253,23 @@ def ce_bwd(logits2d, targets, ignore_index, lse, lossbuf, gscale):
     return dX
 
 
+def ce_bwd_split(logits2d, targets, ignore_index, lse, lossbuf, gscale):
+    """CE gradient as tensor-core operands: returns (d [M,Vp] split, d^T [V,Mp] split, dbias [V])."""
+    M, V = logits2d.shape
+    dev = logits2d.device
+    Vp, Mp = round64(V), round64(M)
+    hi = torch.empty(M, Vp, device=dev, dtype=torch.bfloat16)
+    lo = torch.empty(M, Vp, device=dev, dtype=torch.bfloat16)
+    hiT = torch.empty(V, Mp, device=dev, dtype=torch.bfloat16)
+    loT = torch.empty(V, Mp, device=dev, dtype=torch.bfloat16)
+    dbias = torch.zeros(V, device=dev, dtype=torch.float32)
+    has = ignore_index is not None
+    _cabi.call("caphn_ce_bwd_split", logits2d.data_ptr(), logits2d.stride(0), targets.data_ptr(), M, V, int(has),
+               int(ignore_index) if has else 0, lse.data_ptr(), gscale.data_ptr(), lossbuf.data_ptr(), hi.data_ptr(),
+               lo.data_ptr(), Vp, hiT.data_ptr(), loT.data_ptr(), Mp, dbias.data_ptr(), _stream())
+    return SplitOperand(hi, lo, M, Vp), SplitOperand(hiT, loT, V, Mp), dbias
+
+
 def softmax_argmax(X, want_probs=True, probs_out=None, want_argmax=True):
     _chk(X)
     M, V = X.shape

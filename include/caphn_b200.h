@@ -105,6 +105,11 @@ int caphn_ce_fwd(const float* X, long ld, const long long* tgt, long M, int V, i
 /* dX = gscale[0] * d(mean loss)/dX, using lse / lossbuf from caphn_ce_fwd (no host sync). */
 int caphn_ce_bwd(const float* X, long ld, const long long* tgt, long M, int V, int has_ignore, long long ignore,
                  const float* lse, const float* gscale, const float* lossbuf, float* dX, long lddx, void* stream);
+/* Same gradient, written directly as tensor-core operands (no fp32 dlogits): hi/lo [M,Vp] = split(d), hiT/loT [V,Mp] =
+ * split(d^T) (Vp, Mp multiples of 64), dbias[v] += sum_m d[m,v] (zero-initialised by the caller). */
+int caphn_ce_bwd_split(const float* X, long ld, const long long* tgt, long M, int V, int has_ignore, long long ignore,
+                       const float* lse, const float* gscale, const float* lossbuf, void* hi, void* lo, long Vp,
+                       void* hiT, void* loT, long Mp, float* dbias, void* stream);
 /* Y (optional) = row softmax of X[M,V]; amax (optional, int64) = row argmax, lowest index on ties. */
 int caphn_softmax_argmax(const float* X, long ld, long M, int V, float* Y, long ldy, long long* amax, void* stream);
 /* out[i,:] = table[idx[i],:]  (idx int64; negative idx -> zero row). */

@@ -126,3 +126,31 @@ def test_pooled_vs_oracle_medium(B, T, E, H, V, L):
         if k.startswith("captioner.lstm_cell.") or k.startswith("captioner.layers."):
             continue
         assert grad_close(v.grad, pl[k].grad, TOL_GRAD), k
+
+
+@pytest.mark.parametrize("B,T,E,H,V,ignore", [(64, 20, 200, 150, 2000, None), (48, 12, 64, 48, 777, 0), (5, 4, 8, 6, 50, None)])
+def test_pooled_fused_loss_matches_unfused(B, T, E, H, V, ignore):
+    """forward_loss (decoder + CE in one node, CE gradient emitted as bf16x3 operands) == logits + cross_entropy."""
+    import hypernet_image_captioning_b200 as C
+    p = O.init_params_pooled(2048, E, H, V, L=1, seed=5)
+    g = torch.Generator().manual_seed(99)
+    pooled = torch.relu(torch.randn(B, 2048, generator=g)).cuda()
+    caps = O.synth_captions(B, T, V, g).cuda()
+    style = torch.randn(1, E, generator=g).cuda()
+    h0 = torch.rand(B, H, generator=g).cuda()
+    grads = []
+    for fused in (False, True):
+        m = _model_from(p, E, H, V)
+        captioner = m.forward(style)
+        feats = m.image_encoder(pooled)
+        if fused:
+            loss, logits = captioner.forward_loss(feats, caps, h0=h0, ignore_index=ignore)
+        else:
+            logits = captioner(feats, caps, True, h0=h0)
+            loss = C.cross_entropy(logits, caps, ignore)
+        loss.backward()
+        grads.append((loss.item(), logits.detach(), {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}))
+    assert abs(grads[0][0] - grads[1][0]) < 1e-6 * abs(grads[0][0])
+    assert torch.equal(grads[0][1], grads[1][1])
+    for k, v in grads[0][2].items():
+        assert grad_close(grads[1][2][k], v, TOL_GRAD), k
