@@ -16,6 +16,116 @@ from . import ops
 from .modules import _Base, _HyperNetMixin, _run_grouped
 
 
+def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, fc2_w, fc2_b, emb_w, W_ih, W_hh, b_ih,
+                    b_hh, fc_w, fc_b, Wa_w, Wa_b, Ua_w, Ua_b, va_w, va_b, init_w, init_b):
+    """AttentionGru.forward (models/decoderlstm.py:49-120).  Returns (logits, attn, tensors to save, dims)."""
+    B, P, D = features.shape
+    T = captions.shape[1]
+    E = emb_w.shape[1]
+    H = W_hh.shape[1]
+    Fd = fc2_w.shape[0]
+    V = fc_w.shape[0]
+    dev = features.device
+    caps = captions.contiguous()
+    feats2 = features.reshape(B * P, D)
+    if not feats2.is_contiguous():
+        feats2 = feats2.contiguous()
+    emb_w = emb_w.contiguous()
+    W_ih, W_hh = W_ih.contiguous(), W_hh.contiguous()
+    # ---- loop-invariant part: feature_fc (:61), keys W_a f (attention.py:34, hoisted), h0 (:63,133-134) ----
+    f1 = ops.linear(feats2, fc0_w, fc0_b, relu=True)                  # [B*P, F]
+    f = ops.linear(f1, fc2_w, fc2_b)                                  # [B*P, F]
+    Kp = ops.linear(f, Wa_w, Wa_b)                                    # [B*P, H]
+    fmean = ops.mean_pos(f.view(B, P, Fd))                            # [B, F]
+    h0 = ops.linear(fmean, init_w, init_b)                            # [B, H]
+    lw = ops.AttGruWeights(W_ih, W_hh, Ua_w.contiguous(), E)
+    va = va_w.reshape(-1).contiguous()
+    bv = va_b.reshape(1).contiguous()
+    Ua_b = Ua_b.contiguous()
+    b_hh = b_hh.contiguous()
+    Hall = torch.empty(T + 1, B, H, device=dev, dtype=torch.float32)
+    Hall[0].copy_(h0)
+    Hbm = torch.empty(B, T, H, device=dev, dtype=torch.float32)
+    attn = torch.empty(B, T, P, device=dev, dtype=torch.float32)
+    XC = torch.empty(T * B, E + Fd, device=dev, dtype=torch.float32)   # [x_word | ctx] per (t,b)
+    saved = torch.empty(5, T, B, H, device=dev, dtype=torch.float32) if need_grad else None
+    logits = torch.empty(B, T, V, device=dev, dtype=torch.float32)
+    f3, K3 = f.view(B, P, Fd), Kp.view(B, P, H)
+    W_ih_w = W_ih[:, :E]
+    fed = torch.full((T, B), -1, device=dev, dtype=torch.int64)        # token whose embedding was fed at (t,b)
+
+    if not any(use_sampling):
+        # x_0 = x_1 = 0 (in-place aliasing, :83-88), x_t = Emb[caps[:, t-1]] for t >= 2
+        if T > 2:
+            fed[2:] = caps[:, 1:T - 1].t()
+        Xw = ops.build_inputs(None, emb_w, caps, 1)                    # [T*B, E]
+        XC[:, :E].copy_(Xw)
+        GIw = ops.linear(Xw, W_ih_w, b_ih.contiguous())                # [T*B, 3H]
+        ops.attgru_seq_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, 0, T)
+        ops.linear(Hbm.view(B * T, H), fc_w, fc_b, out=logits.view(B * T, V))
+    else:
+        GIw = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+        for t in range(T):
+            if use_sampling[t]:
+                # :91-96  argmax of log_softmax(logits/0.5) == argmax of logits (lowest index on ties)
+                _, top = ops.softmax_argmax(logits[:, t - 1, :], want_probs=False)
+                fed[t].copy_(top)
+            elif t >= 2:
+                fed[t].copy_(caps[:, t - 1])
+            xw = ops.gather_rows(emb_w, fed[t])                        # zeros where fed == -1
+            XC[t * B:(t + 1) * B, :E].copy_(xw)
+            ops.linear(xw, W_ih_w, b_ih.contiguous(), out=GIw[t * B:(t + 1) * B])
+            ops.attgru_seq_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, t, t + 1)
+            ops.linear(Hall[t + 1], fc_w, fc_b, out=logits[:, t, :])
+    sv = (feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih, W_hh, fc_w, Wa_w, Ua_w,
+          va, init_w)
+    return logits, attn, sv, (B, T, P, D, E, H, Fd, V)
+
+
+def _attgru_backward(sv, dims, vocab, dattn):
+    """vocab = (dfc_w, dfc_b, dHbm [B*T,H]).  Returns the 19 parameter gradients in AttentionGruFn argument order."""
+    (feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih, W_hh, fc_w, Wa_w, Ua_w,
+     va, init_w) = sv
+    B, T, P, D, E, H, Fd, V = dims
+    dfc_w, dfc_b, dHbm = vocab
+    if dattn is not None:
+        dattn = dattn.contiguous()
+    f3, K3 = f.view(B, P, Fd), Kp.view(B, P, H)
+    dGI, dGH, dU, dCTX, dK, dva, dbv, dh0 = ops.attgru_seq_bwd(
+        dHbm.view(B, T, H), dattn, K3, f3, attn, saved, Hall, Ua_w.contiguous(), va, W_ih, W_hh, E)
+    Hprev = Hall[:-1].reshape(T * B, H)
+    dW_ih = ops.matmul_tn(dGI, XC)                                     # [3H, E+F]
+    db_ih = ops.colsum(dGI)
+    dW_hh = ops.matmul_tn(dGH, Hprev)
+    db_hh = ops.colsum(dGH)
+    dUa_w = ops.matmul_tn(dU, Hprev)                                   # [H, H]
+    dUa_b = ops.colsum(dU)
+    # word embeddings (t >= 2 teacher-forced rows, or the fed-back argmax rows)
+    dXw = ops.matmul_nn(dGI, W_ih[:, :E])                              # [T*B, E]
+    demb = torch.zeros_like(emb_w)
+    ops.scatter_add_rows(dXw, fed.reshape(-1), demb)
+    # attention keys / features
+    dK2 = dK.view(B * P, H)
+    dWa_w = ops.matmul_tn(dK2, f)                                      # [H, F]
+    dWa_b = ops.colsum(dK2)
+    df = ops.matmul_nn(dK2, Wa_w.contiguous())                         # [B*P, F]
+    ops.attn_df(attn, dCTX, df.view(B, P, Fd))
+    # init_h
+    dinit_w = ops.matmul_tn(dh0, fmean)                                # [H, F]
+    dinit_b = ops.colsum(dh0)
+    dfmean = ops.matmul_nn(dh0, init_w.contiguous())                   # [B, F]
+    ops.mean_pos_bwd(dfmean, df.view(B, P, Fd))
+    # feature_fc (no gradient w.r.t. the image features: they are a leaf input)
+    dfc2_w = ops.matmul_tn(df, f1)
+    dfc2_b = ops.colsum(df)
+    df1 = ops.matmul_nn(df, fc2_w.contiguous())
+    ops.relu_mask_(f1, df1)
+    dfc0_w = ops.matmul_tn(df1, feats2)                                # [F, D]
+    dfc0_b = ops.colsum(df1)
+    return (dfc0_w, dfc0_b, dfc2_w, dfc2_b, demb, dW_ih, dW_hh, db_ih, db_hh, dfc_w, dfc_b,
+            dWa_w, dWa_b, dUa_w, dUa_b, dva.view(1, H), dbv.view(1), dinit_w, dinit_b)
+
+
 class AttentionGruFn(Function):
     """Whole AttentionGru.forward (models/decoderlstm.py:49-120) as one autograd node.
 
@@ -26,119 +136,49 @@ class AttentionGruFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, features, captions, use_sampling, fc0_w, fc0_b, fc2_w, fc2_b, emb_w, W_ih, W_hh, b_ih, b_hh,
-                fc_w, fc_b, Wa_w, Wa_b, Ua_w, Ua_b, va_w, va_b, init_w, init_b):
-        B, P, D = features.shape
-        T = captions.shape[1]
-        E = emb_w.shape[1]
-        H = W_hh.shape[1]
-        Fd = fc2_w.shape[0]
-        V = fc_w.shape[0]
-        dev = features.device
-        caps = captions.contiguous()
-        feats2 = features.reshape(B * P, D)
-        if not feats2.is_contiguous():
-            feats2 = feats2.contiguous()
-        emb_w = emb_w.contiguous()
-        W_ih, W_hh = W_ih.contiguous(), W_hh.contiguous()
-        # ---- loop-invariant part: feature_fc (:61), keys W_a f (attention.py:34, hoisted), h0 (:63,133-134) ----
-        f1 = ops.linear(feats2, fc0_w, fc0_b, relu=True)                  # [B*P, F]
-        f = ops.linear(f1, fc2_w, fc2_b)                                  # [B*P, F]
-        Kp = ops.linear(f, Wa_w, Wa_b)                                    # [B*P, H]
-        fmean = ops.mean_pos(f.view(B, P, Fd))                            # [B, F]
-        h0 = ops.linear(fmean, init_w, init_b)                            # [B, H]
-        lw = ops.AttGruWeights(W_ih, W_hh, Ua_w.contiguous(), E)
-        va = va_w.reshape(-1).contiguous()
-        bv = va_b.reshape(1).contiguous()
-        Ua_b = Ua_b.contiguous()
-        b_hh = b_hh.contiguous()
-        Hall = torch.empty(T + 1, B, H, device=dev, dtype=torch.float32)
-        Hall[0].copy_(h0)
-        Hbm = torch.empty(B, T, H, device=dev, dtype=torch.float32)
-        attn = torch.empty(B, T, P, device=dev, dtype=torch.float32)
-        XC = torch.empty(T * B, E + Fd, device=dev, dtype=torch.float32)   # [x_word | ctx] per (t,b)
+    def forward(ctx, features, captions, use_sampling, *params):
         need_grad = any(ctx.needs_input_grad)
-        saved = torch.empty(5, T, B, H, device=dev, dtype=torch.float32) if need_grad else None
-        logits = torch.empty(B, T, V, device=dev, dtype=torch.float32)
-        f3, K3 = f.view(B, P, Fd), Kp.view(B, P, H)
-        W_ih_w = W_ih[:, :E]
-        fed = torch.full((T, B), -1, device=dev, dtype=torch.int64)        # token whose embedding was fed at (t,b)
-
-        if not any(use_sampling):
-            # x_0 = x_1 = 0 (in-place aliasing, :83-88), x_t = Emb[caps[:, t-1]] for t >= 2
-            if T > 2:
-                fed[2:] = caps[:, 1:T - 1].t()
-            Xw = ops.build_inputs(None, emb_w, caps, 1)                    # [T*B, E]
-            XC[:, :E].copy_(Xw)
-            GIw = ops.linear(Xw, W_ih_w, b_ih.contiguous())                # [T*B, 3H]
-            ops.attgru_seq_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, 0, T)
-            ops.linear(Hbm.view(B * T, H), fc_w, fc_b, out=logits.view(B * T, V))
-        else:
-            GIw = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
-            for t in range(T):
-                if use_sampling[t]:
-                    # :91-96  argmax of log_softmax(logits/0.5) == argmax of logits (lowest index on ties)
-                    _, top = ops.softmax_argmax(logits[:, t - 1, :], want_probs=False)
-                    fed[t].copy_(top)
-                elif t >= 2:
-                    fed[t].copy_(caps[:, t - 1])
-                xw = ops.gather_rows(emb_w, fed[t])                        # zeros where fed == -1
-                XC[t * B:(t + 1) * B, :E].copy_(xw)
-                ops.linear(xw, W_ih_w, b_ih.contiguous(), out=GIw[t * B:(t + 1) * B])
-                ops.attgru_seq_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, t, t + 1)
-                ops.linear(Hall[t + 1], fc_w, fc_b, out=logits[:, t, :])
+        logits, attn, sv, dims = _attgru_forward(need_grad, features, captions, use_sampling, *params)
         if need_grad:
-            ctx.save_for_backward(feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih,
-                                  W_hh, fc_w, Wa_w, Ua_w, va, init_w)
-            ctx.dims = (B, T, P, D, E, H, Fd, V)
+            ctx.save_for_backward(*sv)
+            ctx.dims = dims
         return logits, attn
 
     @staticmethod
     def backward(ctx, dlogits, dattn):
-        (feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih, W_hh, fc_w, Wa_w, Ua_w,
-         va, init_w) = ctx.saved_tensors
+        sv = ctx.saved_tensors
         B, T, P, D, E, H, Fd, V = ctx.dims
-        dev = f.device
         dl = dlogits.reshape(B * T, V).contiguous()
-        dfc_w = ops.matmul_tn(dl, Hbm.view(B * T, H))
-        dfc_b = ops.colsum(dl)
-        dHbm = ops.matmul_nn(dl, fc_w.contiguous())
-        if dattn is not None:
-            dattn = dattn.contiguous()
-        f3, K3 = f.view(B, P, Fd), Kp.view(B, P, H)
-        dGI, dGH, dU, dCTX, dK, dva, dbv, dh0 = ops.attgru_seq_bwd(
-            dHbm.view(B, T, H), dattn, K3, f3, attn, saved, Hall, Ua_w.contiguous(), va, W_ih, W_hh, E)
-        Hprev = Hall[:-1].reshape(T * B, H)
-        dW_ih = ops.matmul_tn(dGI, XC)                                     # [3H, E+F]
-        db_ih = ops.colsum(dGI)
-        dW_hh = ops.matmul_tn(dGH, Hprev)
-        db_hh = ops.colsum(dGH)
-        dUa_w = ops.matmul_tn(dU, Hprev)                                   # [H, H]
-        dUa_b = ops.colsum(dU)
-        # word embeddings (t >= 2 teacher-forced rows, or the fed-back argmax rows)
-        dXw = ops.matmul_nn(dGI, W_ih[:, :E])                              # [T*B, E]
-        demb = torch.zeros_like(emb_w)
-        ops.scatter_add_rows(dXw, fed.reshape(-1), demb)
-        # attention keys / features
-        dK2 = dK.view(B * P, H)
-        dWa_w = ops.matmul_tn(dK2, f)                                      # [H, F]
-        dWa_b = ops.colsum(dK2)
-        df = ops.matmul_nn(dK2, Wa_w.contiguous())                         # [B*P, F]
-        ops.attn_df(attn, dCTX, df.view(B, P, Fd))
-        # init_h
-        dinit_w = ops.matmul_tn(dh0, fmean)                                # [H, F]
-        dinit_b = ops.colsum(dh0)
-        dfmean = ops.matmul_nn(dh0, init_w.contiguous())                   # [B, F]
-        ops.mean_pos_bwd(dfmean, df.view(B, P, Fd))
-        # feature_fc (no gradient w.r.t. the image features: they are a leaf input)
-        dfc2_w = ops.matmul_tn(df, f1)
-        dfc2_b = ops.colsum(df)
-        df1 = ops.matmul_nn(df, fc2_w.contiguous())
-        ops.relu_mask_(f1, df1)
-        dfc0_w = ops.matmul_tn(df1, feats2)                                # [F, D]
-        dfc0_b = ops.colsum(df1)
-        return (None, None, None, dfc0_w, dfc0_b, dfc2_w, dfc2_b, demb, dW_ih, dW_hh, db_ih, db_hh, dfc_w, dfc_b,
-                dWa_w, dWa_b, dUa_w, dUa_b, dva.view(1, H), dbv.view(1), dinit_w, dinit_b)
+        vocab = Fn.vocab_bwd_from_dlogits(dl, sv[7].view(B * T, H), sv[16])
+        return (None, None, None, *_attgru_backward(sv, ctx.dims, vocab, dattn))
+
+
+class AttentionGruLossFn(Function):
+    """AttentionGru.forward + F.cross_entropy(ignore_index) (cc_train_hypernet.py:152-153) as ONE autograd node:
+    returns (loss, logits, attn); the CE gradient goes straight into tensor-core operands (no fp32 dlogits)."""
+
+    @staticmethod
+    def forward(ctx, ignore_index, features, captions, use_sampling, *params):
+        logits, attn, sv, dims = _attgru_forward(True, features, captions, use_sampling, *params)
+        B, T, V = logits.shape
+        targets = captions.reshape(-1).contiguous()
+        lossbuf, lse = ops.ce_fwd(logits.view(B * T, V), targets, ignore_index)
+        ctx.save_for_backward(*sv, logits, targets, lse, lossbuf)
+        ctx.dims = dims
+        ctx.ignore_index = ignore_index
+        ctx.mark_non_differentiable(logits, attn)
+        ctx.set_materialize_grads(False)
+        return lossbuf[0].clone(), logits, attn
+
+    @staticmethod
+    def backward(ctx, g, _dl, _da):
+        allsv = ctx.saved_tensors
+        sv, (logits, targets, lse, lossbuf) = allsv[:-4], allsv[-4:]
+        B, T, P, D, E, H, Fd, V = ctx.dims
+        g = g.reshape(1).to(torch.float32).contiguous()
+        vocab = Fn.vocab_bwd_fused(logits.view(B * T, V), targets, ctx.ignore_index, lse, lossbuf, g,
+                                   sv[7].view(B * T, H), sv[16])
+        return (None, None, None, None, *_attgru_backward(sv, ctx.dims, vocab, None))
 
 
 class BahdanauAttention(nn.Module):
@@ -198,14 +238,22 @@ class AttentionGru(nn.Module):
                                 [features, captions], len(self._generated_groups))
         return self._forward_one(features, captions, tuple(use), self._gru_weights())
 
-    def _forward_one(self, features, captions, use, gru_w):
+    def _params(self, gru_w):
         W_ih, W_hh, b_ih, b_hh = gru_w
         a = self.attention
-        return AttentionGruFn.apply(
-            features, captions, use, self.feature_fc[0].weight, self.feature_fc[0].bias,
-            self.feature_fc[2].weight, self.feature_fc[2].bias, self.embed.weight, W_ih, W_hh, b_ih, b_hh,
-            self.fc.weight, self.fc.bias, a.W_a.weight, a.W_a.bias, a.U_a.weight, a.U_a.bias, a.v_a.weight, a.v_a.bias,
-            self.init_h.weight, self.init_h.bias)
+        return (self.feature_fc[0].weight, self.feature_fc[0].bias, self.feature_fc[2].weight, self.feature_fc[2].bias,
+                self.embed.weight, W_ih, W_hh, b_ih, b_hh, self.fc.weight, self.fc.bias, a.W_a.weight, a.W_a.bias,
+                a.U_a.weight, a.U_a.bias, a.v_a.weight, a.v_a.bias, self.init_h.weight, self.init_h.bias)
+
+    def _forward_one(self, features, captions, use, gru_w):
+        return AttentionGruFn.apply(features, captions, use, *self._params(gru_w))
+
+    def forward_loss(self, features, captions, sample_prob=0.0, ignore_index=0):
+        """``forward`` fused with ``F.cross_entropy(outputs.view(-1,V), captions.view(-1), ignore_index=<pad>)``
+        (cc_train_hypernet.py:152-153): returns ``(loss, outputs, atten_weights)``; one autograd node."""
+        T = captions.size(1)
+        use = tuple(bool(np.random.random() < (0.0 if t == 0 else sample_prob)) for t in range(T))
+        return AttentionGruLossFn.apply(ignore_index, features, captions, use, *self._params(self._gru_weights()))
 
     def init_hidden(self, features):
         """h0 = init_h(mean over positions) -- models/decoderlstm.py:122-135 (features already through feature_fc)."""

@@ -160,3 +160,29 @@ def test_attention_scheduled_sampling_mixed_matches_oracle():
     assert rel_err(logits, lr) < TOL_LOGITS
     for k in ("captioner.embed.weight", "hn_heads.0.2.weight", "captioner.attention.U_a.weight"):
         assert grad_close(dict(m.named_parameters())[k].grad, pl[k].grad, TOL_GRAD), k
+
+
+@pytest.mark.parametrize("B,T,Fo,E,H,V", [(32, 20, 200, 200, 200, 1500), (6, 5, 16, 12, 20, 60)])
+def test_attention_fused_loss_matches_unfused(B, T, Fo, E, H, V):
+    import hypernet_image_captioning_b200 as C
+    p = O.init_params_attention(2048, Fo, E, H, V, E, seed=7)
+    g = torch.Generator().manual_seed(17)
+    feats = torch.randn(B, 49, 2048, generator=g).cuda()
+    caps = O.synth_captions(B, T, V, g).cuda()
+    style = torch.randn(1, E, generator=g).cuda()
+    res = []
+    for fused in (False, True):
+        m = _model_from(p, Fo, E, H, V, False, 10)
+        captioner = m.forward(style)
+        np.random.seed(0)
+        if fused:
+            loss, logits, att = captioner.forward_loss(feats, caps, 0.0, ignore_index=0)
+        else:
+            logits, att = captioner(feats, caps, 0.0)
+            loss = C.cross_entropy(logits, caps, 0)
+        loss.backward()
+        res.append((loss.item(), logits.detach(), {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}))
+    assert abs(res[0][0] - res[1][0]) < 1e-6 * abs(res[0][0])
+    assert torch.equal(res[0][1], res[1][1])
+    for k, v in res[0][2].items():
+        assert grad_close(res[1][2][k], v, TOL_GRAD), k
