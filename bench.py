@@ -312,10 +312,13 @@ def run_ours(args):
             decode()
         ms_dec = timed(decode, args.steps)
         extras["greedy_decode_captions_per_s"] = B * world * args.steps / (ms_dec * 1e-3)
+        del model
+        torch.cuda.empty_cache()
+        extras.update(attention_extras(args, dev, world, timed))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        del model
+        model = None
         torch.cuda.empty_cache()
         cpu = cpu_reference_arm(steps=3, warmup=1)
 
@@ -334,6 +337,41 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def attention_extras(args, dev, world, timed):
+    """BASELINE configs[2]/[1b]: attention variant (hypernet_attention.HyperNet + AttentionGru), F=E=H=200, P=49, D=2048,
+    B=512/GPU, T=20: teacher-forced fwd+bwd (flow, ignore_index=<pad>) and greedy decode (sample_prob=1.0, test_hn.py)."""
+    import numpy as np
+    import hypernet_image_captioning_b200 as C
+    from oracle import caption_hn_oracle as O
+    B, T, V = args.batch, CFG["T"], CFG["V"]
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = C.HyperNetAttention(200, 200, 200, V, None)
+    model.dp_enabled = world > 1
+    g = torch.Generator().manual_seed(4321)
+    feats = torch.randn(B, 49, 2048, generator=g).to(dev)
+    caps = O.synth_captions(B, T, V, g).to(dev)
+
+    def train():
+        model.zero_grad(set_to_none=True)
+        captioner = model.forward(model.captioner.embed.weight[4:5])
+        loss, _, _ = captioner.forward_loss(feats, caps, 0.0, ignore_index=0)
+        loss.backward()
+
+    def greedy():
+        with torch.no_grad():
+            captioner = model.forward(model.captioner.embed.weight[4:5])
+            return captioner(feats, caps, 1.0)
+
+    out = {}
+    for name, fn in (("attention_train_captions_per_s", train), ("attention_greedy_decode_captions_per_s", greedy)):
+        for _ in range(3):
+            fn()
+        ms = timed(fn, args.steps)
+        out[name] = B * world * args.steps / (ms * 1e-3)
+    return out
 
 
 def main():

@@ -108,7 +108,7 @@ __global__ void rows_bwd_prep_kernel(const float* __restrict__ Y, long ldy, cons
     if (dbias) dbias[n] = accum_bias ? dbias[n] + s : s;
 }
 
-// One pass over W: dW[n,k] (=|+=) sum_g dP[g,n] A[g,k]   and   dA[g,k] += sum_n dP[g,n] W[n,k]  (atomics, dA pre-zeroed).
+// [many-strips variant, K >= ~4096] One pass over W: dW[n,k] (=|+=) sum_g dP[g,n] A[g,k]   and   dA[g,k] += sum_n dP[g,n] W[n,k]  (atomics, dA pre-zeroed).
 // Work item = (block of RB rows) x (strip of 32*QPL aligned quads): a warp touches QPL*512 contiguous bytes of a row per
 // load/store batch (the access shape that reaches ~95 % of copy bandwidth in the forward kernel).  Rows are visited class
 // by class (n & 3 == cls) so that a lane sees the same k for every row of the class and keeps its dA partial sums in
@@ -218,6 +218,121 @@ __global__ void __launch_bounds__(ROWS_BWD_THREADS) rows_bwd_kernel(
     }
 }
 
+// [few-strips variant, small K]
+// One pass over W: dW[n,k] (=|+=) sum_g dP[g,n] A[g,k]   and   dA[g,k] += sum_n dP[g,n] W[n,k]  (dA pre-zeroed).
+// A CTA owns one strip of 32*QPL aligned quads (QPL*512 contiguous bytes of a row per warp access -- the shape that
+// reaches ~95 % of copy bandwidth in the forward kernel) and 8 consecutive row blocks of RB rows, one per warp.  Rows are
+// visited class by class (n & 3 == cls) so that a lane sees the same k for every row of the class and keeps its dA partial
+// sums in registers; RU rows are in flight per lane (RU*QPL 128-bit loads).  The 8 warps' partials are combined in
+// shared memory and leave the CTA as ONE global atomic per (g,k) per class -- 8x fewer same-address atomics, which
+// matters when K is small (few strips => many row blocks).
+template <int GC, int QPL, int RU>
+__global__ void __launch_bounds__(ROWS_BWD_THREADS) rows_bwd_fewstrips_kernel(
+    const float* __restrict__ W, const float* __restrict__ A, long lda, const float* __restrict__ dP, long ldp,
+    float* __restrict__ dW, float* __restrict__ dA, long ldda, long N, int K, int RB, int S, int accum_dw, int need_da) {
+    __shared__ float red[GC * QPL * 32 * 4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ncls = (K & 3) ? 4 : 1;
+    const int s = blockIdx.x % S;
+    const long rb = (long)(blockIdx.x / S) * (ROWS_BWD_THREADS / 32) + warp;
+    const long row0 = rb * RB;
+    const long row1 = (row0 + RB < N) ? row0 + RB : N;
+    for (int cls = 0; cls < ncls; ++cls) {
+        const int m = (cls * (K & 3)) & 3;
+        int k0[QPL];
+        bool full[QPL];
+        float a[GC][QPL][4], acc[GC][QPL][4];
+#pragma unroll
+        for (int u = 0; u < QPL; ++u) {
+            k0[u] = 4 * ((s * QPL + u) * 32 + lane) - m;
+            full[u] = (k0[u] >= 0) && (k0[u] + 3 < K);
+#pragma unroll
+            for (int g = 0; g < GC; ++g)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int k = k0[u] + c;
+                    a[g][u][c] = (k >= 0 && k < K) ? A[(long)g * lda + k] : 0.f;
+                    acc[g][u][c] = 0.f;
+                }
+        }
+        for (long nb = row0 + cls; nb < row1; nb += (long)RU * ncls) {
+            float wv[RU][QPL][4];
+#pragma unroll
+            for (int r = 0; r < RU; ++r) {
+                const long n = nb + (long)r * ncls;
+#pragma unroll
+                for (int u = 0; u < QPL; ++u) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) wv[r][u][c] = 0.f;
+                    if (n < row1) {
+                        const float* p = W + n * (long)K + k0[u];
+                        if (full[u]) {
+                            const float4 t = ldg_stream4(p);
+                            wv[r][u][0] = t.x; wv[r][u][1] = t.y; wv[r][u][2] = t.z; wv[r][u][3] = t.w;
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                if (k0[u] + c >= 0 && k0[u] + c < K) wv[r][u][c] = ldg_stream1(p + c);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RU; ++r) {
+                const long n = nb + (long)r * ncls;
+                if (n < row1) {
+                    float dp[GC];
+#pragma unroll
+                    for (int g = 0; g < GC; ++g) dp[g] = __ldg(dP + (long)g * ldp + n);
+#pragma unroll
+                    for (int u = 0; u < QPL; ++u) {
+                        float dw[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int g = 0; g < GC; ++g)
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                acc[g][u][c] = fmaf(dp[g], wv[r][u][c], acc[g][u][c]);
+                                dw[c] = fmaf(dp[g], a[g][u][c], dw[c]);
+                            }
+                        float* o = dW + n * (long)K + k0[u];
+                        if (full[u]) {
+                            float4 t = make_float4(dw[0], dw[1], dw[2], dw[3]);
+                            if (accum_dw) {
+                                const float4 old = *reinterpret_cast<const float4*>(o);
+                                t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+                            }
+                            stg_stream4(o, t);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                if (k0[u] + c >= 0 && k0[u] + c < K) o[c] = accum_dw ? o[c] + dw[c] : dw[c];
+                        }
+                    }
+                }
+            }
+        }
+        if (need_da) {   // (uniform across the CTA: safe to synchronise)
+            for (int i = threadIdx.x; i < GC * QPL * 128; i += ROWS_BWD_THREADS) red[i] = 0.f;
+            __syncthreads();
+#pragma unroll
+            for (int g = 0; g < GC; ++g)
+#pragma unroll
+                for (int u = 0; u < QPL; ++u)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (acc[g][u][c] != 0.f) atomicAdd(&red[((g * QPL + u) * 32 + lane) * 4 + c], acc[g][u][c]);
+            __syncthreads();
+            for (int i = threadIdx.x; i < GC * QPL * 128; i += ROWS_BWD_THREADS) {
+                const int c = i & 3, ln = (i >> 2) & 31, u = (i >> 7) % QPL, g = i / (QPL * 128);
+                const int k = 4 * ((s * QPL + u) * 32 + ln) - m + c;
+                const float v = red[i];
+                if (k >= 0 && k < K && v != 0.f) atomicAdd(dA + (long)g * ldda + k, v);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 template <int GC>
 static int launch_rows_fwd(const float* W, const float* bias, const float* A, long lda, float* Y, long ldy, long N,
                            int K, int act, float slope, cudaStream_t st) {
@@ -237,7 +352,23 @@ static int launch_rows_fwd(const float* W, const float* bias, const float* A, lo
 }
 
 template <int GC, int QPL, int RU>
-static int launch_rows_bwd(const float* W, const float* A, long lda, const float* dP, long ldp, float* dW, float* dA,
+static int launch_rows_bwd_fewstrips(const float* W, const float* A, long lda, const float* dP, long ldp, float* dW, float* dA,
+                           long ldda, long N, int K, int accum_dw, int need_da, cudaStream_t st) {
+    const int S = ((K + 6) / 4 + 32 * QPL - 1) / (32 * QPL);
+    constexpr int WPB = ROWS_BWD_THREADS / 32;
+    // rows per warp: as large as possible (fewer atomics) while still giving every SM a few CTAs
+    int RB = 256;
+    while (RB > 32 && ((N + (long)RB * WPB - 1) / ((long)RB * WPB)) * S < 4L * kNumSMs) RB >>= 1;
+    const long groups = (N + (long)RB * WPB - 1) / ((long)RB * WPB);
+    const long blocks = groups * S;
+    if (blocks > 0x7fffffffL) return CAPHN_EINVAL;
+    rows_bwd_fewstrips_kernel<GC, QPL, RU><<<(unsigned)blocks, ROWS_BWD_THREADS, 0, st>>>(
+        W, A, lda, dP, ldp, dW, dA, ldda, N, K, RB, S, accum_dw, need_da);
+    CAPHN_RETURN_LAST();
+}
+
+template <int GC, int QPL, int RU>
+static int launch_rows_bwd_manystrips(const float* W, const float* A, long lda, const float* dP, long ldp, float* dW, float* dA,
                            long ldda, long N, int K, int accum_dw, int need_da, cudaStream_t st) {
     const int S = ((K + 6) / 4 + 32 * QPL - 1) / (32 * QPL);
     int RB = 128;
@@ -249,6 +380,15 @@ static int launch_rows_bwd(const float* W, const float* A, long lda, const float
     rows_bwd_kernel<GC, QPL, RU><<<(unsigned)blocks, ROWS_BWD_THREADS, 0, st>>>(W, A, lda, dP, ldp, dW, dA, ldda, N, K,
                                                                                 RB, S, items, accum_dw, need_da);
     CAPHN_RETURN_LAST();
+}
+
+template <int GC, int QPL, int RU>
+static int launch_rows_bwd(const float* W, const float* A, long lda, const float* dP, long ldp, float* dW, float* dA,
+                           long ldda, long N, int K, int accum_dw, int need_da, cudaStream_t st) {
+    const int S = ((K + 6) / 4 + 32 * QPL - 1) / (32 * QPL);
+    if (S >= 8)   // adjacent warps = adjacent strips of the same rows (16 KB contiguous), direct atomics: few per address
+        return launch_rows_bwd_manystrips<GC, QPL, RU>(W, A, lda, dP, ldp, dW, dA, ldda, N, K, accum_dw, need_da, st);
+    return launch_rows_bwd_fewstrips<GC, QPL, RU>(W, A, lda, dP, ldp, dW, dA, ldda, N, K, accum_dw, need_da, st);
 }
 
 }  // namespace caphn
