@@ -29,6 +29,9 @@ SIGNATURES = {
     "caphn_copy_pad": [P, L, P, L, L, I, P],
     "caphn_gru_seq_fwd": [P, P, I, P, P, P, P, P, P, I, I, I, I, P],
     "caphn_gru_seq_bwd": [P, P, P, P, P, I, P, P, P, P, P, P, I, I, I, I, P],
+    "caphn_gru_cluster_plan": [I, P],
+    "caphn_gru_cluster_fwd": [P, P, P, P, P, P, I, I, I, P],
+    "caphn_gru_cluster_bwd": [P, P, P, P, P, P, P, I, I, I, P],
     "caphn_ce_fwd": [P, L, P, L, I, I, LL, P, P, P, P],
     "caphn_ce_bwd": [P, L, P, L, I, I, LL, P, P, P, P, L, P],
     "caphn_ce_bwd_split": [P, L, P, L, I, I, LL, P, P, P, P, P, L, P, P, L, P, P],

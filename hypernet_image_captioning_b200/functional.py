@@ -164,14 +164,19 @@ def _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells):
     emb_w = emb_w.contiguous()
     X = ops.build_inputs(feats, emb_w, caps, 0)                       # [T*B, E]
     GI = ops.linear(X, W_ih.contiguous(), b_ih.contiguous())          # [T*B, 3H]
-    ld3 = ops.round4(3 * H)
-    WhhT = ops.transpose_pad(W_hh.contiguous(), ld3)                  # [H, ld3]
-    extra = []
-    for l in range(1, NL):
-        Wi, Wh, bi, bh = cells[4 * l: 4 * l + 4]
-        extra.append((ops.transpose_pad(Wi.contiguous(), ld3), ops.transpose_pad(Wh.contiguous(), ld3),
-                      bi.contiguous(), bh.contiguous()))
-    Hall, Hbm, saved, Hmid = ops.gru_seq_fwd(GI, WhhT, b_hh.contiguous(), h0.contiguous(), T, save=True, extra=extra)
+    if NL == 1 and ops.gru_cluster_size(H):
+        # weights-resident path: W_hh stays in shared memory (cluster-split) for all T steps
+        Hall, Hbm, saved, Hmid = ops.gru_cluster_fwd(GI, W_hh.contiguous(), b_hh.contiguous(), h0.contiguous(), T)
+    else:
+        ld3 = ops.round4(3 * H)
+        WhhT = ops.transpose_pad(W_hh.contiguous(), ld3)                  # [H, ld3]
+        extra = []
+        for l in range(1, NL):
+            Wi, Wh, bi, bh = cells[4 * l: 4 * l + 4]
+            extra.append((ops.transpose_pad(Wi.contiguous(), ld3), ops.transpose_pad(Wh.contiguous(), ld3),
+                          bi.contiguous(), bh.contiguous()))
+        Hall, Hbm, saved, Hmid = ops.gru_seq_fwd(GI, WhhT, b_hh.contiguous(), h0.contiguous(), T, save=True,
+                                                 extra=extra)
     logits = ops.linear(Hbm.view(B * T, H), fc_w.contiguous(), fc_b)
     return logits.view(B, T, -1), (caps, X, Hall, Hbm, saved, Hmid, emb_w, fc_w)
 
@@ -184,11 +189,14 @@ def _gru_decoder_backward(saved_tensors, NL, need, vocab):
     B, T = caps.shape
     H = W_hh.shape[1]
     dfc_w, dfc_b, dHbm = vocab
-    ldh = ops.round4(H)
-    Whh_p = ops.copy_pad(W_hh.contiguous(), ldh)
-    extra = [(ops.copy_pad(cells[4 * l].contiguous(), ldh), ops.copy_pad(cells[4 * l + 1].contiguous(), ldh))
-             for l in range(1, NL)]
-    dGI, dGH, xdGI, xdGH, dh0 = ops.gru_seq_bwd(dHbm.view(B, T, H), saved, Hall, Hmid, Whh_p, extra=extra)
+    if NL == 1 and ops.gru_cluster_size(H):
+        dGI, dGH, xdGI, xdGH, dh0 = ops.gru_cluster_bwd(dHbm.view(B, T, H), saved, Hall, W_hh.contiguous())
+    else:
+        ldh = ops.round4(H)
+        Whh_p = ops.copy_pad(W_hh.contiguous(), ldh)
+        extra = [(ops.copy_pad(cells[4 * l].contiguous(), ldh), ops.copy_pad(cells[4 * l + 1].contiguous(), ldh))
+                 for l in range(1, NL)]
+        dGI, dGH, xdGI, xdGH, dh0 = ops.gru_seq_bwd(dHbm.view(B, T, H), saved, Hall, Hmid, Whh_p, extra=extra)
     Hprev = Hall[:-1].reshape(T * B, H)
     cell_grads = [ops.matmul_tn(dGI, X) if need[6] else None, ops.matmul_tn(dGH, Hprev) if need[7] else None,
                   ops.colsum(dGI) if need[8] else None, ops.colsum(dGH) if need[9] else None]

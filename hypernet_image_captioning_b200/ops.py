@@ -205,6 +205,48 @@ def gru_seq_fwd(GI, WhhT, bhh, h0, T, save=True, want_bm=True, extra=()):
     return Hall, Hbm, saved, Hmid
 
 
+CLUSTER_RECURRENCE = True   # use the weights-resident cluster kernels when W_hh fits (single layer)
+_cluster_plan_cache = {}
+
+
+def gru_cluster_size(H):
+    """Cluster size of the weights-resident GRU kernels for hidden size H (0 = not applicable)."""
+    if not CLUSTER_RECURRENCE:
+        return 0
+    if H not in _cluster_plan_cache:
+        import ctypes
+        cs = ctypes.c_int(0)
+        _cabi.call("caphn_gru_cluster_plan", H, ctypes.byref(cs))
+        _cluster_plan_cache[H] = int(cs.value)
+    return _cluster_plan_cache[H]
+
+
+def gru_cluster_fwd(GI, W_hh, bhh, h0, T, save=True, want_bm=True):
+    """Single-layer recurrence with W_hh resident in shared memory (cluster + DSMEM).  Same returns as gru_seq_fwd."""
+    B, H = h0.shape
+    dev = GI.device
+    Hall = torch.empty(T + 1, B, H, device=dev, dtype=torch.float32)
+    Hall[0].copy_(h0)
+    Hbm = torch.empty(B, T, H, device=dev, dtype=torch.float32) if want_bm else None
+    saved = torch.empty(1, 4, T, B, H, device=dev, dtype=torch.float32) if save else None
+    _cabi.call("caphn_gru_cluster_fwd", GI.data_ptr(), W_hh.data_ptr(), bhh.data_ptr(), Hall.data_ptr(), _p(Hbm),
+               _p(saved), B, T, H, _stream())
+    return Hall, Hbm, saved, None
+
+
+def gru_cluster_bwd(dHbm, saved, Hall, W_hh):
+    Tp1, B, H = Hall.shape
+    T = Tp1 - 1
+    dev = Hall.device
+    dGI = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+    dGH = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+    dh0 = torch.empty(B, H, device=dev, dtype=torch.float32)
+    assert dHbm.is_contiguous()
+    _cabi.call("caphn_gru_cluster_bwd", dHbm.data_ptr(), saved.data_ptr(), Hall.data_ptr(), W_hh.data_ptr(),
+               dGI.data_ptr(), dGH.data_ptr(), dh0.data_ptr(), B, T, H, _stream())
+    return dGI, dGH, None, None, dh0
+
+
 def gru_seq_bwd(dHbm, saved, Hall, Hmid, Whh_p, extra=()):
     """``extra`` = [(Wih_l, Whh_l) padded [3H,ldh], ...].  Returns dGI, dGH [T*B,3H], xdGI, xdGH [NL-1,T*B,3H] | None, dh0."""
     Tp1, B, H = Hall.shape

@@ -73,6 +73,15 @@ int caphn_gru_seq_bwd(const float* dHbm, const float* saved, const float* Hall, 
                       int ldh, const void* const* extra, float* dGI, float* dGH, float* xdGI, float* xdGH, float* dh0,
                       int NL, int B, int T, int H, void* stream);
 
+/* Weights-resident variant (single layer): W_hh [3H,H] (plain row-major) is loaded ONCE into shared memory, split by hidden
+ * unit over a thread-block cluster; h is exchanged through DSMEM every step.  caphn_gru_cluster_plan: *cs = cluster size
+ * used for hidden size H (0: does not fit -> use caphn_gru_seq_*).  saved = [4][T,B,H] or NULL. */
+int caphn_gru_cluster_plan(int H, int* cs);
+int caphn_gru_cluster_fwd(const float* GI, const float* Whh, const float* bhh, float* Hall, float* Hbm, float* saved,
+                          int B, int T, int H, void* stream);
+int caphn_gru_cluster_bwd(const float* dHbm, const float* saved, const float* Hall, const float* Whh, float* dGI,
+                          float* dGH, float* dh0, int B, int T, int H, void* stream);
+
 /* ---- attention decoder recurrence (models/decoderlstm.py:78-108 AttentionGru loop; models/attention.py:21-46) ------- */
 
 /* Steps [t0,t1) of: u = U_a h + b_u; s_p = v_a.tanh(K_p + u) + b_v; alpha = softmax_p s; ctx = sum_p alpha_p f_p;

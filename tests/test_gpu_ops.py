@@ -161,3 +161,22 @@ def test_softmax_argmax_ties_and_gather():
     table = torch.randn(10, 6).cuda()
     idx = torch.tensor([3, 0, 9]).cuda()
     assert torch.equal(ops.gather_rows(table, idx), table[idx])
+
+
+@pytest.mark.parametrize("B,T,H", [(3, 5, 6), (9, 4, 150), (21, 3, 33), (16, 6, 200), (5, 2, 301)])
+def test_gru_cluster_matches_streaming_kernel(B, T, H):
+    """Weights-resident cluster kernels (W_hh in shared memory, DSMEM state exchange) == L2-streaming kernels."""
+    ops = _ops()
+    assert ops.gru_cluster_size(H) in (2, 4, 8)
+    g = torch.Generator().manual_seed(B * 100 + T * 10 + H)
+    GI = (torch.randn(T * B, 3 * H, generator=g) * 0.5).cuda()
+    W = (torch.randn(3 * H, H, generator=g) / H ** 0.5).cuda()
+    b = (torch.randn(3 * H, generator=g) * 0.1).cuda()
+    h0 = torch.rand(B, H, generator=g).cuda()
+    dH = torch.randn(B, T, H, generator=g).cuda()
+    Hall0, Hbm0, sv0, _ = ops.gru_seq_fwd(GI, ops.transpose_pad(W, ops.round4(3 * H)), b, h0, T)
+    dGI0, dGH0, _, _, dh00 = ops.gru_seq_bwd(dH, sv0, Hall0, None, ops.copy_pad(W, ops.round4(H)))
+    Hall1, Hbm1, sv1, _ = ops.gru_cluster_fwd(GI, W, b, h0, T)
+    dGI1, dGH1, _, _, dh01 = ops.gru_cluster_bwd(dH, sv1, Hall1, W)
+    assert rel_err(Hall1, Hall0) < 2e-6 and rel_err(Hbm1, Hbm0) < 2e-6 and rel_err(sv1, sv0) < 2e-6
+    assert rel_err(dGI1, dGI0) < 1e-5 and rel_err(dGH1, dGH0) < 1e-5 and rel_err(dh01, dh00) < 1e-5
