@@ -69,66 +69,108 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cluster_fwd_kernel(const Gr
     __syncthreads();
     cluster.sync();
 
-    const int NG = CL_THREADS / 256;   // k-range groups (2): thread (kg, lr)
-    const int kg = tid / 256, lr = tid % 256;
+    const int RW = (rows + 31) & ~31;                  // threads per k-range group (warp multiple)
+    const int NG = max(1, CL_THREADS / RW);            // k-range groups
+    const int kg = tid / RW, lr = tid - kg * RW;
     const int kchunk = (H + NG - 1) / NG;
-    const int k0 = kg * kchunk, k1 = min(H, k0 + kchunk);
+    const int k0 = min(H, kg * kchunk), k1 = (kg < NG) ? min(H, k0 + kchunk) : k0;
     float* part = ghs + rows * BT;                     // [NG][rows][BT]
+
+    // per-thread gate items (fixed over time): up to 2 x (unit jl, row b); biases hoisted, GI prefetched one step ahead
+    constexpr int MAXI = 2;
+    int it_j[MAXI], it_b[MAXI];
+    bool it_ok[MAXI];
+    float bh[MAXI][3], gi_next[MAXI][3];
+#pragma unroll
+    for (int q = 0; q < MAXI; ++q) {
+        const int i = tid + q * CL_THREADS;
+        const int jl = i / BT, b = i - jl * BT;
+        it_j[q] = c * HS + jl; it_b[q] = b;
+        it_ok[q] = (i < HS * BT) && (it_j[q] < H);
+        const bool live = it_ok[q] && (b0 + b < B);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+            bh[q][g] = live ? a.bhh[g * H + it_j[q]] : 0.f;
+            gi_next[q][g] = live ? a.GI[((long)0 * B + b0 + b) * H3 + g * H + it_j[q]] : 0.f;
+        }
+    }
 
     for (int t = 0; t < T; ++t) {
         const float* hc = hs + (t & 1) * H * BT;
         float* hn = hs + ((t + 1) & 1) * H * BT;
-        // ---- gh partial: thread = (k half, local weight row) ----
-        for (int r = lr; r < rows; r += 256) {
-            float acc[BT];
+        float gi_cur[MAXI][3];
 #pragma unroll
-            for (int b = 0; b < BT; ++b) acc[b] = 0.f;
-            const float* wr = Ws + r * ldw;
-#pragma unroll 4
-            for (int k = k0; k < k1; ++k) {
-                const float w = wr[k];
-                const float4 h0 = *reinterpret_cast<const float4*>(hc + k * BT);
-                const float4 h1 = *reinterpret_cast<const float4*>(hc + k * BT + 4);
-                acc[0] = fmaf(w, h0.x, acc[0]); acc[1] = fmaf(w, h0.y, acc[1]);
-                acc[2] = fmaf(w, h0.z, acc[2]); acc[3] = fmaf(w, h0.w, acc[3]);
-                acc[4] = fmaf(w, h1.x, acc[4]); acc[5] = fmaf(w, h1.y, acc[5]);
-                acc[6] = fmaf(w, h1.z, acc[6]); acc[7] = fmaf(w, h1.w, acc[7]);
+        for (int q = 0; q < MAXI; ++q) {
+            const bool live = it_ok[q] && (b0 + it_b[q] < B) && (t + 1 < T);
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                gi_cur[q][g] = gi_next[q][g];
+                if (live) gi_next[q][g] = a.GI[((long)(t + 1) * B + b0 + it_b[q]) * H3 + g * H + it_j[q]];
             }
-            float* pp = part + ((long)kg * rows + r) * BT;
-            *reinterpret_cast<float4*>(pp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            *reinterpret_cast<float4*>(pp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        // ---- gh partial: thread = (k range, local weight row) ----
+        if (kg < NG) {
+            for (int r = lr; r < rows; r += RW) {
+                float acc[BT];
+#pragma unroll
+                for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+                const float* wr = Ws + r * ldw;
+#pragma unroll 4
+                for (int k = k0; k < k1; ++k) {
+                    const float w = wr[k];
+                    const float4 h0 = *reinterpret_cast<const float4*>(hc + k * BT);
+                    const float4 h1 = *reinterpret_cast<const float4*>(hc + k * BT + 4);
+                    acc[0] = fmaf(w, h0.x, acc[0]); acc[1] = fmaf(w, h0.y, acc[1]);
+                    acc[2] = fmaf(w, h0.z, acc[2]); acc[3] = fmaf(w, h0.w, acc[3]);
+                    acc[4] = fmaf(w, h1.x, acc[4]); acc[5] = fmaf(w, h1.y, acc[5]);
+                    acc[6] = fmaf(w, h1.z, acc[6]); acc[7] = fmaf(w, h1.w, acc[7]);
+                }
+                float* pp = part + ((long)kg * rows + r) * BT;
+                *reinterpret_cast<float4*>(pp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                *reinterpret_cast<float4*>(pp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
         }
         __syncthreads();
-        // ---- gates for own units; broadcast h' to every CTA of the cluster ----
-        for (int i = tid; i < HS * BT; i += CL_THREADS) {
-            const int jl = i / BT, b = i - jl * BT;
-            const int j = c * HS + jl, gb = b0 + b;
-            if (j < H) {
-                float hnew = 0.f;
-                if (gb < B) {
-                    float ghr = a.bhh[j], ghz = a.bhh[H + j], ghn = a.bhh[2 * H + j];
+        // ---- gates for own units; broadcast h' to every CTA of the cluster; THEN the global stores ----
+        float o_r[MAXI], o_z[MAXI], o_n[MAXI], o_g[MAXI], o_h[MAXI];
+#pragma unroll
+        for (int q = 0; q < MAXI; ++q) {
+            o_r[q] = o_z[q] = o_n[q] = o_g[q] = o_h[q] = 0.f;
+            if (it_ok[q]) {
+                const int j = it_j[q], b = it_b[q], jl = j - c * HS;
+                if (b0 + b < B) {
+                    float ghr = bh[q][0], ghz = bh[q][1], ghn = bh[q][2];
                     for (int g = 0; g < NG; ++g) {
                         const float* pp = part + (long)g * rows * BT;
                         ghr += pp[(jl) * BT + b]; ghz += pp[(HS + jl) * BT + b]; ghn += pp[(2 * HS + jl) * BT + b];
                     }
-                    const float* gi = a.GI + ((long)t * B + gb) * H3;
-                    const float r = sigmoidf_acc(gi[j] + ghr);
-                    const float z = sigmoidf_acc(gi[H + j] + ghz);
-                    const float n = tanhf(gi[2 * H + j] + r * ghn);
+                    const float r = sigmoidf_acc(gi_cur[q][0] + ghr);
+                    const float z = sigmoidf_acc(gi_cur[q][1] + ghz);
+                    const float n = tanhf(gi_cur[q][2] + r * ghn);
                     const float hp = hc[j * BT + b];
-                    hnew = (1.f - z) * n + z * hp;
-                    const long o = ((long)t * B + gb) * H + j;
-                    a.Hall[o + (long)B * H] = hnew;
-                    if (a.Hbm) a.Hbm[((long)gb * T + t) * H + j] = hnew;
-                    if (a.saved) { a.saved[o] = r; a.saved[TBH + o] = z; a.saved[2 * TBH + o] = n; a.saved[3 * TBH + o] = ghn; }
+                    o_r[q] = r; o_z[q] = z; o_n[q] = n; o_g[q] = ghn;
+                    o_h[q] = (1.f - z) * n + z * hp;
                 }
-                for (int rk = 0; rk < CS; ++rk) {
-                    float* dst = cluster.map_shared_rank(hn, rk);
-                    dst[j * BT + b] = hnew;
+                for (int rk = 0; rk < CS; ++rk) cluster.map_shared_rank(hn, rk)[j * BT + b] = o_h[q];
+            }
+        }
+        // release the DSMEM writes now; the (slow) global stores below are not covered by this barrier phase
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < MAXI; ++q) {
+            const int gb = b0 + it_b[q];
+            if (it_ok[q] && gb < B) {
+                const int j = it_j[q];
+                const long o = ((long)t * B + gb) * H + j;
+                a.Hall[o + (long)B * H] = o_h[q];
+                if (a.Hbm) a.Hbm[((long)gb * T + t) * H + j] = o_h[q];
+                if (a.saved) {
+                    a.saved[o] = o_r[q]; a.saved[TBH + o] = o_z[q]; a.saved[2 * TBH + o] = o_n[q];
+                    a.saved[3 * TBH + o] = o_g[q];
                 }
             }
         }
-        cluster.sync();
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
 }
 
@@ -166,60 +208,89 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cluster_bwd_kernel(const Gr
     __syncthreads();
     cluster.sync();
 
-    const int NG = CL_THREADS / 256;
-    const int jg = tid / 256, kk = tid % 256;
+    const int KW = (H + 31) & ~31;                     // threads per row-range group
+    const int NG = max(1, CL_THREADS / KW);
+    const int jg = tid / KW, kk = tid - jg * KW;
     const int jchunk = (rows + NG - 1) / NG;
-    const int j0 = jg * jchunk, j1 = min(rows, j0 + jchunk);
+    const int j0 = min(rows, jg * jchunk), j1 = (jg < NG) ? min(rows, j0 + jchunk) : j0;
+
+    constexpr int MAXI = 2;
+    int it_j[MAXI], it_b[MAXI];
+    bool it_live[MAXI];
+    float nx[MAXI][6];   // prefetched r, z, n, ghn, h_prev, dHbm of the step about to be processed
+#pragma unroll
+    for (int q = 0; q < MAXI; ++q) {
+        const int i = tid + q * CL_THREADS;
+        const int jl = i / BT, b = i - jl * BT;
+        it_j[q] = c * HS + jl; it_b[q] = b;
+        it_live[q] = (i < HS * BT) && (it_j[q] < H) && (b0 + b < B);
+        if (it_live[q]) {
+            const long o = ((long)(T - 1) * B + b0 + b) * H + it_j[q];
+            nx[q][0] = a.saved[o]; nx[q][1] = a.saved[TBH + o]; nx[q][2] = a.saved[2 * TBH + o];
+            nx[q][3] = a.saved[3 * TBH + o]; nx[q][4] = a.Hall[o];
+            nx[q][5] = a.dHbm[((long)(b0 + b) * T + (T - 1)) * H + it_j[q]];
+        }
+    }
 
     for (int t = T - 1; t >= 0; --t) {
         const int par = (T - 1 - t) & 1;
         const float* rc = recv + par * CS * HS * BT;           // written during the previous iteration
         float* rn_local = recv + (par ^ 1) * CS * HS * BT;     // to be written now (for the next iteration)
         // ---- gate gradients for own units ----
-        for (int i = tid; i < HS * BT; i += CL_THREADS) {
-            const int jl = i / BT, b = i - jl * BT;
-            const int j = c * HS + jl, gb = b0 + b;
-            float dar = 0.f, daz = 0.f, danr = 0.f, keep = 0.f;
-            if (j < H && gb < B) {
-                float dht = dhd[i] + a.dHbm[((long)gb * T + t) * H + j];
-                for (int s = 0; s < CS; ++s) dht += rc[(s * HS + jl) * BT + b];
-                const long o = ((long)t * B + gb) * H + j;
-                const float r = a.saved[o], z = a.saved[TBH + o], n = a.saved[2 * TBH + o], ghn = a.saved[3 * TBH + o];
-                const float hp = a.Hall[o];
-                const float dn = dht * (1.f - z);
-                const float dz = dht * (hp - n);
-                const float dan = dn * (1.f - n * n);
-                dar = dan * ghn * r * (1.f - r);
-                daz = dz * z * (1.f - z);
-                danr = dan * r;
-                keep = dht * z;
-                float* gi = a.dGI + ((long)t * B + gb) * H3;
-                float* gh = a.dGH + ((long)t * B + gb) * H3;
-                gi[j] = dar; gi[H + j] = daz; gi[2 * H + j] = dan;
-                gh[j] = dar; gh[H + j] = daz; gh[2 * H + j] = danr;
+#pragma unroll
+        for (int q = 0; q < MAXI; ++q) {
+            const int i = tid + q * CL_THREADS;
+            if (i < HS * BT) {
+                const int jl = i / BT, b = it_b[q], j = it_j[q];
+                float dar = 0.f, daz = 0.f, danr = 0.f, keep = 0.f;
+                if (it_live[q]) {
+                    float dht = dhd[i] + nx[q][5];
+                    for (int sidx = 0; sidx < CS; ++sidx) dht += rc[(sidx * HS + jl) * BT + b];
+                    const float r = nx[q][0], z = nx[q][1], n = nx[q][2], ghn = nx[q][3], hp = nx[q][4];
+                    const float dn = dht * (1.f - z);
+                    const float dz = dht * (hp - n);
+                    const float dan = dn * (1.f - n * n);
+                    dar = dan * ghn * r * (1.f - r);
+                    daz = dz * z * (1.f - z);
+                    danr = dan * r;
+                    keep = dht * z;
+                    const int gb = b0 + b;
+                    float* gi = a.dGI + ((long)t * B + gb) * H3;
+                    float* gh = a.dGH + ((long)t * B + gb) * H3;
+                    gi[j] = dar; gi[H + j] = daz; gi[2 * H + j] = dan;
+                    gh[j] = dar; gh[H + j] = daz; gh[2 * H + j] = danr;
+                    if (t > 0) {   // prefetch the next (earlier) step while the matvec below runs
+                        const long o = ((long)(t - 1) * B + gb) * H + j;
+                        nx[q][0] = a.saved[o]; nx[q][1] = a.saved[TBH + o]; nx[q][2] = a.saved[2 * TBH + o];
+                        nx[q][3] = a.saved[3 * TBH + o]; nx[q][4] = a.Hall[o];
+                        nx[q][5] = a.dHbm[((long)gb * T + (t - 1)) * H + j];
+                    }
+                }
+                dhd[i] = keep;
+                dgs[jl * BT + b] = dar; dgs[(HS + jl) * BT + b] = daz; dgs[(2 * HS + jl) * BT + b] = danr;
             }
-            dhd[i] = keep;
-            dgs[jl * BT + b] = dar; dgs[(HS + jl) * BT + b] = daz; dgs[(2 * HS + jl) * BT + b] = danr;
         }
         __syncthreads();
         // ---- partial dh[b][k] = sum over own rows of dgh[row][b] * W[row][k], for all k ----
-        for (int k = kk; k < H; k += 256) {
-            float acc[BT];
+        if (jg < NG) {
+            for (int k = kk; k < H; k += KW) {
+                float acc[BT];
 #pragma unroll
-            for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+                for (int b = 0; b < BT; ++b) acc[b] = 0.f;
 #pragma unroll 4
-            for (int r = j0; r < j1; ++r) {
-                const float w = Ws[r * ldw + k];
-                const float4 d0 = *reinterpret_cast<const float4*>(dgs + r * BT);
-                const float4 d1 = *reinterpret_cast<const float4*>(dgs + r * BT + 4);
-                acc[0] = fmaf(w, d0.x, acc[0]); acc[1] = fmaf(w, d0.y, acc[1]);
-                acc[2] = fmaf(w, d0.z, acc[2]); acc[3] = fmaf(w, d0.w, acc[3]);
-                acc[4] = fmaf(w, d1.x, acc[4]); acc[5] = fmaf(w, d1.y, acc[5]);
-                acc[6] = fmaf(w, d1.z, acc[6]); acc[7] = fmaf(w, d1.w, acc[7]);
+                for (int r = j0; r < j1; ++r) {
+                    const float w = Ws[r * ldw + k];
+                    const float4 d0 = *reinterpret_cast<const float4*>(dgs + r * BT);
+                    const float4 d1 = *reinterpret_cast<const float4*>(dgs + r * BT + 4);
+                    acc[0] = fmaf(w, d0.x, acc[0]); acc[1] = fmaf(w, d0.y, acc[1]);
+                    acc[2] = fmaf(w, d0.z, acc[2]); acc[3] = fmaf(w, d0.w, acc[3]);
+                    acc[4] = fmaf(w, d1.x, acc[4]); acc[5] = fmaf(w, d1.y, acc[5]);
+                    acc[6] = fmaf(w, d1.z, acc[6]); acc[7] = fmaf(w, d1.w, acc[7]);
+                }
+                float* pp = part + ((long)jg * HP + k) * BT;
+                *reinterpret_cast<float4*>(pp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                *reinterpret_cast<float4*>(pp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
             }
-            float* pp = part + ((long)jg * HP + k) * BT;
-            *reinterpret_cast<float4*>(pp) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            *reinterpret_cast<float4*>(pp + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
         __syncthreads();
         // ---- reduce-scatter: send the partial for unit k to its owner (slot = my rank) ----
@@ -245,14 +316,22 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cluster_bwd_kernel(const Gr
     }
 }
 
+static inline int cl_groups(int n) {   // k / j range groups for a work width of n threads (rounded to a warp)
+    const int w = (n + 31) & ~31;
+    const int g = CL_THREADS / w;
+    return g < 1 ? 1 : g;
+}
+
 static int pick_cluster(int H, int* HS, int* ldw, size_t* smem, bool bwd) {
     const int ld = H | 1;
     for (int CS = 2; CS <= 8; CS *= 2) {
         const int hs = (H + CS - 1) / CS;
         const size_t rows = 3 * (size_t)hs;
         size_t fl = ((rows * ld + 3) & ~(size_t)3);
-        if (!bwd) fl += 2 * (size_t)H * CL_BT + rows * CL_BT + 2 * rows * CL_BT;
-        else fl += rows * CL_BT + (size_t)hs * CL_BT + 2 * (size_t)CS * hs * CL_BT + 2 * (size_t)CS * hs * CL_BT;
+        if (!bwd) fl += 2 * (size_t)H * CL_BT + rows * CL_BT + (size_t)cl_groups((int)rows) * rows * CL_BT;
+        else fl += rows * CL_BT + (size_t)hs * CL_BT + 2 * (size_t)CS * hs * CL_BT +
+                   (size_t)cl_groups(H) * CS * hs * CL_BT;
+        if (rows > CL_THREADS || (size_t)hs * CL_BT > 2 * CL_THREADS) continue;   // thread-mapping limits
         const size_t bytes = fl * sizeof(float);
         if (bytes <= 200 * 1024) { *HS = hs; *ldw = ld; *smem = bytes; return CS; }
     }
@@ -288,7 +367,8 @@ int caphn_gru_cluster_fwd(const float* GI, const float* Whh, const float* bhh, f
     a.HS = (H + cs1 - 1) / cs1;
     a.ldw = H | 1;
     const size_t rows = 3 * (size_t)a.HS;
-    smem = (((rows * a.ldw + 3) & ~(size_t)3) + 2 * (size_t)H * CL_BT + rows * CL_BT + 2 * rows * CL_BT) * sizeof(float);
+    smem = (((rows * a.ldw + 3) & ~(size_t)3) + 2 * (size_t)H * CL_BT + rows * CL_BT +
+            (size_t)cl_groups((int)rows) * rows * CL_BT) * sizeof(float);
     CAPHN_CHECK(cudaFuncSetAttribute(gru_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(ceil_div(B, CL_BT) * cs1));
@@ -313,7 +393,7 @@ int caphn_gru_cluster_bwd(const float* dHbm, const float* saved, const float* Ha
     GruClBwdArgs a{dHbm, saved, Hall, Whh, dGI, dGH, dh0, B, T, H, (H + cs - 1) / cs, H | 1};
     const size_t rows = 3 * (size_t)a.HS;
     const size_t smem = (((rows * a.ldw + 3) & ~(size_t)3) + rows * CL_BT + (size_t)a.HS * CL_BT +
-                         2 * (size_t)cs * a.HS * CL_BT + 2 * (size_t)cs * a.HS * CL_BT) * sizeof(float);
+                         2 * (size_t)cs * a.HS * CL_BT + (size_t)cl_groups(H) * cs * a.HS * CL_BT) * sizeof(float);
     CAPHN_CHECK(cudaFuncSetAttribute(gru_cluster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(ceil_div(B, CL_BT) * cs));

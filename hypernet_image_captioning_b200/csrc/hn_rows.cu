@@ -386,7 +386,9 @@ template <int GC, int QPL, int RU>
 static int launch_rows_bwd(const float* W, const float* A, long lda, const float* dP, long ldp, float* dW, float* dA,
                            long ldda, long N, int K, int accum_dw, int need_da, cudaStream_t st) {
     const int S = ((K + 6) / 4 + 32 * QPL - 1) / (32 * QPL);
-    if (S >= 8)   // adjacent warps = adjacent strips of the same rows (16 KB contiguous), direct atomics: few per address
+    // many strips: adjacent warps = adjacent strips of the same rows (16 KB contiguous), direct atomics (few per address);
+    // tiny matrices are latency-bound either way and skip the shared-memory reduction as well
+    if (S >= 8 || (long)N * K < (1L << 22))
         return launch_rows_bwd_manystrips<GC, QPL, RU>(W, A, lda, dP, ldp, dW, dA, ldda, N, K, accum_dw, need_da, st);
     return launch_rows_bwd_fewstrips<GC, QPL, RU>(W, A, lda, dP, ldp, dW, dA, ldda, N, K, accum_dw, need_da, st);
 }
