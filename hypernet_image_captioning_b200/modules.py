@@ -177,11 +177,12 @@ class DecoderGRU(nn.Module):
         h = h0.contiguous()
         x = features.contiguous()
         logits = torch.empty(B, self.vocab_size, device=features.device, dtype=torch.float32)
+        xproj, vocab = ops.LinearPlan(W_ih, b_ih), ops.LinearPlan(fc_w, fc_b)   # weight splits made once, not per step
         for t in range(max_len):
-            GI = ops.linear(x, W_ih, b_ih)
+            GI = xproj(x)
             Hall, _, _, _ = ops.gru_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False)
             h = Hall[1]
-            ops.linear(h, fc_w, fc_b, out=logits)
+            vocab(h, out=logits)
             _, words = ops.softmax_argmax(logits, want_probs=True, probs_out=outputs[:, t, :])
             if t + 1 < max_len:
                 x = ops.gather_rows(emb, words)

@@ -65,6 +65,7 @@ def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, f
         ops.linear(Hbm.view(B * T, H), fc_w, fc_b, out=logits.view(B * T, V))
     else:
         GIw = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+        xproj, vocab = ops.LinearPlan(W_ih_w, b_ih.contiguous()), ops.LinearPlan(fc_w, fc_b)   # split once, reuse per step
         for t in range(T):
             if use_sampling[t]:
                 # :91-96  argmax of log_softmax(logits/0.5) == argmax of logits (lowest index on ties)
@@ -74,9 +75,9 @@ def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, f
                 fed[t].copy_(caps[:, t - 1])
             xw = ops.gather_rows(emb_w, fed[t])                        # zeros where fed == -1
             XC[t * B:(t + 1) * B, :E].copy_(xw)
-            ops.linear(xw, W_ih_w, b_ih.contiguous(), out=GIw[t * B:(t + 1) * B])
+            xproj(xw, out=GIw[t * B:(t + 1) * B])
             ops.attgru_seq_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, t, t + 1)
-            ops.linear(Hall[t + 1], fc_w, fc_b, out=logits[:, t, :])
+            vocab(Hall[t + 1], out=logits[:, t, :])
     sv = (feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih, W_hh, fc_w, Wa_w, Ua_w,
           va, init_w)
     return logits, attn, sv, (B, T, P, D, E, H, Fd, V)

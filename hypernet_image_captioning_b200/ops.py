@@ -485,3 +485,24 @@ def gemm_tc(A: SplitOperand, Bm: SplitOperand, bias=None, relu=False, out=None, 
     _cabi.call("caphn_gemm_tc", A.hi.data_ptr(), _p(A.lo), Bm.hi.data_ptr(), _p(Bm.lo), A.Kp, out.data_ptr(),
                out.stride(0), _p(bias), M, N, int(relu), 1 if relu else splitk, _stream())
     return out
+
+
+
+class LinearPlan:
+    """y = x W^T + b for a weight that is reused many times (greedy decode: one projection per time step).  The bf16x3
+    split of W is made once; every call only splits the (small) activation."""
+
+    def __init__(self, W, bias=None):
+        _chk(W)
+        assert W.stride(1) == 1
+        self.W, self.bias = W, bias
+        self.N, self.K = W.shape
+        self._split = None
+
+    def __call__(self, X, relu=False, out=None):
+        M = X.shape[0]
+        if _tc_ok(M, self.N, self.K):
+            if self._split is None:
+                self._split = split_bf16(self.W)
+            return gemm_tc(split_bf16(X), self._split, bias=self.bias, relu=relu, out=out)
+        return _gemm(X, X.stride(0), 1, self.W, self.W.stride(0), 1, M, self.N, self.K, self.bias, relu, out)
