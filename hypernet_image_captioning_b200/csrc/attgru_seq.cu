@@ -72,16 +72,28 @@ __global__ void __launch_bounds__(AT_THREADS) attgru_seq_fwd_kernel(const AttFwd
             if (a.Upre && b0 + b < B) a.Upre[((long)t * B + b0 + b) * H + j] = u;
         }
         __syncthreads();
-        for (int pair = warp; pair < BT * P; pair += AT_WARPS) {
-            const int b = pair / P, p = pair - b * P;
-            const int gb = b0 + b;
-            float s = 0.f;
-            if (gb < B) {
-                const float* kp = a.Kp + ((long)gb * P + p) * H;
-                for (int j = lane; j < H; j += 32) s = fmaf(a.va[j], tanhf(kp[j] + us[b * H + j]), s);
+        // scores: one warp per (row, group of 4 positions); v_a and u stay in registers across the 4 positions
+        {
+            const int PG = (P + 3) >> 2;
+            for (int task = warp; task < BT * PG; task += AT_WARPS) {
+                const int b = task / PG, p0 = (task - b * PG) * 4;
+                const int gb = b0 + b;
+                float s4[4] = {0.f, 0.f, 0.f, 0.f};
+                if (gb < B) {
+                    const float* kp = a.Kp + ((long)gb * P + p0) * H;
+                    for (int j = lane; j < H; j += 32) {
+                        const float vj = a.va[j], uj = us[b * H + j];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (p0 + q < P) s4[q] = fmaf(vj, tanh_fast(kp[(long)q * H + j] + uj), s4[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float s = warp_sum(s4[q]);
+                    if (lane == 0 && p0 + q < P) sc[b * PS + p0 + q] = s + bv;
+                }
             }
-            s = warp_sum(s);
-            if (lane == 0) sc[b * PS + p] = s + bv;
         }
         __syncthreads();
         if (warp < BT) {
@@ -281,7 +293,7 @@ __global__ void __launch_bounds__(AT_THREADS) attgru_seq_bwd_kernel(const AttBwd
                     const float* kp = a.Kp + (long)gb * P * H + j;
                     float* dkp = a.dK + (long)gb * P * H + j;
                     for (int p = 0; p < P; ++p) {
-                        const float q = tanhf(kp[(long)p * H] + uj);
+                        const float q = tanh_fast(kp[(long)p * H] + uj);
                         const float ds = dal[b * PS + p];
                         dva_acc[slot] = fmaf(ds, q, dva_acc[slot]);
                         const float dpre = ds * vj * (1.f - q * q);

@@ -61,7 +61,12 @@ def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, f
         Xw = ops.build_inputs(None, emb_w, caps, 1)                    # [T*B, E]
         XC[:, :E].copy_(Xw)
         GIw = ops.linear(Xw, W_ih_w, b_ih.contiguous())                # [T*B, 3H]
-        ops.attgru_seq_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, 0, T)
+        if ops.attgru_cluster_ok(H, Fd, P):
+            # weights-resident path: U_a / W_hh / W_ih[:,E:] stay on chip for all T steps (cluster of 8 CTAs)
+            ops.attgru_cluster_fwd(K3, f3, GIw, Ua_w.contiguous(), Ua_b, va, bv, W_ih, W_hh, b_hh, Hall, Hbm, attn, XC,
+                                   E, saved, 0, T)
+        else:
+            ops.attgru_seq_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, 0, T)
         ops.linear(Hbm.view(B * T, H), fc_w, fc_b, out=logits.view(B * T, V))
     else:
         GIw = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)

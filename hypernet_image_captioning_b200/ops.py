@@ -407,6 +407,37 @@ def attgru_seq_fwd(Kp, f, GIw, lw, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, save
                B, T, P, H, Fd, lw.ldh, lw.ld3, t0, t1, _stream())
 
 
+_attcl_cache = {}
+
+
+ATT_CLUSTER = False   # experimental weights-resident attention forward (correct, not yet faster than streaming)
+
+
+def attgru_cluster_ok(H, Fd, P, force=False):
+    if not (ATT_CLUSTER or force):
+        return False
+    key = (H, Fd, P)
+    if key not in _attcl_cache:
+        import ctypes
+        ok = ctypes.c_int(0)
+        _cabi.call("caphn_attgru_cluster_plan", H, Fd, P, ctypes.byref(ok))
+        _attcl_cache[key] = bool(ok.value)
+    return _attcl_cache[key]
+
+
+def attgru_cluster_fwd(Kp, f, GIw, U_a, bu, va, bv, W_ih, W_hh, bhh, Hall, Hbm, attn, XC, E, saved, t0, t1):
+    """Weights-resident attention recurrence (cluster of 8, register-resident MMA fragments); plain row-major weights."""
+    B, P, H = Kp.shape
+    Fd = f.shape[2]
+    T = Hall.shape[0] - 1
+    sp = [saved[i].data_ptr() for i in range(5)] if saved is not None else [None] * 5
+    ctx_ptr = XC.data_ptr() + 4 * E
+    _cabi.call("caphn_attgru_cluster_fwd", Kp.data_ptr(), f.data_ptr(), GIw.data_ptr(), U_a.data_ptr(), bu.data_ptr(),
+               va.data_ptr(), bv.data_ptr(), W_ih.data_ptr(), W_hh.data_ptr(), bhh.data_ptr(), Hall.data_ptr(),
+               _p(Hbm), attn.data_ptr(), ctx_ptr, XC.stride(0), sp[0], sp[1], sp[2], sp[3], sp[4],
+               B, T, P, H, Fd, E, t0, t1, _stream())
+
+
 def attgru_seq_bwd(dHbm, dattn, Kp, f, attn, saved, Hall, U_a, va, W_ih, W_hh, E):
     B, P, H = Kp.shape
     Fd = f.shape[2]

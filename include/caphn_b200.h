@@ -102,6 +102,16 @@ int caphn_attgru_seq_bwd(const float* dHbm, const float* dattn, const float* Kp,
                          const float* Hall, const float* Ua, const float* va, const float* Wihc, const float* Whh,
                          float* dGI, float* dGH, float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0,
                          int B, int T, int P, int H, int F, int ldh, int ldf, void* stream);
+/* Weights-resident forward variant: U_a, W_hh and W_ih[:,E:] stay on chip for all steps, split by hidden unit over a
+ * cluster of 8 CTAs (register-resident warp-MMA fragments, bf16x3), attention partitioned by batch row, DSMEM exchanges.
+ * Takes the PLAIN row-major weights Ua [H,H], Wih [3H,E+F], Whh [3H,H].  caphn_attgru_cluster_plan: *ok = 1 if the
+ * sizes are supported (H, F <= 208, ...); otherwise use caphn_attgru_seq_fwd. */
+int caphn_attgru_cluster_plan(int H, int F, int P, int* ok);
+int caphn_attgru_cluster_fwd(const float* Kp, const float* f, const float* GIw, const float* Ua, const float* bu,
+                             const float* va, const float* bv, const float* Wih, const float* Whh, const float* bhh,
+                             float* Hall, float* Hbm, float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z,
+                             float* Nn, float* GHN, int B, int T, int P, int H, int F, int E, int t0, int t1,
+                             void* stream);
 /* df[b,p,:] += sum_t attn[b,t,p] * dCTX[t,b,:]  (context-vector backward, deferred out of the BPTT loop). */
 int caphn_attn_df(const float* attn, const float* dCTX, float* df, int B, int T, int P, int F, void* stream);
 

@@ -186,3 +186,29 @@ def test_attention_fused_loss_matches_unfused(B, T, Fo, E, H, V):
     assert torch.equal(res[0][1], res[1][1])
     for k, v in res[0][2].items():
         assert grad_close(res[1][2][k], v, TOL_GRAD), k
+
+
+@pytest.mark.parametrize("B,T,Fo,E,H,P", [(5, 3, 16, 12, 20, 49), (40, 6, 200, 200, 200, 49), (33, 4, 64, 32, 100, 7)])
+def test_attgru_cluster_forward_matches_streaming_kernel(B, T, Fo, E, H, P):
+    """Weights-resident cluster forward (warp-MMA bf16x3 fragments in registers, DSMEM exchanges) == streaming kernel."""
+    from hypernet_image_captioning_b200 import ops
+    assert ops.attgru_cluster_ok(H, Fo, P, force=True)
+    g = torch.Generator().manual_seed(B + T + H)
+    r = lambda *s: torch.randn(*s, generator=g).cuda()
+    Kp, f, GIw = r(B, P, H) * 0.5, r(B, P, Fo) * 0.5, r(T * B, 3 * H) * 0.5
+    Ua, W_ih, W_hh = r(H, H) / H ** 0.5, r(3 * H, E + Fo) / (E + Fo) ** 0.5, r(3 * H, H) / H ** 0.5
+    bu, va, bv, bhh, h0 = r(H) * 0.1, r(H) * 0.3, r(1), r(3 * H) * 0.1, r(B, H) * 0.5
+    outs = []
+    for cluster in (False, True):
+        Hall = torch.empty(T + 1, B, H).cuda(); Hall[0] = h0
+        Hbm, attn = torch.empty(B, T, H).cuda(), torch.empty(B, T, P).cuda()
+        XC, saved = torch.zeros(T * B, E + Fo).cuda(), torch.empty(5, T, B, H).cuda()
+        if cluster:
+            ops.attgru_cluster_fwd(Kp, f, GIw, Ua, bu, va, bv, W_ih, W_hh, bhh, Hall, Hbm, attn, XC, E, saved, 0, T)
+        else:
+            lw = ops.AttGruWeights(W_ih, W_hh, Ua, E)
+            ops.attgru_seq_fwd(Kp, f, GIw, lw, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, saved, 0, T)
+        torch.cuda.synchronize()
+        outs.append((Hall, Hbm, attn, XC, saved))
+    for name, x, y in zip(("Hall", "Hbm", "attn", "XC", "saved"), outs[1], outs[0]):
+        assert rel_err(x, y) < 3e-5, name
