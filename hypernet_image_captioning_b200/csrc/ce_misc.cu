@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const float* __restr
     }
 }
 
-// out[0] = sum(row_loss) / max(sum(row_valid), 1)   out[1] = sum(row_valid)        (single CTA; deterministic)
+// out[0] = sum(row_loss) / sum(row_valid)   out[1] = sum(row_valid)        (single CTA; deterministic)
 __global__ void __launch_bounds__(1024) ce_finish_kernel(const float* __restrict__ row_loss,
                                                          const float* __restrict__ row_valid, long M,
                                                          float* __restrict__ out) {
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(1024) ce_finish_kernel(const float* __restrict
     for (long i = threadIdx.x; i < M; i += 1024) { a += row_loss[i]; c += row_valid[i]; }
     a = block_reduce_sum(a, sh);
     c = block_reduce_sum(c, sh);
-    if (threadIdx.x == 0) { out[0] = a / fmaxf(c, 1.f); out[1] = c; }
+    if (threadIdx.x == 0) { out[0] = a / c; out[1] = c; }   // 0/0 = NaN when every row is ignored, like F.cross_entropy
 }
 
 // dX[m,v] = (exp(x - lse[m]) - [v == tgt[m]]) * gscale[0] / count   for valid rows, 0 otherwise.
