@@ -312,6 +312,14 @@ def run_ours(args):
             decode()
         ms_dec = timed(decode, args.steps)
         extras["greedy_decode_captions_per_s"] = B * world * args.steps / (ms_dec * 1e-3)
+        # bf16 mode (BASELINE configs[1] "fp32 and bf16"): hypernet weights + gradients in bf16, plain-bf16 tensor-core
+        # products, fp32 accumulation / recurrent state; tolerance vs the fp32 oracle stated in tests/test_gpu_bf16.py
+        model.set_precision("bf16")
+        for _ in range(3):
+            step(pooled_d, caps_d, h0_d)
+        ms_bf = timed(lambda: step(pooled_d, caps_d, h0_d), args.steps)
+        extras["bf16_mode_train_captions_per_s"] = B * world * args.steps / (ms_bf * 1e-3)
+        ops.set_precision("fp32")
         del model
         torch.cuda.empty_cache()
         extras.update(attention_extras(args, dev, world, timed))

@@ -21,6 +21,8 @@ F = c_float
 SIGNATURES = {
     "caphn_rows_linear_fwd": [P, P, P, L, P, L, I, L, L, I, F, P],
     "caphn_rows_linear_bwd": [P, P, L, P, L, P, L, P, P, P, P, L, I, L, L, I, F, P],
+    "caphn_rows_linear_fwd_bf16": [P, P, P, L, P, L, I, L, L, I, F, P],
+    "caphn_rows_linear_bwd_bf16": [P, P, L, P, L, P, L, P, P, P, P, L, I, L, L, I, F, P],
     "caphn_gemm_f32": [P, L, I, P, L, I, P, L, P, I, I, I, I, I, I, P],
     "caphn_split_bf16": [P, L, L, I, P, P, L, P],
     "caphn_split_bf16_t": [P, L, I, I, P, P, L, P],

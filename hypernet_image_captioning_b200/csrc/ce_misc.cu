@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) ce_bwd_split_kernel(
             pl.x = (uint32_t)__bfloat16_as_ushort(lw[0]) | ((uint32_t)__bfloat16_as_ushort(lw[1]) << 16);
             pl.y = (uint32_t)__bfloat16_as_ushort(lw[2]) | ((uint32_t)__bfloat16_as_ushort(lw[3]) << 16);
             *reinterpret_cast<uint2*>(hi + (long)m * Vp + v0 + c4) = ph;
-            *reinterpret_cast<uint2*>(lo + (long)m * Vp + v0 + c4) = pl;
+            if (lo) *reinterpret_cast<uint2*>(lo + (long)m * Vp + v0 + c4) = pl;
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) { tile[r][c4 + c] = d[c]; cs[c] += d[c]; }
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) ce_bwd_split_kernel(
                 wl[k] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
             }
             *reinterpret_cast<uint4*>(hiT + (long)v * Mp + m0 + r8) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-            *reinterpret_cast<uint4*>(loT + (long)v * Mp + m0 + r8) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+            if (loT) *reinterpret_cast<uint4*>(loT + (long)v * Mp + m0 + r8) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
         }
     }
 }
@@ -366,6 +366,7 @@ int caphn_ce_bwd(const float* X, long ld, const long long* tgt, long M, int V, i
 
 // Cross-entropy backward written straight into the bf16x3 operand formats of caphn_gemm_tc (see kernel comment):
 // hi/lo [M, Vp], hiT/loT [V, Mp] (Vp, Mp multiples of 64, >= V, M), dbias [V] accumulated (zero-initialised by caller).
+// lo / loT may be NULL (plain bf16 mode).
 int caphn_ce_bwd_split(const float* X, long ld, const long long* tgt, long M, int V, int has_ignore, long long ignore,
                        const float* lse, const float* gscale, const float* lossbuf, void* hi, void* lo, long Vp,
                        void* hiT, void* loT, long Mp, float* dbias, void* stream) {

@@ -59,6 +59,10 @@ class HyperNetThetaFn(Function):
         for j in range(len(grads)):
             if not need[1 + j]:
                 grads[j] = None
+            elif grads[j] is not None and grads[j].dtype != params[j].dtype:
+                grads[j] = grads[j].to(params[j].dtype)   # bf16 mode: bias gradients (weights are already bf16)
+        if dx is not None and dx.dtype != x.dtype:
+            dx = dx.to(x.dtype)
         return (dx if need[0] else None, *grads)
 
 

@@ -63,6 +63,16 @@ class _HyperNetMixin:
             theta = allreduce_grad(theta, self.dp_group)
         return theta
 
+    def set_precision(self, mode: str):
+        """"fp32" (default; parity mode) or "bf16": the hypernet base/head parameters -- and therefore their gradients --
+        are stored in bf16 (half the HBM traffic of the dominant kernels) and the decoder's tensor-core products use
+        plain bf16 operands; activations, theta, the recurrent state and every accumulation stay fp32."""
+        dt = {"fp32": torch.float32, "bf16": torch.bfloat16}[mode]
+        self.hn_base.to(dt)
+        self.hn_heads.to(dt)
+        ops.set_precision(mode)
+        return self
+
     def forward_grouped(self, X: torch.Tensor):
         """Grouped generalisation (BASELINE.json north_star "per-style grouped"): ``X`` = [G, he] style/domain vectors.
         One pass over the hypernet weights generates all G weight sets (the reference would stream them G times, one

@@ -41,17 +41,20 @@ def _aligned16(t: torch.Tensor) -> torch.Tensor:
 def rows_linear_fwd(W, bias, A, act=ACT_NONE, out=None, slope=LEAKY_SLOPE):
     """Y[g,n] = act(A[g,:] . W[n,:] + bias[n]).  A [G,K] (row stride may exceed K), W [N,K] contiguous.
     ``out`` may be a column slice of a wider matrix (e.g. theta[:, a:b])."""
-    _chk(W), _chk(A)
+    _chk(W, W.dtype if W.dtype == torch.bfloat16 else torch.float32), _chk(A)
     W = _aligned16(W)
     N, K = W.shape
     G = A.shape[0]
     assert A.shape[1] == K and A.stride(1) == 1
+    if bias is not None and bias.dtype != torch.float32:
+        bias = bias.float()
     if out is None:
         out = torch.empty(G, N, device=W.device, dtype=torch.float32)
     assert out.shape == (G, N) and out.stride(1) == 1
+    fn = "caphn_rows_linear_fwd_bf16" if W.dtype == torch.bfloat16 else "caphn_rows_linear_fwd"
     for g0 in range(0, G, 8):
         g1 = min(G, g0 + 8)
-        _cabi.call("caphn_rows_linear_fwd", W.data_ptr(), _p(bias), A[g0:g1].data_ptr(), A.stride(0),
+        _cabi.call(fn, W.data_ptr(), _p(bias), A[g0:g1].data_ptr(), A.stride(0),
                    out[g0:g1].data_ptr(), out.stride(0), g1 - g0, N, K, act, slope, _stream())
     return out
 
@@ -59,7 +62,7 @@ def rows_linear_fwd(W, bias, A, act=ACT_NONE, out=None, slope=LEAKY_SLOPE):
 def rows_linear_bwd(W, A, Y, dY, act=ACT_NONE, need_dW=True, need_dA=True, dA=None, slope=LEAKY_SLOPE):
     """Backward of rows_linear_fwd.  Returns (dW [N,K] or None, dbias [N], dA [G,K] or None).
     When ``dA`` is given the input gradient is accumulated into it (atomics)."""
-    _chk(W), _chk(A), _chk(dY)
+    _chk(W, W.dtype if W.dtype == torch.bfloat16 else torch.float32), _chk(A), _chk(dY)
     W = _aligned16(W)
     N, K = W.shape
     G = A.shape[0]
@@ -69,12 +72,12 @@ def rows_linear_bwd(W, A, Y, dY, act=ACT_NONE, need_dW=True, need_dA=True, dA=No
     dev = W.device
     dP = torch.empty(G, N, device=dev, dtype=torch.float32)
     dbias = torch.empty(N, device=dev, dtype=torch.float32)
-    dW = torch.empty(N, K, device=dev, dtype=torch.float32) if (need_dW or need_dA) else None
+    dW = torch.empty(N, K, device=dev, dtype=W.dtype) if (need_dW or need_dA) else None   # bf16 weights -> bf16 gradient
     if need_dA and dA is None:
         dA = torch.zeros(G, K, device=dev, dtype=torch.float32)
     if not need_dA:
         dA = None
-    _cabi.call("caphn_rows_linear_bwd", W.data_ptr(), A.data_ptr(), A.stride(0), _p(Y), Y.stride(0) if Y is not None else 0,
+    _cabi.call("caphn_rows_linear_bwd_bf16" if W.dtype == torch.bfloat16 else "caphn_rows_linear_bwd", W.data_ptr(), A.data_ptr(), A.stride(0), _p(Y), Y.stride(0) if Y is not None else 0,
                dY.data_ptr(), dY.stride(0), dP.data_ptr(), _p(dW), dbias.data_ptr(), _p(dA),
                dA.stride(0) if dA is not None else 0, G, N, K, act, slope, _stream())
     return (dW if need_dW else None), dbias, dA
@@ -103,6 +106,15 @@ def _auto_splitk(M, N, K):
 
 
 TC_ENABLED = True   # route the large dense contractions to the tcgen05 kernel (bf16x3, fp32-class accuracy)
+TC_SPLIT = True     # True: bf16x3 (hi/lo split, fp32-class accuracy); False: single bf16 MMA per k-slice ("bf16 mode")
+
+
+def set_precision(mode: str):
+    """"fp32": tensor-core products use the bf16x3 split (1e-5-class).  "bf16": plain bf16 operands, fp32 accumulate."""
+    global TC_SPLIT
+    if mode not in ("fp32", "bf16"):
+        raise ValueError(mode)
+    TC_SPLIT = mode == "fp32"
 TC_MIN_WORK = 1 << 24
 
 
@@ -301,14 +313,14 @@ def ce_bwd_split(logits2d, targets, ignore_index, lse, lossbuf, gscale):
     dev = logits2d.device
     Vp, Mp = round64(V), round64(M)
     hi = torch.empty(M, Vp, device=dev, dtype=torch.bfloat16)
-    lo = torch.empty(M, Vp, device=dev, dtype=torch.bfloat16)
+    lo = torch.empty(M, Vp, device=dev, dtype=torch.bfloat16) if TC_SPLIT else None
     hiT = torch.empty(V, Mp, device=dev, dtype=torch.bfloat16)
-    loT = torch.empty(V, Mp, device=dev, dtype=torch.bfloat16)
+    loT = torch.empty(V, Mp, device=dev, dtype=torch.bfloat16) if TC_SPLIT else None
     dbias = torch.zeros(V, device=dev, dtype=torch.float32)
     has = ignore_index is not None
     _cabi.call("caphn_ce_bwd_split", logits2d.data_ptr(), logits2d.stride(0), targets.data_ptr(), M, V, int(has),
                int(ignore_index) if has else 0, lse.data_ptr(), gscale.data_ptr(), lossbuf.data_ptr(), hi.data_ptr(),
-               lo.data_ptr(), Vp, hiT.data_ptr(), loT.data_ptr(), Mp, dbias.data_ptr(), _stream())
+               _p(lo), Vp, hiT.data_ptr(), _p(loT), Mp, dbias.data_ptr(), _stream())
     return SplitOperand(hi, lo, M, Vp), SplitOperand(hiT, loT, V, Mp), dbias
 
 
@@ -483,7 +495,8 @@ class SplitOperand:
         self.hi, self.lo, self.rows, self.Kp = hi, lo, rows, Kp
 
 
-def split_bf16(src, want_lo=True):
+def split_bf16(src, want_lo=None):
+    want_lo = TC_SPLIT if want_lo is None else want_lo
     _chk(src)
     assert src.dim() == 2 and src.stride(1) == 1
     R, C = src.shape
@@ -494,8 +507,9 @@ def split_bf16(src, want_lo=True):
     return SplitOperand(hi, lo, R, Kp)
 
 
-def split_bf16_t(src, want_lo=True):
+def split_bf16_t(src, want_lo=None):
     """src [R, C] -> operand for src^T: hi, lo [C, Rp]."""
+    want_lo = TC_SPLIT if want_lo is None else want_lo
     _chk(src)
     assert src.dim() == 2 and src.stride(1) == 1
     R, C = src.shape

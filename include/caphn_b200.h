@@ -32,6 +32,14 @@ int caphn_rows_linear_bwd(const float* W, const float* A, long lda, const float*
                           long lddy, float* dP, float* dW, float* dbias, float* dA, long ldda, int G, long N, long K,
                           int act, float slope, void* stream);
 
+/* bf16-weight variants (bf16 mode): W, dW are bf16 [N,K]; bias, A, Y, dY, dP, dbias, dA stay fp32; fp32 accumulation;
+ * dW rounded to bf16 on store.  Half the HBM bytes. */
+int caphn_rows_linear_fwd_bf16(const void* W, const float* bias, const float* A, long lda, float* Y, long ldy, int G,
+                               long N, long K, int act, float slope, void* stream);
+int caphn_rows_linear_bwd_bf16(const void* W, const float* A, long lda, const float* Y, long ldy, const float* dY,
+                               long lddy, float* dP, void* dW, float* dbias, float* dA, long ldda, int G, long N,
+                               long K, int act, float slope, void* stream);
+
 /* ---- dense fp32 GEMM (addmm behind nn.Linear / nn.GRUCell: models/decoderlstm.py:61,100,105; later.py:411,418,442) -- */
 
 /* C[m*ldc+n] = sum_k A(m,k) B(n,k) (+bias[n]) (ReLU).  A(m,k) = a_kmajor ? A[m*lda+k] : A[k*lda+m]; same for B.
