@@ -166,7 +166,7 @@ def run_ours(args):
     import torch.distributed as dist
     import hypernet_image_captioning_b200 as C
     from hypernet_image_captioning_b200 import _cabi, ops, parallel
-    from oracle import caption_hn_oracle as O  # synthetic-input generators + cpu_baseline leg only
+    from hypernet_image_captioning_b200.synth import synth_captions   # (the oracle is used by the cpu_baseline leg only)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -190,7 +190,7 @@ def run_ours(args):
 
     g = torch.Generator().manual_seed(1234 + rank)
     pooled_h = torch.relu(torch.randn(B, c["D"], generator=g)).pin_memory()
-    caps_h = O.synth_captions(B, T, c["V"], g).pin_memory()
+    caps_h = synth_captions(B, T, c["V"], g).pin_memory()
     pooled_d, caps_d = pooled_h.to(dev), caps_h.to(dev)
     h0_d = torch.rand(B, c["H"], generator=g).to(dev)
     loss_h = torch.empty(1, pin_memory=True)
@@ -352,7 +352,7 @@ def attention_extras(args, dev, world, timed):
     B=512/GPU, T=20: teacher-forced fwd+bwd (flow, ignore_index=<pad>) and greedy decode (sample_prob=1.0, test_hn.py)."""
     import numpy as np
     import hypernet_image_captioning_b200 as C
-    from oracle import caption_hn_oracle as O
+    from hypernet_image_captioning_b200.synth import synth_captions
     B, T, V = args.batch, CFG["T"], CFG["V"]
     torch.manual_seed(0)
     with torch.device(dev):
@@ -360,7 +360,7 @@ def attention_extras(args, dev, world, timed):
     model.dp_enabled = world > 1
     g = torch.Generator().manual_seed(4321)
     feats = torch.randn(B, 49, 2048, generator=g).to(dev)
-    caps = O.synth_captions(B, T, V, g).to(dev)
+    caps = synth_captions(B, T, V, g).to(dev)
 
     def train():
         model.zero_grad(set_to_none=True)

@@ -28,6 +28,18 @@ template <> struct WT<float> {
         o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
     }
     static __device__ __forceinline__ float load1(const float* p) { return ldg_stream1(p); }
+    // raw 128-bit vector in registers (unpacked lazily so that more loads can be kept in flight)
+    static __device__ __forceinline__ uint4 load_raw(const float* p) {
+        const float4 t = ldg_stream4(p);
+        return make_uint4(__float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z), __float_as_uint(t.w));
+    }
+    static __device__ __forceinline__ void put_raw(uint4& r, int c, float v) {
+        const uint32_t b = __float_as_uint(v);
+        if (c == 0) r.x = b; else if (c == 1) r.y = b; else if (c == 2) r.z = b; else r.w = b;
+    }
+    static __device__ __forceinline__ void unpack(const uint4& t, float* o) {
+        o[0] = __uint_as_float(t.x); o[1] = __uint_as_float(t.y); o[2] = __uint_as_float(t.z); o[3] = __uint_as_float(t.w);
+    }
     static __device__ __forceinline__ void load_rw(const float* p, float* o) {
         const float4 t = *reinterpret_cast<const float4*>(p);
         o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
@@ -56,6 +68,17 @@ template <> struct WT<__nv_bfloat16> {
         unsigned short u;
         asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(u) : "l"(p));
         return __uint_as_float((uint32_t)u << 16);
+    }
+    static __device__ __forceinline__ uint4 load_raw(const __nv_bfloat16* p) {
+        uint4 t;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+        return t;
+    }
+    static __device__ __forceinline__ void put_raw(uint4& r, int c, float v) {   // v is exactly representable in bf16
+        const uint32_t b = __float_as_uint(v) >> 16;
+        uint32_t& w = (c >> 1) == 0 ? r.x : ((c >> 1) == 1 ? r.y : ((c >> 1) == 2 ? r.z : r.w));
+        w = (c & 1) ? ((w & 0x0000ffffu) | (b << 16)) : ((w & 0xffff0000u) | b);
     }
     static __device__ __forceinline__ void load_rw(const __nv_bfloat16* p, float* o) {
         unpack(*reinterpret_cast<const uint4*>(p), o);
@@ -105,36 +128,44 @@ __global__ void __launch_bounds__(ROWS_FWD_THREADS) rows_fwd_kernel(
 #pragma unroll
         for (int g = 0; g < GC; ++g) acc[g] = 0.f;
 
-        for (int qb = 0; qb < NQ; qb += 128) {
-            float w[4][V];
+        // software pipeline: the raw vectors of the next batch are in flight while the current batch is consumed
+        auto fetch = [&](int qb, uint4* raw) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int q = qb + u * 32 + lane;
-#pragma unroll
-                for (int c = 0; c < V; ++c) w[u][c] = 0.f;
+                raw[u] = make_uint4(0u, 0u, 0u, 0u);
                 if (q < NQ) {
                     const int k0 = V * q - m;
                     if (k0 >= 0 && k0 + V - 1 < K) {
-                        WT<T>::load(wq + (long)V * q, w[u]);
+                        raw[u] = WT<T>::load_raw(wq + (long)V * q);
                     } else {
 #pragma unroll
                         for (int c = 0; c < V; ++c)
-                            if (k0 + c >= 0 && k0 + c < K) w[u][c] = WT<T>::load1(W + rowoff + k0 + c);
+                            if (k0 + c >= 0 && k0 + c < K) WT<T>::put_raw(raw[u], c, WT<T>::load1(W + rowoff + k0 + c));
                     }
                 }
             }
+        };
+        uint4 cur[4], nxt[4];
+        fetch(0, cur);
+        for (int qb = 0; qb < NQ; qb += 128) {
+            if (qb + 128 < NQ) fetch(qb + 128, nxt);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int q = qb + u * 32 + lane;
                 if (q < NQ) {
+                    float w[V];
+                    WT<T>::unpack(cur[u], w);
 #pragma unroll
                     for (int g = 0; g < GC; ++g) {
                         const float* ag = As + g * V * KQ + q;
 #pragma unroll
-                        for (int c = 0; c < V; ++c) acc[g] = fmaf(w[u][c], ag[aoff[c]], acc[g]);
+                        for (int c = 0; c < V; ++c) acc[g] = fmaf(w[c], ag[aoff[c]], acc[g]);
                     }
                 }
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
         }
 #pragma unroll
         for (int g = 0; g < GC; ++g) acc[g] = warp_sum(acc[g]);
@@ -183,7 +214,10 @@ __global__ void __launch_bounds__(ROWS_BWD_THREADS) rows_bwd_kernel(
     constexpr int V = WT<T>::V;
     __shared__ float red[SMEM_REDUCE ? GC * QPL * 32 * V : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ncls = (K % V) ? V : 1;
+    // rows n and n' have the same misalignment m = (n*K) mod V iff n == n' (mod V / gcd(K mod V, V))
+    int gdiv = K % V;
+    { int y = V; while (y) { const int t = gdiv % y; gdiv = y; y = t; } }     // gcd(K mod V, V)  (gcd(0, V) = V)
+    const int ncls = V / gdiv;
     const long warps_total = (long)gridDim.x * (ROWS_BWD_THREADS / 32);
     long item = SMEM_REDUCE ? 0 : (long)blockIdx.x * (ROWS_BWD_THREADS / 32) + warp;
     const long item_end = SMEM_REDUCE ? 1 : items;
@@ -212,22 +246,21 @@ __global__ void __launch_bounds__(ROWS_BWD_THREADS) rows_bwd_kernel(
                     }
             }
             for (long nb = row0 + cls; nb < row1; nb += (long)RU * ncls) {
-                float wv[RU][QPL][V];
+                uint4 raw[RU][QPL];   // raw 128-bit vectors: RU*QPL loads in flight per lane, unpacked when consumed
 #pragma unroll
                 for (int r = 0; r < RU; ++r) {
                     const long n = nb + (long)r * ncls;
 #pragma unroll
                     for (int u = 0; u < QPL; ++u) {
-#pragma unroll
-                        for (int c = 0; c < V; ++c) wv[r][u][c] = 0.f;
+                        raw[r][u] = make_uint4(0u, 0u, 0u, 0u);
                         if (n < row1) {
                             const T* p = W + n * (long)K + k0[u];
                             if (full[u]) {
-                                WT<T>::load(p, wv[r][u]);
+                                raw[r][u] = WT<T>::load_raw(p);
                             } else {
 #pragma unroll
                                 for (int c = 0; c < V; ++c)
-                                    if (k0[u] + c >= 0 && k0[u] + c < K) wv[r][u][c] = WT<T>::load1(p + c);
+                                    if (k0[u] + c >= 0 && k0[u] + c < K) WT<T>::put_raw(raw[r][u], c, WT<T>::load1(p + c));
                             }
                         }
                     }
@@ -241,14 +274,15 @@ __global__ void __launch_bounds__(ROWS_BWD_THREADS) rows_bwd_kernel(
                         for (int g = 0; g < GC; ++g) dp[g] = __ldg(dP + (long)g * ldp + n);
 #pragma unroll
                         for (int u = 0; u < QPL; ++u) {
-                            float dw[V];
+                            float dw[V], wv[V];
+                            WT<T>::unpack(raw[r][u], wv);
 #pragma unroll
                             for (int c = 0; c < V; ++c) dw[c] = 0.f;
 #pragma unroll
                             for (int g = 0; g < GC; ++g)
 #pragma unroll
                                 for (int c = 0; c < V; ++c) {
-                                    acc[g][u][c] = fmaf(dp[g], wv[r][u][c], acc[g][u][c]);
+                                    acc[g][u][c] = fmaf(dp[g], wv[c], acc[g][u][c]);
                                     dw[c] = fmaf(dp[g], a[g][u][c], dw[c]);
                                 }
                             T* o = dW + n * (long)K + k0[u];
@@ -332,8 +366,12 @@ static int launch_rows_bwd(const T* W, const float* A, long lda, const float* dP
     const int S = ((K + 2 * (V - 1)) / V + 32 * QPL - 1) / (32 * QPL);
     if (S >= 8 || (long)N * K < (1L << 22)) {
         // many strips (or tiny, latency-bound matrices): warp-granular work items
-        int RB = 128;
-        while (RB > 16 && ((N + RB - 1) / RB) * S < 8L * kNumSMs * WPB) RB >>= 1;
+        // >= 32 rows per misalignment class per work item keeps the dA atomics <= ~10 % of the memory instructions
+        int gdiv = K % V;
+        { int y = V; while (y) { const int t = gdiv % y; gdiv = y; y = t; } }
+        const int ncls = V / gdiv;
+        int RB = 128 * (ncls > 4 ? ncls / 4 : 1);
+        while (RB > 32 * ncls && RB > 16 && ((N + RB - 1) / RB) * S < 8L * kNumSMs * WPB) RB >>= 1;
         const long items = ((N + RB - 1) / RB) * S;
         long blocks = (items + WPB - 1) / WPB;
         const long cap = (long)kNumSMs * 64;
@@ -407,8 +445,8 @@ static int rows_linear_bwd_t(const T* W, const float* A, long lda, const float* 
         } else {
             switch (gc) {
                 case 4: rc = launch_rows_bwd<T, 4, 1, 2>(W, Ag, lda, dPg, N, dW, dAg, ldda, N, (int)K, acc, nda, st); break;
-                case 2: rc = launch_rows_bwd<T, 2, 1, 2>(W, Ag, lda, dPg, N, dW, dAg, ldda, N, (int)K, acc, nda, st); break;
-                default: rc = launch_rows_bwd<T, 1, 2, 2>(W, Ag, lda, dPg, N, dW, dAg, ldda, N, (int)K, acc, nda, st); break;
+                case 2: rc = launch_rows_bwd<T, 2, 1, 4>(W, Ag, lda, dPg, N, dW, dAg, ldda, N, (int)K, acc, nda, st); break;
+                default: rc = launch_rows_bwd<T, 1, 2, 4>(W, Ag, lda, dPg, N, dW, dAg, ldda, N, (int)K, acc, nda, st); break;
             }
         }
         if (rc) return rc;

@@ -8,7 +8,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import hypernet_image_captioning_b200 as C  # noqa: E402
-from oracle import caption_hn_oracle as O  # noqa: E402  (synthetic inputs only)
+from hypernet_image_captioning_b200.synth import synth_captions  # noqa: E402
 
 
 def main():
@@ -25,7 +25,7 @@ def main():
     B, T, V = a.batch, a.T, 9684
     g = torch.Generator().manual_seed(1)
     torch.manual_seed(0)
-    caps = O.synth_captions(B, T, V, g).to(dev)
+    caps = synth_captions(B, T, V, g).to(dev)
     if a.variant == "attention":
         with torch.device(dev):
             m = C.HyperNetAttention(200, 200, 200, V, None)
