@@ -176,11 +176,19 @@ class DecoderGRU(nn.Module):
 
     @torch.no_grad()
     def infer(self, features, max_len=50, h0=None):
-        """Greedy decode, reference later.py:459-490: argmax feedback, first cell only, returns softmax probs."""
+        """Greedy decode, reference later.py:459-490: argmax feedback, first cell only, returns softmax probs.
+        The whole loop (~5 launches per step) is captured into a CUDA graph per (batch, max_len) and replayed."""
+        from . import graphs
         W_ih, W_hh, b_ih, b_hh = [t.detach().contiguous() for t in self._cells()[0]]
-        B, H = features.size(0), self.hidden_size
         if h0 is None:
             h0 = self._h0(features)
+        key = ("DecoderGRU.infer", id(self), tuple(features.shape), int(max_len), features.device.index,
+               self.embed.weight.data_ptr(), self.fc_out.weight.data_ptr(), self.fc_out.bias.data_ptr())
+        return graphs.graphed_call(key, lambda f, h, wi, wh, bi, bh: self._infer_loop(f, h, wi, wh, bi, bh, max_len),
+                                   [features.contiguous().float(), h0.contiguous().float(), W_ih, W_hh, b_ih, b_hh])[0]
+
+    def _infer_loop(self, features, h0, W_ih, W_hh, b_ih, b_hh, max_len):
+        B, H = features.size(0), self.hidden_size
         emb, fc_w, fc_b = self.embed.weight.detach(), self.fc_out.weight.detach(), self.fc_out.bias.detach()
         WhhT = ops.transpose_pad(W_hh, ops.round4(3 * H))
         outputs = torch.empty(B, max_len, self.vocab_size, device=features.device, dtype=torch.float32)

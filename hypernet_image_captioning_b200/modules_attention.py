@@ -242,6 +242,21 @@ class AttentionGru(nn.Module):
         if groups is not None:
             return _run_grouped(lambda g, f, c: self._forward_one(f, c, tuple(use), self._gru_weights(g)), groups,
                                 [features, captions], len(self._generated_groups))
+        if any(use) and not torch.is_grad_enabled():
+            # decode (test_hn.py path, cc_train_hypernet.py:230): ~10 launches per step -> captured into a CUDA graph
+            from . import graphs
+            ps = [p.detach() for p in self._params(self._gru_weights())]
+            gen = [ps[5].contiguous(), ps[6].contiguous(), ps[7].contiguous(), ps[8].contiguous()]   # generated weights
+            key = ("AttentionGru.decode", id(self), tuple(features.shape), tuple(captions.shape), tuple(use),
+                   features.device.index) + tuple(p.data_ptr() for i, p in enumerate(ps) if i not in (5, 6, 7, 8))
+
+            def run(f, c, wi, wh, bi, bh):
+                q = list(ps)
+                q[5], q[6], q[7], q[8] = wi, wh, bi, bh
+                return AttentionGruFn.apply(f, c, tuple(use), *q)
+
+            out = graphs.graphed_call(key, run, [features.contiguous().float(), captions.contiguous()] + gen)
+            return out[0], out[1]
         return self._forward_one(features, captions, tuple(use), self._gru_weights())
 
     def _params(self, gru_w):
