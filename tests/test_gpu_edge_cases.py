@@ -109,3 +109,47 @@ def test_hypernet_cc_embedding_front_ends():
         cap = m.forward(style.cuda())
         got = torch.cat([getattr(cap.gru, k).detach().flatten() for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")])
         assert rel_err(got, theta_ref) < 1e-5
+
+
+def test_sweep_dims_attention_hidden_256():
+    """BASELINE config 5 direction: larger hidden size (H = 256, E = F = 200): exercises wider recurrence tiles."""
+    import hypernet_image_captioning_b200 as C
+    B, T, Fo, E, H, V = 24, 16, 200, 200, 256, 500
+    p = O.init_params_attention(2048, Fo, E, H, V, E, seed=31)
+    g = torch.Generator().manual_seed(2)
+    feats = torch.randn(B, 49, 2048, generator=g)
+    caps = O.synth_captions(B, T, V, g)
+    style = torch.randn(1, E, generator=g)
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    lr, ar, _, _ = O.path_attention(pl, style, feats, caps, 0.0, np.random.RandomState(0))
+    O.caption_loss(lr, caps, 0).backward()
+    m = _load(C.HyperNetAttention(Fo, E, H, V, None), p)
+    loss, logits, att = m.forward(style.cuda()).forward_loss(feats.cuda(), caps.cuda(), 0.0, ignore_index=0)
+    loss.backward()
+    assert rel_err(logits, lr) < 1e-4 and rel_err(att, ar) < 1e-4
+    for k in ("hn_heads.0.2.weight", "hn_heads.1.2.weight", "captioner.attention.U_a.weight", "captioner.fc.weight"):
+        assert grad_close(dict(m.named_parameters())[k].grad, pl[k].grad, 1e-3), k
+
+
+@pytest.mark.parametrize("H,E", [(96, 32), (200, 16), (33, 24)])
+def test_sweep_dims_pooled_cluster_sizes(H, E):
+    """Hidden sizes that make the weights-resident GRU kernel pick cluster sizes 2 / 4 (and odd strides)."""
+    import hypernet_image_captioning_b200 as C
+    from hypernet_image_captioning_b200 import ops
+    B, T, V = 40, 24, 300
+    assert ops.gru_cluster_size(H) in (2, 4, 8)
+    p = O.init_params_pooled(2048, E, H, V, seed=41)
+    g = torch.Generator().manual_seed(3)
+    pooled = torch.relu(torch.randn(B, 2048, generator=g))
+    caps = O.synth_captions(B, T, V, g)
+    style, h0 = torch.randn(1, E, generator=g), torch.rand(B, H, generator=g)
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    lr, _, _ = O.path_pooled(pl, style, pooled, caps, h0)
+    O.caption_loss(lr, caps, None).backward()
+    m = _load(C.HyperNetPooled(E, H, V, None), p)
+    cap = m.forward(style.cuda())
+    loss, logits = cap.forward_loss(m.image_encoder(pooled.cuda()), caps.cuda(), h0=h0.cuda())
+    loss.backward()
+    assert rel_err(logits, lr) < 1e-4
+    for k in ("hn_heads.1.2.weight", "captioner.embed.weight", "captioner.fc_out.weight", "image_encoder.fc.weight"):
+        assert grad_close(dict(m.named_parameters())[k].grad, pl[k].grad, 1e-3), k
