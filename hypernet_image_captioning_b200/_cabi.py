@@ -27,6 +27,7 @@ SIGNATURES = {
     "caphn_split_bf16": [P, L, L, I, P, P, L, P],
     "caphn_split_bf16_t": [P, L, I, I, P, P, L, P],
     "caphn_gemm_tc": [P, P, P, P, L, P, L, P, I, I, I, I, P],
+    "caphn_gemm_tc_ex": [P, P, L, I, P, P, L, I, L, P, L, P, I, I, I, I, P],
     "caphn_transpose_pad": [P, L, P, L, I, I, P],
     "caphn_copy_pad": [P, L, P, L, L, I, P],
     "caphn_gru_seq_fwd": [P, P, I, P, P, P, P, P, P, I, I, I, I, P],

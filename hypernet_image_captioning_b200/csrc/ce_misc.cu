@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) ce_bwd_split_kernel(
         const int item = tid + it * 256;
         const int c = item >> 3, r8 = (item & 7) * 8;
         const int v = v0 + c;
-        if (v < V) {
+        if (hiT != nullptr && v < V) {
             uint32_t wh[4], wl[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -366,7 +366,7 @@ int caphn_ce_bwd(const float* X, long ld, const long long* tgt, long M, int V, i
 
 // Cross-entropy backward written straight into the bf16x3 operand formats of caphn_gemm_tc (see kernel comment):
 // hi/lo [M, Vp], hiT/loT [V, Mp] (Vp, Mp multiples of 64, >= V, M), dbias [V] accumulated (zero-initialised by caller).
-// lo / loT may be NULL (plain bf16 mode).
+// lo / loT may be NULL (plain bf16 mode); hiT == NULL skips the transposed copy (the GEMM reads d MN-major in place).
 int caphn_ce_bwd_split(const float* X, long ld, const long long* tgt, long M, int V, int has_ignore, long long ignore,
                        const float* lse, const float* gscale, const float* lossbuf, void* hi, void* lo, long Vp,
                        void* hiT, void* loT, long Mp, float* dbias, void* stream) {

@@ -64,10 +64,13 @@ __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.f
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): start address >> 4 in
 // bits [0,14), LBO = 1 (16-byte units; fixed for swizzled K-major), SBO = 1024 B (8 rows x 128 B) in bits [32,46),
 // version = 1 (Blackwell) in bits [46,48), layout type 2 (SWIZZLE_128B) in bits [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major = false) {
+    // K-major : canonical ((8,n),2):((8,SBO),1)        -> LBO = 1 (unused), SBO = 1024 B (8 rows x 128 B)
+    // MN-major: canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: 64 MN elements (128 B) contiguous, k rows 128 B
+    //           apart, groups of 8 k rows SBO = 1024 B apart, next 64 MN elements LBO = 8192 B apart (= one 64x64 TMA box)
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(mn_major ? (8192 >> 4) : 1) << 16;
     d |= (uint64_t)(1024 >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
@@ -75,8 +78,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 // Instruction descriptor for kind::f16: D = F32 (bits [4,6) = 1), A = B = BF16 (bits [7,10) = [10,13) = 1), both K-major,
 // N >> 3 in bits [17,23), M >> 4 in bits [24,29).
-__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, bool a_mn = false, bool b_mn = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -121,6 +125,7 @@ struct TcParams {
     int kb_per;      // k-blocks per split
     int stages, stage_bytes, b_bytes;
     uint32_t tmem_cols;
+    int a_mn, b_mn;  // operand stored MN-major ([K rows, MN cols] row-major) instead of K-major ([MN rows, K cols])
 };
 
 template <bool SPLIT>
@@ -173,11 +178,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     mbar_wait(empty + stage, phase ^ 1);
                     mbar_expect_tx(full + stage, (uint32_t)p.stage_bytes);
                     uint8_t* st = tiles + (size_t)stage * p.stage_bytes;
-                    tma_load_2d(st + offAh, &tmAh, full + stage, kb * BK, mb * BM);
-                    tma_load_2d(st + offBh, &tmBh, full + stage, kb * BK, nb * BN);
-                    if (SPLIT) {
-                        tma_load_2d(st + offAl, &tmAl, full + stage, kb * BK, mb * BM);
-                        tma_load_2d(st + offBl, &tmBl, full + stage, kb * BK, nb * BN);
+                    // K-major operand: one box [64 k x rows].  MN-major operand: boxes of [64 mn x 64 k] (8 KiB each).
+                    if (!p.a_mn) {
+                        tma_load_2d(st + offAh, &tmAh, full + stage, kb * BK, mb * BM);
+                        if (SPLIT) tma_load_2d(st + offAl, &tmAl, full + stage, kb * BK, mb * BM);
+                    } else {
+                        for (int h = 0; h < BM / 64; ++h) {
+                            tma_load_2d(st + offAh + h * 8192, &tmAh, full + stage, mb * BM + h * 64, kb * BK);
+                            if (SPLIT) tma_load_2d(st + offAl + h * 8192, &tmAl, full + stage, mb * BM + h * 64, kb * BK);
+                        }
+                    }
+                    if (!p.b_mn) {
+                        tma_load_2d(st + offBh, &tmBh, full + stage, kb * BK, nb * BN);
+                        if (SPLIT) tma_load_2d(st + offBl, &tmBl, full + stage, kb * BK, nb * BN);
+                    } else {
+                        for (int h = 0; h < BN / 64; ++h) {
+                            tma_load_2d(st + offBh + h * 8192, &tmBh, full + stage, nb * BN + h * 64, kb * BK);
+                            if (SPLIT) tma_load_2d(st + offBl + h * 8192, &tmBl, full + stage, nb * BN + h * 64, kb * BK);
+                        }
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
@@ -185,7 +203,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(BM, BN);
+            const uint32_t idesc = make_idesc(BM, BN, p.a_mn != 0, p.b_mn != 0);
+            // advance per 16-wide k step: 32 B inside the 128 B swizzle row (K-major) / two 8-row k groups (MN-major)
+            const uint64_t stepA = p.a_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
+            const uint64_t stepB = p.b_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -201,15 +222,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     mbar_wait(full + stage, phase);
                     tcgen05_fence_after();
                     const uint32_t sbase = smem_u32(tiles + (size_t)stage * p.stage_bytes);
-                    const uint64_t dAh = make_desc(sbase + offAh), dBh = make_desc(sbase + offBh);
-                    const uint64_t dAl = make_desc(sbase + offAl), dBl = make_desc(sbase + offBl);
+                    const uint64_t dAh = make_desc(sbase + offAh, p.a_mn), dBh = make_desc(sbase + offBh, p.b_mn);
+                    const uint64_t dAl = make_desc(sbase + offAl, p.a_mn), dBl = make_desc(sbase + offBl, p.b_mn);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t ko = (uint64_t)((k * 16 * 2) >> 4);  // +32 bytes along K inside the swizzle atom
-                        umma_f16(tmem_d, dAh + ko, dBh + ko, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        const uint64_t ka = stepA * k, kbo = stepB * k;
+                        umma_f16(tmem_d, dAh + ka, dBh + kbo, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                         if (SPLIT) {
-                            umma_f16(tmem_d, dAh + ko, dBl + ko, idesc, 1u);
-                            umma_f16(tmem_d, dAl + ko, dBh + ko, idesc, 1u);
+                            umma_f16(tmem_d, dAh + ka, dBl + kbo, idesc, 1u);
+                            umma_f16(tmem_d, dAl + ka, dBh + kbo, idesc, 1u);
                         }
                     }
                     umma_commit(empty + stage);   // frees this smem stage once the MMAs above have read it
@@ -377,11 +398,12 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D map over a row-major bf16 matrix [rows, Kp]: box = 64 (K) x box_rows, 128-byte swizzle, zero fill out of bounds.
-static int make_map(CUtensorMap* m, const void* base, long rows, long Kp, int box_rows) {
+static int make_map(CUtensorMap* m, const void* base, long rows, long Kp, int box_rows, long pitch = 0) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return CAPHN_EINVAL;
+    if (pitch == 0) pitch = Kp;
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)Kp * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
@@ -415,21 +437,27 @@ int caphn_split_bf16_t(const float* src, long lds, int R, int C, void* hi, void*
     CAPHN_RETURN_LAST();
 }
 
-// C[M,N] (fp32, row stride ldc) = A B^T (+bias[n]) (ReLU) on the tensor cores.  A = (Ahi, Alo) [M, Kp], B = (Bhi, Blo)
-// [N, Kp] in the split format above (16-byte aligned, Kp % 64 == 0).  Alo == Blo == NULL selects plain bf16.
-// splitk: 0 = choose automatically, 1 = none, > 1 = split the K loop and add partial tiles atomically (C is zeroed here).
-int caphn_gemm_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, long Kp, float* C, long ldc,
-                  const float* bias, int M, int N, int relu, int splitk, void* stream) {
-    if (M <= 0 || N <= 0 || Kp <= 0 || (Kp & 63) || ((Alo == nullptr) != (Blo == nullptr))) return CAPHN_EINVAL;
-    if (((uintptr_t)Ahi & 15) || ((uintptr_t)Bhi & 15) || ((uintptr_t)Alo & 15) || ((uintptr_t)Blo & 15))
+// C[M,N] (fp32, row stride ldc) = A B^T (+bias[n]) (ReLU) on the tensor cores, general operand layouts.
+//   K-major operand  (x_mn = 0): hi/lo [rows = M or N, K cols], row pitch x_ld elements (x_ld % 8 == 0), zero padded to x_ld
+//                                when K % 64 != 0 is irrelevant: TMA zero-fills out-of-range columns.
+//   MN-major operand (x_mn = 1): hi/lo [K rows, M or N cols], row pitch x_ld -- i.e. the operand of a TRANSPOSED product
+//                                (dW = dY^T X) read in place, no transposed copy.
+// Alo == Blo == NULL selects plain bf16.  splitk: 0 = automatic, 1 = none, > 1 = split K, partial tiles added atomically.
+int caphn_gemm_tc_ex(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
+                     int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, int relu, int splitk,
+                     void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0 || ((Alo == nullptr) != (Blo == nullptr))) return CAPHN_EINVAL;
+    if (((uintptr_t)Ahi & 15) || ((uintptr_t)Bhi & 15) || ((uintptr_t)Alo & 15) || ((uintptr_t)Blo & 15) ||
+        (a_ld & 7) || (b_ld & 7))
         return CAPHN_EINVAL;
     const bool split = Alo != nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     tc::TcParams p{};
-    p.C = C; p.ldc = ldc; p.bias = bias; p.M = M; p.N = N; p.relu = relu;
-    p.num_kb = (int)(Kp / tc::BK);
-    // N tile: one tile when N <= 256 (rounded up to 16), otherwise 128-wide tiles
-    p.BN = (N <= 256) ? ((N + 15) / 16) * 16 : 128;
+    p.C = C; p.ldc = ldc; p.bias = bias; p.M = M; p.N = N; p.relu = relu; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
+    p.num_kb = (int)((K + tc::BK - 1) / tc::BK);
+    // N tile: one tile when N <= 256 (rounded up to 16, or to 64 for an MN-major B whose boxes are 64 wide), else 128
+    if (N <= 256) p.BN = b_mn ? ((N + 63) / 64) * 64 : ((N + 15) / 16) * 16;
+    else p.BN = 128;
     const int tiles = ceil_div(M, tc::BM) * ceil_div(N, p.BN);
     if (splitk <= 0) {
         // smallest split whose unit count fills the 148 SMs to >= 90 % (or the best available), >= 4 k-blocks per unit
@@ -466,10 +494,21 @@ int caphn_gemm_tc(const void* Ahi, const void* Alo, const void* Bhi, const void*
     }
     CUtensorMap mAh, mAl, mBh, mBl;
     int rc;
-    if ((rc = tc::make_map(&mAh, Ahi, M, Kp, tc::BM))) return rc;
-    if ((rc = tc::make_map(&mBh, Bhi, N, Kp, p.BN))) return rc;
-    if ((rc = tc::make_map(&mAl, split ? Alo : Ahi, M, Kp, tc::BM))) return rc;
-    if ((rc = tc::make_map(&mBl, split ? Blo : Bhi, N, Kp, p.BN))) return rc;
+    // K-major: dims {K, rows}, box {64, rows-tile}.  MN-major: dims {MN, K}, box {64, 64}.
+    if (!a_mn) {
+        if ((rc = tc::make_map(&mAh, Ahi, M, K, tc::BM, a_ld))) return rc;
+        if ((rc = tc::make_map(&mAl, split ? Alo : Ahi, M, K, tc::BM, a_ld))) return rc;
+    } else {
+        if ((rc = tc::make_map(&mAh, Ahi, K, M, 64, a_ld))) return rc;
+        if ((rc = tc::make_map(&mAl, split ? Alo : Ahi, K, M, 64, a_ld))) return rc;
+    }
+    if (!b_mn) {
+        if ((rc = tc::make_map(&mBh, Bhi, N, K, p.BN, b_ld))) return rc;
+        if ((rc = tc::make_map(&mBl, split ? Blo : Bhi, N, K, p.BN, b_ld))) return rc;
+    } else {
+        if ((rc = tc::make_map(&mBh, Bhi, K, N, 64, b_ld))) return rc;
+        if ((rc = tc::make_map(&mBl, split ? Blo : Bhi, K, N, 64, b_ld))) return rc;
+    }
     const long units = (long)tiles * p.splitk;
     const int grid = units < kNumSMs ? (int)units : kNumSMs;
     if (split) {
@@ -480,6 +519,13 @@ int caphn_gemm_tc(const void* Ahi, const void* Alo, const void* Bhi, const void*
         tc::gemm_tc_kernel<false><<<grid, tc::THREADS_V2, smem, st>>>(mAh, mAl, mBh, mBl, p);
     }
     CAPHN_RETURN_LAST();
+}
+
+// Both operands K-major with the same padded pitch Kp (Kp % 64 == 0): the original entry point.
+int caphn_gemm_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, long Kp, float* C, long ldc,
+                  const float* bias, int M, int N, int relu, int splitk, void* stream) {
+    if (Kp <= 0 || (Kp & 63)) return CAPHN_EINVAL;
+    return caphn_gemm_tc_ex(Ahi, Alo, Kp, 0, Bhi, Blo, Kp, 0, Kp, C, ldc, bias, M, N, relu, splitk, stream);
 }
 
 }  // extern "C"

@@ -371,7 +371,8 @@ static int launch_rows_bwd(const T* W, const float* A, long lda, const float* dP
         { int y = V; while (y) { const int t = gdiv % y; gdiv = y; y = t; } }
         const int ncls = V / gdiv;
         int RB = 128 * (ncls > 4 ? ncls / 4 : 1);
-        while (RB > 32 * ncls && RB > 16 && ((N + RB - 1) / RB) * S < 8L * kNumSMs * WPB) RB >>= 1;
+        const int rb_min = ((long)N * K < (1L << 22)) ? 16 : 32 * ncls;   // tiny matrices: parallelism beats atomics
+        while (RB > rb_min && RB > 16 && ((N + RB - 1) / RB) * S < 8L * kNumSMs * WPB) RB >>= 1;
         const long items = ((N + RB - 1) / RB) * S;
         long blocks = (items + WPB - 1) / WPB;
         const long cap = (long)kNumSMs * 64;

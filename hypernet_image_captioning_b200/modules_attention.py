@@ -33,7 +33,13 @@ def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, f
     emb_w = emb_w.contiguous()
     W_ih, W_hh = W_ih.contiguous(), W_hh.contiguous()
     # ---- loop-invariant part: feature_fc (:61), keys W_a f (attention.py:34, hoisted), h0 (:63,133-134) ----
-    f1 = ops.linear(feats2, fc0_w, fc0_b, relu=True)                  # [B*P, F]
+    # the bf16x3 split of the image features (the largest input, 205 MB at B=512) is made once and reused by the backward
+    # as the in-place MN-major operand of dW1 = df1^T . features
+    fsplit = ops.split_bf16(feats2) if ops._tc_ok(B * P, Fd, D) else None
+    if fsplit is not None:
+        f1 = ops.gemm_tc(fsplit, ops.split_bf16(fc0_w.contiguous()), bias=fc0_b, relu=True)   # [B*P, F]
+    else:
+        f1 = ops.linear(feats2, fc0_w, fc0_b, relu=True)
     f = ops.linear(f1, fc2_w, fc2_b)                                  # [B*P, F]
     Kp = ops.linear(f, Wa_w, Wa_b)                                    # [B*P, H]
     fmean = ops.mean_pos(f.view(B, P, Fd))                            # [B, F]
@@ -84,14 +90,14 @@ def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, f
             ops.attgru_seq_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, t, t + 1)
             vocab(Hall[t + 1], out=logits[:, t, :])
     sv = (feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih, W_hh, fc_w, Wa_w, Ua_w,
-          va, init_w)
+          va, init_w, fsplit.hi if fsplit is not None else None, fsplit.lo if fsplit is not None else None)
     return logits, attn, sv, (B, T, P, D, E, H, Fd, V)
 
 
 def _attgru_backward(sv, dims, vocab, dattn):
     """vocab = (dfc_w, dfc_b, dHbm [B*T,H]).  Returns the 19 parameter gradients in AttentionGruFn argument order."""
     (feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih, W_hh, fc_w, Wa_w, Ua_w,
-     va, init_w) = sv
+     va, init_w, fs_hi, fs_lo) = sv
     B, T, P, D, E, H, Fd, V = dims
     dfc_w, dfc_b, dHbm = vocab
     if dattn is not None:
@@ -126,7 +132,11 @@ def _attgru_backward(sv, dims, vocab, dattn):
     dfc2_b = ops.colsum(df)
     df1 = ops.matmul_nn(df, fc2_w.contiguous())
     ops.relu_mask_(f1, df1)
-    dfc0_w = ops.matmul_tn(df1, feats2)                                # [F, D]
+    if fs_hi is not None and (fs_lo is not None) == ops.TC_SPLIT:
+        feats_op = ops.SplitOperand(fs_hi, fs_lo, D, B * P, fs_hi.shape[1], True)      # features^T, read in place
+        dfc0_w = ops.gemm_tc(ops.split_bf16(df1, mn=True), feats_op)                   # [F, D]
+    else:
+        dfc0_w = ops.matmul_tn(df1, feats2)                                            # [F, D]
     dfc0_b = ops.colsum(df1)
     return (dfc0_w, dfc0_b, dfc2_w, dfc2_b, demb, dW_ih, dW_hh, db_ih, db_hh, dfc_w, dfc_b,
             dWa_w, dWa_b, dUa_w, dUa_b, dva.view(1, H), dbv.view(1), dinit_w, dinit_b)

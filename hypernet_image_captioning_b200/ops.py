@@ -122,6 +122,14 @@ def _tc_ok(M, N, K, accumulate=False):
     return TC_ENABLED and not accumulate and M >= 128 and N >= 16 and K >= 32 and M * N * K >= TC_MIN_WORK
 
 
+def _operand_of_transpose(Bm):
+    """B operand ([N, K]) of a product with Bm = [K, N] stored row-major.  Large matrices are read in place (MN-major; the
+    N tile is then a multiple of 64); small ones go through the transposing split so the N tile can hug N (e.g. 160)."""
+    if Bm.numel() >= (1 << 22) and (Bm.shape[1] > 256 or Bm.shape[1] % 64 == 0):
+        return split_bf16(Bm, mn=True)
+    return split_bf16_t(Bm)
+
+
 def linear(X, W, bias=None, relu=False, out=None):
     """out[M,N] = X[M,K] @ W[N,K]^T + bias (optional ReLU)."""
     _chk(X), _chk(W)
@@ -136,7 +144,7 @@ def matmul_nn(A, Bm, out=None, accumulate=False):
     _chk(A), _chk(Bm)
     assert A.stride(1) == 1 and Bm.stride(1) == 1 and A.shape[1] == Bm.shape[0]
     if _tc_ok(A.shape[0], Bm.shape[1], A.shape[1], accumulate):
-        return gemm_tc(split_bf16(A), split_bf16_t(Bm), out=out)
+        return gemm_tc(split_bf16(A), _operand_of_transpose(Bm), out=out)
     return _gemm(A, A.stride(0), 1, Bm, Bm.stride(0), 0, A.shape[0], Bm.shape[1], A.shape[1], out=out,
                  accumulate=accumulate)
 
@@ -148,7 +156,7 @@ def matmul_tn(A, Bm, out=None, accumulate=False):
     K, M = A.shape
     N = Bm.shape[1]
     if _tc_ok(M, N, K, accumulate):
-        return gemm_tc(split_bf16_t(A), split_bf16_t(Bm), out=out)
+        return gemm_tc(split_bf16(A, mn=True), _operand_of_transpose(Bm), out=out)
     sk = _auto_splitk(M, N, K)
     if out is not None and sk > 1 and not accumulate:
         out.zero_()
@@ -308,20 +316,20 @@ def ce_bwd(logits2d, targets, ignore_index, lse, lossbuf, gscale):
 
 
 def ce_bwd_split(logits2d, targets, ignore_index, lse, lossbuf, gscale):
-    """CE gradient as tensor-core operands: returns (d [M,Vp] split, d^T [V,Mp] split, dbias [V])."""
+    """CE gradient d [M,V] as tensor-core operands, written once: returns (d as K-major operand [M rows, K=V],
+    the SAME buffers viewed as the MN-major operand of d^T [V rows, K=M], dbias [V])."""
     M, V = logits2d.shape
     dev = logits2d.device
     Vp, Mp = round64(V), round64(M)
     hi = torch.empty(M, Vp, device=dev, dtype=torch.bfloat16)
     lo = torch.empty(M, Vp, device=dev, dtype=torch.bfloat16) if TC_SPLIT else None
-    hiT = torch.empty(V, Mp, device=dev, dtype=torch.bfloat16)
-    loT = torch.empty(V, Mp, device=dev, dtype=torch.bfloat16) if TC_SPLIT else None
+    hiT = loT = None
     dbias = torch.zeros(V, device=dev, dtype=torch.float32)
     has = ignore_index is not None
     _cabi.call("caphn_ce_bwd_split", logits2d.data_ptr(), logits2d.stride(0), targets.data_ptr(), M, V, int(has),
                int(ignore_index) if has else 0, lse.data_ptr(), gscale.data_ptr(), lossbuf.data_ptr(), hi.data_ptr(),
-               _p(lo), Vp, hiT.data_ptr(), _p(loT), Mp, dbias.data_ptr(), _stream())
-    return SplitOperand(hi, lo, M, Vp), SplitOperand(hiT, loT, V, Mp), dbias
+               _p(lo), Vp, _p(hiT), _p(loT), Mp, dbias.data_ptr(), _stream())
+    return SplitOperand(hi, lo, M, V, Vp), SplitOperand(hi, lo, V, M, Vp, True), dbias
 
 
 def softmax_argmax(X, want_probs=True, probs_out=None, want_argmax=True):
@@ -488,14 +496,21 @@ def round64(n):
 
 
 class SplitOperand:
-    """fp32 matrix [R, C] in the bf16x3 operand format: hi, lo [R, Kp] bf16 (lo None in plain-bf16 mode)."""
-    __slots__ = ("hi", "lo", "rows", "Kp")
+    """fp32 matrix in the bf16x3 operand format: hi, lo bf16 (lo None in plain-bf16 mode).
+    K-major  (mn=False): source [rows, K]  -> hi/lo [rows, ld], operand rows = source rows.
+    MN-major (mn=True):  source [K, rows]  -> hi/lo [K, ld]: the operand of a transposed product, read in place."""
+    __slots__ = ("hi", "lo", "rows", "K", "ld", "mn")
 
-    def __init__(self, hi, lo, rows, Kp):
-        self.hi, self.lo, self.rows, self.Kp = hi, lo, rows, Kp
+    def __init__(self, hi, lo, rows, K, ld, mn=False):
+        self.hi, self.lo, self.rows, self.K, self.ld, self.mn = hi, lo, rows, K, ld, mn
+
+    @property
+    def Kp(self):   # kept for the K-major call sites
+        return self.ld
 
 
-def split_bf16(src, want_lo=None):
+def split_bf16(src, want_lo=None, mn=False):
+    """mn=False: operand rows = src rows (K-major).  mn=True: operand = src^T without a transposed copy (MN-major)."""
     want_lo = TC_SPLIT if want_lo is None else want_lo
     _chk(src)
     assert src.dim() == 2 and src.stride(1) == 1
@@ -504,7 +519,9 @@ def split_bf16(src, want_lo=None):
     hi = torch.empty(R, Kp, device=src.device, dtype=torch.bfloat16)
     lo = torch.empty(R, Kp, device=src.device, dtype=torch.bfloat16) if want_lo else None
     _cabi.call("caphn_split_bf16", src.data_ptr(), src.stride(0), R, C, hi.data_ptr(), _p(lo), Kp, _stream())
-    return SplitOperand(hi, lo, R, Kp)
+    if mn:
+        return SplitOperand(hi, lo, C, R, Kp, True)
+    return SplitOperand(hi, lo, R, C, Kp, False)
 
 
 def split_bf16_t(src, want_lo=None):
@@ -517,20 +534,20 @@ def split_bf16_t(src, want_lo=None):
     hi = torch.empty(C, Rp, device=src.device, dtype=torch.bfloat16)
     lo = torch.empty(C, Rp, device=src.device, dtype=torch.bfloat16) if want_lo else None
     _cabi.call("caphn_split_bf16_t", src.data_ptr(), src.stride(0), R, C, hi.data_ptr(), _p(lo), Rp, _stream())
-    return SplitOperand(hi, lo, C, Rp)
+    return SplitOperand(hi, lo, C, R, Rp, False)
 
 
 def gemm_tc(A: SplitOperand, Bm: SplitOperand, bias=None, relu=False, out=None, splitk=0):
-    """out[M,N] = A B^T (+bias) on the tensor cores; A [M,Kp], B [N,Kp] split operands with equal Kp."""
-    assert A.Kp == Bm.Kp and (A.lo is None) == (Bm.lo is None)
+    """out[M,N] = A B^T (+bias) on the tensor cores; operands K-major or MN-major (see SplitOperand), equal K."""
+    assert A.K == Bm.K and (A.lo is None) == (Bm.lo is None)
     M, N = A.rows, Bm.rows
     if out is None:
         out = torch.empty(M, N, device=A.hi.device, dtype=torch.float32)
     assert out.stride(1) == 1
-    _cabi.call("caphn_gemm_tc", A.hi.data_ptr(), _p(A.lo), Bm.hi.data_ptr(), _p(Bm.lo), A.Kp, out.data_ptr(),
-               out.stride(0), _p(bias), M, N, int(relu), 1 if relu else splitk, _stream())
+    _cabi.call("caphn_gemm_tc_ex", A.hi.data_ptr(), _p(A.lo), A.ld, int(A.mn), Bm.hi.data_ptr(), _p(Bm.lo), Bm.ld,
+               int(Bm.mn), A.K, out.data_ptr(), out.stride(0), _p(bias), M, N, int(relu), 1 if relu else splitk,
+               _stream())
     return out
-
 
 
 class LinearPlan:

@@ -60,6 +60,13 @@ int caphn_split_bf16_t(const float* src, long lds, int R, int C, void* hi, void*
 int caphn_gemm_tc(const void* Ahi, const void* Alo, const void* Bhi, const void* Blo, long Kp, float* C, long ldc,
                   const float* bias, int M, int N, int relu, int splitk, void* stream);
 
+/* General operand layouts: x_mn = 0: K-major hi/lo [rows, K] with row pitch x_ld; x_mn = 1: MN-major hi/lo [K rows, MN cols]
+ * with row pitch x_ld, i.e. the operand of a transposed product (dW = dY^T X) is read in place (UMMA MN-major shared-memory
+ * descriptors + 64x64 TMA boxes), no transposed copy.  x_ld % 8 == 0. */
+int caphn_gemm_tc_ex(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
+                     int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, int relu, int splitk,
+                     void* stream);
+
 /* dst[c*ldd+r] = src[r*lds+c] (zero padded to ldd) / dst[r*ldd+c] = src[r*lds+c] (zero padded): lay generated
  * weights out with 16-byte rows for the recurrence kernels. */
 int caphn_transpose_pad(const float* src, long lds, float* dst, long ldd, int R, int C, void* stream);

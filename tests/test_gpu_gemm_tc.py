@@ -63,3 +63,23 @@ def test_gemm_tc_tile_shapes_and_splitk(M, N, K, splitk):
     out = ops.gemm_tc(ops.split_bf16(A), ops.split_bf16(W), bias=b, splitk=splitk)
     ref = A.double() @ W.double().t() + b.double()
     assert rel_err(out, ref) < (2e-5 if K <= 2048 else 1e-4)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (700, 150, 1536), (9684, 150, 2048), (200, 2048, 3000), (257, 130, 100)])
+def test_gemm_tc_mn_major_operands(M, N, K):
+    """Transposed products read in place: A and/or B stored [K, MN] (MN-major UMMA descriptors, 64x64 TMA boxes)."""
+    from hypernet_image_captioning_b200 import ops
+    g = torch.Generator().manual_seed(M + 2 * N + 3 * K)
+    At = torch.randn(K, M, generator=g).cuda()      # A^T  (A is [M, K])
+    Bt = torch.randn(K, N, generator=g).cuda()      # B^T  (B is [N, K])
+    ref = At.double().t() @ Bt.double()
+    tol = 2e-5 if K <= 2048 else 1e-4
+    # A MN-major, B K-major (via transposing split)
+    out = ops.gemm_tc(ops.split_bf16(At, mn=True), ops.split_bf16_t(Bt))
+    assert rel_err(out, ref) < tol
+    # A K-major, B MN-major
+    out = ops.gemm_tc(ops.split_bf16_t(At), ops.split_bf16(Bt, mn=True))
+    assert rel_err(out, ref) < tol
+    # both MN-major
+    out = ops.gemm_tc(ops.split_bf16(At, mn=True), ops.split_bf16(Bt, mn=True))
+    assert rel_err(out, ref) < tol
