@@ -63,6 +63,21 @@ class _HyperNetMixin:
             theta = allreduce_grad(theta, self.dp_group)
         return theta
 
+    def regression_loss(self, style_embed: torch.Tensor, target_params):
+        """Hypernet regression pre-training objective of train_init.py:70-123: sum over the generated GRU parameters of
+        MSE(head_i(hn_base(style)).flatten(), target_i.flatten()).  ``target_params`` = the pretrained cell's parameters
+        in named_parameters() order (weight_ih, weight_hh, bias_ih, bias_hh[, next cell ...]).  The head forward /
+        backward run in the weight-streaming kernels; the MSE itself is a few hundred thousand elements."""
+        theta = self.generate_theta(style_embed)[0]
+        loss, a = theta.new_zeros(()), 0
+        for tgt in target_params:
+            n = tgt.numel()
+            loss = loss + torch.nn.functional.mse_loss(theta[a:a + n], tgt.detach().reshape(-1).to(theta.dtype))
+            a += n
+        if a != theta.numel():
+            raise ValueError(f"target parameters cover {a} of {theta.numel()} generated values")
+        return loss
+
     def set_precision(self, mode: str):
         """"fp32" (default; parity mode) or "bf16": the hypernet base/head parameters -- and therefore their gradients --
         are stored in bf16 (half the HBM traffic of the dominant kernels) and the decoder's tensor-core products use

@@ -286,6 +286,43 @@ class AttentionGru(nn.Module):
         use = tuple(bool(np.random.random() < (0.0 if t == 0 else sample_prob)) for t in range(T))
         return AttentionGruLossFn.apply(ignore_index, features, captions, use, *self._params(self._gru_weights()))
 
+    @torch.no_grad()
+    def greedy_search(self, features, end_sentence=2, max_sentence=20):
+        """B = 1 greedy decoding with EOS stop -- models/decoderlstm.py:138-175.  ``features`` have ALREADY been through
+        ``feature_fc`` ([1, P, F]); the first input word is index 0; returns (tokens list[int], list of attention
+        weights [1, P]).  All ``max_sentence`` steps run on the device without host round trips; the token list is cut
+        after the first ``end_sentence`` (the steps after it do not influence the ones before)."""
+        f3 = features.contiguous().float()
+        B, P, Fd = f3.shape
+        W_ih, W_hh, b_ih, b_hh = [w.detach().contiguous() for w in self._gru_weights()]
+        E, H, T = self.embedding_dim, self.hidden_dim, int(max_sentence)
+        dev = f3.device
+        a = self.attention
+        emb_w = self.embed.weight.detach()
+        Kp = ops.linear(f3.view(B * P, Fd), a.W_a.weight.detach(), a.W_a.bias.detach()).view(B, P, H)
+        h0 = ops.linear(ops.mean_pos(f3), self.init_h.weight.detach(), self.init_h.bias.detach())
+        lw = ops.AttGruWeights(W_ih, W_hh, a.U_a.weight.detach().contiguous(), E)
+        va, bv = a.v_a.weight.detach().reshape(-1).contiguous(), a.v_a.bias.detach().reshape(1).contiguous()
+        Hall = torch.empty(T + 1, B, H, device=dev, dtype=torch.float32)
+        Hall[0].copy_(h0)
+        attn = torch.empty(B, T, P, device=dev, dtype=torch.float32)
+        XC = torch.empty(T * B, E + Fd, device=dev, dtype=torch.float32)
+        GIw = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+        logits = torch.empty(B, self.vocab_size, device=dev, dtype=torch.float32)
+        tokens = torch.zeros(T + 1, B, device=dev, dtype=torch.int64)          # tokens[0] = 0: the first input word
+        W_ih_w = W_ih[:, :E]
+        for t in range(T):
+            xw = ops.gather_rows(emb_w, tokens[t])
+            ops.linear(xw, W_ih_w, b_ih, out=GIw[t * B:(t + 1) * B])
+            ops.attgru_seq_fwd(Kp, f3, GIw, lw, a.U_a.bias.detach(), va, bv, b_hh, Hall, None, attn, XC, E, None, t, t + 1)
+            ops.linear(Hall[t + 1], self.fc.weight.detach(), self.fc.bias.detach(), out=logits)
+            _, top = ops.softmax_argmax(logits, want_probs=False)
+            tokens[t + 1].copy_(top)
+        sent = tokens[1:, 0].tolist()
+        if end_sentence in sent:
+            sent = sent[:sent.index(end_sentence) + 1]
+        return sent, [attn[0:1, t, :].clone() for t in range(len(sent))]
+
     def init_hidden(self, features):
         """h0 = init_h(mean over positions) -- models/decoderlstm.py:122-135 (features already through feature_fc)."""
         B, P, Fd = features.shape

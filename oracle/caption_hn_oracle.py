@@ -185,6 +185,29 @@ def attention_gru_forward(p: Params, gru_w, features: torch.Tensor, captions: to
     return torch.stack(outs, 1), torch.stack(atts, 1)
 
 
+def attention_gru_greedy_search(p: Params, gru_w, features_fc: torch.Tensor, end_sentence: int = 2,
+                                max_sentence: int = 20, pre: str = "captioner."):
+    """AttentionGru.greedy_search (models/decoderlstm.py:138-175), B = 1: ``features_fc`` has ALREADY been through
+    feature_fc; the first input is Emb[0] (not zeros); stops after ``max_sentence`` tokens or right after ``end_sentence``.
+    Returns (tokens list[int], attention weights [len, P])."""
+    f = features_fc
+    emb_w = p[pre + "embed.weight"]
+    h = F.linear(f.mean(dim=1), p[pre + "init_h.weight"], p[pre + "init_h.bias"])
+    word = torch.tensor([0])
+    sentence, weights = [], []
+    while True:
+        ctx, alpha = bahdanau(p, f, h, pre + "attention.")
+        h = gru_cell(torch.cat([F.embedding(word, emb_w), ctx], 1), h, *gru_w)
+        out = F.linear(h, p[pre + "fc.weight"], p[pre + "fc.bias"])
+        top = F.log_softmax(out, dim=1)[0].topk(1)[1]
+        sentence.append(int(top.item()))
+        weights.append(alpha.reshape(-1))
+        word = top
+        if len(sentence) >= max_sentence or int(top.item()) == end_sentence:
+            break
+    return sentence, torch.stack(weights, 0)
+
+
 def caption_loss(logits: torch.Tensor, captions: torch.Tensor, ignore_index: Optional[int] = 0) -> torch.Tensor:
     """cc_train_hypernet.py:153 (ignore_index=<pad>=0) / hypernet.py:145 (ignore_index=None)."""
     V = logits.shape[-1]

@@ -100,6 +100,15 @@ def case_attention(ref, name, cc, style, Fo=16, E=12, H=20, V=50, he=10, B=2, T=
         glogits, gatt = captioner(features, caps, 1.0)
     out["greedy/logits"], out["greedy/attn"] = glogits, gatt
 
+    # B = 1 greedy_search with EOS stop (models/decoderlstm.py:138-175): takes features ALREADY through feature_fc
+    with torch.no_grad():
+        captioner = model.forward(style)
+        for bi in range(B):
+            fproj = captioner.feature_fc(features[bi:bi + 1])
+            sent, wts = captioner.greedy_search(fproj, end_sentence=2, max_sentence=7)
+            out[f"gs/{bi}/tokens"] = torch.tensor(sent)
+            out[f"gs/{bi}/weights"] = torch.stack([w.reshape(-1) for w in wts], 0)
+
     # flow mode gradients (harness-side patch of set_all_parameters only)
     import hypernet_attention as ref_hna
     orig = ref_hna.set_all_parameters

@@ -212,3 +212,41 @@ def test_attgru_cluster_forward_matches_streaming_kernel(B, T, Fo, E, H, P):
         outs.append((Hall, Hbm, attn, XC, saved))
     for name, x, y in zip(("Hall", "Hbm", "attn", "XC", "saved"), outs[1], outs[0]):
         assert rel_err(x, y) < 3e-5, name
+
+
+@pytest.mark.parametrize("name,cc,he", CASES)
+def test_greedy_search_golden(name, cc, he):
+    """B = 1 greedy_search with EOS stop (models/decoderlstm.py:138-175) against the reference's own output."""
+    c = load_case(name)
+    m = _model_from(params_of(c), 16, 12, 20, 50, cc, he)
+    captioner = m.forward(c["style"].cuda())
+    for bi in range(c["features"].shape[0]):
+        with torch.no_grad():
+            fproj = captioner.feature_fc(c["features"][bi:bi + 1].cuda())     # torch nn.Sequential, as the caller does
+        toks, wts = captioner.greedy_search(fproj, end_sentence=2, max_sentence=7)
+        assert toks == c[f"gs/{bi}/tokens"].tolist()
+        assert rel_err(torch.cat(wts, 0), c[f"gs/{bi}/weights"]) < TOL_LOGITS
+
+
+def test_regression_pretraining_loss_matches_reference_recipe():
+    """train_init.py:70-123: loss = sum_i MSE(head_i(hn_base(style)), W_i) ; gradients reach heads and base."""
+    import torch.nn.functional as F
+    Fo, E, H, V = 16, 12, 20, 60
+    p = O.init_params_attention(2048, Fo, E, H, V, E, seed=23)
+    g = torch.Generator().manual_seed(4)
+    style = torch.randn(1, E, generator=g)
+    targets = [torch.randn(*shp, generator=g) * 0.1 for _, shp in O.gru_param_shapes_attention(E, Fo, H)]
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    theta = O.hypernet_theta(pl, style, 4)
+    loss_ref, a = 0.0, 0
+    for t in targets:
+        loss_ref = loss_ref + F.mse_loss(theta[a:a + t.numel()], t.flatten())
+        a += t.numel()
+    loss_ref.backward()
+    m = _model_from(p, Fo, E, H, V, False, 10)
+    loss = m.regression_loss(style.cuda(), [t.cuda() for t in targets])
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-5 * abs(loss_ref.item())
+    for k, v in m.named_parameters():
+        if k.startswith("hn_"):
+            assert grad_close(v.grad, pl[k].grad, TOL_GRAD), k

@@ -98,3 +98,20 @@ def test_pooled_variant_flow_grads(name, L):
             assert grad_close(p[k[10:]].grad, v, 1e-5), k
             n += 1
     assert n >= 12
+
+
+@pytest.mark.parametrize("name", ["attn_flickr", "attn_cc"])
+def test_attention_greedy_search_matches_reference(name):
+    c = load_case(name)
+    p = params_of(c)
+    E, Fo, H = O.dims_attention(p)
+    with torch.no_grad():
+        gw = O.split_theta_attention(O.hypernet_theta(p, c["style"], 4), E, Fo, H)
+        for bi in range(c["features"].shape[0]):
+            f = c["features"][bi:bi + 1]
+            fproj = torch.nn.functional.linear(torch.relu(torch.nn.functional.linear(
+                f, p["captioner.feature_fc.0.weight"], p["captioner.feature_fc.0.bias"])),
+                p["captioner.feature_fc.2.weight"], p["captioner.feature_fc.2.bias"])
+            toks, wts = O.attention_gru_greedy_search(p, gw, fproj, 2, 7)
+            assert toks == c[f"gs/{bi}/tokens"].tolist()
+            assert rel_err(wts, c[f"gs/{bi}/weights"]) < TOL
