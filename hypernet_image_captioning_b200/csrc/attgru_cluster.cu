@@ -4,14 +4,15 @@
 // Same reference calls as attgru_seq.cu (models/decoderlstm.py:97-100 + models/attention.py:33-45 per step); that
 // L2-streaming kernel remains the fallback (odd sizes) and still provides the backward pass.
 //
-// Decomposition (cluster = 8 CTAs = 32 batch rows; CTA c owns hidden units [c*HS, (c+1)*HS), HS = ceil(H/8)):
+// Decomposition (cluster = 8 CTAs = 16 batch rows; CTA c owns hidden units [c*HS, (c+1)*HS), HS = ceil(H/8)):
 //   * the CTA's weight rows -- U_a[j,:], W_hh[{r,z,n} j, :] (inputs: h) and W_ih[{r,z,n} j, E:] (input: ctx) for its
 //     units j -- are held as bf16 hi/lo A-fragments of warp-level MMAs (mma.sync m16n8k16) in REGISTERS: one 16-row tile
 //     per warp, loaded once, reused for every step.  fp32 accuracy comes from the same bf16x3 scheme as the GEMMs
 //     (hi*hi + hi*lo + lo*hi, fp32 accumulate).  The per-step products are tiny (112 x 32 x 208): warp MMAs with
 //     register-resident weights have far lower latency than a tcgen05/TMEM round trip, which is why they are used here.
 //   * the attention itself is partitioned by batch row: CTA c scores / soft-maxes / forms the context for rows
-//     4c..4c+3 of the cluster, reading K = W_a f + b_a and f for those rows (coalesced, L2 resident).
+//     2c, 2c+1 of the cluster.  K = W_a f + b_a and f of those two rows (157 KB fp32 at P=49, H=F=200) are loaded into
+//     shared memory ONCE and stay there for all steps: the per-step attention touches no global memory.
 //   * three DSMEM exchanges per step: u (all-to-all, so every CTA has the full u of its 4 rows), ctx (all-gather),
 //     h' (all-gather), each followed by a cluster barrier.
 // Per step: [MMA: u_slice, gh_slice = W.h] -> exchange u -> scores, softmax, ctx for own rows -> exchange ctx ->
@@ -28,11 +29,12 @@ namespace caphn {
 constexpr int AC_WARPS = 12;
 constexpr int AC_THREADS = AC_WARPS * 32;
 constexpr int AC_CS = 8;        // cluster size
-constexpr int AC_BT = 32;       // batch rows per cluster (4 MMA n-tiles)
-constexpr int AC_RPC = AC_BT / AC_CS;   // attention rows per CTA (4)
+constexpr int AC_BT = 16;       // batch rows per cluster (2 MMA n-tiles): K and f of these rows fit in the cluster's smem
+constexpr int AC_NT = AC_BT / 8;
+constexpr int AC_RPC = AC_BT / AC_CS;   // attention rows per CTA (2)
 constexpr int AC_KT = 13;       // max k-tiles of 16 (H, F <= 208)
 constexpr int AC_KP = AC_KT * 16 + 8;   // bf16 row pitch of the B-operand arrays (216: conflict-free fragment loads)
-constexpr int AC_MAXI = 3;      // gate items per thread: HS * 32 <= 3 * 384  (HS <= 36)
+constexpr int AC_MAXI = 2;      // gate items per thread: HS * 16 <= 2 * 384  (HS <= 48)
 
 struct AttClArgs {
     const float* Kp;    // [B,P,H]
@@ -70,19 +72,46 @@ __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b
 }
 __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-// value of local weight row lr, column k, of this CTA's slice.  group 0 (input h): [U_a | W_hh r | W_hh z | W_hh n];
-// group 1 (input ctx): [W_ih r | z | n][:, E + k].
-__device__ __forceinline__ float slice_w(const AttClArgs& a, int group, int c, int lr, int k) {
+// local weight row lr of this CTA's slice.  group 0 (input h): [U_a | W_hh r | W_hh z | W_hh n]; group 1 (input ctx):
+// [W_ih r | z | n][:, E:].  Returns the row pointer (nullptr: padding row) and its length.
+__device__ __forceinline__ const float* slice_row(const AttClArgs& a, int group, int c, int lr, int& klen) {
     const int HS = a.HS, H = a.H;
     const int blk = lr / HS, jl = lr - blk * HS;
     const int j = c * HS + jl;
-    if (j >= H) return 0.f;
-    if (group == 0) {
-        if (blk > 3 || k >= H) return 0.f;
-        return blk == 0 ? a.Ua[(long)j * H + k] : a.Whh[((long)(blk - 1) * H + j) * H + k];
+    klen = group == 0 ? H : a.F;
+    if (j >= H || blk > (group == 0 ? 3 : 2)) return nullptr;
+    if (group == 0) return blk == 0 ? a.Ua + (long)j * H : a.Whh + ((long)(blk - 1) * H + j) * H;
+    return a.Wih + ((long)blk * H + j) * (a.E + a.F) + a.E;
+}
+__device__ __forceinline__ float row_at(const float* row, int k, int klen) { return (row && k < klen) ? __ldg(row + k) : 0.f; }
+
+#ifdef CAPHN_ATTCL_TIMING
+__device__ long long g_attcl_ts[32];
+#define TS(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && t == a.t0 + 3) g_attcl_ts[i] = clock64(); } while (0)
+#define TSP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_attcl_ts[i] = clock64(); } while (0)
+#else
+#define TS(i)
+#define TSP(i)
+#endif
+
+// r(x) = 1 / (exp(2x) + 1)  (tanh x = 1 - 2 r(x); sigmoid(x) = r(-x/2)) with ex2.approx / rcp.approx: ~1e-7 absolute
+__device__ __forceinline__ float recip_exp2x_p1(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));   // 2 * log2(e)
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return recip_exp2x_p1(-0.5f * x); }
+
+// push `n4` float4 from my shared memory to the same offset in every other CTA of the cluster (coalesced DSMEM stores)
+__device__ __forceinline__ void cluster_push(cg::cluster_group& cluster, float* buf, int off_floats, int n4, int my_rank) {
+    const float4* src = reinterpret_cast<const float4*>(buf + off_floats);
+    for (int i = threadIdx.x; i < n4 * (AC_CS - 1); i += AC_THREADS) {
+        int rk = i / n4;
+        const int e = i - rk * n4;
+        rk += (rk >= my_rank);
+        reinterpret_cast<float4*>(cluster.map_shared_rank(buf, rk) + off_floats)[e] = src[e];
     }
-    if (blk > 2 || k >= a.F) return 0.f;
-    return a.Wih[((long)blk * H + j) * (a.E + a.F) + a.E + k];
 }
 
 __global__ void __launch_bounds__(AC_THREADS, 1) attgru_cluster_fwd_kernel(const AttClArgs a) {
@@ -92,76 +121,98 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attgru_cluster_fwd_kernel(const
     const int H = a.H, F = a.F, P = a.P, B = a.B, T = a.T, HS = a.HS, H3 = 3 * a.H;
     const int PS = (P + 3) & ~3;
     // ---- shared memory carve-up ----
-    __nv_bfloat16* hb_hi = reinterpret_cast<__nv_bfloat16*>(smem_raw);          // [32][KP]  h as MMA B operand
-    __nv_bfloat16* hb_lo = hb_hi + AC_BT * AC_KP;
-    __nv_bfloat16* cb_hi = hb_lo + AC_BT * AC_KP;                               // [32][KP]  ctx as MMA B operand
-    __nv_bfloat16* cb_lo = cb_hi + AC_BT * AC_KP;
-    float* hx = reinterpret_cast<float*>(cb_lo + AC_BT * AC_KP);                // [32][H]   fp32 h' staging (DSMEM target)
-    float* cxs = hx + AC_BT * H;                                                // [32][F]   fp32 ctx staging (DSMEM target)
-    float* us = cxs + AC_BT * F;                                                // [RPC][H]  u of my attention rows (DSMEM)
-    float* res_h = us + AC_RPC * H;                                             // [4*HS][32] u | gh_r | gh_z | gh_n
-    float* res_c = res_h + 4 * HS * AC_BT;                                      // [3*HS][32] gi_ctx r | z | n
-    float* hown = res_c + 3 * HS * AC_BT;                                       // [HS][32]  fp32 state of my units
+    float* Ks = reinterpret_cast<float*>(smem_raw);                             // [RPC][P][H]  keys of my attention rows
+    float* fs = Ks + AC_RPC * P * H;                                            // [RPC][P][F]  features of my rows
+    float* stage_c = fs + AC_RPC * P * F;                                       // [BT][F]       ctx of all rows   (DSMEM target)
+    float* stage_h = stage_c + AC_BT * F;                                       // [CS][BT][HS]  h' by owner slice (DSMEM target)
+    float* us = stage_h + AC_CS * AC_BT * HS;                                   // [RPC][H]  u of my attention rows (DSMEM target)
+    float* res_h = us + AC_RPC * H;                                             // [4*HS][BT] u | gh_r | gh_z | gh_n
+    float* res_c = res_h + 4 * HS * AC_BT;                                      // [3*HS][BT] gi_ctx r | z | n
+    float* hown = res_c + 3 * HS * AC_BT;                                       // [HS][BT]  fp32 state of my units
     float* sc = hown + HS * AC_BT;                                              // [RPC][PS]
+    int* hmap = reinterpret_cast<int*>(sc + AC_RPC * PS);                       // [H] offset of unit j inside stage_h (row 0)
+    __nv_bfloat16* hb_hi = reinterpret_cast<__nv_bfloat16*>(hmap + ((H + 3) & ~3));   // [BT][KP]  h as MMA B operand
+    __nv_bfloat16* hb_lo = hb_hi + AC_BT * AC_KP;
+    __nv_bfloat16* cb_hi = hb_lo + AC_BT * AC_KP;                               // [BT][KP]  ctx as MMA B operand
+    __nv_bfloat16* cb_lo = cb_hi + AC_BT * AC_KP;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = (blockIdx.x / AC_CS) * AC_BT;
-    const int KHT = (H + 15) >> 4, KFT = (F + 15) >> 4;
     const int MTH = (4 * HS + 15) >> 4;                 // m-tiles of the h group; the ctx group uses the remaining warps
     const int group = warp < MTH ? 0 : 1;
     const int lr0 = (group == 0 ? warp : warp - MTH) * 16;
-    const int nkt = group == 0 ? KHT : KFT;
 
+    TSP(20);
     // ---- weight fragments: loaded once, live in registers for all steps ----
     uint32_t Ahi[AC_KT][4], Alo[AC_KT][4];
     {
-        const int ra = lr0 + (lane >> 2), rb = ra + 8, kc = (lane & 3) * 2;
+        const int kc = (lane & 3) * 2;
+        int klen;
+        const float* rowa = slice_row(a, group, c, lr0 + (lane >> 2), klen);
+        const float* rowb = slice_row(a, group, c, lr0 + (lane >> 2) + 8, klen);
 #pragma unroll
         for (int kt = 0; kt < AC_KT; ++kt) {
-            if (kt < nkt) {
-                const int k = kt * 16 + kc;
-                split2(slice_w(a, group, c, ra, k), slice_w(a, group, c, ra, k + 1), Ahi[kt][0], Alo[kt][0]);
-                split2(slice_w(a, group, c, rb, k), slice_w(a, group, c, rb, k + 1), Ahi[kt][1], Alo[kt][1]);
-                split2(slice_w(a, group, c, ra, k + 8), slice_w(a, group, c, ra, k + 9), Ahi[kt][2], Alo[kt][2]);
-                split2(slice_w(a, group, c, rb, k + 8), slice_w(a, group, c, rb, k + 9), Ahi[kt][3], Alo[kt][3]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { Ahi[kt][i] = 0u; Alo[kt][i] = 0u; }
-            }
+            const int k = kt * 16 + kc;
+            split2(row_at(rowa, k, klen), row_at(rowa, k + 1, klen), Ahi[kt][0], Alo[kt][0]);
+            split2(row_at(rowb, k, klen), row_at(rowb, k + 1, klen), Ahi[kt][1], Alo[kt][1]);
+            split2(row_at(rowa, k + 8, klen), row_at(rowa, k + 9, klen), Ahi[kt][2], Alo[kt][2]);
+            split2(row_at(rowb, k + 8, klen), row_at(rowb, k + 9, klen), Ahi[kt][3], Alo[kt][3]);
         }
     }
-    // ---- initial state ----
-    for (int i = tid; i < AC_BT * AC_KP; i += AC_THREADS) {
-        const int b = i / AC_KP, k = i - b * AC_KP;
-        float v = 0.f;
-        if (k < H && b0 + b < B) v = a.Hall[((long)a.t0 * B + b0 + b) * H + k];
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
-        hb_hi[i] = h;
-        hb_lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
-        cb_hi[i] = __float2bfloat16_rn(0.f);
-        cb_lo[i] = __float2bfloat16_rn(0.f);
+    TSP(21);
+    // ---- K and f of my attention rows: read ONCE, resident for all steps ----
+    for (int bl = 0; bl < AC_RPC; ++bl) {
+        const int gb = b0 + c * AC_RPC + bl;
+        const float4* ksrc = reinterpret_cast<const float4*>(a.Kp + (long)gb * P * H);
+        const float4* fsrc = reinterpret_cast<const float4*>(a.f + (long)gb * P * F);
+        float4* kd = reinterpret_cast<float4*>(Ks + bl * P * H);
+        float4* fd = reinterpret_cast<float4*>(fs + bl * P * F);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < (P * H) >> 2; i += AC_THREADS) kd[i] = gb < B ? ksrc[i] : z4;
+        for (int i = tid; i < (P * F) >> 2; i += AC_THREADS) fd[i] = gb < B ? fsrc[i] : z4;
     }
-    for (int i = tid; i < HS * AC_BT; i += AC_THREADS) {
-        const int jl = i / AC_BT, b = i - jl * AC_BT;
-        const int j = c * HS + jl;
-        hown[i] = (j < H && b0 + b < B) ? a.Hall[((long)a.t0 * B + b0 + b) * H + j] : 0.f;
+    TSP(22);
+    // ---- initial state ----
+    for (int j = tid; j < H; j += AC_THREADS) hmap[j] = (j / HS) * AC_BT * HS + (j % HS);
+    for (int b = warp; b < AC_BT; b += AC_WARPS) {
+        for (int k = lane; k < AC_KP; k += 32) {
+            float v = 0.f;
+            if (k < H && b0 + b < B) v = a.Hall[((long)a.t0 * B + b0 + b) * H + k];
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            hb_hi[b * AC_KP + k] = h;
+            hb_lo[b * AC_KP + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+            cb_hi[b * AC_KP + k] = __float2bfloat16_rn(0.f);
+            cb_lo[b * AC_KP + k] = __float2bfloat16_rn(0.f);
+        }
     }
     // gate items of this thread (fixed over time): (unit jl, row b), lanes run over b
     int it_jl[AC_MAXI], it_b[AC_MAXI];
-    bool it_live[AC_MAXI];
+    bool it_in[AC_MAXI], it_live[AC_MAXI];
     float bh[AC_MAXI][3], bu_r[AC_MAXI];
 #pragma unroll
     for (int q = 0; q < AC_MAXI; ++q) {
         const int i = tid + q * AC_THREADS;
         it_jl[q] = i / AC_BT; it_b[q] = i - it_jl[q] * AC_BT;
         const int j = c * HS + it_jl[q];
-        it_live[q] = (i < HS * AC_BT) && (j < H) && (b0 + it_b[q] < B);
+        it_in[q] = (i < HS * AC_BT) && (j < H);
+        it_live[q] = it_in[q] && (b0 + it_b[q] < B);
 #pragma unroll
         for (int g = 0; g < 3; ++g) bh[q][g] = it_live[q] ? a.bhh[g * H + j] : 0.f;
-        bu_r[q] = it_live[q] ? a.bu[j] : 0.f;
+        bu_r[q] = it_in[q] ? a.bu[j] : 0.f;
+        if (i < HS * AC_BT) hown[i] = it_live[q] ? a.Hall[((long)a.t0 * B + b0 + it_b[q]) * H + j] : 0.f;
     }
-    const float bv = a.bv[0];
+    // v_a slice of this lane (scores: lanes run over j); tanh = 1 - 2r  =>  score = b_v + sum(v) - 2 sum(v r)
+    constexpr int JI = (AC_KT * 16 + 31) / 32;
+    float va_r[JI];
+    int jc[JI];
+#pragma unroll
+    for (int i = 0; i < JI; ++i) jc[i] = min(lane + 32 * i, H - 1);
+    float sumva = 0.f;
+#pragma unroll
+    for (int i = 0; i < JI; ++i) { va_r[i] = (lane + 32 * i < H) ? a.va[lane + 32 * i] : 0.f; sumva += va_r[i]; }
+    sumva = warp_sum(sumva) + a.bv[0];
     __syncthreads();
     cluster.sync();
+    TSP(23);
 
     for (int t = a.t0; t < a.t1; ++t) {
         // prefetch the word half of the input projection for the gate phase of this step
@@ -172,128 +223,191 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attgru_cluster_fwd_kernel(const
             for (int g = 0; g < 3; ++g)
                 giw[q][g] = it_live[q] ? a.GIw[((long)t * B + b0 + it_b[q]) * H3 + g * H + c * HS + it_jl[q]] : 0.f;
 
-        // ---- P1: [u | gh] slice = W_h-group . h   (warp MMA, weights from registers) ----
+        TS(0);
+        // ---- P1: [u | gh] slice = W_h-group . h   (warp MMA, weights from registers; 4 independent accumulator chains) ----
         if (group == 0) {
+            float acc[2][AC_NT][4];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                const int n = nt * 8 + (lane >> 2);
-                const uint32_t* bh_p = reinterpret_cast<const uint32_t*>(hb_hi + n * AC_KP + (lane & 3) * 2);
-                const uint32_t* bl_p = reinterpret_cast<const uint32_t*>(hb_lo + n * AC_KP + (lane & 3) * 2);
+            for (int e = 0; e < 2; ++e)
 #pragma unroll
-                for (int kt = 0; kt < AC_KT; ++kt) {
-                    if (kt < nkt) {
-                        const uint32_t h0 = bh_p[kt * 8], h1 = bh_p[kt * 8 + 4];
-                        const uint32_t l0 = bl_p[kt * 8], l1 = bl_p[kt * 8 + 4];
-                        mma_bf16(acc, Ahi[kt], h0, h1);
-                        mma_bf16(acc, Ahi[kt], l0, l1);
-                        mma_bf16(acc, Alo[kt], h0, h1);
-                    }
+                for (int nt = 0; nt < AC_NT; ++nt) { acc[e][nt][0] = acc[e][nt][1] = acc[e][nt][2] = acc[e][nt][3] = 0.f; }
+            const int nrow = lane >> 2, kc = (lane & 3) * 2;
+#pragma unroll
+            for (int kt = 0; kt < AC_KT; ++kt) {     // unconditional: fragments / operand columns beyond the real K are zero
+#pragma unroll
+                for (int nt = 0; nt < AC_NT; ++nt) {
+                    const uint32_t* bh_p = reinterpret_cast<const uint32_t*>(hb_hi + (nt * 8 + nrow) * AC_KP + kt * 16 + kc);
+                    const uint32_t* bl_p = reinterpret_cast<const uint32_t*>(hb_lo + (nt * 8 + nrow) * AC_KP + kt * 16 + kc);
+                    const uint32_t h0 = bh_p[0], h1 = bh_p[4], l0 = bl_p[0], l1 = bl_p[4];
+                    mma_bf16(acc[kt & 1][nt], Ahi[kt], h0, h1);
+                    mma_bf16(acc[kt & 1][nt], Ahi[kt], l0, l1);
+                    mma_bf16(acc[kt & 1][nt], Alo[kt], h0, h1);
                 }
-                const int ra = lr0 + (lane >> 2), col = nt * 8 + (lane & 3) * 2;
-                if (ra < 4 * HS) { res_h[ra * AC_BT + col] = acc[0]; res_h[ra * AC_BT + col + 1] = acc[1]; }
-                if (ra + 8 < 4 * HS) { res_h[(ra + 8) * AC_BT + col] = acc[2]; res_h[(ra + 8) * AC_BT + col + 1] = acc[3]; }
+            }
+            const int ra = lr0 + (lane >> 2);
+#pragma unroll
+            for (int nt = 0; nt < AC_NT; ++nt) {
+                const int col = nt * 8 + (lane & 3) * 2;
+                if (ra < 4 * HS) {
+                    res_h[ra * AC_BT + col] = acc[0][nt][0] + acc[1][nt][0];
+                    res_h[ra * AC_BT + col + 1] = acc[0][nt][1] + acc[1][nt][1];
+                }
+                if (ra + 8 < 4 * HS) {
+                    res_h[(ra + 8) * AC_BT + col] = acc[0][nt][2] + acc[1][nt][2];
+                    res_h[(ra + 8) * AC_BT + col + 1] = acc[0][nt][3] + acc[1][nt][3];
+                }
             }
         }
         __syncthreads();
+        TS(1);
         // ---- exchange u: element (unit jl, row b) goes to the CTA that attends row b ----
 #pragma unroll
         for (int q = 0; q < AC_MAXI; ++q) {
-            const int i = tid + q * AC_THREADS;
-            if (i < HS * AC_BT) {
+            if (it_in[q]) {
                 const int jl = it_jl[q], b = it_b[q], j = c * HS + jl;
-                if (j < H) {
-                    const float u = res_h[jl * AC_BT + b] + bu_r[q];
-                    float* dst = cluster.map_shared_rank(us, b / AC_RPC);
-                    dst[(b % AC_RPC) * H + j] = u;
-                    if (a.Upre && it_live[q]) a.Upre[((long)t * B + b0 + b) * H + j] = u;
-                }
+                const float u = res_h[jl * AC_BT + b] + bu_r[q];
+                cluster.map_shared_rank(us, b / AC_RPC)[(b % AC_RPC) * H + j] = u;
+                if (a.Upre && it_live[q]) a.Upre[((long)t * B + b0 + b) * H + j] = u;
             }
         }
+        TS(2);
         cl_arrive();
         cl_wait();
-        // ---- P2: attention for my rows: scores -> softmax -> context ----
-        for (int pair = warp; pair < AC_RPC * P; pair += AC_WARPS) {
-            const int bl = pair / P, p = pair - bl * P;
-            const int gb = b0 + c * AC_RPC + bl;
-            float s = 0.f;
-            if (gb < B) {
-                const float* kp = a.Kp + ((long)gb * P + p) * H;
-                for (int j = lane; j < H; j += 32) s = fmaf(a.va[j], tanh_fast(kp[j] + us[bl * H + j]), s);
+        TS(3);
+        // ---- P2: attention for my rows, everything from shared memory: scores -> softmax -> context ----
+        for (int pair = warp; pair < AC_RPC * P; pair += 2 * AC_WARPS) {     // two (row, position) pairs per iteration
+            const int pair2 = pair + AC_WARPS;
+            const bool two = pair2 < AC_RPC * P;
+            const int bl1 = pair / P, p1 = pair - bl1 * P;
+            const int bl2 = two ? pair2 / P : bl1, p2 = two ? pair2 - bl2 * P : p1;
+            const float* k1 = Ks + (bl1 * P + p1) * H;
+            const float* k2 = Ks + (bl2 * P + p2) * H;
+            const float* u1 = us + bl1 * H;
+            const float* u2 = us + bl2 * H;
+            float kv1[JI], kv2[JI], uv1[JI], uv2[JI];
+#pragma unroll
+            for (int i = 0; i < JI; ++i) {      // clamped index: branch-free, all loads issued before the math (v_a is 0 beyond H)
+                kv1[i] = k1[jc[i]]; uv1[i] = u1[jc[i]];
+                kv2[i] = k2[jc[i]]; uv2[i] = u2[jc[i]];
             }
-            s = warp_sum(s);
-            if (lane == 0) sc[bl * PS + p] = s + bv;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < JI; ++i) {
+                s1 = fmaf(va_r[i], recip_exp2x_p1(kv1[i] + uv1[i]), s1);
+                s2 = fmaf(va_r[i], recip_exp2x_p1(kv2[i] + uv2[i]), s2);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            if (lane == 0) {
+                sc[bl1 * PS + p1] = sumva - 2.f * s1;
+                if (two) sc[bl2 * PS + p2] = sumva - 2.f * s2;
+            }
         }
         __syncthreads();
+        TS(4);
         if (warp < AC_RPC) {
             const int bl = warp, gb = b0 + c * AC_RPC + bl;
-            float mx = -INFINITY;
-            for (int p = lane; p < P; p += 32) mx = fmaxf(mx, sc[bl * PS + p]);
-            mx = warp_max(mx);
-            float sum = 0.f;
-            for (int p = lane; p < P; p += 32) sum += expf(sc[bl * PS + p] - mx);
-            sum = warp_sum(sum);
-            for (int p = lane; p < P; p += 32) {
-                const float al = expf(sc[bl * PS + p] - mx) / sum;
+            const float x0 = lane < P ? sc[bl * PS + lane] : -INFINITY;
+            const float x1 = lane + 32 < P ? sc[bl * PS + lane + 32] : -INFINITY;
+            const float mx = warp_max(fmaxf(x0, x1));
+            const float e0 = lane < P ? __expf(x0 - mx) : 0.f;
+            const float e1 = lane + 32 < P ? __expf(x1 - mx) : 0.f;
+            const float inv = 1.f / warp_sum(e0 + e1);
+            if (lane < P) { sc[bl * PS + lane] = e0 * inv; if (gb < B) a.attn[((long)gb * T + t) * P + lane] = e0 * inv; }
+            if (lane + 32 < P) { sc[bl * PS + lane + 32] = e1 * inv; if (gb < B) a.attn[((long)gb * T + t) * P + lane + 32] = e1 * inv; }
+            for (int p = lane + 64; p < P; p += 32) {   // P > 64: generic tail (not the 7x7 case)
+                const float al = __expf(sc[bl * PS + p] - mx) * inv;
                 sc[bl * PS + p] = al;
                 if (gb < B) a.attn[((long)gb * T + t) * P + p] = al;
             }
         }
         __syncthreads();
+        TS(5);
         for (int i = tid; i < AC_RPC * F; i += AC_THREADS) {
             const int bl = i / F, fi = i - bl * F;
             const int brow = c * AC_RPC + bl, gb = b0 + brow;
-            float cv = 0.f;
-            if (gb < B) {
-                const float* fp = a.f + (long)gb * P * F + fi;
-                for (int p = 0; p < P; ++p) cv = fmaf(sc[bl * PS + p], fp[(long)p * F], cv);
-                a.ctx[((long)t * B + gb) * a.ldctx + fi] = cv;
-            }
+            const float* fp = fs + bl * P * F + fi;
+            const float* al = sc + bl * PS;
+            float cv0 = 0.f, cv1 = 0.f;
+            int p = 0;
+            for (; p + 8 <= P; p += 8) {
+                float fv[8], av[8];
 #pragma unroll
-            for (int rk = 0; rk < AC_CS; ++rk) cluster.map_shared_rank(cxs, rk)[brow * F + fi] = cv;
+                for (int e = 0; e < 8; ++e) { fv[e] = fp[(p + e) * F]; av[e] = al[p + e]; }
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) { cv0 = fmaf(av[e], fv[e], cv0); cv1 = fmaf(av[e + 1], fv[e + 1], cv1); }
+            }
+            for (; p < P; ++p) cv0 = fmaf(al[p], fp[p * F], cv0);
+            const float cv = cv0 + cv1;
+            if (gb < B) a.ctx[((long)t * B + gb) * a.ldctx + fi] = cv;
+            stage_c[brow * F + fi] = cv;
         }
+        __syncthreads();
+        cluster_push(cluster, stage_c, c * AC_RPC * F, (AC_RPC * F) >> 2, c);
+        TS(6);
         cl_arrive();
         cl_wait();
+        TS(7);
         // ---- ctx -> bf16 hi/lo B operand (local), then P3: gi_ctx slice = W_ihc-group . ctx ----
-        for (int i = tid; i < AC_BT * F; i += AC_THREADS) {
-            const int b = i / F, k = i - b * F;
-            const float v = cxs[i];
-            const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            cb_hi[b * AC_KP + k] = h;
-            cb_lo[b * AC_KP + k] = __float2bfloat16_rn(v - __bfloat162float(h));
-        }
-        __syncthreads();
-        if (group == 1 && lr0 < 3 * HS) {
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                const int n = nt * 8 + (lane >> 2);
-                const uint32_t* bh_p = reinterpret_cast<const uint32_t*>(cb_hi + n * AC_KP + (lane & 3) * 2);
-                const uint32_t* bl_p = reinterpret_cast<const uint32_t*>(cb_lo + n * AC_KP + (lane & 3) * 2);
-#pragma unroll
-                for (int kt = 0; kt < AC_KT; ++kt) {
-                    if (kt < nkt) {
-                        const uint32_t h0 = bh_p[kt * 8], h1 = bh_p[kt * 8 + 4];
-                        const uint32_t l0 = bl_p[kt * 8], l1 = bl_p[kt * 8 + 4];
-                        mma_bf16(acc, Ahi[kt], h0, h1);
-                        mma_bf16(acc, Ahi[kt], l0, l1);
-                        mma_bf16(acc, Alo[kt], h0, h1);
-                    }
-                }
-                const int ra = lr0 + (lane >> 2), col = nt * 8 + (lane & 3) * 2;
-                if (ra < 3 * HS) { res_c[ra * AC_BT + col] = acc[0]; res_c[ra * AC_BT + col + 1] = acc[1]; }
-                if (ra + 8 < 3 * HS) { res_c[(ra + 8) * AC_BT + col] = acc[2]; res_c[(ra + 8) * AC_BT + col + 1] = acc[3]; }
+        {
+            const int halfF = F >> 1;
+            for (int i = tid; i < AC_BT * halfF; i += AC_THREADS) {
+                const int b = i / halfF, k = (i - b * halfF) * 2;
+                const float2 v = *reinterpret_cast<const float2*>(stage_c + b * F + k);
+                uint32_t hi, lo;
+                split2(v.x, v.y, hi, lo);
+                *reinterpret_cast<uint32_t*>(cb_hi + b * AC_KP + k) = hi;
+                *reinterpret_cast<uint32_t*>(cb_lo + b * AC_KP + k) = lo;
             }
         }
         __syncthreads();
-        // ---- P4: gates + state update for my units; broadcast h' (fp32) to every CTA ----
+        TS(8);
+        if (group == 1 && lr0 < 3 * HS) {
+            float acc[2][AC_NT][4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int nt = 0; nt < AC_NT; ++nt) { acc[e][nt][0] = acc[e][nt][1] = acc[e][nt][2] = acc[e][nt][3] = 0.f; }
+            const int nrow = lane >> 2, kc = (lane & 3) * 2;
+#pragma unroll
+            for (int kt = 0; kt < AC_KT; ++kt) {
+#pragma unroll
+                for (int nt = 0; nt < AC_NT; ++nt) {
+                    const uint32_t* bh_p = reinterpret_cast<const uint32_t*>(cb_hi + (nt * 8 + nrow) * AC_KP + kt * 16 + kc);
+                    const uint32_t* bl_p = reinterpret_cast<const uint32_t*>(cb_lo + (nt * 8 + nrow) * AC_KP + kt * 16 + kc);
+                    const uint32_t h0 = bh_p[0], h1 = bh_p[4], l0 = bl_p[0], l1 = bl_p[4];
+                    mma_bf16(acc[kt & 1][nt], Ahi[kt], h0, h1);
+                    mma_bf16(acc[kt & 1][nt], Ahi[kt], l0, l1);
+                    mma_bf16(acc[kt & 1][nt], Alo[kt], h0, h1);
+                }
+            }
+            const int ra = lr0 + (lane >> 2);
+#pragma unroll
+            for (int nt = 0; nt < AC_NT; ++nt) {
+                const int col = nt * 8 + (lane & 3) * 2;
+                if (ra < 3 * HS) {
+                    res_c[ra * AC_BT + col] = acc[0][nt][0] + acc[1][nt][0];
+                    res_c[ra * AC_BT + col + 1] = acc[0][nt][1] + acc[1][nt][1];
+                }
+                if (ra + 8 < 3 * HS) {
+                    res_c[(ra + 8) * AC_BT + col] = acc[0][nt][2] + acc[1][nt][2];
+                    res_c[(ra + 8) * AC_BT + col + 1] = acc[0][nt][3] + acc[1][nt][3];
+                }
+            }
+        }
+        __syncthreads();
+        TS(9);
+        // ---- P4: gates + state update for my units (written into my slice of stage_h), then pushed to every CTA ----
         float o_r[AC_MAXI], o_z[AC_MAXI], o_n[AC_MAXI], o_g[AC_MAXI], o_h[AC_MAXI];
 #pragma unroll
         for (int q = 0; q < AC_MAXI; ++q) {
-            const int i = tid + q * AC_THREADS;
             o_r[q] = o_z[q] = o_n[q] = o_g[q] = o_h[q] = 0.f;
+            const int i = tid + q * AC_THREADS;
             if (i < HS * AC_BT) {
-                const int jl = it_jl[q], b = it_b[q], j = c * HS + jl;
+                const int jl = it_jl[q], b = it_b[q];
                 if (it_live[q]) {
                     const float ghr = res_h[(HS + jl) * AC_BT + b] + bh[q][0];
                     const float ghz = res_h[(2 * HS + jl) * AC_BT + b] + bh[q][1];
@@ -301,20 +415,20 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attgru_cluster_fwd_kernel(const
                     const float gir = giw[q][0] + res_c[jl * AC_BT + b];
                     const float giz = giw[q][1] + res_c[(HS + jl) * AC_BT + b];
                     const float gin = giw[q][2] + res_c[(2 * HS + jl) * AC_BT + b];
-                    const float r = sigmoidf_acc(gir + ghr);
-                    const float z = sigmoidf_acc(giz + ghz);
-                    const float n = tanhf(gin + r * ghn);
+                    const float r = sigmoid_fast(gir + ghr);
+                    const float z = sigmoid_fast(giz + ghz);
+                    const float n = 1.f - 2.f * recip_exp2x_p1(gin + r * ghn);
                     const float hp = hown[i];
                     o_r[q] = r; o_z[q] = z; o_n[q] = n; o_g[q] = ghn;
                     o_h[q] = (1.f - z) * n + z * hp;
                     hown[i] = o_h[q];
                 }
-                if (j < H) {
-#pragma unroll
-                    for (int rk = 0; rk < AC_CS; ++rk) cluster.map_shared_rank(hx, rk)[b * H + j] = o_h[q];
-                }
+                stage_h[(c * AC_BT + b) * HS + jl] = o_h[q];
             }
         }
+        __syncthreads();
+        cluster_push(cluster, stage_h, c * AC_BT * HS, (AC_BT * HS) >> 2, c);
+        TS(10);
         cl_arrive();
 #pragma unroll
         for (int q = 0; q < AC_MAXI; ++q) {
@@ -327,24 +441,35 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attgru_cluster_fwd_kernel(const
             }
         }
         cl_wait();
+        TS(11);
         // ---- h' -> bf16 hi/lo B operand (local) for the next step ----
-        for (int i = tid; i < AC_BT * H; i += AC_THREADS) {
-            const int b = i / H, k = i - b * H;
-            const float v = hx[i];
-            const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            hb_hi[b * AC_KP + k] = h;
-            hb_lo[b * AC_KP + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+        {
+            const int halfH = (H + 1) >> 1;
+            for (int i = tid; i < AC_BT * halfH; i += AC_THREADS) {
+                const int b = i / halfH, j = (i - b * halfH) * 2;
+                const float v0 = stage_h[hmap[j] + b * HS];
+                const float v1 = (j + 1 < H) ? stage_h[hmap[j + 1] + b * HS] : 0.f;
+                uint32_t hi, lo;
+                split2(v0, v1, hi, lo);
+                *reinterpret_cast<uint32_t*>(hb_hi + b * AC_KP + j) = hi;
+                *reinterpret_cast<uint32_t*>(hb_lo + b * AC_KP + j) = lo;
+            }
         }
         __syncthreads();
+        TS(12);
+        // (stage_c / stage_h / us are single-buffered: each is rewritten by peers only after a cluster barrier that every
+        //  CTA reaches after its last read of the previous contents -- see the phase order above.)
     }
     cluster.sync();   // nobody exits while peers may still address its shared memory
+    TSP(24);
 }
 
 static size_t attcl_smem(int H, int F, int P, int HS) {
     const int PS = (P + 3) & ~3;
-    return (size_t)4 * AC_BT * AC_KP * 2 +
-           ((size_t)AC_BT * H + (size_t)AC_BT * F + (size_t)AC_RPC * H + (size_t)7 * HS * AC_BT + (size_t)HS * AC_BT +
-            (size_t)AC_RPC * PS) * sizeof(float);
+    return ((size_t)AC_RPC * P * H + (size_t)AC_RPC * P * F + (size_t)AC_BT * F + (size_t)AC_CS * AC_BT * HS +
+            (size_t)AC_RPC * H + (size_t)7 * HS * AC_BT + (size_t)HS * AC_BT + (size_t)AC_RPC * PS + (size_t)((H + 3) & ~3)) *
+               sizeof(float) +
+           (size_t)4 * AC_BT * AC_KP * 2;
 }
 
 }  // namespace caphn
@@ -358,7 +483,8 @@ int caphn_attgru_cluster_plan(int H, int F, int P, int* ok) {
     const int HS = (H + AC_CS - 1) / AC_CS;
     const int MTH = (4 * HS + 15) / 16, MTC = (3 * HS + 15) / 16;
     *ok = (H >= 8 && H <= AC_KT * 16 && F >= 1 && F <= AC_KT * 16 && MTH + MTC <= AC_WARPS &&
-           HS * AC_BT <= AC_MAXI * AC_THREADS && P >= 1 && attcl_smem(H, F, P, HS) <= 200 * 1024) ? 1 : 0;
+           HS * AC_BT <= AC_MAXI * AC_THREADS && P >= 1 && attcl_smem(H, F, P, HS) <= 226 * 1024 && (P * H) % 4 == 0 && (P * F) % 4 == 0 && F % 4 == 0 &&
+           (AC_BT * HS) % 4 == 0) ? 1 : 0;
     return CAPHN_OK;
 }
 
@@ -390,5 +516,27 @@ int caphn_attgru_cluster_fwd(const float* Kp, const float* f, const float* GIw, 
     CAPHN_CHECK(cudaLaunchKernelEx(&cfg, attgru_cluster_fwd_kernel, a));
     CAPHN_RETURN_LAST();
 }
+
+#ifdef CAPHN_ATTCL_TIMING
+int caphn_attcl_timestamps(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, caphn::g_attcl_ts, sizeof(long long) * 32);
+}
+int caphn_attcl_max_clusters(int H, int F, int P) {
+    const int HS = (H + caphn::AC_CS - 1) / caphn::AC_CS;
+    const size_t smem = caphn::attcl_smem(H, F, P, HS);
+    cudaFuncSetAttribute(caphn::attgru_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(caphn::AC_CS * 64);
+    cfg.blockDim = dim3(caphn::AC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = caphn::AC_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = -1;
+    cudaOccupancyMaxActiveClusters(&n, caphn::attgru_cluster_fwd_kernel, &cfg);
+    return n;
+}
+#endif
 
 }  // extern "C"
