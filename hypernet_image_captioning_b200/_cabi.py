@@ -48,6 +48,9 @@ SIGNATURES = {
     "caphn_attgru_seq_bwd": [P] * 23 + [I] * 7 + [P],
     "caphn_attgru_cluster_plan": [I, I, I, P],
     "caphn_attgru_cluster_fwd": [P] * 14 + [L] + [P] * 5 + [I] * 8 + [P],
+    "caphn_attstep_pack_size": [I, I, I, I, P, P],
+    "caphn_attstep_pack": [P, P, P, I, I, I, P, P],
+    "caphn_attstep_fwd": [P] * 13 + [L] + [P] * 5 + [I] * 8 + [P],
     "caphn_attn_df": [P, P, P, I, I, I, I, P],
     "caphn_mean_pos": [P, I, I, I, P, P],
     "caphn_mean_pos_bwd": [P, I, I, I, P, P],

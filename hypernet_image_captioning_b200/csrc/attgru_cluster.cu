@@ -18,8 +18,8 @@
 // Per step: [MMA: u_slice, gh_slice = W.h] -> exchange u -> scores, softmax, ctx for own rows -> exchange ctx ->
 //           [MMA: gi_ctx_slice = W_ihc.ctx] -> gates, state update for own units -> exchange h'.
 #include "seq_common.cuh"
+#include "mma_common.cuh"
 #include <cooperative_groups.h>
-#include <cuda_bf16.h>
 #include <math.h>
 
 namespace cg = cooperative_groups;
@@ -56,20 +56,6 @@ struct AttClArgs {
     int B, T, P, H, F, E, HS, t0, t1;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
-    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-    hi = pack_bf16(h0, h1);
-    lo = pack_bf16(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
-}
-__device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // local weight row lr of this CTA's slice.  group 0 (input h): [U_a | W_hh r | W_hh z | W_hh n]; group 1 (input ctx):

@@ -44,7 +44,7 @@ def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, f
     Kp = ops.linear(f, Wa_w, Wa_b)                                    # [B*P, H]
     fmean = ops.mean_pos(f.view(B, P, Fd))                            # [B, F]
     h0 = ops.linear(fmean, init_w, init_b)                            # [B, H]
-    lw = ops.AttGruWeights(W_ih, W_hh, Ua_w.contiguous(), E)
+    lw = ops.AttGruWeights(W_ih, W_hh, Ua_w.contiguous(), E, P)
     va = va_w.reshape(-1).contiguous()
     bv = va_b.reshape(1).contiguous()
     Ua_b = Ua_b.contiguous()
@@ -72,7 +72,7 @@ def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, f
             ops.attgru_cluster_fwd(K3, f3, GIw, Ua_w.contiguous(), Ua_b, va, bv, W_ih, W_hh, b_hh, Hall, Hbm, attn, XC,
                                    E, saved, 0, T)
         else:
-            ops.attgru_seq_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, 0, T)
+            ops.attgru_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, 0, T)
         ops.linear(Hbm.view(B * T, H), fc_w, fc_b, out=logits.view(B * T, V))
     else:
         GIw = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
@@ -87,7 +87,7 @@ def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, f
             xw = ops.gather_rows(emb_w, fed[t])                        # zeros where fed == -1
             XC[t * B:(t + 1) * B, :E].copy_(xw)
             xproj(xw, out=GIw[t * B:(t + 1) * B])
-            ops.attgru_seq_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, t, t + 1)
+            ops.attgru_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, t, t + 1)
             vocab(Hall[t + 1], out=logits[:, t, :])
     sv = (feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih, W_hh, fc_w, Wa_w, Ua_w,
           va, init_w, fsplit.hi if fsplit is not None else None, fsplit.lo if fsplit is not None else None)
@@ -301,7 +301,7 @@ class AttentionGru(nn.Module):
         emb_w = self.embed.weight.detach()
         Kp = ops.linear(f3.view(B * P, Fd), a.W_a.weight.detach(), a.W_a.bias.detach()).view(B, P, H)
         h0 = ops.linear(ops.mean_pos(f3), self.init_h.weight.detach(), self.init_h.bias.detach())
-        lw = ops.AttGruWeights(W_ih, W_hh, a.U_a.weight.detach().contiguous(), E)
+        lw = ops.AttGruWeights(W_ih, W_hh, a.U_a.weight.detach().contiguous(), E, P)
         va, bv = a.v_a.weight.detach().reshape(-1).contiguous(), a.v_a.bias.detach().reshape(1).contiguous()
         Hall = torch.empty(T + 1, B, H, device=dev, dtype=torch.float32)
         Hall[0].copy_(h0)
@@ -314,7 +314,7 @@ class AttentionGru(nn.Module):
         for t in range(T):
             xw = ops.gather_rows(emb_w, tokens[t])
             ops.linear(xw, W_ih_w, b_ih, out=GIw[t * B:(t + 1) * B])
-            ops.attgru_seq_fwd(Kp, f3, GIw, lw, a.U_a.bias.detach(), va, bv, b_hh, Hall, None, attn, XC, E, None, t, t + 1)
+            ops.attgru_fwd(Kp, f3, GIw, lw, a.U_a.bias.detach(), va, bv, b_hh, Hall, None, attn, XC, E, None, t, t + 1)
             ops.linear(Hall[t + 1], self.fc.weight.detach(), self.fc.bias.detach(), out=logits)
             _, top = ops.softmax_argmax(logits, want_probs=False)
             tokens[t + 1].copy_(top)

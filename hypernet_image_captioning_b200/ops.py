@@ -401,16 +401,66 @@ def relu_mask_(ref, y):
     return y
 
 
-class AttGruWeights:
-    """Generated / attention weights laid out for the recurrence kernels (16-byte rows)."""
+ATT_STEP = True   # two batch-wide kernels per step (attention | tensor-core gates) instead of the persistent streaming kernel
 
-    def __init__(self, W_ih, W_hh, U_a, E):
+
+_attstep_sizes = {}
+
+
+def _attstep_bytes(H, Fd, P, B):
+    """(pack bytes, workspace bytes) of the step-split recurrence; pack bytes == 0: shape not covered."""
+    key = (H, Fd, P, B)
+    if key not in _attstep_sizes:
+        import ctypes
+        n, w = ctypes.c_long(0), ctypes.c_long(0)
+        _cabi.call("caphn_attstep_pack_size", H, Fd, P, B, ctypes.byref(n), ctypes.byref(w))
+        _attstep_sizes[key] = (int(n.value), int(w.value))
+    return _attstep_sizes[key]
+
+
+class AttGruWeights:
+    """Generated / attention weights laid out for the recurrence kernels: the mma-fragment pack of W_ih[:, E:], W_hh and
+    U_a (step-split path, needs the number of positions P), or their k-major transposes with 16-byte rows (persistent
+    streaming path)."""
+
+    def __init__(self, W_ih, W_hh, U_a, E, P=None, step=None):
         H = W_hh.shape[1]
         Fd = W_ih.shape[1] - E
         self.ldh, self.ld3, self.ldf = round4(H), round4(3 * H), round4(Fd)
-        self.UaT = transpose_pad(U_a, self.ldh)
-        self.WhhT = transpose_pad(W_hh, self.ld3)
-        self.WihcT = transpose_pad(W_ih[:, E:], self.ld3)
+        use_step = (ATT_STEP if step is None else step) and P is not None
+        n = _attstep_bytes(H, Fd, P, 0)[0] if use_step else 0
+        self.pack = self.UaT = self.WhhT = self.WihcT = self.work = self._resume = None
+        if n > 0:
+            W_ih, W_hh, U_a = W_ih.contiguous(), W_hh.contiguous(), U_a.contiguous()
+            self.pack = torch.empty(n, device=W_hh.device, dtype=torch.uint8)
+            _cabi.call("caphn_attstep_pack", W_ih.data_ptr(), W_hh.data_ptr(), U_a.data_ptr(), E, Fd, H,
+                       self.pack.data_ptr(), _stream())
+        else:
+            self.UaT = transpose_pad(U_a, self.ldh)
+            self.WhhT = transpose_pad(W_hh, self.ld3)
+            self.WihcT = transpose_pad(W_ih[:, E:], self.ld3)
+
+
+def attgru_fwd(Kp, f, GIw, lw, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, saved, t0, t1):
+    """Steps [t0,t1) of the attention-GRU recurrence on whichever layout `lw` was prepared for."""
+    if lw.pack is None:
+        return attgru_seq_fwd(Kp, f, GIw, lw, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, saved, t0, t1)
+    B, P, H = Kp.shape
+    Fd = f.shape[2]
+    T = Hall.shape[0] - 1
+    sp = [saved[i].data_ptr() for i in range(5)] if saved is not None else [None] * 5
+    ctx_ptr = XC.data_ptr() + 4 * E
+    wbytes = _attstep_bytes(H, Fd, P, B)[1]
+    if lw.work is None or lw.work.numel() < wbytes:
+        lw.work = torch.empty(wbytes, device=Kp.device, dtype=torch.uint8)
+        lw._resume = None
+    # one-step-per-call decode: the workspace still holds the operand rows of Hall[t0] from the previous call
+    resume = 1 if lw._resume == (Hall.data_ptr(), t0) else 0
+    _cabi.call("caphn_attstep_fwd", Kp.data_ptr(), f.data_ptr(), GIw.data_ptr(), bu.data_ptr(), va.data_ptr(),
+               bv.data_ptr(), lw.pack.data_ptr(), lw.work.data_ptr(), bhh.data_ptr(), Hall.data_ptr(), _p(Hbm),
+               attn.data_ptr(), ctx_ptr, XC.stride(0), sp[0], sp[1], sp[2], sp[3], sp[4], B, T, P, H, Fd, t0, t1, resume,
+               _stream())
+    lw._resume = (Hall.data_ptr(), t1)
 
 
 def attgru_seq_fwd(Kp, f, GIw, lw, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, saved, t0, t1):

@@ -117,6 +117,25 @@ int caphn_attgru_seq_bwd(const float* dHbm, const float* dattn, const float* Kp,
                          const float* Hall, const float* Ua, const float* va, const float* Wihc, const float* Whh,
                          float* dGI, float* dGH, float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0,
                          int B, int T, int P, int H, int F, int ldh, int ldf, void* stream);
+/* Step-split forward (default for H, F <= 208): three batch-wide launches per time step instead of one persistent
+ * kernel, chained with programmatic dependent launch -- U: u = U_a h + b_u on the warp tensor cores (bf16 hi/lo split,
+ * fp32 accumulate); A: one CTA per batch row, K_b / f_b fetched into shared memory by bulk TMA copies, scores, softmax,
+ * ctx; Y: gi_ctx / gh on the warp tensor cores + the r/z/n gates.  Replaces the same reference lines as
+ * caphn_attgru_seq_fwd (models/decoderlstm.py:97-100, models/attention.py:33-45).
+ * caphn_attstep_pack_size: *pack_bytes = size of the weight pack (0: shape not covered, use caphn_attgru_seq_fwd),
+ *   *work_bytes = size of the scratch buffer for batch B (u and the bf16 hi/lo operand rows passed between the kernels).
+ * caphn_attstep_pack: builds the mma-fragment-ordered bf16 hi/lo pack of Wih[:, E:E+F], Whh (plain row-major
+ *   [3H,E+F], [3H,H]) and Ua [H,H]; once per generated theta.
+ * caphn_attstep_fwd: steps [t0,t1); tensors as in caphn_attgru_seq_fwd.  work: 256-byte aligned.  resume != 0: the
+ *   previous call ran up to step t0 on the same work / Hall buffers (one-step-per-call decode), skip the re-conversion
+ *   of Hall[t0]. */
+int caphn_attstep_pack_size(int H, int F, int P, int B, long* pack_bytes, long* work_bytes);
+int caphn_attstep_pack(const float* Wih, const float* Whh, const float* Ua, int E, int F, int H, void* pack,
+                       void* stream);
+int caphn_attstep_fwd(const float* Kp, const float* f, const float* GIw, const float* bu, const float* va,
+                      const float* bv, const void* pack, void* work, const float* bhh, float* Hall, float* Hbm,
+                      float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z, float* Nn, float* GHN, int B,
+                      int T, int P, int H, int F, int t0, int t1, int resume, void* stream);
 /* Weights-resident forward variant: U_a, W_hh and W_ih[:,E:] stay on chip for all steps, split by hidden unit over a
  * cluster of 8 CTAs (register-resident warp-MMA fragments, bf16x3), attention partitioned by batch row, DSMEM exchanges.
  * Takes the PLAIN row-major weights Ua [H,H], Wih [3H,E+F], Whh [3H,H].  caphn_attgru_cluster_plan: *ok = 1 if the

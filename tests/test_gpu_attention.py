@@ -206,12 +206,47 @@ def test_attgru_cluster_forward_matches_streaming_kernel(B, T, Fo, E, H, P):
         if cluster:
             ops.attgru_cluster_fwd(Kp, f, GIw, Ua, bu, va, bv, W_ih, W_hh, bhh, Hall, Hbm, attn, XC, E, saved, 0, T)
         else:
-            lw = ops.AttGruWeights(W_ih, W_hh, Ua, E)
+            lw = ops.AttGruWeights(W_ih, W_hh, Ua, E, P, step=False)
             ops.attgru_seq_fwd(Kp, f, GIw, lw, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, saved, 0, T)
         torch.cuda.synchronize()
         outs.append((Hall, Hbm, attn, XC, saved))
     for name, x, y in zip(("Hall", "Hbm", "attn", "XC", "saved"), outs[1], outs[0]):
         assert rel_err(x, y) < 3e-5, name
+
+
+@pytest.mark.parametrize("B,T,Fo,E,H,P", [(5, 3, 16, 12, 20, 49), (40, 6, 200, 200, 200, 49), (33, 4, 64, 32, 100, 7),
+                                          (70, 3, 36, 8, 200, 5), (3, 2, 8, 5, 12, 3), (37, 3, 20, 6, 208, 4),
+                                          (3, 2, 7, 5, 9, 3)])
+def test_attgru_step_split_forward_matches_streaming_kernel(B, T, Fo, E, H, P):
+    """Step-split path (U / attention / gates kernels, PDL-chained) == persistent streaming kernel, also one step at a
+    time (the decode call pattern, workspace resumed between calls) and for ragged sizes (H, F not multiples of 16).
+    The last case is a shape the step-split path does not cover (P*H not a multiple of 4): it must fall back."""
+    from hypernet_image_captioning_b200 import ops
+    g = torch.Generator().manual_seed(B + T + H)
+    r = lambda *s: torch.randn(*s, generator=g).cuda()
+    Kp, f, GIw = r(B, P, H) * 0.5, r(B, P, Fo) * 0.5, r(T * B, 3 * H) * 0.5
+    Ua, W_ih, W_hh = r(H, H) / H ** 0.5, r(3 * H, E + Fo) / (E + Fo) ** 0.5, r(3 * H, H) / H ** 0.5
+    bu, va, bv, bhh, h0 = r(H) * 0.1, r(H) * 0.3, r(1), r(3 * H) * 0.1, r(B, H) * 0.5
+    outs = []
+    for mode in ("stream", "step", "step1"):
+        Hall = torch.empty(T + 1, B, H).cuda(); Hall[0] = h0
+        Hbm, attn = torch.empty(B, T, H).cuda(), torch.empty(B, T, P).cuda()
+        XC, saved = torch.zeros(T * B, E + Fo).cuda(), torch.empty(5, T, B, H).cuda()
+        lw = ops.AttGruWeights(W_ih, W_hh, Ua, E, P, step=(mode != "stream"))
+        covered = ops._attstep_bytes(H, Fo, P, 0)[0] > 0
+        assert covered == (H % 4 == 0 and (P * Fo) % 4 == 0 and max(H, Fo) <= 208)
+        assert (lw.pack is not None) == (mode != "stream" and covered)
+        if mode == "step1":
+            for t in range(T):
+                ops.attgru_fwd(Kp, f, GIw, lw, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, saved, t, t + 1)
+        else:
+            ops.attgru_fwd(Kp, f, GIw, lw, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, saved, 0, T)
+        torch.cuda.synchronize()
+        outs.append((Hall, Hbm, attn, XC, saved))
+    for name, x, y in zip(("Hall", "Hbm", "attn", "XC", "saved"), outs[1], outs[0]):
+        assert rel_err(x, y) < 3e-5, name
+    for name, x, y in zip(("Hall", "Hbm", "attn", "XC", "saved"), outs[2], outs[1]):
+        assert torch.equal(x, y), name
 
 
 @pytest.mark.parametrize("name,cc,he", CASES)

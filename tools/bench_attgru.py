@@ -1,4 +1,4 @@
-"""Micro-benchmark: attention recurrence forward, L2-streaming kernel vs weights/K/f-resident cluster kernel."""
+"""Micro-benchmark: attention recurrence forward -- persistent L2-streaming kernel, resident cluster kernel, step-split path."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hypernet_image_captioning_b200 import ops
@@ -13,15 +13,18 @@ bu, va, bv, bhh, h0 = r(H) * 0.1, r(H) * 0.3, r(1), r(3 * H) * 0.1, r(B, H) * 0.
 Hall = torch.empty(T + 1, B, H, device=dev); Hall[0] = h0
 Hbm, attn = torch.empty(B, T, H, device=dev), torch.empty(B, T, P, device=dev)
 XC, saved = torch.zeros(T * B, E + Fo, device=dev), torch.empty(5, T, B, H, device=dev)
-lw = ops.AttGruWeights(W_ih, W_hh, Ua, E)
+lw = ops.AttGruWeights(W_ih, W_hh, Ua, E, P, step=False)
+lws = ops.AttGruWeights(W_ih, W_hh, Ua, E, P, step=True)
 
 def run(cluster):
-    if cluster:
+    if cluster == 2:
+        ops.attgru_fwd(Kp, f, GIw, lws, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, saved, 0, T)
+    elif cluster:
         ops.attgru_cluster_fwd(Kp, f, GIw, Ua, bu, va, bv, W_ih, W_hh, bhh, Hall, Hbm, attn, XC, E, saved, 0, T)
     else:
         ops.attgru_seq_fwd(Kp, f, GIw, lw, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, saved, 0, T)
 
-for cl in (False, True):
+for cl in (0, 1, 2):
     for _ in range(2):
         run(cl)
     torch.cuda.synchronize()
@@ -30,4 +33,4 @@ for cl in (False, True):
     for _ in range(5):
         run(cl)
     e1.record(); torch.cuda.synchronize()
-    print("cluster (resident)" if cl else "streaming         ", f"{e0.elapsed_time(e1) / 5 * 1e3:9.1f} us  ({e0.elapsed_time(e1) / 5 / T * 1e3:.1f} us/step)")
+    print(("streaming         ", "cluster (resident)", "step-split        ")[cl], f"{e0.elapsed_time(e1) / 5 * 1e3:9.1f} us  ({e0.elapsed_time(e1) / 5 / T * 1e3:.1f} us/step)")
