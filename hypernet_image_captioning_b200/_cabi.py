@@ -51,6 +51,9 @@ SIGNATURES = {
     "caphn_attstep_pack_size": [I, I, I, I, P, P],
     "caphn_attstep_pack": [P, P, P, I, I, I, P, P],
     "caphn_attstep_fwd": [P] * 13 + [L] + [P] * 5 + [I] * 8 + [P],
+    "caphn_attstep_bwd_size": [I, I, I, I, I, P, P],
+    "caphn_attstep_bwd_pack": [P, P, P, I, I, I, P, P],
+    "caphn_attstep_bwd": [P] * 22 + [I] * 5 + [P],
     "caphn_attn_df": [P, P, P, I, I, I, I, P],
     "caphn_mean_pos": [P, I, I, I, P, P],
     "caphn_mean_pos_bwd": [P, I, I, I, P, P],

@@ -103,7 +103,7 @@ def _attgru_backward(sv, dims, vocab, dattn):
     if dattn is not None:
         dattn = dattn.contiguous()
     f3, K3 = f.view(B, P, Fd), Kp.view(B, P, H)
-    dGI, dGH, dU, dCTX, dK, dva, dbv, dh0 = ops.attgru_seq_bwd(
+    dGI, dGH, dU, dCTX, dK, dva, dbv, dh0 = ops.attgru_bwd(
         dHbm.view(B, T, H), dattn, K3, f3, attn, saved, Hall, Ua_w.contiguous(), va, W_ih, W_hh, E)
     Hprev = Hall[:-1].reshape(T * B, H)
     dW_ih = ops.matmul_tn(dGI, XC)                                     # [3H, E+F]

@@ -531,6 +531,45 @@ def attgru_seq_bwd(dHbm, dattn, Kp, f, attn, saved, Hall, U_a, va, W_ih, W_hh, E
     return dGI, dGH, dU, dCTX, dK, dva, dbv, dh0
 
 
+_attstep_bwd_sizes = {}
+
+
+def _attstep_bwd_bytes(H, Fd, P, B, T):
+    key = (H, Fd, P, B, T)
+    if key not in _attstep_bwd_sizes:
+        import ctypes
+        n, w = ctypes.c_long(0), ctypes.c_long(0)
+        _cabi.call("caphn_attstep_bwd_size", H, Fd, P, B, T, ctypes.byref(n), ctypes.byref(w))
+        _attstep_bwd_sizes[key] = (int(n.value), int(w.value))
+    return _attstep_bwd_sizes[key]
+
+
+def attgru_bwd(dHbm, dattn, Kp, f, attn, saved, Hall, U_a, va, W_ih, W_hh, E, step=None):
+    """BPTT of the attention-GRU recurrence: step-split kernels when the shape is covered, else the persistent kernel.
+    Returns dGI, dGH [T*B,3H], dU [T*B,H], dCTX [T*B,F], dK [B,P,H], dva [H], dbv [1], dh0 [B,H]."""
+    B, P, H = Kp.shape
+    Fd = f.shape[2]
+    T = Hall.shape[0] - 1
+    nbytes, wbytes = _attstep_bwd_bytes(H, Fd, P, B, T) if (ATT_STEP if step is None else step) else (0, 0)
+    if nbytes == 0:
+        return attgru_seq_bwd(dHbm, dattn, Kp, f, attn, saved, Hall, U_a, va, W_ih, W_hh, E)
+    dev = Kp.device
+    W_ih, W_hh, U_a = W_ih.contiguous(), W_hh.contiguous(), U_a.contiguous()
+    pack = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    work = torch.empty(wbytes, device=dev, dtype=torch.uint8)
+    _cabi.call("caphn_attstep_bwd_pack", W_ih.data_ptr(), W_hh.data_ptr(), U_a.data_ptr(), E, Fd, H, pack.data_ptr(),
+               _stream())
+    e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    dGI, dGH, dU, dCTX = e(T * B, 3 * H), e(T * B, 3 * H), e(T * B, H), e(T * B, Fd)
+    dK, dva, dbv, dh0 = e(B, P, H), e(H), e(1), e(B, H)
+    _cabi.call("caphn_attstep_bwd", dHbm.data_ptr(), _p(dattn), Kp.data_ptr(), f.data_ptr(), attn.data_ptr(),
+               saved[0].data_ptr(), saved[1].data_ptr(), saved[2].data_ptr(), saved[3].data_ptr(), saved[4].data_ptr(),
+               Hall.data_ptr(), va.data_ptr(), pack.data_ptr(), work.data_ptr(), dGI.data_ptr(), dGH.data_ptr(),
+               dU.data_ptr(), dCTX.data_ptr(), dK.data_ptr(), dva.data_ptr(), dbv.data_ptr(), dh0.data_ptr(),
+               B, T, P, H, Fd, _stream())
+    return dGI, dGH, dU, dCTX, dK, dva, dbv, dh0
+
+
 def attn_df(attn, dCTX, df):
     B, T, P = attn.shape
     Fd = df.shape[-1]

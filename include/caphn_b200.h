@@ -136,6 +136,21 @@ int caphn_attstep_fwd(const float* Kp, const float* f, const float* GIw, const f
                       const float* bv, const void* pack, void* work, const float* bhh, float* Hall, float* Hbm,
                       float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z, float* Nn, float* GHN, int B,
                       int T, int P, int H, int F, int t0, int t1, int resume, void* stream);
+/* Step-split BPTT (default when covered): the backward of caphn_attstep_fwd as three launches per time step --
+ * G1: dh_t (du_{t+1} U_a on the warp tensor cores + carries) and the GRU gate gradients; G2: dctx_t = dgi_t W_ih[:,E:]
+ * and dgh_t W_hh on the warp tensor cores; A': attention backward per row (K_b / f_b tiles by bulk TMA) -- plus one
+ * deferred kernel for dK and dv_a.  Same tensors and results as caphn_attgru_seq_bwd; dK / dva / dbv need no
+ * zero-initialisation.
+ * caphn_attstep_bwd_size: *pack_bytes (0: shape not covered, use caphn_attgru_seq_bwd), *work_bytes for (B, T).
+ * caphn_attstep_bwd_pack: transposed-weight fragment pack of U_a, Wih[:, E:E+F], Whh (plain row-major). */
+int caphn_attstep_bwd_size(int H, int F, int P, int B, int T, long* pack_bytes, long* work_bytes);
+int caphn_attstep_bwd_pack(const float* Wih, const float* Whh, const float* Ua, int E, int F, int H, void* pack,
+                           void* stream);
+int caphn_attstep_bwd(const float* dHbm, const float* dattn, const float* Kp, const float* f, const float* attn,
+                      const float* Upre, const float* R, const float* Z, const float* Nn, const float* GHN,
+                      const float* Hall, const float* va, const void* pack, void* work, float* dGI, float* dGH,
+                      float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0, int B, int T, int P, int H,
+                      int F, void* stream);
 /* Weights-resident forward variant: U_a, W_hh and W_ih[:,E:] stay on chip for all steps, split by hidden unit over a
  * cluster of 8 CTAs (register-resident warp-MMA fragments, bf16x3), attention partitioned by batch row, DSMEM exchanges.
  * Takes the PLAIN row-major weights Ua [H,H], Wih [3H,E+F], Whh [3H,H].  caphn_attgru_cluster_plan: *ok = 1 if the

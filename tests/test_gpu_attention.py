@@ -249,6 +249,35 @@ def test_attgru_step_split_forward_matches_streaming_kernel(B, T, Fo, E, H, P):
         assert torch.equal(x, y), name
 
 
+@pytest.mark.parametrize("B,T,Fo,E,H,P,ext", [(5, 3, 16, 12, 20, 49, True), (70, 5, 200, 200, 200, 49, False),
+                                              (33, 4, 64, 32, 100, 7, True), (130, 2, 36, 8, 208, 5, False),
+                                              (3, 2, 8, 5, 12, 3, True)])
+def test_attgru_step_split_backward_matches_streaming_kernel(B, T, Fo, E, H, P, ext):
+    """Step-split BPTT (tensor-core gate / GEMM kernels, TMA-fed attention backward, deferred dK) == persistent kernel."""
+    from hypernet_image_captioning_b200 import ops
+    g = torch.Generator().manual_seed(B + T + H)
+    r = lambda *s: torch.randn(*s, generator=g).cuda()
+    Kp, f, GIw = r(B, P, H) * 0.5, r(B, P, Fo) * 0.5, r(T * B, 3 * H) * 0.5
+    Ua, W_ih, W_hh = r(H, H) / H ** 0.5, r(3 * H, E + Fo) / (E + Fo) ** 0.5, r(3 * H, H) / H ** 0.5
+    bu, va, bv, bhh, h0 = r(H) * 0.1, r(H) * 0.3, r(1), r(3 * H) * 0.1, r(B, H) * 0.5
+    Hall = torch.empty(T + 1, B, H).cuda(); Hall[0] = h0
+    Hbm, attn = torch.empty(B, T, H).cuda(), torch.empty(B, T, P).cuda()
+    XC, saved = torch.zeros(T * B, E + Fo).cuda(), torch.empty(5, T, B, H).cuda()
+    lw = ops.AttGruWeights(W_ih, W_hh, Ua, E, P, step=False)
+    ops.attgru_fwd(Kp, f, GIw, lw, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, saved, 0, T)
+    dHbm = r(B, T, H) * 0.3
+    dattn = r(B, T, P) * 0.2 if ext else None
+    assert ops._attstep_bwd_bytes(H, Fo, P, B, T)[0] > 0
+    ref = ops.attgru_bwd(dHbm, dattn, Kp, f, attn, saved, Hall, Ua, va, W_ih, W_hh, E, step=False)
+    out = ops.attgru_bwd(dHbm, dattn, Kp, f, attn, saved, Hall, Ua, va, W_ih, W_hh, E, step=True)
+    torch.cuda.synchronize()
+    for name, x, y in zip(("dGI", "dGH", "dU", "dCTX", "dK", "dva", "dbv", "dh0"), out, ref):
+        if name == "dbv":      # analytically zero (softmax is shift invariant): both are rounding noise
+            assert abs(float(x) - float(y)) < 1e-5
+        else:
+            assert rel_err(x, y) < 5e-5, name
+
+
 @pytest.mark.parametrize("name,cc,he", CASES)
 def test_greedy_search_golden(name, cc, he):
     """B = 1 greedy_search with EOS stop (models/decoderlstm.py:138-175) against the reference's own output."""

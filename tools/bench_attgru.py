@@ -34,3 +34,17 @@ for cl in (0, 1, 2):
         run(cl)
     e1.record(); torch.cuda.synchronize()
     print(("streaming         ", "cluster (resident)", "step-split        ")[cl], f"{e0.elapsed_time(e1) / 5 * 1e3:9.1f} us  ({e0.elapsed_time(e1) / 5 / T * 1e3:.1f} us/step)")
+
+# ---- backward: persistent streaming kernel vs step-split ----
+ops.attgru_fwd(Kp, f, GIw, lws, bu, va, bv, bhh, Hall, Hbm, attn, XC, E, saved, 0, T)
+dHbm = r(B, T, H) * 0.3
+for step in (False, True):
+    for _ in range(2):
+        ops.attgru_bwd(dHbm, None, Kp, f, attn, saved, Hall, Ua, va, W_ih, W_hh, E, step=step)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.attgru_bwd(dHbm, None, Kp, f, attn, saved, Hall, Ua, va, W_ih, W_hh, E, step=step)
+    e1.record(); torch.cuda.synchronize()
+    print("bwd step-split        " if step else "bwd streaming         ", f"{e0.elapsed_time(e1) / 5 * 1e3:9.1f} us  ({e0.elapsed_time(e1) / 5 / T * 1e3:.1f} us/step)")
