@@ -312,6 +312,30 @@ def run_ours(args):
             decode()
         ms_dec = timed(decode, args.steps)
         extras["greedy_decode_captions_per_s"] = B * world * args.steps / (ms_dec * 1e-3)
+        # optimizer step: FusedAdam with the global-norm clip folded in, on the gradients of the
+        # last training step; Adam moves 28 bytes per parameter (p,g,m,v read; p,m,v written) + 4 for the norm pass
+        from hypernet_image_captioning_b200 import FusedAdam
+        step(pooled_d, caps_d, h0_d)
+        opt_params = [p_ for p_ in model.parameters() if p_.grad is not None]
+        n_opt = sum(p_.numel() for p_ in opt_params)
+        opt = FusedAdam(opt_params, lr=1e-6, max_grad_norm=5.0)
+        for _ in range(2):
+            opt.step()
+        ms_opt = timed(opt.step, 5) / 5
+        extras["optimizer"] = {"kind": "FusedAdam + clip_grad_norm 5.0 (hypernet heads/base, embed, image fc)",
+                               "params": n_opt, "ms_per_step": ms_opt,
+                               "alg_bytes": 32.0 * n_opt, "achieved_gbs": 32.0 * n_opt / (ms_opt * 1e-3) / 1e9,
+                               "hbm_frac": 32.0 * n_opt / (ms_opt * 1e-3) / 1e9 / peak}
+        def step_opt():
+            step(pooled_d, caps_d, h0_d)
+            opt.step()
+        for _ in range(2):
+            step_opt()
+        ms_full = timed(step_opt, args.steps)
+        extras["train_with_optimizer_captions_per_s"] = B * world * args.steps / (ms_full * 1e-3)
+        del opt, opt_params
+        model.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
         # bf16 mode (BASELINE configs[1] "fp32 and bf16"): hypernet weights + gradients in bf16, plain-bf16 tensor-core
         # products, fp32 accumulation / recurrent state; tolerance vs the fp32 oracle stated in tests/test_gpu_bf16.py
         model.set_precision("bf16")

@@ -6,7 +6,7 @@ call fails, this module raises.
 """
 import ctypes
 import os
-from ctypes import c_float, c_int, c_long, c_longlong, c_void_p
+from ctypes import c_double, c_float, c_int, c_long, c_longlong, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libcaphn_b200.so")
@@ -16,6 +16,7 @@ I = c_int
 L = c_long
 LL = c_longlong
 F = c_float
+D = c_double
 
 # name -> argtypes (mirrors include/caphn_b200.h)
 SIGNATURES = {
@@ -58,6 +59,9 @@ SIGNATURES = {
     "caphn_mean_pos": [P, I, I, I, P, P],
     "caphn_mean_pos_bwd": [P, I, I, I, P, P],
     "caphn_relu_mask": [P, P, L, P],
+    "caphn_sumsq": [P, L, P, P],
+    "caphn_clip_coef": [P, F, P, P, P],
+    "caphn_adam_step": [P, P, P, P, L, D, D, D, D, D, I, P, P],
     "caphn_launch_count": [P],
     "caphn_build_arch": [P],
 }

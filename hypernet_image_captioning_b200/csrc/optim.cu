@@ -1,0 +1,161 @@
+// Optimizer step for the hypernet parameters: torch.optim.Adam as configured by the reference
+// (cc_train_hypernet.py:110-122, hypernet.py:116-123: Adam(params, lr), default betas/eps, no weight decay) together
+// with Lightning's gradient_clip_val=5. (cc_train_hypernet.py:405: torch.nn.utils.clip_grad_norm_ over all parameters).
+//
+// The head parameters are 6.46 GB (pooled) / 0.58 GB (attention) in fp32, so the step is pure HBM streaming: per
+// element 16 bytes read (p, g, m, v) + 12 written (p, m, v).  One pass, 128-bit vectors, the clip coefficient applied
+// to the gradient on the fly (read from a device scalar: no host synchronisation, the gradients themselves are left
+// untouched), the global norm accumulated in double by a separate read-only pass over the gradients.
+#include "common.cuh"
+#include <math.h>
+
+namespace caphn {
+
+// p, m, v are rewritten by the same kernel: a coherent (non-.nc) streaming load
+__device__ __forceinline__ float4 ld_rw4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+constexpr int OPT_THREADS = 256;
+constexpr int OPT_UNROLL = 4;      // float4 per thread in flight
+
+__global__ void __launch_bounds__(OPT_THREADS) sumsq_kernel(const float* __restrict__ x, long n, double* __restrict__ out) {
+    const long n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float acc[OPT_UNROLL] = {0.f, 0.f, 0.f, 0.f};
+    const long stride = (long)gridDim.x * OPT_THREADS;
+    long i = (long)blockIdx.x * OPT_THREADS + threadIdx.x;
+    for (; i + (OPT_UNROLL - 1) * stride < n4; i += OPT_UNROLL * stride) {
+        float4 v[OPT_UNROLL];
+#pragma unroll
+        for (int e = 0; e < OPT_UNROLL; ++e) v[e] = ldg_stream4(reinterpret_cast<const float*>(x4 + i + e * stride));
+#pragma unroll
+        for (int e = 0; e < OPT_UNROLL; ++e)
+            acc[e] += v[e].x * v[e].x + v[e].y * v[e].y + v[e].z * v[e].z + v[e].w * v[e].w;
+    }
+    for (; i < n4; i += stride) {
+        const float4 v = ldg_stream4(reinterpret_cast<const float*>(x4 + i));
+        acc[0] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float t = x[(n4 << 2) + threadIdx.x]; acc[1] += t * t; }
+    double s = (double)acc[0] + (double)acc[1] + (double)acc[2] + (double)acc[3];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double ws[OPT_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < OPT_THREADS / 32; ++w) t += ws[w];
+        atomicAdd(out, t);
+    }
+}
+
+// coef = min(1, max_norm / (||g|| + 1e-6))    (torch.nn.utils.clip_grad_norm_)
+__global__ void clip_coef_kernel(const double* __restrict__ sumsq, float max_norm, float* __restrict__ coef,
+                                 float* __restrict__ norm_out) {
+    const float norm = (float)sqrt(*sumsq);
+    const float c = max_norm / (norm + 1e-6f);
+    *coef = c < 1.f ? c : 1.f;
+    if (norm_out) *norm_out = norm;
+}
+
+struct AdamArgs {
+    float* p; const float* g; float* m; float* v;
+    long n;
+    float beta2, omb1, omb2, eps, weight_decay, step_size, bc2_sqrt;   // omb = 1 - beta, rounded from double like torch does
+    const float* gscale;     // device scalar multiplied into the gradient (clip coefficient), or null
+};
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamArgs& a, float gs) {
+    g *= gs;
+    if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);
+    m = fmaf(a.omb1, g - m, m);                              // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(a.omb2, g * g, v * a.beta2);                    // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    p -= a.step_size * (m / denom);                          // param.addcdiv_(exp_avg, denom, value=-lr / bias_correction1)
+}
+
+__global__ void __launch_bounds__(OPT_THREADS) adam_kernel(const AdamArgs a) {
+    const float gs = a.gscale ? *a.gscale : 1.f;
+    const long n4 = a.n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(a.p);
+    float4* m4 = reinterpret_cast<float4*>(a.m);
+    float4* v4 = reinterpret_cast<float4*>(a.v);
+    const float4* g4 = reinterpret_cast<const float4*>(a.g);
+    const long stride = (long)gridDim.x * OPT_THREADS;
+    for (long i = (long)blockIdx.x * OPT_THREADS + threadIdx.x; i < n4; i += 2 * stride) {
+        const bool two = i + stride < n4;
+        const long i2 = two ? i + stride : i;
+        // 8 independent 128-bit loads in flight per thread
+        float4 p0 = ld_rw4(p4 + i), g0 = ldg_stream4(reinterpret_cast<const float*>(g4 + i));
+        float4 m0 = ld_rw4(m4 + i), v0 = ld_rw4(v4 + i);
+        float4 p1 = ld_rw4(p4 + i2), g1 = ldg_stream4(reinterpret_cast<const float*>(g4 + i2));
+        float4 m1 = ld_rw4(m4 + i2), v1 = ld_rw4(v4 + i2);
+        adam_one(p0.x, g0.x, m0.x, v0.x, a, gs); adam_one(p0.y, g0.y, m0.y, v0.y, a, gs);
+        adam_one(p0.z, g0.z, m0.z, v0.z, a, gs); adam_one(p0.w, g0.w, m0.w, v0.w, a, gs);
+        stg_stream4(reinterpret_cast<float*>(p4 + i), p0);
+        stg_stream4(reinterpret_cast<float*>(m4 + i), m0);
+        stg_stream4(reinterpret_cast<float*>(v4 + i), v0);
+        if (two) {
+            adam_one(p1.x, g1.x, m1.x, v1.x, a, gs); adam_one(p1.y, g1.y, m1.y, v1.y, a, gs);
+            adam_one(p1.z, g1.z, m1.z, v1.z, a, gs); adam_one(p1.w, g1.w, m1.w, v1.w, a, gs);
+            stg_stream4(reinterpret_cast<float*>(p4 + i2), p1);
+            stg_stream4(reinterpret_cast<float*>(m4 + i2), m1);
+            stg_stream4(reinterpret_cast<float*>(v4 + i2), v1);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (a.n & 3)) {
+        const long i = (n4 << 2) + threadIdx.x;
+        float p = a.p[i], m = a.m[i], v = a.v[i];
+        adam_one(p, a.g[i], m, v, a, gs);
+        a.p[i] = p; a.m[i] = m; a.v[i] = v;
+    }
+}
+
+static inline int opt_grid(long n4) {
+    long blocks = (n4 + (long)OPT_THREADS * 2 - 1) / ((long)OPT_THREADS * 2);
+    const long cap = (long)kNumSMs * 16;            // 16 resident CTAs of 256 threads per SM x 148: grid-stride beyond that
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace caphn
+
+using namespace caphn;
+
+extern "C" {
+
+// *sumsq (double, device) += sum_i x[i]^2.  x must be 16-byte aligned.
+int caphn_sumsq(const float* x, long n, double* sumsq, void* stream) {
+    if (n < 0 || !sumsq || ((uintptr_t)x & 15)) return CAPHN_EINVAL;
+    if (n == 0) return CAPHN_OK;
+    sumsq_kernel<<<opt_grid(n >> 2), OPT_THREADS, 0, (cudaStream_t)stream>>>(x, n, sumsq);
+    CAPHN_RETURN_LAST();
+}
+
+// *coef = min(1, max_norm / (sqrt(*sumsq) + 1e-6)); *norm (optional) = sqrt(*sumsq).   torch.nn.utils.clip_grad_norm_.
+int caphn_clip_coef(const double* sumsq, float max_norm, float* coef, float* norm, void* stream) {
+    if (!sumsq || !coef) return CAPHN_EINVAL;
+    clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, max_norm, coef, norm);
+    CAPHN_RETURN_LAST();
+}
+
+// One Adam step (torch.optim.Adam semantics, amsgrad=False, maximize=False) on a flat fp32 tensor; `step` is the 1-based
+// step count; gscale (device scalar or NULL) multiplies the gradient first (the clip coefficient).  Hyper-parameters are
+// doubles because torch derives 1 - beta, lr / (1 - beta1^t) and sqrt(1 - beta2^t) in double before rounding to fp32.
+int caphn_adam_step(float* p, const float* g, float* m, float* v, long n, double lr, double beta1, double beta2,
+                    double eps, double weight_decay, int step, const float* gscale, void* stream) {
+    if (n < 0 || step < 1 || (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15)) return CAPHN_EINVAL;
+    if (n == 0) return CAPHN_OK;
+    const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
+    AdamArgs a{p, g, m, v, n, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)weight_decay,
+               (float)(lr / bc1), (float)sqrt(bc2), gscale};
+    adam_kernel<<<opt_grid(n >> 2), OPT_THREADS, 0, (cudaStream_t)stream>>>(a);
+    CAPHN_RETURN_LAST();
+}
+
+}  // extern "C"

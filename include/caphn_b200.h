@@ -200,6 +200,17 @@ int caphn_mean_pos_bwd(const float* g, int B, int P, int Fd, float* dX, void* st
 int caphn_relu_mask(const float* ref, float* y, long n, void* stream);
 
 /* ---- bookkeeping -------------------------------------------------------------------------------------------------- */
+/* ---- optimizer step -------------------------------------------------------------------
+ * torch.optim.Adam(params, lr) of cc_train_hypernet.py:110-122 / hypernet.py:116-123 and Lightning's
+ * gradient_clip_val=5. (cc_train_hypernet.py:405 = torch.nn.utils.clip_grad_norm_), as single-pass HBM streaming kernels.
+ * caphn_sumsq: *sumsq (device double) += sum x[i]^2.   caphn_clip_coef: *coef = min(1, max_norm / (sqrt(*sumsq) + 1e-6)).
+ * caphn_adam_step: one Adam step on a flat fp32 tensor (amsgrad=False); step is 1-based; gscale (device scalar or NULL)
+ * multiplies the gradient on the fly (the clip coefficient -- the stored gradient is not modified). */
+int caphn_sumsq(const float* x, long n, double* sumsq, void* stream);
+int caphn_clip_coef(const double* sumsq, float max_norm, float* coef, float* norm, void* stream);
+int caphn_adam_step(float* p, const float* g, float* m, float* v, long n, double lr, double beta1, double beta2,
+                    double eps, double weight_decay, int step, const float* gscale, void* stream);
+
 /* *out = number of CUDA kernels launched by this library so far (host-side counter). */
 int caphn_launch_count(unsigned long long* out);
 /* *out = 100 (library compiled for sm_100a). */

@@ -1,0 +1,95 @@
+"""FusedAdam (+ folded gradient clipping) against torch.optim.Adam + torch.nn.utils.clip_grad_norm_ -- the optimizer the
+reference trainers configure (cc_train_hypernet.py:110-122,405)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _params(shapes, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.nn.Parameter((torch.randn(*s, generator=g) * 0.3).cuda()) for s in shapes]
+
+
+@pytest.mark.parametrize("clip", [None, 5.0, 0.05])
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_fused_adam_matches_torch_adam(clip, wd):
+    import hypernet_image_captioning_b200 as C
+    shapes = [(257, 33), (1000,), (3,), (64, 64), (1,), (90000, 13)]
+    ref_p, our_p = _params(shapes, 1), _params(shapes, 1)
+    ref = torch.optim.Adam(ref_p, lr=3e-3, weight_decay=wd)
+    our = C.FusedAdam(our_p, lr=3e-3, weight_decay=wd, max_grad_norm=clip)
+    g = torch.Generator().manual_seed(2)
+    for it in range(4):
+        grads = [(torch.randn(*s, generator=g) * (0.5 if it else 3.0)).cuda() for s in shapes]
+        for p, q, gr in zip(ref_p, our_p, grads):
+            p.grad, q.grad = gr.clone(), gr.clone()
+        if clip is not None:
+            n_ref = torch.nn.utils.clip_grad_norm_(ref_p, clip)
+        ref.step()
+        our.step()
+        if clip is not None:
+            assert abs(float(our.last_grad_norm) - float(n_ref)) <= 2e-6 * float(n_ref)
+            for q, gr in zip(our_p, grads):
+                assert torch.equal(q.grad, gr)          # the stored gradient is not modified
+        # with weight decay a few elements have clip*g + wd*p ~ 0: there m/(sqrt(v)+eps) is ill-conditioned and the last
+        # bit of the global norm (fp32 in torch, double here) moves the update by ~0.3 % of lr
+        tol = 2e-6 if wd == 0.0 else 2e-5
+        for p, q in zip(ref_p, our_p):
+            assert (p - q).abs().max().item() <= tol * max(1.0, p.abs().max().item()), (it, tuple(p.shape))
+    for p, q in zip(ref_p, our_p):
+        sr, so = ref.state[p], our.state[q]
+        assert int(sr["step"]) == int(so["step"])
+        for k in ("exp_avg", "exp_avg_sq"):      # elementwise ulp-level differences relative to the tensor's scale
+            assert (sr[k] - so[k]).abs().max().item() <= tol * sr[k].abs().max().item(), k
+
+
+def test_fused_adam_state_dict_roundtrip_and_lr_scheduler():
+    """state_dict()/load_state_dict() and ReduceLROnPlateau (cc_train_hypernet.py:121) work as with torch's Adam."""
+    import hypernet_image_captioning_b200 as C
+    p = _params([(50, 7)], 3)
+    opt = C.FusedAdam(p, lr=1e-2, max_grad_norm=5.0)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, cooldown=2, factor=0.5, patience=0)
+    p[0].grad = torch.ones_like(p[0])
+    opt.step()
+    sched.step(1.0); sched.step(2.0)
+    assert opt.param_groups[0]["lr"] == pytest.approx(5e-3)
+    import copy
+    sd = copy.deepcopy(opt.state_dict())      # a checkpoint (torch.save / torch.load) owns its tensors
+    q = _params([(50, 7)], 3)
+    opt2 = C.FusedAdam(q, lr=1e-2, max_grad_norm=5.0)
+    opt2.load_state_dict(sd)
+    q[0].data.copy_(p[0].data)
+    p[0].grad = torch.full_like(p[0], 0.5); q[0].grad = torch.full_like(q[0], 0.5)
+    opt.step(); opt2.step()
+    assert torch.equal(p[0], q[0])
+
+
+def test_fused_adam_trains_the_attention_hypernet_like_torch_adam():
+    """Three optimizer steps of the flow-mode caption loss on the tiny attention model: same losses as torch Adam + clip."""
+    import hypernet_image_captioning_b200 as C
+    from hypernet_image_captioning_b200.synth import synth_captions
+    losses = []
+    for fused in (False, True):
+        torch.manual_seed(0)
+        with torch.device("cuda"):
+            m = C.HyperNetAttention(16, 12, 20, 50, None)
+        g = torch.Generator().manual_seed(5)
+        feats = torch.randn(6, 49, 2048, generator=g).cuda()
+        caps = synth_captions(6, 7, 50, g).cuda()
+        params = [p for n, p in m.named_parameters() if not n.startswith("captioner.gru.")]
+        opt = C.FusedAdam(params, lr=1e-2, max_grad_norm=5.0) if fused else torch.optim.Adam(params, lr=1e-2)
+        ls = []
+        for _ in range(3):
+            opt.zero_grad(set_to_none=True)
+            cap = m.forward(m.captioner.embed.weight[4:5].detach())
+            loss, _, _ = cap.forward_loss(feats, caps, 0.0, ignore_index=0)
+            loss.backward()
+            if not fused:
+                torch.nn.utils.clip_grad_norm_(params, 5.0)
+            opt.step()
+            ls.append(float(loss.detach()))
+        losses.append(ls)
+    assert losses[0][0] == pytest.approx(losses[1][0], rel=1e-6)
+    assert losses[0][2] == pytest.approx(losses[1][2], rel=1e-4)
+    assert losses[1][2] < losses[1][0]
