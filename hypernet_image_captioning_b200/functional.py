@@ -70,6 +70,31 @@ def hypernet_theta(x2d: torch.Tensor, params: Sequence[torch.Tensor]) -> torch.T
     return HyperNetThetaFn.apply(x2d, *params)
 
 
+class RowsLinearFn(Function):
+    """y = act(x W^T + b) for a handful of rows (G <= a few) on the weight-streaming kernels; act = LeakyReLU(0.01) or none.
+    Used by the domain-embedding front-ends (cc_train_hypernet.py:90-106), whose input is one vector per step."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, leaky):
+        act = ACT_LEAKY if leaky else ops.ACT_NONE
+        y = ops.rows_linear_fwd(W, b, x, act)
+        ctx.save_for_backward(x, W, y)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        dW, db, dx = ops.rows_linear_bwd(W, x, y if ctx.act != ops.ACT_NONE else None, dy.contiguous(), ctx.act,
+                                         need_dW=need[1], need_dA=need[0])
+        return (dx if need[0] else None, dW if need[1] else None, db if need[2] else None, None)
+
+
+def rows_linear(x, W, b, leaky=False):
+    return RowsLinearFn.apply(x, W, b, leaky)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # y = x W^T + b (ReLU optional)        -- nn.Linear replacement (image_encoder.fc hypernet.py:46, feature_fc, init_h ...)
 # ----------------------------------------------------------------------------------------------------------------------

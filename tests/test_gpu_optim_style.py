@@ -93,3 +93,37 @@ def test_fused_adam_trains_the_attention_hypernet_like_torch_adam():
     assert losses[0][0] == pytest.approx(losses[1][0], rel=1e-6)
     assert losses[0][2] == pytest.approx(losses[1][2], rel=1e-4)
     assert losses[1][2] < losses[1][0]
+
+
+@pytest.mark.parametrize("kind,nin", [("one hot", None), ("embedding", None), ("histogram", 61), ("JSD", 2)])
+def test_domain_embedding_front_ends_match_torch_modules(kind, nin):
+    """cc_train_hypernet.py:86-106,137-149: the four ways a domain name becomes the hypernet input; values and gradients
+    against the same torch modules (nn.Embedding / nn.Sequential(Linear, LeakyReLU, ...))."""
+    import hypernet_image_captioning_b200 as C
+    domains = ["news\n", "sport", "food", "travel"]
+    g = torch.Generator().manual_seed(11)
+    vectors = {d.replace("\n", ""): torch.randn(nin, generator=g) for d in domains} if nin else None
+    torch.manual_seed(1)
+    m = C.DomainEmbedding(kind, domains, hyper_emb=10, in_features=nin, vectors=vectors).cuda()
+    assert m.dict_domain == {"news": 0, "sport": 1, "food": 2, "travel": 3}
+    out = m("food")
+    assert out.shape == (len(domains) if kind == "one hot" else 10,) and out.is_cuda
+    if kind == "one hot":
+        assert out.tolist() == [0.0, 0.0, 1.0, 0.0]
+        return
+    w = torch.randn(10, generator=g).cuda()
+    (out * w).sum().backward()
+    if kind == "embedding":
+        ref = m.embed.weight.detach()[2]
+        assert torch.equal(out.detach(), ref)
+        assert torch.allclose(m.embed.weight.grad[2], w) and float(m.embed.weight.grad[[0, 1, 3]].abs().max()) == 0.0
+        return
+    import copy
+    ref_m = copy.deepcopy(m.embed)
+    for p_ in ref_m.parameters():
+        p_.grad = None
+    ref = ref_m(vectors["food"].cuda())
+    (ref * w).sum().backward()
+    assert torch.allclose(out.detach(), ref.detach(), rtol=1e-5, atol=1e-6)
+    for (n1, p1), (_, p2) in zip(m.embed.named_parameters(), ref_m.named_parameters()):
+        assert torch.allclose(p1.grad, p2.grad, rtol=1e-4, atol=1e-6), n1
