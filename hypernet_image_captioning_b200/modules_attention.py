@@ -287,6 +287,87 @@ class AttentionGru(nn.Module):
         return AttentionGruLossFn.apply(ignore_index, features, captions, use, *self._params(self._gru_weights()))
 
     @torch.no_grad()
+    def beam_search(self, features, beam_size=3, end_sentence=2, max_steps=50):
+        """Beam search for ONE image -- the loop of HyperNet.test_step, hypernet_attention.py:247-326 (``beam_size`` = 3 at
+        :44).  ``features`` [1, P, D] are the encoder features (``feature_fc`` is applied here, :249).  Returns the best
+        complete sequence as a list of token ids (leading 0, trailing ``end_sentence``) or ``None`` when the reference
+        computes no beam caption (a beam is still open after ``max_steps`` + 1 steps, :308-311).
+
+        Reference quirks kept: every row starts from word 0 and ALL rows get a zero word embedding whenever the first
+        row's previous word is 0 (:265-266); step 1 ranks ``scores[0]`` only (:274-275); scores are summed
+        log-probabilities without length normalisation; finished beams leave the batch (:296-303).
+        Each step runs the recurrence kernels on the k live rows; the top-k bookkeeping is host logic as in the reference."""
+        feats = features.contiguous().float()
+        if feats.dim() != 3 or feats.shape[0] != 1:
+            raise ValueError("beam_search expects the features of one image: [1, P, D]")
+        _, P, D = feats.shape
+        W_ih, W_hh, b_ih, b_hh = [w.detach().contiguous() for w in self._gru_weights()]
+        E, H, V = self.embedding_dim, self.hidden_dim, self.vocab_size
+        dev = feats.device
+        a = self.attention
+        emb_w = self.embed.weight.detach()
+        fc0, fc2 = self.feature_fc[0], self.feature_fc[2]
+        f1 = ops.linear(feats.view(P, D), fc0.weight.detach(), fc0.bias.detach(), relu=True)
+        f = ops.linear(f1, fc2.weight.detach(), fc2.bias.detach())                       # [P, F]
+        Fd = f.shape[1]
+        K1 = ops.linear(f, a.W_a.weight.detach(), a.W_a.bias.detach())                     # [P, H]
+        k = int(beam_size)
+        f3 = f.view(1, P, Fd).expand(k, P, Fd).contiguous()
+        Kp = K1.view(1, P, H).expand(k, P, H).contiguous()
+        h0 = ops.linear(ops.mean_pos(f3[:1].contiguous()), self.init_h.weight.detach(), self.init_h.bias.detach())
+        h = h0.expand(k, H).contiguous()
+        lw = ops.AttGruWeights(W_ih, W_hh, a.U_a.weight.detach().contiguous(), E, P)
+        va, bv = a.v_a.weight.detach().reshape(-1).contiguous(), a.v_a.bias.detach().reshape(1).contiguous()
+        bu = a.U_a.bias.detach().contiguous()
+        fc_w, fc_b = self.fc.weight.detach(), self.fc.bias.detach()
+        W_ih_w = W_ih[:, :E]
+        prev = [0] * k
+        seqs = [[0] for _ in range(k)]
+        top_scores = torch.zeros(k, device=dev)
+        complete, complete_scores = [], []
+        step = 1
+        while True:
+            kc = len(prev)
+            prev_t = torch.tensor(prev, device=dev, dtype=torch.int64)
+            xw = ops.gather_rows(emb_w, prev_t)
+            if prev[0] == 0:
+                xw.zero_()
+            GIw = ops.linear(xw, W_ih_w, b_ih)
+            Hall = torch.empty(2, kc, H, device=dev, dtype=torch.float32)
+            Hall[0].copy_(h)
+            attn = torch.empty(kc, 1, P, device=dev, dtype=torch.float32)
+            XC = torch.empty(kc, E + Fd, device=dev, dtype=torch.float32)
+            ops.attgru_fwd(Kp[:kc], f3[:kc], GIw, lw, bu, va, bv, b_hh, Hall, None, attn, XC, E, None, 0, 1)
+            h = Hall[1]
+            logits = ops.linear(h, fc_w, fc_b)                                            # [kc, V]
+            _, lse = ops.ce_fwd(logits, torch.zeros(kc, device=dev, dtype=torch.int64), None)
+            scores = top_scores[:kc, None] + (logits - lse[:, None])                      # log_softmax + running score
+            flat = scores[0] if step == 1 else scores.reshape(-1)
+            top_scores, top_words = flat.topk(k, 0, True, True)
+            words = top_words.tolist()
+            prev_inds = [w // V for w in words]
+            next_inds = [w % V for w in words]
+            seqs = [seqs[pi] + [ni] for pi, ni in zip(prev_inds, next_inds)]
+            incomplete = [i for i, w in enumerate(next_inds) if w != end_sentence]
+            done = [i for i in range(len(next_inds)) if i not in incomplete]
+            if done:
+                sc = top_scores.tolist()
+                complete.extend(seqs[i] for i in done)
+                complete_scores.extend(sc[i] for i in done)
+            k -= len(done)
+            if k == 0:
+                break
+            seqs = [seqs[i] for i in incomplete]
+            sel = torch.tensor([prev_inds[i] for i in incomplete], device=dev, dtype=torch.int64)
+            h = h.index_select(0, sel)
+            top_scores = top_scores[torch.tensor(incomplete, device=dev, dtype=torch.int64)]
+            prev = [next_inds[i] for i in incomplete]
+            if step > max_steps:
+                return None
+            step += 1
+        return complete[complete_scores.index(max(complete_scores))]
+
+    @torch.no_grad()
     def greedy_search(self, features, end_sentence=2, max_sentence=20):
         """B = 1 greedy decoding with EOS stop -- models/decoderlstm.py:138-175.  ``features`` have ALREADY been through
         ``feature_fc`` ([1, P, F]); the first input word is index 0; returns (tokens list[int], list of attention

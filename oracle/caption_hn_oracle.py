@@ -208,6 +208,63 @@ def attention_gru_greedy_search(p: Params, gru_w, features_fc: torch.Tensor, end
     return sentence, torch.stack(weights, 0)
 
 
+def attention_beam_search(p: Params, gru_w, features: torch.Tensor, beam_size: int = 3, end_sentence: int = 2,
+                          max_steps: int = 50, pre: str = "captioner."):
+    """Beam search of HyperNet.test_step (hypernet_attention.py:247-326) for ONE image: ``features`` [1,P,D] are the
+    encoder features, feature_fc is applied here (:249).  Returns the best complete sequence as a list of token ids
+    (leading 0, trailing </s>), or None when the reference computes no beam caption (some beam still open after
+    ``max_steps`` + 1 steps: ``compute = False`` at :311).
+
+    Kept quirks: all k rows start from word 0 and the embeddings of EVERY row are zeroed whenever the first row's
+    previous word is 0 (:265-266); step 1 ranks scores[0] only (:274-275); scores are summed log-probabilities with no
+    length normalisation; finished beams are removed and k shrinks (:296-303).
+    """
+    emb_w = p[pre + "embed.weight"]
+    V = p[pre + "fc.weight"].shape[0]
+    enc = F.linear(F.relu(F.linear(features, p[pre + "feature_fc.0.weight"], p[pre + "feature_fc.0.bias"])),
+                   p[pre + "feature_fc.2.weight"], p[pre + "feature_fc.2.bias"])
+    k = beam_size
+    enc = enc.expand(k, enc.shape[1], enc.shape[2])
+    prev = torch.zeros(k, dtype=torch.long)
+    seqs = prev.unsqueeze(1)
+    top_scores = torch.zeros(k, 1)
+    complete, complete_scores = [], []
+    h = F.linear(enc.mean(dim=1), p[pre + "init_h.weight"], p[pre + "init_h.bias"])
+    step = 1
+    while True:
+        emb = F.embedding(prev, emb_w)
+        if int(prev[0]) == 0:
+            emb = torch.zeros_like(emb)
+        ctx, _ = bahdanau(p, enc, h, pre + "attention.")
+        h = gru_cell(torch.cat([emb, ctx], 1), h, *gru_w)
+        scores = F.log_softmax(F.linear(h, p[pre + "fc.weight"], p[pre + "fc.bias"]), dim=1)
+        scores = top_scores.expand_as(scores) + scores
+        if step == 1:
+            top_scores, top_words = scores[0].topk(k, 0, True, True)
+        else:
+            top_scores, top_words = scores.reshape(-1).topk(k, 0, True, True)
+        prev_inds = torch.div(top_words, V, rounding_mode="floor")
+        next_inds = top_words % V
+        seqs = torch.cat([seqs[prev_inds], next_inds.unsqueeze(1)], dim=1)
+        incomplete = [i for i, w in enumerate(next_inds.tolist()) if w != end_sentence]
+        done = [i for i in range(len(next_inds)) if i not in incomplete]
+        if done:
+            complete.extend(seqs[done].tolist())
+            complete_scores.extend(top_scores[done].tolist())
+        k -= len(done)
+        if k == 0:
+            break
+        seqs = seqs[incomplete]
+        h = h[prev_inds[incomplete]]
+        enc = enc[prev_inds[incomplete]]
+        top_scores = top_scores[incomplete].unsqueeze(1)
+        prev = next_inds[incomplete]
+        if step > max_steps:
+            return None
+        step += 1
+    return complete[complete_scores.index(max(complete_scores))]
+
+
 def caption_loss(logits: torch.Tensor, captions: torch.Tensor, ignore_index: Optional[int] = 0) -> torch.Tensor:
     """cc_train_hypernet.py:153 (ignore_index=<pad>=0) / hypernet.py:145 (ignore_index=None)."""
     V = logits.shape[-1]

@@ -60,6 +60,10 @@ def _flow_set_all_parameters(module, theta):
     return count
 
 
+# (tag, step at which the </s> logit crosses zero, its gain, scale of the other fc rows); None: </s> never wins
+BEAM_CASES = [("a", 3, 60.0, 8.0), ("b", 3, 200.0, 8.0), ("c", 6, 60.0, 3.0), ("d", 2, 20.0, 8.0), ("noeos", None, 0.0, 1.0)]
+
+
 def case_attention(ref, name, cc, style, Fo=16, E=12, H=20, V=50, he=10, B=2, T=6):
     torch.manual_seed(0)
     model = ref.HyperNetAttention(Fo, E, H, V, ref.vocab, cc=cc, hyper_emb=he)
@@ -108,6 +112,62 @@ def case_attention(ref, name, cc, style, Fo=16, E=12, H=20, V=50, he=10, B=2, T=
             sent, wts = captioner.greedy_search(fproj, end_sentence=2, max_sentence=7)
             out[f"gs/{bi}/tokens"] = torch.tensor(sent)
             out[f"gs/{bi}/weights"] = torch.stack([w.reshape(-1) for w in wts], 0)
+
+    # beam search k = 3: the reference's own test_step (hypernet_attention.py:240-326), unmodified.  Harness-side only:
+    # image_encoder is the identity (precomputed features are passed as "imgs"), the metric functions are replaced by a
+    # recorder of caps_pred_beam, and the </s> logit bias is shifted so that beams do (eos) / never (noeos) terminate.
+    if not cc:
+        import hypernet_attention as ref_hna0
+        captured = []
+        saved = (ref_hna0.metric_score_test, ref_hna0.metric_score, model.image_encoder)
+        ref_hna0.metric_score_test = lambda c_, pred, v_, m_: (captured.append(pred.clone()), (0,) * 6)[1]
+        ref_hna0.metric_score = lambda *a_, **k_: (0,) * 6
+        object.__setattr__(model, "image_encoder", lambda imgs: imgs)
+        model._modules.pop("image_encoder", None)
+        base_bias = model.captioner.fc.bias.detach().clone()
+        base_w = model.captioner.fc.weight.detach().clone()
+        # With random weights h_t converges within a few steps, so </s> is either in the top-k at step 1 or never.  To get
+        # beams that end after a few words, the </s> row of fc is pointed along the drift of the hidden state: its logit
+        # grows with t and crosses the other words' logits around step `cross`.
+        with torch.no_grad():
+            cap0 = model.forward(model.captioner.embed(torch.tensor([ref.vocab("<unk>")])))
+            enc = cap0.feature_fc(features[0:1])
+            hs, h = [], cap0.init_hidden(enc)
+            x = torch.zeros(1, E)
+            for _ in range(12):
+                ctx_, _ = cap0.attention(enc, h)
+                h = cap0.gru(torch.cat([x, ctx_], 1), h)
+                hs.append(h[0].clone())
+                x = cap0.embed(cap0.fc(h).argmax(1))
+        try:
+            for tag, cross, gain, wscale in BEAM_CASES:
+                with torch.no_grad():
+                    model.captioner.fc.bias.copy_(base_bias)
+                    model.captioner.fc.weight.copy_(base_w * wscale)     # sharper word distributions
+                    if cross is None:
+                        model.captioner.fc.bias[2] = -100.0
+                    else:
+                        d = hs[-1] - hs[0]
+                        d = d / d.dot(d)                                  # d . (h_t - h_1) goes 0 -> 1
+                        prog = d.dot(hs[cross] - hs[0])
+                        model.captioner.fc.weight[2] = gain * d
+                        model.captioner.fc.bias[2] = -gain * (d.dot(hs[0]) + prog)   # logit(</s>) = gain (progress_t - progress_cross)
+                out[f"beam/{tag}/fc_bias"] = model.captioner.fc.bias.detach().clone()
+                out[f"beam/{tag}/fc_weight"] = model.captioner.fc.weight.detach().clone()
+                for bi in range(B):
+                    captured.clear()
+                    np.random.seed(0)
+                    with torch.no_grad():
+                        model.test_step((features[bi:bi + 1], ("<unk>", (caps[bi:bi + 1], None))), 0)
+                    out[f"beam/{tag}/{bi}"] = captured[0] if captured else torch.tensor([-1])
+                    print(name, "beam", tag, bi, out[f"beam/{tag}/{bi}"].tolist())
+        finally:
+            ref_hna0.metric_score_test, ref_hna0.metric_score = saved[0], saved[1]
+            model._modules["image_encoder"] = saved[2]
+            with torch.no_grad():
+                model.captioner.fc.bias.copy_(base_bias)
+                model.captioner.fc.weight.copy_(base_w)
+        out["beam/style_id"] = torch.tensor(ref.vocab("<unk>"))
 
     # flow mode gradients (harness-side patch of set_all_parameters only)
     import hypernet_attention as ref_hna

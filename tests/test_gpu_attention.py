@@ -314,3 +314,19 @@ def test_regression_pretraining_loss_matches_reference_recipe():
     for k, v in m.named_parameters():
         if k.startswith("hn_"):
             assert grad_close(v.grad, pl[k].grad, TOL_GRAD), k
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d", "noeos"])
+def test_beam_search_golden(tag):
+    """Beam search k = 3 (hypernet_attention.py:247-326) against the caption the unmodified reference's test_step produced."""
+    c = load_case("attn_flickr")
+    p = params_of(c)
+    p["captioner.fc.bias"] = c[f"beam/{tag}/fc_bias"]
+    p["captioner.fc.weight"] = c[f"beam/{tag}/fc_weight"]
+    m = _model_from(p, 16, 12, 20, 50, False, 10)
+    style = m.captioner.embed.weight.detach()[int(c["beam/style_id"])].reshape(1, -1)     # :244-246
+    captioner = m.forward(style)
+    for bi in range(c["features"].shape[0]):
+        got = captioner.beam_search(c["features"][bi:bi + 1].cuda(), beam_size=3, end_sentence=2, max_steps=50)
+        want = c[f"beam/{tag}/{bi}"].tolist()
+        assert (got if got is not None else [-1]) == want, (tag, bi)

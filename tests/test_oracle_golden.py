@@ -115,3 +115,24 @@ def test_attention_greedy_search_matches_reference(name):
             toks, wts = O.attention_gru_greedy_search(p, gw, fproj, 2, 7)
             assert toks == c[f"gs/{bi}/tokens"].tolist()
             assert rel_err(wts, c[f"gs/{bi}/weights"]) < TOL
+
+
+BEAM_TAGS = ["a", "b", "c", "d", "noeos"]
+
+
+@pytest.mark.parametrize("tag", BEAM_TAGS)
+def test_attention_beam_search_matches_reference_test_step(tag):
+    """Beam search k = 3 of HyperNet.test_step (hypernet_attention.py:247-326): golden = the caption the unmodified
+    reference hands to metric_score_test (or no caption at all when a beam is still open after 51 steps)."""
+    c = load_case("attn_flickr")
+    p = params_of(c)
+    p["captioner.fc.bias"] = c[f"beam/{tag}/fc_bias"]
+    p["captioner.fc.weight"] = c[f"beam/{tag}/fc_weight"]
+    E, Fo, H = O.dims_attention(p)
+    with torch.no_grad():
+        style = p["captioner.embed.weight"][int(c["beam/style_id"])].reshape(1, -1)     # :244-246
+        gw = O.split_theta_attention(O.hypernet_theta(p, style, 4), E, Fo, H)
+        for bi in range(c["features"].shape[0]):
+            got = O.attention_beam_search(p, gw, c["features"][bi:bi + 1], 3, 2, 50)
+            want = c[f"beam/{tag}/{bi}"].tolist()
+            assert (got if got is not None else [-1]) == want, (tag, bi)
