@@ -172,15 +172,17 @@ struct AttStepA {
     long ldctx;
     __nv_bfloat16* csp;  // [2][B][KP] ctx hi, lo
     int B, T, t, P, H, F, KP, RPC;   // RPC = rows per CTA = ceil(B / grid)
+    int NBUF;                        // tile buffers per CTA: 1 (two co-resident CTAs per SM overlap each other) or 2
 };
 
-__global__ void __launch_bounds__(AS_THREADS, 1) attstep_attn_kernel(const AttStepA a) {
+__global__ void __launch_bounds__(AS_THREADS, 2) attstep_attn_kernel(const AttStepA a) {
     extern __shared__ __align__(16) float asmem[];
     const int H = a.H, F = a.F, P = a.P, KP = a.KP, B = a.B;
     const int PS = (P + 3) & ~3, H4 = (H + 3) & ~3;
     const int tile = P * H + P * F;                      // floats per buffer: K_b then f_b
     float* bufs = asmem;                                 // [2][tile]
-    float* us = bufs + 2 * tile;                         // [RPC][H4]
+    const int NBUF = a.NBUF;
+    float* us = bufs + NBUF * tile;                      // [RPC][H4]
     float* vs = us + a.RPC * H4;                         // [H4]
     float* sc = vs + H4;                                 // [PS]
     float* cpart = sc + PS;                              // [PSPL][KP]
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attstep_attn_kernel(const AttSt
     if (tid == 0) {
         st_mbar_init(&mbar[0], 1);
         st_mbar_init(&mbar[1], 1);
-        for (int i = 0; i < 2 && i < nrows; ++i) {
+        for (int i = 0; i < NBUF && i < nrows; ++i) {
             const long b = blockIdx.x + (long)i * gridDim.x;
             st_mbar_expect_tx(&mbar[i], kb + fb);
             st_bulk_g2s(bufs + i * tile, a.Kp + b * P * H, kb, &mbar[i]);
@@ -213,10 +215,11 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attstep_attn_kernel(const AttSt
     const long plane = (long)B * KP;
     for (int i = 0; i < nrows; ++i) {
         const long b = blockIdx.x + (long)i * gridDim.x;
-        const float* Ks = bufs + (i & 1) * tile;
+        const int bi = NBUF == 2 ? (i & 1) : 0, ph = NBUF == 2 ? ((i >> 1) & 1) : (i & 1);
+        const float* Ks = bufs + bi * tile;
         const float* fs = Ks + P * H;
         const float* ur = us + i * H4;
-        st_mbar_wait(&mbar[i & 1], (i >> 1) & 1);
+        st_mbar_wait(&mbar[bi], ph);
         if (i == 0) XTS(3);
         // scores: one warp per group of 4 positions; v_a and u are reused across the 4 positions
         {
@@ -300,12 +303,12 @@ __global__ void __launch_bounds__(AS_THREADS, 1) attstep_attn_kernel(const AttSt
         }
         __syncthreads();
         // both tiles of this buffer are dead now: fetch the row after next into it
-        if (tid == 0 && i + 2 < nrows) {
-            const long bn = blockIdx.x + (long)(i + 2) * gridDim.x;
-            float* dst = bufs + (i & 1) * tile;
-            st_mbar_expect_tx(&mbar[i & 1], kb + fb);
-            st_bulk_g2s(dst, a.Kp + bn * P * H, kb, &mbar[i & 1]);
-            st_bulk_g2s(dst + P * H, a.f + bn * P * F, fb, &mbar[i & 1]);
+        if (tid == 0 && i + NBUF < nrows) {
+            const long bn = blockIdx.x + (long)(i + NBUF) * gridDim.x;
+            float* dst = bufs + bi * tile;
+            st_mbar_expect_tx(&mbar[bi], kb + fb);
+            st_bulk_g2s(dst, a.Kp + bn * P * H, kb, &mbar[bi]);
+            st_bulk_g2s(dst + P * H, a.f + bn * P * F, fb, &mbar[bi]);
         }
         if (tid < 128 && tid * 2 < KP) {
             const int k = tid * 2;
@@ -462,9 +465,9 @@ static inline int ys_kp(int H, int F) { return ((((H > F ? H : F) + 15) >> 4) <<
 static inline size_t ys_smem(int KP) {
     return (size_t)4 * YS_NB * KP * 2 + ((size_t)6 * 16 * YS_RP + (size_t)YS_NB * 64 + 48) * sizeof(float) + 16;
 }
-static inline size_t as_smem(int P, int H, int F, int rpc) {
+static inline size_t as_smem(int P, int H, int F, int rpc, int nbuf = 2) {
     const int KP = ys_kp(H, F);
-    return (2 * ((size_t)P * H + (size_t)P * F) + (size_t)(rpc + 1) * ((H + 3) & ~3) + (size_t)((P + 3) & ~3) +
+    return (nbuf * ((size_t)P * H + (size_t)P * F) + (size_t)(rpc + 1) * ((H + 3) & ~3) + (size_t)((P + 3) & ~3) +
             (size_t)AS_PSPL * KP + (KP & 1)) * sizeof(float) + 16;
 }
 // persistent grid of the attention kernel: one CTA per SM, more only when a CTA's u rows would not fit in shared memory
@@ -532,8 +535,14 @@ int caphn_attstep_fwd(const float* Kp, const float* f, const float* GIw, const f
     __nv_bfloat16* hsp1 = (__nv_bfloat16*)((uint8_t*)hsp0 + 2 * plane2);
     auto hbuf = [&](int t) { return (t & 1) ? hsp1 : hsp0; };
     cudaStream_t st = (cudaStream_t)stream;
-    const int agrid = as_grid(B, P, H, F), rpc = (B + agrid - 1) / agrid;
-    const size_t usmem = (size_t)2 * US_NB * KP * 2 + 16, asmem = as_smem(P, H, F, rpc), ysmem = ys_smem(KP);
+    // attention kernel: two single-buffered CTAs per SM when they fit (their phases overlap each other), else one
+    // double-buffered CTA per SM
+    int agrid = B < 2 * kNumSMs ? B : 2 * kNumSMs, nbuf = 1;
+    int rpc = (B + agrid - 1) / agrid;
+    if (2 * (as_smem(P, H, F, rpc, 1) + 1024) > 227 * 1024 || getenv("CAPHN_ATT_DOUBLE_BUFFER")) {
+        agrid = as_grid(B, P, H, F); rpc = (B + agrid - 1) / agrid; nbuf = 2;
+    }
+    const size_t usmem = (size_t)2 * US_NB * KP * 2 + 16, asmem = as_smem(P, H, F, rpc, nbuf), ysmem = ys_smem(KP);
     if (asmem > 227 * 1024) return CAPHN_EINVAL;
     CAPHN_CHECK(cudaFuncSetAttribute(attstep_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
     CAPHN_CHECK(cudaFuncSetAttribute(attstep_gates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
@@ -548,7 +557,7 @@ int caphn_attstep_fwd(const float* Kp, const float* f, const float* GIw, const f
         CAPHN_CHECK(launch_pdl(attstep_u_kernel, dim3(ceil_div(NUT, US_WARPS), ceil_div(B, US_NB)), dim3(US_THREADS), usmem,
                                st, pdl && !(t == t0 && resume), u));
         ++caphn_launch_counter;
-        AttStepA x{Kp, f, va, bv, ut, attn, ctx + (long)t * B * ldctx, ldctx, csp, B, T, t, P, H, F, KP, rpc};
+        AttStepA x{Kp, f, va, bv, ut, attn, ctx + (long)t * B * ldctx, ldctx, csp, B, T, t, P, H, F, KP, rpc, nbuf};
         CAPHN_CHECK(launch_pdl(attstep_attn_kernel, dim3(agrid), dim3(AS_THREADS), asmem, st, pdl, x));
         ++caphn_launch_counter;
         AttStepY y{csp, hbuf(t), hbuf(t + 1), Hall + t * BH, GIw + (long)t * B * 3 * H, (const uint4*)pack, bhh,

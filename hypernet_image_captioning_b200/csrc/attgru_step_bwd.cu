@@ -289,15 +289,17 @@ struct BwdA {
     __nv_bfloat16* dusp;         // [2][B][KP]
     float* dbv;                  // [1] atomically accumulated
     int B, T, t, P, H, F, KP, RPC;
+    int NBUF;                    // tile buffers per CTA (see attstep_attn_kernel)
 };
 
-__global__ void __launch_bounds__(BA_THREADS, 1) attbwd_attn_kernel(const BwdA a) {
+__global__ void __launch_bounds__(BA_THREADS, 2) attbwd_attn_kernel(const BwdA a) {
     extern __shared__ __align__(16) float basm[];
     const int H = a.H, F = a.F, P = a.P, KP = a.KP, B = a.B;
     const int PS = (P + 3) & ~3, H4 = (H + 3) & ~3, F4 = (F + 3) & ~3;
     const int tile = P * H + P * F;
     float* bufs = basm;                                  // [2][tile]
-    float* us = bufs + 2 * tile;                         // [RPC][H4]
+    const int NBUF = a.NBUF;
+    float* us = bufs + NBUF * tile;                      // [RPC][H4]
     float* dcs = us + a.RPC * H4;                        // [RPC][F4]
     float* als = dcs + a.RPC * F4;                       // [RPC][PS]
     float* vs = als + a.RPC * PS;                        // [H4]
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(BA_THREADS, 1) attbwd_attn_kernel(const BwdA a
     if (tid == 0) {
         st_mbar_init(&mbar[0], 1);
         st_mbar_init(&mbar[1], 1);
-        for (int i = 0; i < 2 && i < nrows; ++i) {
+        for (int i = 0; i < NBUF && i < nrows; ++i) {
             const long b = blockIdx.x + (long)i * gridDim.x;
             st_mbar_expect_tx(&mbar[i], kb + fb);
             st_bulk_g2s(bufs + i * tile, a.Kp + b * P * H, kb, &mbar[i]);
@@ -337,12 +339,13 @@ __global__ void __launch_bounds__(BA_THREADS, 1) attbwd_attn_kernel(const BwdA a
     float dbv_acc = 0.f;
     for (int i = 0; i < nrows; ++i) {
         const long b = blockIdx.x + (long)i * gridDim.x;
-        const float* Ks = bufs + (i & 1) * tile;
+        const int bi = NBUF == 2 ? (i & 1) : 0, ph = NBUF == 2 ? ((i >> 1) & 1) : (i & 1);
+        const float* Ks = bufs + bi * tile;
         const float* fs = Ks + P * H;
         const float* ur = us + i * H4;
         const float* dc = dcs + i * F4;
         const float* alr = als + i * PS;
-        st_mbar_wait(&mbar[i & 1], (i >> 1) & 1);
+        st_mbar_wait(&mbar[bi], ph);
         // d alpha_p = <dctx, f_p> (+ external gradient of the returned attention weights)
         for (int p = warp; p < P; p += BA_WARPS) {
             float s = 0.f;
@@ -395,12 +398,12 @@ __global__ void __launch_bounds__(BA_THREADS, 1) attbwd_attn_kernel(const BwdA a
             }
         }
         __syncthreads();
-        if (tid == 0 && i + 2 < nrows) {      // both tiles of this buffer are dead: fetch the row after next
-            const long bn = blockIdx.x + (long)(i + 2) * gridDim.x;
-            float* dst = bufs + (i & 1) * tile;
-            st_mbar_expect_tx(&mbar[i & 1], kb + fb);
-            st_bulk_g2s(dst, a.Kp + bn * P * H, kb, &mbar[i & 1]);
-            st_bulk_g2s(dst + P * H, a.f + bn * P * F, fb, &mbar[i & 1]);
+        if (tid == 0 && i + NBUF < nrows) {   // both tiles of this buffer are dead: fetch this CTA's next row for it
+            const long bn = blockIdx.x + (long)(i + NBUF) * gridDim.x;
+            float* dst = bufs + bi * tile;
+            st_mbar_expect_tx(&mbar[bi], kb + fb);
+            st_bulk_g2s(dst, a.Kp + bn * P * H, kb, &mbar[bi]);
+            st_bulk_g2s(dst + P * H, a.f + bn * P * F, fb, &mbar[bi]);
         }
         if (tid < 128 && tid * 2 < KP) {
             const int k = tid * 2;
@@ -540,9 +543,9 @@ static inline size_t g1_smem(int KP) {
 static inline size_t g2_smem(int KP3) {
     return (size_t)2 * G2_NB * KP3 * 2 + ((size_t)4 * 16 * G2_RP + 2) * sizeof(float) + 16;
 }
-static inline size_t ba_smem(int P, int H, int F, int rpc) {
+static inline size_t ba_smem(int P, int H, int F, int rpc, int nbuf = 2) {
     const int PS = (P + 3) & ~3, H4 = (H + 3) & ~3, F4 = (F + 3) & ~3;
-    return (2 * ((size_t)P * H + (size_t)P * F) + (size_t)rpc * (H4 + F4 + PS) + 3 * (size_t)H4 + PS) * sizeof(float) + 16;
+    return (nbuf * ((size_t)P * H + (size_t)P * F) + (size_t)rpc * (H4 + F4 + PS) + 3 * (size_t)H4 + PS) * sizeof(float) + 16;
 }
 static inline size_t bd_smem(int P, int H, int T) {
     const int PS = (P + 3) & ~3, H4 = (H + 3) & ~3;
@@ -621,8 +624,12 @@ int caphn_attstep_bwd(const float* dHbm, const float* dattn, const float* Kp, co
     const uint4* p0 = (const uint4*)pack;
     const uint4* p1 = p0 + (long)NUT * NKT * 64;
     const uint4* p2 = p1 + (long)NFT * NKT3 * 64;
-    const int agrid = ba_grid(B, P, H, F), rpc = (B + agrid - 1) / agrid;
-    const size_t s1 = g1_smem(KP), s2 = g2_smem(KP3), sa = ba_smem(P, H, F, rpc), sd = bd_smem(P, H, T);
+    int agrid = B < 2 * kNumSMs ? B : 2 * kNumSMs, nbuf = 1;
+    int rpc = (B + agrid - 1) / agrid;
+    if (2 * (ba_smem(P, H, F, rpc, 1) + 1024) > 227 * 1024 || getenv("CAPHN_ATT_DOUBLE_BUFFER")) {
+        agrid = ba_grid(B, P, H, F); rpc = (B + agrid - 1) / agrid; nbuf = 2;
+    }
+    const size_t s1 = g1_smem(KP), s2 = g2_smem(KP3), sa = ba_smem(P, H, F, rpc, nbuf), sd = bd_smem(P, H, T);
     if (sa > 227 * 1024) return CAPHN_EINVAL;
     CAPHN_CHECK(cudaFuncSetAttribute(attbwd_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
     CAPHN_CHECK(cudaFuncSetAttribute(attbwd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
@@ -641,7 +648,7 @@ int caphn_attstep_bwd(const float* dHbm, const float* dattn, const float* Kp, co
         CAPHN_CHECK(launch_pdl(attbwd_gemm_kernel, dim3(NG1 + NG2, ceil_div(B, G2_NB)), dim3(G2_THREADS), s2, st, pdl, g2));
         ++caphn_launch_counter;
         BwdA ba{Kp, f, va, dCTX + (long)t * B * F, attn, dattn, Upre + t * BH, dS, dU + t * BH, dusp, dbv,
-                B, T, t, P, H, F, KP, rpc};
+                B, T, t, P, H, F, KP, rpc, nbuf};
         CAPHN_CHECK(launch_pdl(attbwd_attn_kernel, dim3(agrid), dim3(BA_THREADS), sa, st, pdl, ba));
         ++caphn_launch_counter;
     }
