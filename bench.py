@@ -336,6 +336,28 @@ def run_ours(args):
         del opt, opt_params
         model.zero_grad(set_to_none=True)
         torch.cuda.empty_cache()
+        # rank-G head gradients: dW2 = dtheta^T a stays a (dtheta, a) pair; FusedAdam forms it on the fly
+        model.head_grad_mode = "lowrank"
+        opt = FusedAdam([p_ for p_ in model.parameters() if not any(p_ is q_ for q_ in model.captioner.lstm_cell.parameters())],
+                        lr=1e-6, max_grad_norm=5.0)
+        def step_lr():
+            step(pooled_d, caps_d, h0_d)
+            opt.step()
+        for _ in range(3):
+            step_lr()
+        ms_bwd_lr = timed(lambda: step(pooled_d, caps_d, h0_d), args.steps)
+        step(pooled_d, caps_d, h0_d)
+        ms_full_lr = timed(step_lr, args.steps)
+        extras["lowrank_head_grad"] = {
+            "train_fwd_bwd_captions_per_s": B * world * args.steps / (ms_bwd_lr * 1e-3),
+            "train_with_optimizer_captions_per_s": B * world * args.steps / (ms_full_lr * 1e-3),
+            "note": "head dW kept as (dtheta, a): backward streams W once (dA only), Adam reads/writes p,m,v only"}
+        model.head_grad_mode = "materialize"
+        del opt
+        for p_ in model.parameters():
+            p_.grad_lowrank = None
+        model.zero_grad(set_to_none=True)
+        torch.cuda.empty_cache()
         # bf16 mode (BASELINE configs[1] "fp32 and bf16"): hypernet weights + gradients in bf16, plain-bf16 tensor-core
         # products, fp32 accumulation / recurrent state; tolerance vs the fp32 oracle stated in tests/test_gpu_bf16.py
         model.set_precision("bf16")

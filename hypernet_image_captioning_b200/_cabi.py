@@ -62,6 +62,9 @@ SIGNATURES = {
     "caphn_sumsq": [P, L, P, P],
     "caphn_clip_coef": [P, F, P, P, P],
     "caphn_adam_step": [P, P, P, P, L, D, D, D, D, D, I, P, P],
+    "caphn_gram": [P, L, I, L, P, P],
+    "caphn_sumsq_lowrank": [P, P, I, P, P],
+    "caphn_adam_step_lowrank": [P, P, P, P, L, P, L, I, L, L, D, D, D, D, D, I, P, P],
     "caphn_launch_count": [P],
     "caphn_build_arch": [P],
 }

@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(ROWS_BWD_THREADS) rows_bwd_kernel(
                                     acc[g][u][c] = fmaf(dp[g], wv[c], acc[g][u][c]);
                                     dw[c] = fmaf(dp[g], a[g][u][c], dw[c]);
                                 }
+                            if (!dW) continue;       // dA-only pass (the weight gradient stays in its rank-G form)
                             T* o = dW + n * (long)K + k0[u];
                             if (full[u]) {
                                 if (accum_dw) {
@@ -426,7 +427,6 @@ static int rows_linear_bwd_t(const T* W, const float* A, long lda, const float* 
     rows_bwd_prep_kernel<<<ceil_div(N, 256), 256, 0, st>>>(Y, ldy, dY, lddy, dP, N, dbias, G, N, act, slope, 0);
     CAPHN_LAUNCH_CHECK();
     if (!dW && !dA) return CAPHN_OK;
-    if (!dW) return CAPHN_EINVAL;   // the pass writes dW while it reads W; a dA-only pass is not provided
     constexpr bool F32 = (WT<T>::V == 4);
     int g0 = 0;
     while (g0 < G) {
@@ -472,7 +472,8 @@ int caphn_rows_linear_fwd(const float* W, const float* bias, const float* A, lon
 // Backward of caphn_rows_linear_fwd.  Y is the forward output (needed only for act == 1), dY its gradient.
 //   dP (scratch, [G, N] dense) <- dY * act'(Y);  dbias[n] = sum_g dP;  dW[n,k] = sum_g dP[g,n] A[g,k];
 //   dA[g,k] += sum_n dP[g,n] W[n,k]   (dA must be zero-initialised by the caller; pass NULL to skip).
-// dW / dbias may be NULL (dW only when dA is NULL too).  Streams W once and writes dW once.
+// dW / dbias may be NULL.  dW == NULL with dA != NULL is the dA-only pass (W streamed once, nothing W-sized written):
+// the caller keeps the weight gradient in its rank-G form (dP, A) -- see caphn_adam_step_lowrank.
 int caphn_rows_linear_bwd(const float* W, const float* A, long lda, const float* Y, long ldy, const float* dY,
                           long lddy, float* dP, float* dW, float* dbias, float* dA, long ldda, int G, long N, long K,
                           int act, float slope, void* stream) {

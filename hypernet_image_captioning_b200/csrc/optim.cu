@@ -116,6 +116,132 @@ __global__ void __launch_bounds__(OPT_THREADS) adam_kernel(const AdamArgs a) {
     }
 }
 
+// ---- rank-G weight gradient: g[n,k] = sum_q dP[q,n] A[q,k] formed on the fly (never materialised) ----------------------
+// The hypernet head layer y = a W^T has dW = dP^T a with G = #style groups rows (1 at every reference call site), so the
+// 6.46 GB gradient of the benchmark model is a 0.4 MB pair (dP, a).  The update reads p, m, v and writes p, m, v: 24
+// bytes per parameter instead of 8 (backward writes dW, norm pass reads it) + 28 (Adam).
+constexpr int LR_MAXG = 4;
+
+struct AdamLrArgs {
+    float* p; float* m; float* v;
+    const float* dP; long ldp; const float* A; long lda;
+    int G; long N; int K;
+    float beta2, omb1, omb2, eps, weight_decay, step_size, bc2_sqrt;
+    const float* gscale;
+};
+
+template <int G>
+__device__ __forceinline__ float lowrank_g(const AdamLrArgs& a, long n, int k) {
+    float g = 0.f;
+#pragma unroll
+    for (int q = 0; q < G; ++q) g = fmaf(__ldg(a.dP + q * a.ldp + n), __ldg(a.A + q * a.lda + k), g);
+    return g;
+}
+
+constexpr int LR_UNR = 4;     // float4 triples (p, m, v) in flight per thread: 12 x 16 B
+
+template <int G>
+__global__ void __launch_bounds__(OPT_THREADS) adam_lowrank_kernel(const AdamLrArgs a) {
+    const float gs = a.gscale ? *a.gscale : 1.f;
+    const long total = a.N * a.K;
+    const long n4 = total >> 2;
+    float4* p4 = reinterpret_cast<float4*>(a.p);
+    float4* m4 = reinterpret_cast<float4*>(a.m);
+    float4* v4 = reinterpret_cast<float4*>(a.v);
+    AdamArgs h{nullptr, nullptr, nullptr, nullptr, 0, a.beta2, a.omb1, a.omb2, a.eps, a.weight_decay, a.step_size, a.bc2_sqrt,
+               nullptr};
+    const long stride = (long)gridDim.x * OPT_THREADS;
+    // (row, column) of this thread's float4s, advanced incrementally: 64-bit divisions only once per thread
+    const long i0 = (long)blockIdx.x * OPT_THREADS + threadIdx.x;
+    long nn[LR_UNR];
+    int kk[LR_UNR];
+#pragma unroll
+    for (int u = 0; u < LR_UNR; ++u) {
+        const long e = (i0 + u * stride) << 2;
+        nn[u] = e / a.K;
+        kk[u] = (int)(e - nn[u] * a.K);
+    }
+    const long step4 = (stride * LR_UNR) << 2;
+    const long dq = step4 / a.K;
+    const int dr = (int)(step4 - dq * a.K);
+    for (long i = i0; i < n4; i += LR_UNR * stride) {
+        float4 pv[LR_UNR], mv[LR_UNR], vv[LR_UNR];
+        long idx[LR_UNR];
+#pragma unroll
+        for (int u = 0; u < LR_UNR; ++u) {
+            idx[u] = i + u * stride < n4 ? i + u * stride : i;     // clamped duplicates are loaded but not stored
+            pv[u] = ld_rw4(p4 + idx[u]); mv[u] = ld_rw4(m4 + idx[u]); vv[u] = ld_rw4(v4 + idx[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < LR_UNR; ++u) {
+            float g[4];
+            long n = nn[u]; int k = kk[u];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { g[c] = lowrank_g<G>(a, n, k); if (++k == a.K) { k = 0; ++n; } }
+            nn[u] += dq; kk[u] += dr; if (kk[u] >= a.K) { kk[u] -= a.K; ++nn[u]; }
+            if (u == 0 || i + u * stride < n4) {
+                adam_one(pv[u].x, g[0], mv[u].x, vv[u].x, h, gs); adam_one(pv[u].y, g[1], mv[u].y, vv[u].y, h, gs);
+                adam_one(pv[u].z, g[2], mv[u].z, vv[u].z, h, gs); adam_one(pv[u].w, g[3], mv[u].w, vv[u].w, h, gs);
+                stg_stream4(reinterpret_cast<float*>(p4 + idx[u]), pv[u]);
+                stg_stream4(reinterpret_cast<float*>(m4 + idx[u]), mv[u]);
+                stg_stream4(reinterpret_cast<float*>(v4 + idx[u]), vv[u]);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (total & 3)) {
+        const long e = (n4 << 2) + threadIdx.x;
+        const long n = e / a.K;
+        float p = a.p[e], m = a.m[e], v = a.v[e];
+        adam_one(p, lowrank_g<G>(a, n, (int)(e - n * a.K)), m, v, h, gs);
+        a.p[e] = p; a.m[e] = m; a.v[e] = v;
+    }
+}
+
+// out[q*G + r] += sum_i X[q*ld + i] X[r*ld + i]     (G <= LR_MAXG)
+__global__ void __launch_bounds__(OPT_THREADS) gram_kernel(const float* __restrict__ X, long ld, int G, long L,
+                                                           double* __restrict__ out) {
+    float acc[LR_MAXG][LR_MAXG];
+#pragma unroll
+    for (int q = 0; q < LR_MAXG; ++q)
+#pragma unroll
+        for (int r = 0; r < LR_MAXG; ++r) acc[q][r] = 0.f;
+    for (long i = (long)blockIdx.x * OPT_THREADS + threadIdx.x; i < L; i += (long)gridDim.x * OPT_THREADS) {
+        float x[LR_MAXG];
+#pragma unroll
+        for (int q = 0; q < LR_MAXG; ++q) x[q] = q < G ? X[q * ld + i] : 0.f;
+#pragma unroll
+        for (int q = 0; q < LR_MAXG; ++q)
+#pragma unroll
+            for (int r = 0; r < LR_MAXG; ++r) acc[q][r] = fmaf(x[q], x[r], acc[q][r]);
+    }
+    __shared__ double ws[OPT_THREADS / 32];
+#pragma unroll
+    for (int q = 0; q < LR_MAXG; ++q)
+#pragma unroll
+        for (int r = 0; r < LR_MAXG; ++r) {
+            if (q >= G || r >= G) continue;                 // uniform
+            double s = (double)acc[q][r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0.0;
+                for (int w = 0; w < OPT_THREADS / 32; ++w) t += ws[w];
+                atomicAdd(out + q * G + r, t);
+            }
+            __syncthreads();
+        }
+}
+
+// *sumsq += || sum_q dP_q (x) A_q ||_F^2 = sum_{q,r} (dP_q . dP_r)(A_q . A_r)
+__global__ void sumsq_lowrank_kernel(const double* __restrict__ gp, const double* __restrict__ ga, int G,
+                                     double* __restrict__ sumsq) {
+    double s = 0.0;
+    for (int i = 0; i < G * G; ++i) s += gp[i] * ga[i];
+    atomicAdd(sumsq, s);
+}
+
 static inline int opt_grid(long n4) {
     long blocks = (n4 + (long)OPT_THREADS * 2 - 1) / ((long)OPT_THREADS * 2);
     const long cap = (long)kNumSMs * 16;            // 16 resident CTAs of 256 threads per SM x 148: grid-stride beyond that
@@ -155,6 +281,46 @@ int caphn_adam_step(float* p, const float* g, float* m, float* v, long n, double
     AdamArgs a{p, g, m, v, n, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)weight_decay,
                (float)(lr / bc1), (float)sqrt(bc2), gscale};
     adam_kernel<<<opt_grid(n >> 2), OPT_THREADS, 0, (cudaStream_t)stream>>>(a);
+    CAPHN_RETURN_LAST();
+}
+
+// out[G*G] (device double, caller-zeroed) += X X^T for X [G, L] (row stride ld), G <= 4.
+int caphn_gram(const float* X, long ld, int G, long L, double* out, void* stream) {
+    if (G < 1 || G > LR_MAXG || L < 0 || !out) return CAPHN_EINVAL;
+    if (L == 0) return CAPHN_OK;
+    long blocks = (L + OPT_THREADS * 4 - 1) / (OPT_THREADS * 4);
+    if (blocks > 4L * kNumSMs) blocks = 4L * kNumSMs;
+    gram_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), OPT_THREADS, 0, (cudaStream_t)stream>>>(X, ld, G, L, out);
+    CAPHN_RETURN_LAST();
+}
+
+// *sumsq += ||dP^T A||_F^2 from the two Gram matrices (the norm of a rank-G gradient without forming it).
+int caphn_sumsq_lowrank(const double* gram_dp, const double* gram_a, int G, double* sumsq, void* stream) {
+    if (G < 1 || G > LR_MAXG || !gram_dp || !gram_a || !sumsq) return CAPHN_EINVAL;
+    sumsq_lowrank_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(gram_dp, gram_a, G, sumsq);
+    CAPHN_RETURN_LAST();
+}
+
+// caphn_adam_step with the gradient given in rank-G form: g[n,k] = sum_q dP[q*ldp + n] * A[q*lda + k], p/m/v [N,K].
+int caphn_adam_step_lowrank(float* p, float* m, float* v, const float* dP, long ldp, const float* A, long lda, int G,
+                            long N, long K, double lr, double beta1, double beta2, double eps, double weight_decay,
+                            int step, const float* gscale, void* stream) {
+    if (N <= 0 || K <= 0 || K > (1L << 30) || G < 1 || G > LR_MAXG || step < 1 ||
+        (((uintptr_t)p | (uintptr_t)m | (uintptr_t)v) & 15))
+        return CAPHN_EINVAL;
+    const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
+    AdamLrArgs a{p, m, v, dP, ldp, A, lda, G, N, (int)K, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps,
+                 (float)weight_decay, (float)(lr / bc1), (float)sqrt(bc2), gscale};
+    long blocks = ((N * K) >> 2) / ((long)OPT_THREADS * LR_UNR) + 1;
+    if (blocks > (long)kNumSMs * 8) blocks = (long)kNumSMs * 8;
+    const unsigned grid = (unsigned)blocks;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (G) {
+        case 1: adam_lowrank_kernel<1><<<grid, OPT_THREADS, 0, st>>>(a); break;
+        case 2: adam_lowrank_kernel<2><<<grid, OPT_THREADS, 0, st>>>(a); break;
+        case 3: adam_lowrank_kernel<3><<<grid, OPT_THREADS, 0, st>>>(a); break;
+        default: adam_lowrank_kernel<4><<<grid, OPT_THREADS, 0, st>>>(a); break;
+    }
     CAPHN_RETURN_LAST();
 }
 

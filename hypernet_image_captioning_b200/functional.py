@@ -11,6 +11,13 @@ from .ops import ACT_LEAKY, ACT_NONE
 # ----------------------------------------------------------------------------------------------------------------------
 # hypernetwork: X[G,he] -> Theta[G,theta]      (reference hypernet_attention.py:111-118 / hypernet.py:104-111)
 # ----------------------------------------------------------------------------------------------------------------------
+# Rank-G head gradients (see optim.FusedAdam): when > 0, the backward of a head's second Linear whose weight has at least
+# this many elements does NOT materialise dW2 = dtheta^T a; it attaches ``(dtheta_slice [G,N], a [G,K])`` to the parameter
+# as ``.grad_lowrank`` and leaves ``.grad`` untouched.  Set by ``hypernet.head_grad_mode = "lowrank"``.
+LOWRANK_MIN_NUMEL = 0
+LOWRANK_MAX_G = 4
+
+
 class HyperNetThetaFn(Function):
     """params = [base0.W, base0.b, base2.W, base2.b, (head_i.0.W, head_i.0.b, head_i.2.W, head_i.2.b) * n_heads]."""
 
@@ -29,6 +36,8 @@ class HyperNetThetaFn(Function):
             mids.append(a)
             off += sizes[i]
         ctx.save_for_backward(x, b0, b1, *mids, *params)
+        ctx.lowrank_targets = [params[4 + 4 * i + 2] for i in range(nh)]    # the Parameter objects (saved tensors are views)
+        ctx.lowrank_min = LOWRANK_MIN_NUMEL
         ctx.nh = nh
         ctx.sizes = sizes
         return theta
@@ -48,8 +57,21 @@ class HyperNetThetaFn(Function):
         for i in range(nh):
             W1, c1, W2, c2 = params[4 + 4 * i: 8 + 4 * i]
             pi = 4 + 4 * i
-            dW2, dc2, da = ops.rows_linear_bwd(W2, mids[i], None, dtheta[:, off:off + sizes[i]], ACT_NONE,
-                                               need_dW=need[1 + pi + 2])
+            tgt = ctx.lowrank_targets[i]
+            prev = getattr(tgt, "grad_lowrank", None)
+            lowrank = (ctx.lowrank_min > 0 and need[1 + pi + 2] and W2.numel() >= ctx.lowrank_min
+                       and W2.dtype == torch.float32
+                       and x.shape[0] + (prev[0].shape[0] if prev is not None else 0) <= LOWRANK_MAX_G)
+            if lowrank:
+                _, dc2, da, dP = ops.rows_linear_bwd(W2, mids[i], None, dtheta[:, off:off + sizes[i]], ACT_NONE,
+                                                     need_dW=False, return_dP=True)
+                # a second backward before the optimizer step accumulates by growing the rank
+                tgt.grad_lowrank = (dP, mids[i]) if prev is None else (torch.cat([prev[0], dP], 0),
+                                                                        torch.cat([prev[1], mids[i]], 0))
+                dW2 = None
+            else:
+                dW2, dc2, da = ops.rows_linear_bwd(W2, mids[i], None, dtheta[:, off:off + sizes[i]], ACT_NONE,
+                                                   need_dW=need[1 + pi + 2])
             dW1, dc1, _ = ops.rows_linear_bwd(W1, b1, mids[i], da, ACT_LEAKY, need_dW=need[1 + pi], dA=db1)
             grads[pi], grads[pi + 1], grads[pi + 2], grads[pi + 3] = dW1, dc1, dW2, dc2
             off += sizes[i]

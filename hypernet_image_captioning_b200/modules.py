@@ -51,9 +51,22 @@ class _HyperNetMixin:
     dp_group = None      # set dp_enabled = True under torch.distributed to all-reduce d(theta) (parallel.py)
     dp_enabled = False
 
+    # "materialize" (default): .grad of every hypernet parameter is a dense tensor, as torch autograd gives.
+    # "lowrank": the backward keeps dW2 = dtheta^T a of the large head matrices as the pair (dtheta, a) on
+    # ``param.grad_lowrank`` (param.grad stays None) -- for caphn.FusedAdam, which forms the gradient on the fly.
+    head_grad_mode = "materialize"
+    lowrank_min_numel = 1 << 22
+
+    def zero_grad(self, set_to_none: bool = True):
+        super().zero_grad(set_to_none)
+        for p in self.parameters():            # rank-G gradients live beside .grad
+            if getattr(p, "grad_lowrank", None) is not None:
+                p.grad_lowrank = None
+
     def generate_theta(self, x: torch.Tensor) -> torch.Tensor:
         x2 = x.reshape(1, -1) if x.dim() == 1 else x
         x2 = x2.to(torch.float32).contiguous()
+        Fn.LOWRANK_MIN_NUMEL = self.lowrank_min_numel if self.head_grad_mode == "lowrank" else 0
         if self.grad_mode == "literal":
             with torch.no_grad():
                 return Fn.hypernet_theta(x2, _hn_params(self))

@@ -59,7 +59,7 @@ def rows_linear_fwd(W, bias, A, act=ACT_NONE, out=None, slope=LEAKY_SLOPE):
     return out
 
 
-def rows_linear_bwd(W, A, Y, dY, act=ACT_NONE, need_dW=True, need_dA=True, dA=None, slope=LEAKY_SLOPE):
+def rows_linear_bwd(W, A, Y, dY, act=ACT_NONE, need_dW=True, need_dA=True, dA=None, slope=LEAKY_SLOPE, return_dP=False):
     """Backward of rows_linear_fwd.  Returns (dW [N,K] or None, dbias [N], dA [G,K] or None).
     When ``dA`` is given the input gradient is accumulated into it (atomics)."""
     _chk(W, W.dtype if W.dtype == torch.bfloat16 else torch.float32), _chk(A), _chk(dY)
@@ -72,7 +72,7 @@ def rows_linear_bwd(W, A, Y, dY, act=ACT_NONE, need_dW=True, need_dA=True, dA=No
     dev = W.device
     dP = torch.empty(G, N, device=dev, dtype=torch.float32)
     dbias = torch.empty(N, device=dev, dtype=torch.float32)
-    dW = torch.empty(N, K, device=dev, dtype=W.dtype) if (need_dW or need_dA) else None   # bf16 weights -> bf16 gradient
+    dW = torch.empty(N, K, device=dev, dtype=W.dtype) if need_dW else None   # bf16 weights -> bf16 gradient; None: dA-only pass
     if need_dA and dA is None:
         dA = torch.zeros(G, K, device=dev, dtype=torch.float32)
     if not need_dA:
@@ -80,7 +80,9 @@ def rows_linear_bwd(W, A, Y, dY, act=ACT_NONE, need_dW=True, need_dA=True, dA=No
     _cabi.call("caphn_rows_linear_bwd_bf16" if W.dtype == torch.bfloat16 else "caphn_rows_linear_bwd", W.data_ptr(), A.data_ptr(), A.stride(0), _p(Y), Y.stride(0) if Y is not None else 0,
                dY.data_ptr(), dY.stride(0), dP.data_ptr(), _p(dW), dbias.data_ptr(), _p(dA),
                dA.stride(0) if dA is not None else 0, G, N, K, act, slope, _stream())
-    return (dW if need_dW else None), dbias, dA
+    if return_dP:
+        return dW, dbias, dA, dP
+    return dW, dbias, dA
 
 
 # ----------------------------------------------------------------------------------------------------------------------

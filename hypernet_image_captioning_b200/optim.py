@@ -6,6 +6,12 @@ cc_train_hypernet.py:405).  `FusedAdam` is a drop-in `torch.optim.Optimizer` wit
 `exp_avg_sq`), so `ReduceLROnPlateau` and `state_dict()` / `load_state_dict()` keep working; `max_grad_norm` folds the
 clipping into the step: the norm is reduced on the device, the coefficient is applied to the gradient on the fly
 (no host synchronisation, `.grad` is left untouched).
+
+Rank-G head gradients: with `hypernet.head_grad_mode = "lowrank"` the backward leaves the gradient of the large head
+matrices as the pair `(dtheta [G,N], a [G,K])` on `param.grad_lowrank` (G = number of style groups, 1 at every reference
+call site) instead of writing the dense `dW = dtheta^T a`; `FusedAdam.step()` takes the norm from two G x G Gram matrices
+and forms `g[n,k]` on the fly inside the update.  Per head parameter and training step: 4 (forward) + 4 (backward, dA only)
++ 24 (update) = 32 bytes of HBM traffic instead of 4 + 8 + 32 = 44.
 """
 import torch
 
@@ -28,6 +34,22 @@ class FusedAdam(torch.optim.Optimizer):
                              torch.zeros(1, device=dev))
         return self._scratch
 
+    def zero_grad(self, set_to_none: bool = True):
+        super().zero_grad(set_to_none)
+        for group in self.param_groups:
+            for p in group["params"]:
+                if getattr(p, "grad_lowrank", None) is not None:
+                    p.grad_lowrank = None
+
+    def _state_of(self, p):
+        st = self.state[p]
+        if not st:
+            st["step"] = 0
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        st["step"] = int(st["step"]) + 1
+        return st
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
@@ -37,17 +59,19 @@ class FusedAdam(torch.optim.Optimizer):
         items = []
         for group in self.param_groups:
             for p in group["params"]:
+                lowrank = getattr(p, "grad_lowrank", None)
+                if p.grad is None and lowrank is not None:
+                    if p.dtype != torch.float32 or not p.is_contiguous() or p.dim() != 2:
+                        raise _cabi.CaphnError("rank-G gradients need contiguous fp32 [N,K] parameters")
+                    st = self._state_of(p)
+                    items.append((group, p, lowrank, st))
+                    continue
                 if p.grad is None:
                     continue
                 if p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous():
                     raise _cabi.CaphnError("FusedAdam needs contiguous fp32 CUDA parameters")
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-                st = self.state[p]
-                if not st:
-                    st["step"] = 0
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                st["step"] = int(st["step"]) + 1
+                st = self._state_of(p)
                 items.append((group, p, g, st))
         if not items:
             return loss
@@ -56,12 +80,28 @@ class FusedAdam(torch.optim.Optimizer):
             sumsq, coef, norm = self._scratch_on(items[0][1].device)
             sumsq.zero_()
             for _, _, g, _ in items:
-                _cabi.call("caphn_sumsq", g.data_ptr(), g.numel(), sumsq.data_ptr(), _stream())
+                if isinstance(g, tuple):      # ||dP^T a||_F^2 = sum_{q,r} (dP_q . dP_r)(a_q . a_r): no W-sized pass
+                    dP, a = g
+                    G = dP.shape[0]
+                    gram = torch.zeros(2, G * G, device=dP.device, dtype=torch.float64)
+                    _cabi.call("caphn_gram", dP.data_ptr(), dP.stride(0), G, dP.shape[1], gram[0].data_ptr(), _stream())
+                    _cabi.call("caphn_gram", a.data_ptr(), a.stride(0), G, a.shape[1], gram[1].data_ptr(), _stream())
+                    _cabi.call("caphn_sumsq_lowrank", gram[0].data_ptr(), gram[1].data_ptr(), G, sumsq.data_ptr(), _stream())
+                else:
+                    _cabi.call("caphn_sumsq", g.data_ptr(), g.numel(), sumsq.data_ptr(), _stream())
             _cabi.call("caphn_clip_coef", sumsq.data_ptr(), float(self.max_grad_norm), coef.data_ptr(), norm.data_ptr(),
                        _stream())
             gscale, self.last_grad_norm = coef.data_ptr(), norm
         for group, p, g, st in items:
             b1, b2 = group["betas"]
+            if isinstance(g, tuple):
+                dP, a = g
+                _cabi.call("caphn_adam_step_lowrank", p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                           dP.data_ptr(), dP.stride(0), a.data_ptr(), a.stride(0), dP.shape[0], p.shape[0], p.shape[1],
+                           float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                           st["step"], gscale, _stream())
+                p.grad_lowrank = None         # consumed (zero_grad() does not know about it)
+                continue
             _cabi.call("caphn_adam_step", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                        p.numel(), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
                        float(group["weight_decay"]), st["step"], gscale, _stream())

@@ -210,6 +210,16 @@ int caphn_sumsq(const float* x, long n, double* sumsq, void* stream);
 int caphn_clip_coef(const double* sumsq, float max_norm, float* coef, float* norm, void* stream);
 int caphn_adam_step(float* p, const float* g, float* m, float* v, long n, double lr, double beta1, double beta2,
                     double eps, double weight_decay, int step, const float* gscale, void* stream);
+/* Rank-G form of the head-weight gradient (dW = dP^T A, G = #style groups <= 4; caphn_rows_linear_bwd with dW == NULL
+ * leaves it in that form): its squared norm from two G x G Gram matrices, and the Adam step that forms g[n,k] on the fly
+ * -- 24 bytes per parameter instead of 8 (dW write + norm read) + 28.
+ * caphn_gram: out[G*G] (device double, caller-zeroed) += X X^T, X [G,L] row stride ld.
+ * caphn_sumsq_lowrank: *sumsq += sum_{q,r} gram_dp[q,r] * gram_a[q,r] = ||dP^T A||_F^2. */
+int caphn_gram(const float* X, long ld, int G, long L, double* out, void* stream);
+int caphn_sumsq_lowrank(const double* gram_dp, const double* gram_a, int G, double* sumsq, void* stream);
+int caphn_adam_step_lowrank(float* p, float* m, float* v, const float* dP, long ldp, const float* A, long lda, int G,
+                            long N, long K, double lr, double beta1, double beta2, double eps, double weight_decay,
+                            int step, const float* gscale, void* stream);
 
 /* *out = number of CUDA kernels launched by this library so far (host-side counter). */
 int caphn_launch_count(unsigned long long* out);
