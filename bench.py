@@ -176,6 +176,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0's stdout must be exactly one JSON line: NCCL prints its version banner to stdout at VERSION/INFO level
+        os.environ["NCCL_DEBUG"] = os.environ.get("CAPHN_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     _cabi.load()
 
