@@ -13,6 +13,7 @@
 // accesses.  Templated on the weight type: float (fp32 mode) or __nv_bfloat16 (bf16 mode: half the bytes; fp32
 // activations / accumulation, gradients rounded to bf16 on store).
 #include "common.cuh"
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 namespace caphn {
@@ -85,8 +86,9 @@ template <> struct WT<__nv_bfloat16> {
     }
     static __device__ __forceinline__ float load1_rw(const __nv_bfloat16* p) { return __bfloat162float(*p); }
     static __device__ __forceinline__ uint32_t pk(float a, float b) {
-        return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) |
-               ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+        uint32_t r;                                        // one cvt.rn.bf16x2.f32: low half = a, high half = b
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+        return r;
     }
     static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
         const uint32_t a = pk(v[0], v[1]), b = pk(v[2], v[3]), c = pk(v[4], v[5]), d = pk(v[6], v[7]);
