@@ -170,8 +170,10 @@ class DecoderGRU(nn.Module):
         return [(c.weight_ih, c.weight_hh, c.bias_ih, c.bias_hh) for c in cells]
 
     def _h0(self, features):
-        # reference later.py:393-394: global CPU RNG, then type_as(features)
-        return torch.rand(size=(features.size(0), self.hidden_size)).to(features.device, features.dtype)
+        # reference later.py:393-394: global CPU RNG, then type_as(features).  Same CPU random stream, but drawn into
+        # pinned memory and copied asynchronously: a pageable copy would block the host until the device has drained.
+        h0 = torch.rand(size=(features.size(0), self.hidden_size), pin_memory=features.is_cuda)
+        return h0.to(features.device, features.dtype, non_blocking=True)
 
     def forward(self, features, captions, teacher_forcing=True, h0=None, groups=None):
         if not teacher_forcing:
