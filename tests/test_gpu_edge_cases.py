@@ -277,3 +277,32 @@ def test_sweep_corner_batch_4096_is_batch_invariant(variant):
             loss = C.cross_entropy(big, caps, None)
     assert rel_err(big[1000:1000 + Bs], small) < 2e-5
     assert torch.isfinite(loss)
+
+
+@pytest.mark.parametrize("he", [100, 150])
+def test_conceptual_captions_one_hot_domains(he):
+    """BASELINE configs[3] / SURVEY C4: cc=True with a one-hot domain vector of 100 / 150 domains as the hypernet input
+    (cc_train_hypernet.py:86-89,141-144: 1-D [he] float), against the oracle: logits, loss, gradients, greedy tokens."""
+    import hypernet_image_captioning_b200 as C
+    Fo, E, H, V, B, T = 16, 12, 56, 60, 7, 5          # 3H = 168 >= he: the reference's sane head branch (hypernet_attention.py:85-99)
+    p = O.init_params_attention(2048, Fo, E, H, V, he, seed=he)
+    g = torch.Generator().manual_seed(he)
+    feats = torch.randn(B, 49, 2048, generator=g)
+    caps = O.synth_captions(B, T, V, g)
+    style = torch.zeros(he)
+    style[he // 3] = 1.0
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    lr, ar, _, _ = O.path_attention(pl, style, feats, caps, 0.0, np.random.RandomState(0))
+    loss_ref = O.caption_loss(lr, caps, 0)
+    loss_ref.backward()
+    m = _load(C.HyperNetAttention(Fo, E, H, V, None, cc=True, hyper_emb=he), p)
+    loss, logits, att = m.forward(style.cuda()).forward_loss(feats.cuda(), caps.cuda(), 0.0, ignore_index=0)
+    loss.backward()
+    assert rel_err(logits, lr) < 1e-4 and rel_err(att, ar) < 1e-4
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 1e-4 * abs(float(loss_ref.detach()))
+    for k in ("hn_base.0.weight", "hn_heads.0.0.weight", "hn_heads.0.2.weight", "hn_heads.3.2.bias", "captioner.embed.weight"):
+        assert grad_close(dict(m.named_parameters())[k].grad, pl[k].grad, 1e-3), k
+    with torch.no_grad():
+        gl_ref, _, _, _ = O.path_attention(p, style, feats, caps, 1.0, np.random.RandomState(0))
+        gl, _ = m.forward(style.cuda())(feats.cuda(), caps.cuda(), 1.0)
+    assert torch.equal(gl.argmax(-1).cpu(), gl_ref.argmax(-1))
