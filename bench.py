@@ -439,11 +439,18 @@ def attention_extras(args, dev, world, timed):
     feats = torch.randn(B, 49, 2048, generator=g).to(dev)
     caps = synth_captions(B, T, V, g).to(dev)
 
+    from hypernet_image_captioning_b200 import parallel as par
+    shared = par.shared_parameters(model)
+
     def train():
         model.zero_grad(set_to_none=True)
         captioner = model.forward(model.captioner.embed.weight[4:5])
         loss, _, _ = captioner.forward_loss(feats, caps, 0.0, ignore_index=0)
-        loss.backward()
+        if world > 1:      # exact global-batch masked mean: weight by this rank's share of the non-pad tokens
+            (loss * par.loss_weight(caps, 0)).backward()
+            par.allreduce_shared_grads(shared)
+        else:
+            loss.backward()
 
     def greedy():
         with torch.no_grad():

@@ -56,3 +56,18 @@ def allreduce_shared_grads(params: Iterable[torch.nn.Parameter], group=None, ext
         n = g.numel()
         g.copy_(flat[off:off + n].view_as(g))
         off += n
+
+
+def loss_weight(captions: torch.Tensor, ignore_index: Optional[int] = None, group=None) -> torch.Tensor:
+    """Weight that turns this rank's mean caption loss into its share of the GLOBAL-batch mean:
+    ``n_valid(local) / n_valid(all ranks)`` (one 8-byte all-reduce).  With ``ignore_index`` (cc_train_hypernet.py:153)
+    ranks hold different numbers of non-pad tokens, so the plain 1/N average of per-rank means is not the global mean;
+    ``(loss * loss_weight(caps, pad)).backward()`` on every rank followed by the gradient all-reduces reproduces the
+    single-process gradients of the concatenated batch exactly.  Without ``ignore_index`` it is B_local / B_global."""
+    n = (captions != ignore_index).sum() if ignore_index is not None else torch.tensor(captions.numel(), device=captions.device)
+    n = n.to(torch.float64).reshape(1)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return torch.ones((), device=captions.device)
+    tot = n.clone()
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+    return (n / tot).to(torch.float32).reshape(())

@@ -64,3 +64,44 @@ def test_shared_parameter_selection():
     names = {n for n, p in m.named_parameters() if any(p is q for q in shared_parameters(m))}
     assert all(not n.startswith("hn_") for n in names)
     assert {"captioner.embed.weight", "captioner.fc_out.weight", "image_encoder.fc.weight"} <= names
+
+
+def _worker_masked(rank, world, port, out):
+    """Masked mean loss (ignore_index = 0) with different numbers of valid tokens per rank."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hypernet_image_captioning_b200.parallel import allreduce_shared_grads, loss_weight
+    g = torch.Generator().manual_seed(0)
+    W = torch.nn.Parameter(torch.randn(6, 7, generator=g))
+    x = torch.randn(8, 5, 6, generator=g)
+    caps = torch.randint(1, 7, (8, 5), generator=g)
+    caps[0:4, 3:] = 0                       # rank 0 holds the heavily padded rows
+    caps[5, 4] = 0
+    xb, cb = x[rank * 4:(rank + 1) * 4], caps[rank * 4:(rank + 1) * 4]
+    loss = torch.nn.functional.cross_entropy((xb @ W).reshape(-1, 7), cb.reshape(-1), ignore_index=0)
+    w = loss_weight(cb, 0)
+    (loss * w).backward()
+    allreduce_shared_grads([W])
+    torch.save({"W_grad": W.grad, "w": w}, os.path.join(out, f"m{rank}.pt"))
+    dist.destroy_process_group()
+
+
+def test_dp_masked_loss_weight_reproduces_global_mean(tmp_path):
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_masked, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(0)
+    W = torch.nn.Parameter(torch.randn(6, 7, generator=g))
+    x = torch.randn(8, 5, 6, generator=g)
+    caps = torch.randint(1, 7, (8, 5), generator=g)
+    caps[0:4, 3:] = 0
+    caps[5, 4] = 0
+    torch.nn.functional.cross_entropy((x @ W).reshape(-1, 7), caps.reshape(-1), ignore_index=0).backward()
+    ws = []
+    for r in range(world):
+        d = torch.load(os.path.join(str(tmp_path), f"m{r}.pt"))
+        assert torch.allclose(d["W_grad"], W.grad, atol=1e-6)      # == gradient of the global-batch masked mean
+        ws.append(float(d["w"]))
+    n0, n1 = int((caps[:4] != 0).sum()), int((caps[4:] != 0).sum())
+    assert ws[0] == pytest.approx(n0 / (n0 + n1)) and ws[1] == pytest.approx(n1 / (n0 + n1)) and n0 != n1
