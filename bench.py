@@ -176,8 +176,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # rank 0's stdout must be exactly one JSON line: NCCL prints its version banner to stdout at VERSION/INFO level
-        os.environ["NCCL_DEBUG"] = os.environ.get("CAPHN_NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     _cabi.load()
 
@@ -468,10 +466,18 @@ def attention_extras(args, dev, world, timed):
 
 def main():
     args = parse()
+    # The contract is ONE JSON line on stdout.  Libraries write banners to file descriptor 1 from native code (the
+    # "NCCL version ..." line at communicator creation, on every rank): park fd 1 on stderr while the benchmark runs and
+    # hand the real stdout back to Python's sys.stdout only for the final print.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
