@@ -5,10 +5,10 @@ C-ABI declared in include/caphn_b200.h.  Importing the package does not need a G
 """
 from . import _cabi, ops, functional  # noqa: F401
 from .functional import cross_entropy, linear, hypernet_theta  # noqa: F401
-from .modules import DecoderGRU, HyperNetPooled, PooledFeatureEncoder  # noqa: F401
+from .modules import DecoderGRU, DecoderRNN, HyperNetPooled, PooledFeatureEncoder  # noqa: F401
 from .modules_attention import AttentionGru, BahdanauAttention, HyperNetAttention, SpatialFeatureEncoder  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
 from .style import DomainEmbedding  # noqa: F401
 
 __all__ = ["FusedAdam", "DomainEmbedding", "AttentionGru", "BahdanauAttention", "HyperNetAttention", "SpatialFeatureEncoder",
-           "DecoderGRU", "HyperNetPooled", "PooledFeatureEncoder", "cross_entropy", "linear", "hypernet_theta"]
+           "DecoderGRU", "DecoderRNN", "HyperNetPooled", "PooledFeatureEncoder", "cross_entropy", "linear", "hypernet_theta"]

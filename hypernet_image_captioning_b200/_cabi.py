@@ -45,6 +45,8 @@ SIGNATURES = {
     "caphn_embed_scatter_add": [P, P, I, I, I, I, P, P],
     "caphn_scatter_add_rows": [P, L, P, L, I, P, P],
     "caphn_colsum": [P, L, L, I, P, P],
+    "caphn_lstm_seq_fwd": [P, P, I, P, P, P, P, P, P, P, P, I, I, I, I, P],
+    "caphn_lstm_seq_bwd": [P, P, P, I, P, P, P, I, I, I, I, P],
     "caphn_attgru_seq_fwd": [P] * 14 + [L] + [P] * 5 + [I] * 9 + [P],
     "caphn_attgru_seq_bwd": [P] * 23 + [I] * 7 + [P],
     "caphn_attgru_cluster_plan": [I, I, I, P],

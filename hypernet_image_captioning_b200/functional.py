@@ -270,6 +270,117 @@ def _gru_decoder_backward(saved_tensors, NL, need, vocab):
             dfc_b if need[5] else None, *cell_grads)
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Variant A decoder with LSTM cells: teacher-forced DecoderRNN.forward  (reference later.py:254-324)
+# ----------------------------------------------------------------------------------------------------------------------
+def _lstm_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells):
+    B, T = captions.shape
+    NL = len(cells) // 4
+    W_ih, W_hh, b_ih, b_hh = cells[0:4]
+    H = W_hh.shape[1]
+    caps = captions.contiguous()
+    X = ops.build_inputs(feats.contiguous(), emb_w.contiguous(), caps, 0)      # [T*B, E]: features at t = 0 (:277)
+    GI = ops.linear(X, W_ih.contiguous(), b_ih.contiguous())                   # [T*B, 4H]
+    ld4 = ops.round4(4 * H)
+    WhhT = ops.transpose_pad(W_hh.contiguous(), ld4)
+    extra = []
+    for l in range(1, NL):
+        Wi, Wh, bi, bh = cells[4 * l: 4 * l + 4]
+        extra.append((ops.transpose_pad(Wi.contiguous(), ld4), ops.transpose_pad(Wh.contiguous(), ld4),
+                      bi.contiguous(), bh.contiguous()))
+    Hall, Hbm, saved, Hmid = ops.lstm_seq_fwd(GI, WhhT, b_hh.contiguous(), h0.contiguous(), T, save=True, extra=extra)
+    logits = ops.linear(Hbm.view(B * T, H), fc_w.contiguous(), fc_b)
+    return logits.view(B, T, -1), (caps, X, Hall, Hbm, saved, Hmid if Hmid is not None else Hall.new_empty(0),
+                                   emb_w.contiguous(), fc_w)
+
+
+def _lstm_decoder_backward(saved_tensors, NL, need, vocab):
+    """need = needs_input_grad of (feats, captions, h0, emb_w, fc_w, fc_b, *cells); vocab = (dfc_w, dfc_b, dHbm)."""
+    caps, X, Hall, Hbm, saved, Hmid, emb_w, fc_w = saved_tensors[:8]
+    cells = saved_tensors[8:]
+    W_ih, W_hh = cells[0], cells[1]
+    B, T = caps.shape
+    H = W_hh.shape[1]
+    dfc_w, dfc_b, dHbm = vocab
+    ldh = ops.round4(H)
+    Whh_p = ops.copy_pad(W_hh.contiguous(), ldh)
+    extra = [(ops.copy_pad(cells[4 * l].contiguous(), ldh), ops.copy_pad(cells[4 * l + 1].contiguous(), ldh))
+             for l in range(1, NL)]
+    dG, dh0 = ops.lstm_seq_bwd(dHbm.view(B, T, H), saved, Hall, Whh_p, extra=extra)
+    Hprev = Hall[:-1].reshape(T * B, H)
+    db0 = ops.colsum(dG[0]) if (need[8] or need[9]) else None
+    cell_grads = [ops.matmul_tn(dG[0], X) if need[6] else None, ops.matmul_tn(dG[0], Hprev) if need[7] else None,
+                  db0 if need[8] else None, (db0.clone() if need[8] else db0) if need[9] else None]
+    for l in range(1, NL):
+        Hin = Hmid[l - 1].reshape(T * B, H)                            # input == state of cell l
+        n0 = 6 + 4 * l
+        dWl = ops.matmul_tn(dG[l], Hin) if (need[n0] or need[n0 + 1]) else None
+        dbl = ops.colsum(dG[l]) if (need[n0 + 2] or need[n0 + 3]) else None
+        cell_grads += [dWl if need[n0] else None, (dWl.clone() if need[n0] else dWl) if need[n0 + 1] else None,
+                       dbl if need[n0 + 2] else None, (dbl.clone() if need[n0 + 2] else dbl) if need[n0 + 3] else None]
+    dfeats = demb = None
+    if need[0] or need[3]:
+        dX = ops.matmul_nn(dG[0], W_ih.contiguous())                   # [T*B, E]
+        if need[0]:
+            dfeats = dX[:B].clone()
+        if need[3]:
+            demb = torch.zeros_like(emb_w)
+            ops.embed_scatter_add(dX, caps, demb, 1)
+    return (dfeats, None, (dh0 if need[2] else None), demb, dfc_w if need[4] else None,
+            dfc_b if need[5] else None, *cell_grads)
+
+
+class DecoderRNNSeqFn(Function):
+    """LSTM counterpart of DecoderGRUSeqFn: inputs feats, captions, h0, emb_w, fc_w, fc_b, then (W_ih, W_hh, b_ih, b_hh)
+    of every LSTM cell.  Extra cells are applied as (h, c) = cell_l(h, (h, c)) (later.py:279-281)."""
+
+    @staticmethod
+    def forward(ctx, feats, captions, h0, emb_w, fc_w, fc_b, *cells):
+        logits, sv = _lstm_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells)
+        ctx.save_for_backward(*sv, *cells)
+        ctx.NL = len(cells) // 4
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        sv = ctx.saved_tensors
+        Hbm, fc_w = sv[3], sv[7]
+        B, T, H = Hbm.shape
+        need = ctx.needs_input_grad
+        dl = dlogits.reshape(B * T, -1).contiguous()
+        vocab = vocab_bwd_from_dlogits(dl, Hbm.view(B * T, H), fc_w, need[4], need[5])
+        return _lstm_decoder_backward(sv, ctx.NL, need, vocab)
+
+
+class DecoderRNNLossFn(Function):
+    """DecoderRNN + mean cross-entropy as one autograd node (see DecoderGRULossFn)."""
+
+    @staticmethod
+    def forward(ctx, ignore_index, feats, captions, h0, emb_w, fc_w, fc_b, *cells):
+        logits, sv = _lstm_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells)
+        B, T, V = logits.shape
+        targets = captions.reshape(-1).contiguous()
+        lossbuf, lse = ops.ce_fwd(logits.view(B * T, V), targets, ignore_index)
+        ctx.save_for_backward(*sv, *cells, logits, targets, lse, lossbuf)
+        ctx.NL = len(cells) // 4
+        ctx.ignore_index = ignore_index
+        ctx.mark_non_differentiable(logits)
+        ctx.set_materialize_grads(False)
+        return lossbuf[0].clone(), logits
+
+    @staticmethod
+    def backward(ctx, g, _unused):
+        allsv = ctx.saved_tensors
+        sv, (logits, targets, lse, lossbuf) = allsv[:-4], allsv[-4:]
+        Hbm, fc_w = sv[3], sv[7]
+        B, T, H = Hbm.shape
+        need = ctx.needs_input_grad[1:]
+        g = g.reshape(1).to(torch.float32).contiguous()
+        vocab = vocab_bwd_fused(logits.view(B * T, -1), targets, ctx.ignore_index, lse, lossbuf, g,
+                                Hbm.view(B * T, H), fc_w)
+        return (None, *_lstm_decoder_backward(sv, ctx.NL, need, vocab))
+
+
 class DecoderGRUSeqFn(Function):
     """inputs: feats, captions, h0, emb_w, fc_w, fc_b, then (W_ih, W_hh, b_ih, b_hh) for every GRU cell (layer 0 first).
     Extra layers are applied as h = cell_l(h, h) at every step (later.py:413-414, 420-421).  Returns logits [B,T,V]."""

@@ -237,13 +237,64 @@ class DecoderGRU(nn.Module):
         return outputs
 
 
+class DecoderRNN(DecoderGRU):
+    """Drop-in for later.py:227 DecoderRNN: the LSTM captioner the pooled hypernet builds when ``type != 'gru'``
+    (hypernet.py:50-53).  Same attribute names as the reference (``lstm_cell``, ``layers``, ``fc_out``, ``embed``);
+    (h, c) start at zero (later.py:256-259: no RNG draw); extra cells are applied as ``(h, c) = cell(h, (h, c))``."""
+
+    def __init__(self, embed_size, hidden_size, vocab_size, num_layers=1, dropout=False):
+        super().__init__(embed_size, hidden_size, vocab_size, num_layers=num_layers, dropout=dropout)
+        self.lstm_cell = nn.LSTMCell(input_size=embed_size, hidden_size=hidden_size)
+        if num_layers > 1:
+            self.layers = nn.ModuleList([nn.LSTMCell(hidden_size, hidden_size) for _ in range(num_layers - 1)])
+        # re-register in the reference's order: lstm_cell, layers, fc_out, embed (later.py:241-249)
+        fc_out, embed = self.fc_out, self.embed
+        del self.fc_out, self.embed
+        self.fc_out, self.embed = fc_out, embed
+
+    def _h0(self, features):
+        return torch.zeros(features.size(0), self.hidden_size, device=features.device, dtype=features.dtype)
+
+    def forward_loss(self, features, captions, h0=None, ignore_index=None):
+        if h0 is None:
+            h0 = self._h0(features)
+        flat = [w for cell in self._cells() for w in cell]
+        return Fn.DecoderRNNLossFn.apply(ignore_index, features, captions, h0, self.embed.weight, self.fc_out.weight,
+                                         self.fc_out.bias, *flat)
+
+    def _forward_one(self, features, captions, h0, cells):
+        if len(cells) > 4:
+            raise NotImplementedError("DecoderRNN with more than 4 layers")
+        flat = [w for cell in cells for w in cell]
+        return Fn.DecoderRNNSeqFn.apply(features, captions, h0, self.embed.weight, self.fc_out.weight,
+                                        self.fc_out.bias, *flat)
+
+    def _infer_loop(self, features, h0, W_ih, W_hh, b_ih, b_hh, max_len):
+        """Greedy decode of later.py:326-360: argmax feedback, first cell only, returns softmax probs."""
+        B, H = features.size(0), self.hidden_size
+        emb, fc_w, fc_b = self.embed.weight.detach(), self.fc_out.weight.detach(), self.fc_out.bias.detach()
+        WhhT = ops.transpose_pad(W_hh, ops.round4(4 * H))
+        outputs = torch.empty(B, max_len, self.vocab_size, device=features.device, dtype=torch.float32)
+        h, c = h0.contiguous(), None
+        x = features.contiguous()
+        logits = torch.empty(B, self.vocab_size, device=features.device, dtype=torch.float32)
+        xproj, vocab = ops.LinearPlan(W_ih, b_ih), ops.LinearPlan(fc_w, fc_b)
+        for t in range(max_len):
+            GI = xproj(x)
+            Hall, _, _, _, c = ops.lstm_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False, c0=c, want_c=True)
+            h = Hall[1]
+            vocab(h, out=logits)
+            _, words = ops.softmax_argmax(logits, want_probs=True, probs_out=outputs[:, t, :])
+            if t + 1 < max_len:
+                x = ops.gather_rows(emb, words)
+        return outputs
+
+
 class HyperNetPooled(_HyperNetMixin, _Base):
     """Drop-in for hypernet.py:26 HyperNet (pooled-feature variant)."""
 
     def __init__(self, embed_size, hidden_size, vocab_size, vocab, num_layers=1, type='gru', lr=1e-6):
         super().__init__()
-        if type != 'gru':
-            raise NotImplementedError("LSTM captioner (hypernet.py:53) is outside the hot path")
         self.hparams['vocab_size'] = vocab_size
         self.hparams['embed_size'] = embed_size
         self.hparams['hidden_size'] = hidden_size
@@ -252,7 +303,10 @@ class HyperNetPooled(_HyperNetMixin, _Base):
         self.hparams['num_layers'] = num_layers
         self.teacher_forcing_proba = 1.0
         self.image_encoder = PooledFeatureEncoder(2048, embed_size)
-        self.captioner = DecoderGRU(embed_size, hidden_size, vocab_size, num_layers=num_layers, dropout=False)
+        if type == 'gru':       # hypernet.py:50-53
+            self.captioner = DecoderGRU(embed_size, hidden_size, vocab_size, num_layers=num_layers, dropout=False)
+        else:
+            self.captioner = DecoderRNN(embed_size, hidden_size, vocab_size, num_layers=num_layers)
         E = embed_size
         self.hn_base = nn.Sequential(nn.Linear(E, 4 * E), nn.LeakyReLU(), nn.Linear(4 * E, 8 * E), nn.LeakyReLU())
         heads = []

@@ -227,6 +227,40 @@ def gru_seq_fwd(GI, WhhT, bhh, h0, T, save=True, want_bm=True, extra=()):
     return Hall, Hbm, saved, Hmid
 
 
+def lstm_seq_fwd(GI, WhhT, bhh, h0, T, save=True, want_bm=True, extra=(), c0=None, want_c=False):
+    """LSTM analogue of gru_seq_fwd: GI [T*B,4H], WhhT [H,ld4]; saved [NL,6,T,B,H] = (i, f, g, o, c_prev, tanh c)."""
+    B, H = h0.shape
+    NL = 1 + len(extra)
+    dev = GI.device
+    Hall = torch.empty(T + 1, B, H, device=dev, dtype=torch.float32)
+    Hall[0].copy_(h0)
+    Hbm = torch.empty(B, T, H, device=dev, dtype=torch.float32) if want_bm else None
+    saved = torch.empty(NL, 6, T, B, H, device=dev, dtype=torch.float32) if save else None
+    Hmid = torch.empty(NL - 1, T, B, H, device=dev, dtype=torch.float32) if (save and NL > 1) else None
+    arr = _ptr_array([t for cell in extra for t in cell])
+    cT = torch.empty(B, H, device=dev, dtype=torch.float32) if want_c else None
+    _cabi.call("caphn_lstm_seq_fwd", GI.data_ptr(), WhhT.data_ptr(), WhhT.stride(0), bhh.data_ptr(), Hall.data_ptr(),
+               _p(Hbm), _p(saved), _p(Hmid), arr if NL > 1 else None, _p(c0), _p(cT), NL, B, T, H, _stream())
+    if want_c:
+        return Hall, Hbm, saved, Hmid, cT
+    return Hall, Hbm, saved, Hmid
+
+
+def lstm_seq_bwd(dHbm, saved, Hall, Whh_p, extra=()):
+    """``extra`` = [(Wih_l, Whh_l) padded [4H,ldh], ...].  Returns dG [NL, T*B, 4H], dh0 [B,H]."""
+    Tp1, B, H = Hall.shape
+    T = Tp1 - 1
+    NL = 1 + len(extra)
+    dev = Hall.device
+    dG = torch.empty(NL, T * B, 4 * H, device=dev, dtype=torch.float32)
+    dh0 = torch.empty(B, H, device=dev, dtype=torch.float32)
+    assert dHbm.is_contiguous()
+    arr = _ptr_array([t for cell in extra for t in cell])
+    _cabi.call("caphn_lstm_seq_bwd", dHbm.data_ptr(), saved.data_ptr(), Whh_p.data_ptr(), Whh_p.stride(0),
+               arr if NL > 1 else None, dG.data_ptr(), dh0.data_ptr(), NL, B, T, H, _stream())
+    return dG, dh0
+
+
 CLUSTER_RECURRENCE = True   # use the weights-resident cluster kernels when W_hh fits (single layer)
 _cluster_plan_cache = {}
 

@@ -117,6 +117,17 @@ int caphn_attgru_seq_bwd(const float* dHbm, const float* dattn, const float* Kp,
                          const float* Hall, const float* Ua, const float* va, const float* Wihc, const float* Whh,
                          float* dGI, float* dGH, float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0,
                          int B, int T, int P, int H, int F, int ldh, int ldf, void* stream);
+/* LSTM recurrence of the pooled variant's DecoderRNN (hypernet.py:53 with type != 'gru'; later.py:254-324 forward,
+ * :326-360 infer): torch nn.LSTMCell, gate order i,f,g,o, zero initial (h, c); extra layers as (h,c) = layer(h,(h,c))
+ * (later.py:279-281).  GI [T,B,4H] = layer-0 input projection incl. b_ih; WhhT [H,ld4] k-major; Hall [T+1,B,H] with
+ * Hall[0] = h0; c0 / cT [B,H] = cell state in / out (NULL: zeros / not returned); `extra` = HOST array of 4*(NL-1)
+ * device pointers {WihT_l, WhhT_l, bih_l, bhh_l}; saved [NL][6][T,B,H].
+ * Backward: Whh [4H,ldh] row-major padded, `extra` = HOST array of 2*(NL-1) pointers {Wih_l, Whh_l}; dG [NL][T,B,4H]. */
+int caphn_lstm_seq_fwd(const float* GI, const float* WhhT, int ld4, const float* bhh, float* Hall, float* Hbm,
+                       float* saved, float* Hmid, const void* const* extra, const float* c0, float* cT, int NL, int B,
+                       int T, int H, void* stream);
+int caphn_lstm_seq_bwd(const float* dHbm, const float* saved, const float* Whh, int ldh, const void* const* extra,
+                       float* dG, float* dh0, int NL, int B, int T, int H, void* stream);
 /* Step-split forward (default for H, F <= 208): three batch-wide launches per time step instead of one persistent
  * kernel, chained with programmatic dependent launch -- U: u = U_a h + b_u on the warp tensor cores (bf16 hi/lo split,
  * fp32 accumulate); A: one CTA per batch row, K_b / f_b fetched into shared memory by bulk TMA copies, scores, softmax,

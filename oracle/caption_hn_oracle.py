@@ -44,13 +44,15 @@ def head_dims_attention(he: int, w_size: int, N: int = 1, M: int = 500) -> Tuple
     return (N * he, w_size // M, w_size // M)  # :91-96
 
 
-def gru_param_shapes_pooled(E: int, H: int, L: int) -> List[Tuple[str, Tuple[int, ...]]]:
-    """DecoderGRU.named_parameters() minus embed/fc_out, in order (later.py:376-381, hypernet.py:62-68)."""
-    out = [("lstm_cell.weight_ih", (3 * H, E)), ("lstm_cell.weight_hh", (3 * H, H)),
-           ("lstm_cell.bias_ih", (3 * H,)), ("lstm_cell.bias_hh", (3 * H,))]
+def gru_param_shapes_pooled(E: int, H: int, L: int, gates: int = 3) -> List[Tuple[str, Tuple[int, ...]]]:
+    """DecoderGRU (gates = 3) / DecoderRNN (LSTM, gates = 4) named_parameters() minus embed/fc_out, in order
+    (later.py:376-381 / 241-244, hypernet.py:62-68)."""
+    G = gates
+    out = [("lstm_cell.weight_ih", (G * H, E)), ("lstm_cell.weight_hh", (G * H, H)),
+           ("lstm_cell.bias_ih", (G * H,)), ("lstm_cell.bias_hh", (G * H,))]
     for l in range(L - 1):
-        out += [(f"layers.{l}.weight_ih", (3 * H, H)), (f"layers.{l}.weight_hh", (3 * H, H)),
-                (f"layers.{l}.bias_ih", (3 * H,)), (f"layers.{l}.bias_hh", (3 * H,))]
+        out += [(f"layers.{l}.weight_ih", (G * H, H)), (f"layers.{l}.weight_hh", (G * H, H)),
+                (f"layers.{l}.bias_ih", (G * H,)), (f"layers.{l}.bias_hh", (G * H,))]
     return out
 
 
@@ -95,7 +97,7 @@ def split_theta_attention(theta: torch.Tensor, E: int, Fo: int, H: int):
     return tuple(out)
 
 
-def split_theta_pooled(theta: torch.Tensor, E: int, H: int, L: int):
+def split_theta_pooled(theta: torch.Tensor, E: int, H: int, L: int, gates: int = 3):
     """Per-cell weights of DecoderGRU from theta -- utils.py:44-69.
 
     ``count`` restarts at 0 inside every recursive call (utils.py:45), and the return value of the child call is the
@@ -105,14 +107,14 @@ def split_theta_pooled(theta: torch.Tensor, E: int, H: int, L: int):
     cells = []
     a = 0
     cell = []
-    for _, shp in gru_param_shapes_pooled(E, H, 1):
+    for _, shp in gru_param_shapes_pooled(E, H, 1, gates):
         n = int(np.prod(shp))
         cell.append(theta[a:a + n].reshape(shp))
         a += n
     cells.append(tuple(cell))
     for _ in range(L - 1):
         a, cell = 0, []
-        for shp in ((3 * H, H), (3 * H, H), (3 * H,), (3 * H,)):
+        for shp in ((gates * H, H), (gates * H, H), (gates * H,), (gates * H,)):
             n = int(np.prod(shp))
             cell.append(theta[a:a + n].reshape(shp))
             a += n
@@ -265,6 +267,14 @@ def attention_beam_search(p: Params, gru_w, features: torch.Tensor, beam_size: i
     return complete[complete_scores.index(max(complete_scores))]
 
 
+def lstm_cell(x, h, c, W_ih, W_hh, b_ih, b_hh):
+    """torch nn.LSTMCell, gate order i,f,g,o (called at later.py:277-291, 344-351)."""
+    g = F.linear(x, W_ih, b_ih) + F.linear(h, W_hh, b_hh)
+    i, f, gg, o = g.chunk(4, dim=1)
+    c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+    return torch.sigmoid(o) * torch.tanh(c2), c2
+
+
 def caption_loss(logits: torch.Tensor, captions: torch.Tensor, ignore_index: Optional[int] = 0) -> torch.Tensor:
     """cc_train_hypernet.py:153 (ignore_index=<pad>=0) / hypernet.py:145 (ignore_index=None)."""
     V = logits.shape[-1]
@@ -312,6 +322,36 @@ def decoder_gru_infer(p: Params, cells, features: torch.Tensor, max_len: int, h0
     return torch.stack(outs, 1)
 
 
+def decoder_rnn_forward(p: Params, cells, features: torch.Tensor, captions: torch.Tensor, pre: str = "captioner."):
+    """Teacher-forced DecoderRNN.forward (later.py:254-324): (h, c) start at zero (:256-259); t = 0 feeds ``features``
+    (:277), t >= 1 feeds Emb[caps[:,t-1]] (:284); every extra cell is applied as ``(h, c) = layer(h, (h, c))``
+    (:279-281, :286-288).  Returns logits [B,T,V]."""
+    emb = F.embedding(captions, p[pre + "embed.weight"])
+    B, H = features.shape[0], cells[0][1].shape[1]
+    h, c = torch.zeros(B, H), torch.zeros(B, H)
+    outs = []
+    for t in range(captions.shape[1]):
+        x = features if t == 0 else emb[:, t - 1, :]
+        h, c = lstm_cell(x, h, c, *cells[0])
+        for cl in cells[1:]:
+            h, c = lstm_cell(h, h, c, *cl)
+        outs.append(F.linear(h, p[pre + "fc_out.weight"], p[pre + "fc_out.bias"]))
+    return torch.stack(outs, 1)
+
+
+def decoder_rnn_infer(p: Params, cells, features: torch.Tensor, max_len: int, pre: str = "captioner."):
+    """DecoderRNN.infer (later.py:326-360): greedy argmax feedback, first cell only, returns softmax probs."""
+    B, H = features.shape[0], cells[0][1].shape[1]
+    h, c = torch.zeros(B, H), torch.zeros(B, H)
+    outs, out = [], None
+    for t in range(max_len):
+        x = features if t == 0 else F.embedding(torch.argmax(out, dim=1), p[pre + "embed.weight"])
+        h, c = lstm_cell(x, h, c, *cells[0])
+        out = F.softmax(F.linear(h, p[pre + "fc_out.weight"], p[pre + "fc_out.bias"]), dim=1)
+        outs.append(out)
+    return torch.stack(outs, 1)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # whole-path helpers (hypernet + decoder), used by tests and by bench.py's CPU baseline
 # ----------------------------------------------------------------------------------------------------------------------
@@ -334,15 +374,21 @@ def path_attention(p: Params, style: torch.Tensor, features, captions, sample_pr
     return logits, att, theta, gw
 
 
-def path_pooled(p: Params, style: torch.Tensor, pooled, captions, h0, L=1, flow=True, infer_len=None):
-    """hypernet.HyperNet.forward + image_encoder.fc (hypernet.py:46,134) + DecoderGRU.forward / infer."""
+def path_pooled(p: Params, style: torch.Tensor, pooled, captions, h0, L=1, flow=True, infer_len=None, cell="gru"):
+    """hypernet.HyperNet.forward + image_encoder.fc (hypernet.py:46,134) + DecoderGRU.forward / infer, or -- with
+    ``cell="lstm"`` (hypernet.py:53, type != 'gru') -- DecoderRNN.forward / infer (``h0`` unused: zero initial state)."""
     E = p["captioner.embed.weight"].shape[1]
     H = p["captioner.fc_out.weight"].shape[1]
+    gates = 3 if cell == "gru" else 4
     theta = hypernet_theta(p, style, 4 * L)
-    cells = split_theta_pooled(theta, E, H, L)
+    cells = split_theta_pooled(theta, E, H, L, gates)
     if not flow:
         cells = [tuple(w.detach().requires_grad_(True) for w in c) for c in cells]
     feats = F.linear(pooled, p["image_encoder.fc.weight"], p["image_encoder.fc.bias"])
+    if cell != "gru":
+        if infer_len is not None:
+            return decoder_rnn_infer(p, cells, feats, infer_len), theta, cells
+        return decoder_rnn_forward(p, cells, feats, captions), theta, cells
     if infer_len is not None:
         return decoder_gru_infer(p, cells, feats, infer_len, h0), theta, cells
     return decoder_gru_forward(p, cells, feats, captions, h0), theta, cells
@@ -397,7 +443,7 @@ def init_params_attention(D, Fo, E, H, V, he, seed=0) -> Params:
     return p
 
 
-def init_params_pooled(D, E, H, V, L=1, seed=0) -> Params:
+def init_params_pooled(D, E, H, V, L=1, seed=0, gates=3) -> Params:
     gen = torch.Generator().manual_seed(seed)
     p: Params = {}
 
@@ -409,7 +455,7 @@ def init_params_pooled(D, E, H, V, L=1, seed=0) -> Params:
     p["captioner.embed.weight"] = torch.randn(V, E, generator=gen)
     lin("hn_base.0", 4 * E, E)
     lin("hn_base.2", 8 * E, 4 * E)
-    for i, (_, shp) in enumerate(gru_param_shapes_pooled(E, H, L)):
+    for i, (_, shp) in enumerate(gru_param_shapes_pooled(E, H, L, gates)):
         w = int(np.prod(shp))
         i0, mid, i2 = head_dims_pooled(E, w)
         lin(f"hn_heads.{i}.0", mid, i0)

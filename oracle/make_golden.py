@@ -191,10 +191,10 @@ def case_attention(ref, name, cc, style, Fo=16, E=12, H=20, V=50, he=10, B=2, T=
     print(name, "loss", float(loss), "logits", tuple(logits.shape))
 
 
-def case_pooled(ref, name, L, E=8, H=6, B=2, T=5, max_len=4):
-    V = 9684  # later.py:449 hard-codes it
+def case_pooled(ref, name, L, E=8, H=6, B=2, T=5, max_len=4, kind="gru"):
+    V = 9684  # later.py:449 / :311 hard-code it
     torch.manual_seed(0)
-    model = ref.HyperNetPooled(E, H, V, ref.vocab, num_layers=L)
+    model = ref.HyperNetPooled(E, H, V, ref.vocab, num_layers=L, type=kind)
     sd = _sd(model)
     g = torch.Generator().manual_seed(4321)
     pooled = torch.relu(torch.randn(B, 2048, generator=g))
@@ -235,7 +235,7 @@ def case_pooled(ref, name, L, E=8, H=6, B=2, T=5, max_len=4):
     ref_hn.set_all_parameters = _flow_set_all_parameters
     try:
         torch.manual_seed(0)
-        model2 = ref.HyperNetPooled(E, H, V, ref.vocab, num_layers=L)
+        model2 = ref.HyperNetPooled(E, H, V, ref.vocab, num_layers=L, type=kind)
         captioner = model2.forward(style)
         torch.manual_seed(1)
         logits2 = captioner(model2.image_encoder.fc(pooled), caps, True)
@@ -261,6 +261,8 @@ def main():
     case_attention(ref, "attn_cc", cc=True, style=onehot, he=10)
     case_pooled(ref, "pooled_l1", L=1)
     case_pooled(ref, "pooled_l2", L=2)
+    case_pooled(ref, "pooled_lstm_l1", L=1, kind="lstm")      # hypernet.py:53: DecoderRNN (later.py:227), zero (h, c)
+    case_pooled(ref, "pooled_lstm_l2", L=2, kind="lstm")
 
 
 if __name__ == "__main__":

@@ -13,9 +13,12 @@ TOL_LOGITS = 1e-4   # BASELINE.json north_star: fp32 mode within 1e-4 relative o
 TOL_GRAD = 1e-3     # gradients <= 1e-3 relative
 
 
-def _model_from(p, E, H, V, L=1, mode="flow"):
+POOLED_CASES = [("pooled_l1", 1, "gru"), ("pooled_l2", 2, "gru"), ("pooled_lstm_l1", 1, "lstm"), ("pooled_lstm_l2", 2, "lstm")]
+
+
+def _model_from(p, E, H, V, L=1, mode="flow", cell="gru"):
     import hypernet_image_captioning_b200 as C
-    m = C.HyperNetPooled(E, H, V, None, num_layers=L)
+    m = C.HyperNetPooled(E, H, V, None, num_layers=L, type=cell)
     sd = m.state_dict()
     missing = [k for k in p if k not in sd]
     assert not missing, missing
@@ -26,12 +29,12 @@ def _model_from(p, E, H, V, L=1, mode="flow"):
     return m.cuda()
 
 
-@pytest.mark.parametrize("name,L", [("pooled_l1", 1), ("pooled_l2", 2)])
-def test_state_dict_layout_matches_reference(name, L):
+@pytest.mark.parametrize("name,L,kind", POOLED_CASES)
+def test_state_dict_layout_matches_reference(name, L, kind):
     c = load_case(name)
     p = params_of(c)
     import hypernet_image_captioning_b200 as C
-    m = C.HyperNetPooled(8, 6, 9684, None, num_layers=L)
+    m = C.HyperNetPooled(8, 6, 9684, None, num_layers=L, type=kind)
     sd = m.state_dict()
     gen = {"captioner.lstm_cell." + k for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")}
     gen |= {f"captioner.layers.{l}.{k}" for l in range(L - 1) for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")}
@@ -40,13 +43,14 @@ def test_state_dict_layout_matches_reference(name, L):
         assert tuple(sd[k].shape) == tuple(v.shape), k
 
 
-@pytest.mark.parametrize("name,L", [("pooled_l1", 1), ("pooled_l2", 2)])
+@pytest.mark.parametrize("name,L,kind", POOLED_CASES)
 @pytest.mark.parametrize("mode", ["literal", "flow"])
-def test_pooled_golden(name, L, mode):
-    """L = 2 exercises the offset-0 aliasing of utils.py:45,68 (layer 2 reads theta[0:...]) and `h = layer(h, h)`."""
+def test_pooled_golden(name, L, kind, mode):
+    """L = 2 exercises the offset-0 aliasing of utils.py:45,68 (layer 2 reads theta[0:...]) and `h = layer(h, h)` /
+    `(h, c) = layer(h, (h, c))`; cell = "lstm" is the DecoderRNN captioner of hypernet.py:53 (zero initial state)."""
     c = load_case(name)
     p = params_of(c)
-    m = _model_from(p, 8, 6, 9684, L=L, mode=mode)
+    m = _model_from(p, 8, 6, 9684, L=L, mode=mode, cell=kind)
     import hypernet_image_captioning_b200 as C
     captioner = m.forward(c["style"].cuda())
     cells_mod = [captioner.lstm_cell] + (list(captioner.layers) if captioner.layers else [])
@@ -54,7 +58,8 @@ def test_pooled_golden(name, L, mode):
         for k in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
             assert rel_err(getattr(cell, k), c[f"gen/{ci}/{k}"]) < 1e-5, (ci, k)
     feats = m.image_encoder(c["pooled"].cuda())
-    logits = captioner(feats, c["captions"].cuda(), True, h0=c["h0"].cuda())
+    h0 = c["h0"].cuda() if kind == "gru" else None        # DecoderRNN starts from zeros (later.py:256-259)
+    logits = captioner(feats, c["captions"].cuda(), True, h0=h0)
     assert rel_err(logits, c["tf/logits"]) < TOL_LOGITS
     loss = C.cross_entropy(logits, c["captions"].cuda(), None)
     assert abs(loss.item() - c["tf/loss"].item()) < TOL_LOGITS * abs(c["tf/loss"].item())
@@ -77,14 +82,14 @@ def test_pooled_golden(name, L, mode):
         assert n >= 12
 
 
-@pytest.mark.parametrize("name,L", [("pooled_l1", 1), ("pooled_l2", 2)])
-def test_pooled_infer_golden_token_exact(name, L):
+@pytest.mark.parametrize("name,L,kind", POOLED_CASES)
+def test_pooled_infer_golden_token_exact(name, L, kind):
     c = load_case(name)
-    m = _model_from(params_of(c), 8, 6, 9684, L=L)
+    m = _model_from(params_of(c), 8, 6, 9684, L=L, cell=kind)
     with torch.no_grad():
         captioner = m.forward(c["style"].cuda())
         probs = captioner.infer(m.image_encoder(c["pooled"].cuda()), max_len=c["infer/probs"].shape[1],
-                                h0=c["h0"].cuda())
+                                h0=c["h0"].cuda() if kind == "gru" else None)
     assert torch.equal(probs.argmax(-1).cpu(), c["infer/probs"].argmax(-1))
     assert rel_err(probs, c["infer/probs"]) < TOL_LOGITS
 
@@ -154,3 +159,40 @@ def test_pooled_fused_loss_matches_unfused(B, T, E, H, V, ignore):
     assert torch.equal(grads[0][1], grads[1][1])
     for k, v in grads[0][2].items():
         assert grad_close(grads[1][2][k], v, TOL_GRAD), k
+
+
+@pytest.mark.parametrize("B,T,E,H,V,L", [(37, 9, 24, 30, 311, 1), (64, 20, 200, 150, 2000, 1), (21, 6, 24, 30, 211, 2),
+                                         (130, 5, 16, 12, 97, 3)])
+@pytest.mark.parametrize("fused", [False, True])
+def test_pooled_lstm_vs_oracle_medium(B, T, E, H, V, L, fused):
+    """DecoderRNN (LSTM, hypernet.py:53) through the hypernet, flow mode: logits, loss and every gradient against the
+    oracle at sizes up to the benchmark's E = 200, H = 150; fused = the decoder + cross-entropy node."""
+    import hypernet_image_captioning_b200 as C
+    p = O.init_params_pooled(2048, E, H, V, L=L, seed=6, gates=4)
+    g = torch.Generator().manual_seed(98)
+    pooled = torch.relu(torch.randn(B, 2048, generator=g))
+    caps = O.synth_captions(B, T, V, g)
+    style = torch.randn(1, E, generator=g)
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    logits_ref, _, _ = O.path_pooled(pl, style, pooled, caps, None, L=L, flow=True, cell="lstm")
+    loss_ref = O.caption_loss(logits_ref, caps, None)
+    loss_ref.backward()
+    m = _model_from(p, E, H, V, L=L, cell="lstm")
+    captioner = m.forward(style.cuda())
+    feats = m.image_encoder(pooled.cuda())
+    if fused:
+        loss, logits = captioner.forward_loss(feats, caps.cuda())
+    else:
+        logits = captioner(feats, caps.cuda(), True)
+        loss = C.cross_entropy(logits, caps.cuda(), None)
+    loss.backward()
+    assert rel_err(logits, logits_ref) < TOL_LOGITS
+    assert abs(loss.item() - loss_ref.item()) < TOL_LOGITS * abs(loss_ref.item())
+    for k, v in m.named_parameters():
+        if k.startswith("captioner.lstm_cell.") or k.startswith("captioner.layers."):
+            continue
+        assert grad_close(v.grad, pl[k].grad, TOL_GRAD), k
+    with torch.no_grad():
+        probs_ref, _, _ = O.path_pooled(p, style, pooled, None, None, L=L, infer_len=6, cell="lstm")
+        probs = m.forward(style.cuda()).infer(m.image_encoder(pooled.cuda()), max_len=6)
+    assert torch.equal(probs.argmax(-1).cpu(), probs_ref.argmax(-1))

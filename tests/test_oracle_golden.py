@@ -63,11 +63,15 @@ def test_attention_variant_greedy_token_exact(name):
     assert rel_err(att, c["greedy/attn"]) < TOL
 
 
-@pytest.mark.parametrize("name,L", [("pooled_l1", 1), ("pooled_l2", 2)])
-def test_pooled_variant_matches_reference(name, L):
+POOLED_CASES = [("pooled_l1", 1, "gru"), ("pooled_l2", 2, "gru"), ("pooled_lstm_l1", 1, "lstm"), ("pooled_lstm_l2", 2, "lstm")]
+
+
+@pytest.mark.parametrize("name,L,kind", POOLED_CASES)
+def test_pooled_variant_matches_reference(name, L, kind):
+    """GRU (DecoderGRU) and LSTM (DecoderRNN, hypernet.py:53) captioners of the pooled hypernet."""
     c = load_case(name)
     p = _leafify(params_of(c))
-    logits, theta, cells = O.path_pooled(p, c["style"], c["pooled"], c["captions"], c["h0"], L=L, flow=False)
+    logits, theta, cells = O.path_pooled(p, c["style"], c["pooled"], c["captions"], c["h0"], L=L, flow=False, cell=kind)
     for ci, cell in enumerate(cells):
         for k, w in zip(("weight_ih", "weight_hh", "bias_ih", "bias_hh"), cell):
             assert rel_err(w, c[f"gen/{ci}/{k}"]) < TOL, (ci, k)
@@ -81,16 +85,17 @@ def test_pooled_variant_matches_reference(name, L):
     for k in ("image_encoder.fc.weight", "captioner.embed.weight", "captioner.fc_out.weight", "captioner.fc_out.bias"):
         assert grad_close(p[k].grad, c["tf/grad/" + k], 1e-5), k
     with torch.no_grad():
-        probs, _, _ = O.path_pooled(p, c["style"], c["pooled"], None, c["h0"], L=L, infer_len=c["infer/probs"].shape[1])
+        probs, _, _ = O.path_pooled(p, c["style"], c["pooled"], None, c["h0"], L=L, infer_len=c["infer/probs"].shape[1],
+                                    cell=kind)
     assert torch.equal(probs.argmax(-1), c["infer/probs"].argmax(-1))
     assert rel_err(probs, c["infer/probs"]) < TOL
 
 
-@pytest.mark.parametrize("name,L", [("pooled_l1", 1), ("pooled_l2", 2)])
-def test_pooled_variant_flow_grads(name, L):
+@pytest.mark.parametrize("name,L,kind", POOLED_CASES)
+def test_pooled_variant_flow_grads(name, L, kind):
     c = load_case(name)
     p = _leafify(params_of(c))
-    logits, _, _ = O.path_pooled(p, c["style"], c["pooled"], c["captions"], c["h0"], L=L, flow=True)
+    logits, _, _ = O.path_pooled(p, c["style"], c["pooled"], c["captions"], c["h0"], L=L, flow=True, cell=kind)
     O.caption_loss(logits, c["captions"], None).backward()
     n = 0
     for k, v in c.items():
