@@ -398,6 +398,7 @@ def run_ours(args):
         del model
         torch.cuda.empty_cache()
         extras.update(attention_extras(args, dev, world, timed))
+        extras.update(lstm_extras(args, dev, world, timed))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -462,6 +463,38 @@ def attention_extras(args, dev, world, timed):
         ms = timed(fn, args.steps)
         out[name] = B * world * args.steps / (ms * 1e-3)
     return out
+
+
+def lstm_extras(args, dev, world, timed):
+    """The LSTM captioner of the pooled hypernet (hypernet.py:53, DecoderRNN): same sizes as the headline workload;
+    the generated cell is 4H x (E + H) instead of 3H x (E + H), so the hypernet heads are 8.6 GB instead of 6.46 GB."""
+    import hypernet_image_captioning_b200 as C
+    from hypernet_image_captioning_b200 import parallel as par
+    from hypernet_image_captioning_b200.synth import synth_captions
+    c = CFG
+    B, T, V = args.batch, c["T"], c["V"]
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = C.HyperNetPooled(c["E"], c["H"], V, None, num_layers=c["L"], type="lstm")
+    model.dp_enabled = world > 1
+    shared = par.shared_parameters(model)
+    g = torch.Generator().manual_seed(4321)
+    pooled = torch.relu(torch.randn(B, c["D"], generator=g)).to(dev)
+    caps = synth_captions(B, T, V, g).to(dev)
+
+    def train():
+        model.zero_grad(set_to_none=True)
+        cap = model.forward(model.captioner.embed.weight[4:5])
+        loss, _ = cap.forward_loss(model.image_encoder(pooled), caps)
+        ((loss / world) if world > 1 else loss).backward()
+        if world > 1:
+            par.allreduce_shared_grads(shared)
+
+    for _ in range(3):
+        train()
+    ms = timed(train, args.steps)
+    n_head = sum(p_.numel() for n_, p_ in model.named_parameters() if n_.startswith("hn_"))
+    return {"lstm_train_captions_per_s": B * world * args.steps / (ms * 1e-3), "lstm_hypernet_params": n_head}
 
 
 def main():
