@@ -210,8 +210,20 @@ def run_ours(args):
     # inputs are copied host->device inside the timed region (on a copy stream, one step ahead, into one of two device
     # buffers), and every step's loss is read back to the host (asynchronously; the host waits for step i-1's value
     # before it enqueues step i+1, so it never runs more than one step ahead of the device).
+    # The whole step (forward + backward + gradient all-reduces) is captured into ONE CUDA graph and replayed
+    # (graphs.GraphedStep; CAPHN_BENCH_GRAPH=0 or a failed capture runs the same kernels eagerly).
+    from hypernet_image_captioning_b200 import graphs
+    gstep = None
+    if os.environ.get("CAPHN_BENCH_GRAPH", "1") != "0":
+        gstep = graphs.GraphedStep(step, (pooled_d, caps_d, h0_d), params=list(model.parameters()),
+                                   release=model.release_graph)
+        if not gstep.captured:
+            gstep = None
+    run_step = gstep if gstep is not None else step
+
     copy_stream = torch.cuda.Stream(device=dev)
-    dbuf = [(torch.empty_like(pooled_d), torch.empty_like(caps_d)) for _ in range(2)]
+    dbuf = [(torch.empty_like(pooled_d), torch.empty_like(caps_d), torch.empty_like(h0_d)) for _ in range(2)]
+    h0_pin = [torch.empty(B, c["H"]).pin_memory() for _ in range(2)]
     ev_copied = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
     ev_loss = [torch.cuda.Event() for _ in range(2)]
@@ -219,10 +231,13 @@ def run_ours(args):
     e2e_state = {"i": 0, "primed": False, "losses": []}
 
     def _issue_copy(j):
+        ev_copied[j % 2].synchronize()                        # the last copy out of this pinned h0 buffer is done
+        torch.rand(B, c["H"], out=h0_pin[j % 2])              # h0 drawn on the host per call like the reference (later.py:393)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_free[j % 2])            # the step that last used this buffer has finished
             dbuf[j % 2][0].copy_(pooled_h, non_blocking=True)
             dbuf[j % 2][1].copy_(caps_h, non_blocking=True)
+            dbuf[j % 2][2].copy_(h0_pin[j % 2], non_blocking=True)
             ev_copied[j % 2].record(copy_stream)
 
     def step_e2e():
@@ -233,7 +248,7 @@ def run_ours(args):
             e2e_state["primed"] = True
         _issue_copy(i + 1)                                    # next step's inputs fly while this step computes
         cur.wait_event(ev_copied[i % 2])
-        loss = step(dbuf[i % 2][0], dbuf[i % 2][1], None)     # h0 drawn on the host like the reference (later.py:393)
+        loss = run_step(*dbuf[i % 2])
         ev_free[i % 2].record(cur)
         loss_ring[i % 2].copy_(loss.detach().reshape(1), non_blocking=True)
         ev_loss[i % 2].record(cur)
@@ -267,10 +282,12 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     for _ in range(max(3, args.warmup)):
-        step(pooled_d, caps_d, h0_d)
+        run_step(pooled_d, caps_d, h0_d)
     l0 = _cabi.launches()
-    ms = timed(lambda: step(pooled_d, caps_d, h0_d), args.steps)
+    ms = timed(lambda: run_step(pooled_d, caps_d, h0_d), args.steps)
     launches = _cabi.launches() - l0
+    if gstep is not None:                                     # replayed launches are not seen by the library's counter
+        launches = gstep.launches_per_step * args.steps
     value = B * world * args.steps / (ms * 1e-3)
 
     for _ in range(2):
@@ -322,6 +339,11 @@ def run_ours(args):
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650 GB/s",
                 "alg_bytes_per_launch": alg_bytes, "ms_per_launch": k_ms}
+
+    graphed = gstep is not None
+    gstep = run_step = None                                   # release the graph's memory pool (gradients + activations)
+    model.zero_grad(set_to_none=True)
+    torch.cuda.empty_cache()
 
     extras = {}
     if not args.no_extras:
@@ -411,7 +433,7 @@ def run_ours(args):
             "metric": "hypernet-GRU train captions/s", "value": value, "unit": "captions/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, world),
+            "config": dict(workload_config(args, world), cuda_graph=graphed),
             "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
@@ -462,6 +484,16 @@ def attention_extras(args, dev, world, timed):
             fn()
         ms = timed(fn, args.steps)
         out[name] = B * world * args.steps / (ms * 1e-3)
+    if os.environ.get("CAPHN_BENCH_GRAPH", "1") != "0":       # the same training step replayed from one CUDA graph
+        from hypernet_image_captioning_b200 import graphs
+        gtrain = graphs.GraphedStep(train, (), params=list(model.parameters()), release=model.release_graph)
+        if gtrain.captured:
+            for _ in range(3):
+                gtrain()
+            ms = timed(gtrain, args.steps)
+            out["attention_train_eager_captions_per_s"] = out["attention_train_captions_per_s"]
+            out["attention_train_captions_per_s"] = B * world * args.steps / (ms * 1e-3)
+        del gtrain
     return out
 
 
@@ -490,9 +522,14 @@ def lstm_extras(args, dev, world, timed):
         if world > 1:
             par.allreduce_shared_grads(shared)
 
+    run = train
+    if os.environ.get("CAPHN_BENCH_GRAPH", "1") != "0":
+        from hypernet_image_captioning_b200 import graphs
+        gtrain = graphs.GraphedStep(train, (), params=list(model.parameters()), release=model.release_graph)
+        run = gtrain if gtrain.captured else train
     for _ in range(3):
-        train()
-    ms = timed(train, args.steps)
+        run()
+    ms = timed(run, args.steps)
     n_head = sum(p_.numel() for n_, p_ in model.named_parameters() if n_.startswith("hn_"))
     return {"lstm_train_captions_per_s": B * world * args.steps / (ms * 1e-3), "lstm_hypernet_params": n_head}
 

@@ -311,7 +311,15 @@ __global__ void colsum_kernel(const float* __restrict__ X, long ld, long M, int 
     const long m1 = min(M, m0 + rows_per_block);
     if (n >= N) return;
     float s = 0.f;
-    for (long m = m0; m < m1; ++m) s += X[m * ld + n];
+    long m = m0;
+    for (; m + 8 <= m1; m += 8) {          // 8 independent loads in flight per thread
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(X + (m + u) * ld + n);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; m < m1; ++m) s += __ldg(X + m * ld + n);
     atomicAdd(out + n, s);
 }
 
@@ -415,8 +423,11 @@ int caphn_scatter_add_rows(const float* dX, long ldx, const long long* idx, long
 // out[n] += sum_m X[m,n]   (caller zeroes out for a plain sum)
 int caphn_colsum(const float* X, long ld, long M, int N, float* out, void* stream) {
     if (M <= 0 || N <= 0) return CAPHN_EINVAL;
+    // enough row blocks for ~8 CTAs per SM (the kernel is a latency chain of loads otherwise), >= 16 rows each
+    const long xb = ceil_div(N, 128);
     long rpb = 256;
-    dim3 grid(ceil_div(N, 128), ceil_div(M, rpb));
+    while (rpb > 16 && xb * ceil_div(M, rpb) < 8L * kNumSMs) rpb >>= 1;
+    dim3 grid(xb, ceil_div(M, rpb));
     colsum_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(X, ld, M, N, rpb, out);
     CAPHN_RETURN_LAST();
 }

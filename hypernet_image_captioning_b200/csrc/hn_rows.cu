@@ -367,14 +367,22 @@ static int launch_rows_bwd(const T* W, const float* A, long lda, const float* dP
     constexpr int V = WT<T>::V;
     constexpr int WPB = ROWS_BWD_THREADS / 32;
     const int S = ((K + 2 * (V - 1)) / V + 32 * QPL - 1) / (32 * QPL);
-    if (S >= 8 || (long)N * K < (1L << 22)) {
-        // many strips (or tiny, latency-bound matrices): warp-granular work items
+    int gdiv = K % V;
+    { int y = V; while (y) { const int t = gdiv % y; gdiv = y; y = t; } }
+    const int ncls = V / gdiv;
+    if ((long)N * K < (1L << 22)) {
+        // tiny matrices (hn_base, the bias heads): a chain of dependent HBM round trips, not bandwidth.  One batch of
+        // RU rows per misalignment class per warp (every load of a warp is issued at once), as many warps as that
+        // gives, and the CTA-level reduction so the dA atomics stay at N/(8 RU ncls) per address.
+        const int RB = RU * ncls;
+        const long groups = (N + (long)RB * WPB - 1) / ((long)RB * WPB);
+        rows_bwd_kernel<T, GC, QPL, RU, true><<<(unsigned)(groups * S), ROWS_BWD_THREADS, 0, st>>>(
+            W, A, lda, dP, ldp, dW, dA, ldda, N, K, RB, S, 0, accum_dw, need_da);
+    } else if (S >= 8) {
+        // many strips: warp-granular work items
         // >= 32 rows per misalignment class per work item keeps the dA atomics <= ~10 % of the memory instructions
-        int gdiv = K % V;
-        { int y = V; while (y) { const int t = gdiv % y; gdiv = y; y = t; } }
-        const int ncls = V / gdiv;
         int RB = 128 * (ncls > 4 ? ncls / 4 : 1);
-        const int rb_min = ((long)N * K < (1L << 22)) ? 16 : 32 * ncls;   // tiny matrices: parallelism beats atomics
+        const int rb_min = 32 * ncls;
         while (RB > rb_min && RB > 16 && ((N + RB - 1) / RB) * S < 8L * kNumSMs * WPB) RB >>= 1;
         const long items = ((N + RB - 1) / RB) * S;
         long blocks = (items + WPB - 1) / WPB;

@@ -63,6 +63,13 @@ class _HyperNetMixin:
             if getattr(p, "grad_lowrank", None) is not None:
                 p.grad_lowrank = None
 
+    def release_graph(self):
+        """Forget the generated weights of the last ``forward`` (flow mode: they carry the hypernet's autograd graph, which
+        the captioner otherwise keeps alive until the next ``forward``).  The injected ``captioner.<cell>.weight_*`` values
+        stay, as in the reference."""
+        self.captioner._generated = None
+        self.captioner._generated_groups = None
+
     def generate_theta(self, x: torch.Tensor) -> torch.Tensor:
         x2 = x.reshape(1, -1) if x.dim() == 1 else x
         x2 = x2.to(torch.float32).contiguous()

@@ -196,3 +196,51 @@ def test_pooled_lstm_vs_oracle_medium(B, T, E, H, V, L, fused):
         probs_ref, _, _ = O.path_pooled(p, style, pooled, None, None, L=L, infer_len=6, cell="lstm")
         probs = m.forward(style.cuda()).infer(m.image_encoder(pooled.cuda()), max_len=6)
     assert torch.equal(probs.argmax(-1).cpu(), probs_ref.argmax(-1))
+
+
+@pytest.mark.parametrize("mode", ["literal", "flow"])
+def test_graphed_step_matches_eager(mode):
+    """graphs.GraphedStep: the whole fwd+bwd step replayed from one CUDA graph gives the eager step's loss and gradients
+    (and, transitively, the reference's: the eager step is pinned by test_pooled_golden), also on fresh inputs."""
+    from hypernet_image_captioning_b200 import graphs
+    c = load_case("pooled_l1")
+    p = params_of(c)
+    m = _model_from(p, 8, 6, 9684, L=1, mode=mode)
+    pooled, caps, h0 = c["pooled"].cuda(), c["captions"].cuda(), c["h0"].cuda()
+    style = c["style"].cuda()
+
+    def step(pooled, caps, h0):
+        m.zero_grad(set_to_none=True)
+        captioner = m.forward(style)
+        loss, _ = captioner.forward_loss(m.image_encoder(pooled), caps, h0=h0, ignore_index=None)
+        loss.backward()
+        return loss
+
+    def grads():
+        named = dict(m.named_parameters())
+        return {k: v.grad.detach().clone() for k, v in named.items() if v.grad is not None}
+
+    g = torch.Generator().manual_seed(7)
+    pooled2 = torch.relu(torch.randn(pooled.shape, generator=g)).cuda()
+    caps2 = caps.flip(0).contiguous()
+    h02 = torch.rand(h0.shape, generator=g).cuda()
+    eager = []
+    for inp in ((pooled, caps, h0), (pooled2, caps2, h02)):
+        loss = step(*inp)
+        eager.append((loss.item(), grads()))
+        del loss        # a live loss keeps the eager autograd graph (and its default-stream AccumulateGrad nodes) alive
+    assert abs(eager[0][0] - c["tf/loss"].item()) < TOL_LOGITS * abs(c["tf/loss"].item())
+
+    gstep = graphs.GraphedStep(step, (pooled, caps, h0), params=list(m.parameters()), release=m.release_graph)
+    assert gstep.captured and gstep.launches_per_step > 10
+    for rep in range(2):
+        for inp, (l_ref, g_ref) in zip(((pooled, caps, h0), (pooled2, caps2, h02)), eager):
+            loss = gstep(*inp)
+            assert abs(loss.item() - l_ref) <= 1e-6 * abs(l_ref)
+            got = grads()
+            assert set(got) == set(g_ref)
+            for k in g_ref:
+                assert grad_close(got[k], g_ref[k], 1e-5), (mode, rep, k)
+    m.zero_grad(set_to_none=True)          # a user dropping .grad between replays gets them back after the next call
+    gstep(pooled, caps, h0)
+    assert set(grads()) == set(eager[0][1])
