@@ -3,7 +3,7 @@
 Public API mirrors the reference modules (see modules.py / modules_attention.py); kernels live in csrc/ behind the
 C-ABI declared in include/caphn_b200.h.  Importing the package does not need a GPU; calling any op does.
 """
-from . import _cabi, ops, functional  # noqa: F401
+from . import _cabi, ops, functional, graphs, metrics  # noqa: F401
 from .functional import cross_entropy, linear, hypernet_theta  # noqa: F401
 from .modules import DecoderGRU, DecoderRNN, HyperNetPooled, PooledFeatureEncoder  # noqa: F401
 from .modules_attention import AttentionGru, BahdanauAttention, HyperNetAttention, SpatialFeatureEncoder  # noqa: F401

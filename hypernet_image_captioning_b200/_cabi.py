@@ -67,6 +67,8 @@ SIGNATURES = {
     "caphn_gram": [P, L, I, L, P, P],
     "caphn_sumsq_lowrank": [P, P, I, P, P],
     "caphn_adam_step_lowrank": [P, P, P, P, L, P, L, I, L, L, D, D, D, D, D, I, P, P],
+    "caphn_caption_compact": [P, L, I, I, LL, LL, LL, P, P, P],
+    "caphn_bleu_counts": [P, P, I, P, P, I, I, I, P, P],
     "caphn_launch_count": [P],
     "caphn_build_arch": [P],
 }

@@ -232,6 +232,20 @@ int caphn_adam_step_lowrank(float* p, float* m, float* v, const float* dP, long 
                             long N, long K, double lr, double beta1, double beta2, double eps, double weight_decay,
                             int step, const float* gscale, void* stream);
 
+/* ---- caption metrics, token-level part (csrc/metrics.cu) ------------------------------------------------------------
+ * Replaces the per-token `.item()` loops of utils.py:161-190 (cap_to_text / cap_to_text_gt) that metric_score
+ * (utils.py:229-262) runs inside every training_step (cc_train_hypernet.py:154).
+ * out[b, :len[b]] = tokens of tok[b, :T] (row stride ldt) that are neither pad nor start, up to (excluding) the first end
+ * token; out[b, len[b]:] = pad.  out is [B,T] int64, len is [B] int32. */
+int caphn_caption_compact(const long long* tok, long ldt, int B, int T, long long pad, long long start, long long end,
+                          long long* out, int* len, void* stream);
+/* Corpus-BLEU sufficient statistics (the `datasets` "bleu" metric == tensorflow/nmt compute_bleu, requested with
+ * max_order 1..4 at utils.py:250-258) of B (hypothesis, single reference) pairs of compacted captions hyp [B,Th] /
+ * ref [B,Tr] int64 with lengths int32, ADDED into counts[2*max_order + 2] (uint64, zeroed by the caller): clipped n-gram
+ * matches per order, candidate n-grams per order, total hypothesis length, total reference length.  max_order <= 4. */
+int caphn_bleu_counts(const long long* hyp, const int* hyp_len, int Th, const long long* ref, const int* ref_len, int Tr,
+                      int B, int max_order, unsigned long long* counts, void* stream);
+
 /* *out = number of CUDA kernels launched by this library so far (host-side counter). */
 int caphn_launch_count(unsigned long long* out);
 /* *out = 100 (library compiled for sm_100a). */

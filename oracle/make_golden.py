@@ -251,6 +251,44 @@ def case_pooled(ref, name, L, E=8, H=6, B=2, T=5, max_len=4, kind="gru"):
     print(name, "loss", float(loss), "logits", tuple(logits.shape))
 
 
+def case_metrics(ref, name="metrics", B=8, T=12):
+    """utils.py:161-190 cap_to_text / cap_to_text_gt of the unmodified reference with its own data/vocab.pkl, mapped back
+    to token ids (vocab.w2i).  Logits are rebuilt by the tests from `pred_ids` / `tie_ids` exactly as here: zeros, 1.0 at
+    pred_ids[b,t] and -- a tie, resolved to the lower index by torch.argmax -- 1.0 at tie_ids[b,t] >= pred_ids[b,t]."""
+    voc = ref.vocab
+    V = len(voc.i2w)
+    g = torch.Generator().manual_seed(11)
+    def draw():
+        ids = torch.randint(7, V, (B, T), generator=g)
+        special = torch.randint(0, 10, (B, T), generator=g)
+        ids[special == 0] = 0      # <pad> in the middle of a caption is skipped, not a stop
+        ids[special == 1] = 1      # <s>
+        ids[special == 2] = 2      # </s>: everything after the first one is dropped
+        return ids
+    pred_ids, gt_ids = draw(), draw()
+    pred_ids[0, :] = torch.randint(7, V, (T,), generator=g)        # no </s> at all: full length
+    pred_ids[1, 0] = 2                                             # empty caption
+    gt_ids[2, :3] = torch.tensor([1, 0, 2])                        # <s> <pad> </s>: empty reference
+    tie_ids = torch.minimum(pred_ids + torch.randint(0, 5, (B, T), generator=g), torch.tensor(V - 1))
+    logits = torch.zeros(B, T, V)
+    logits.scatter_(2, pred_ids.unsqueeze(-1), 1.0)
+    logits.scatter_(2, tie_ids.unsqueeze(-1), 1.0)
+    out = {"pred_ids": pred_ids, "tie_ids": tie_ids, "gt_ids": gt_ids}
+    hyp = torch.zeros(B, T, dtype=torch.int64)
+    refc = torch.zeros(B, T, dtype=torch.int64)
+    hl, rl = torch.zeros(B, dtype=torch.int32), torch.zeros(B, dtype=torch.int32)
+    for b in range(B):
+        words = ref.utils.cap_to_text(logits[b], voc, tokenized=True)
+        assert ref.utils.cap_to_text(logits[b], voc, tokenized=False) == " ".join(words)
+        gwords = ref.utils.cap_to_text_gt(gt_ids[b], voc, tokenized=True)
+        hl[b], rl[b] = len(words), len(gwords)
+        hyp[b, :len(words)] = torch.tensor([voc.w2i[w] for w in words], dtype=torch.int64)
+        refc[b, :len(gwords)] = torch.tensor([voc.w2i[w] for w in gwords], dtype=torch.int64)
+    out.update({"hyp": hyp, "hyp_len": hl, "ref": refc, "ref_len": rl, "V": torch.tensor(V)})
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(out))
+    print(name, "hyp_len", hl.tolist(), "ref_len", rl.tolist())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_harness.load()
@@ -263,6 +301,7 @@ def main():
     case_pooled(ref, "pooled_l2", L=2)
     case_pooled(ref, "pooled_lstm_l1", L=1, kind="lstm")      # hypernet.py:53: DecoderRNN (later.py:227), zero (h, c)
     case_pooled(ref, "pooled_lstm_l2", L=2, kind="lstm")
+    case_metrics(ref)
 
 
 if __name__ == "__main__":

@@ -141,3 +141,48 @@ def test_attention_beam_search_matches_reference_test_step(tag):
             got = O.attention_beam_search(p, gw, c["features"][bi:bi + 1], 3, 2, 50)
             want = c[f"beam/{tag}/{bi}"].tolist()
             assert (got if got is not None else [-1]) == want, (tag, bi)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# caption metrics, token-level part (oracle/metrics_oracle.py)
+# ----------------------------------------------------------------------------------------------------------------------
+def _metrics_logits(c):
+    B, T = c["pred_ids"].shape
+    logits = torch.zeros(B, T, int(c["V"]))
+    logits.scatter_(2, c["pred_ids"].unsqueeze(-1), 1.0)
+    logits.scatter_(2, c["tie_ids"].unsqueeze(-1), 1.0)
+    return logits
+
+
+def test_metrics_oracle_token_filter_matches_reference_cap_to_text():
+    """tests/golden/metrics.npz = utils.cap_to_text / cap_to_text_gt of the unmodified reference (with its vocab.pkl)."""
+    from golden_util import load_case
+    from oracle import metrics_oracle as MO
+    c = load_case("metrics")
+    logits = _metrics_logits(c)
+    for b in range(logits.shape[0]):
+        hyp = MO.cap_tokens_from_logits(logits[b])
+        assert hyp == c["hyp"][b, :int(c["hyp_len"][b])].tolist(), b
+        ref = MO.cap_tokens(c["gt_ids"][b].tolist())
+        assert ref == c["ref"][b, :int(c["ref_len"][b])].tolist(), b
+    assert int(c["hyp_len"][1]) == 0 and int(c["ref_len"][2]) == 0 and int(c["hyp_len"][0]) == logits.shape[1]
+
+
+def test_metrics_oracle_bleu_known_answers():
+    """compute_bleu (tensorflow/nmt scripts/bleu.py, wrapped by the `datasets` "bleu" metric): hand-computed cases."""
+    import math
+    from oracle import metrics_oracle as MO
+    a = [5, 6, 7, 8, 9, 10]
+    assert MO.compute_bleu([a], [a], 4) == pytest.approx(1.0)
+    # clipping: "the the the the the the the" vs "the cat is on the mat" -> unigram precision 2/7, longer hypothesis: bp = 1
+    hyp, ref = [1] * 7, [1, 2, 3, 4, 1, 5]
+    assert MO.compute_bleu([hyp], [ref], 1) == pytest.approx(2.0 / 7.0)
+    assert MO.compute_bleu([hyp], [ref], 2) == 0.0                      # no bigram match, no smoothing
+    # brevity penalty: hypothesis = first 4 of 6 reference tokens: p1 = p2 = 1, bp = exp(1 - 6/4)
+    assert MO.compute_bleu([a[:4]], [a], 2) == pytest.approx(math.exp(1.0 - 6.0 / 4.0))
+    # corpus level: statistics are summed over sentence pairs before the ratio is taken
+    m, p, hl, rl = MO.bleu_counts([a, hyp], [a, ref], 4)
+    assert (m, p, hl, rl) == ([8, 5, 4, 3], [13, 11, 9, 7], 13, 12)
+    assert MO.bleu_from_counts(m, p, hl, rl, 4) == pytest.approx(math.exp(sum(math.log(x) for x in
+                                                                      (8 / 13, 5 / 11, 4 / 9, 3 / 7)) / 4))
+    assert MO.compute_bleu([[]], [a], 4) == 0.0
