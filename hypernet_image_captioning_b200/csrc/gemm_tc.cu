@@ -16,6 +16,7 @@
 // H = 150), and long-K / few-tile products are split along K so that ~148 CTAs are busy.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 namespace caphn {
@@ -456,8 +457,25 @@ int caphn_gemm_tc_ex(const void* Ahi, const void* Alo, long a_ld, int a_mn, cons
     p.C = C; p.ldc = ldc; p.bias = bias; p.M = M; p.N = N; p.relu = relu; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
     p.num_kb = (int)((K + tc::BK - 1) / tc::BK);
     // N tile: one tile when N <= 256 (rounded up to 16, or to 64 for an MN-major B whose boxes are 64 wide), else 128
-    if (N <= 256) p.BN = b_mn ? ((N + 63) / 64) * 64 : ((N + 15) / 16) * 16;
-    else p.BN = 128;
+    if (N <= 256) {
+        p.BN = b_mn ? ((N + 63) / 64) * 64 : ((N + 15) / 16) * 16;
+    } else {
+        // wide N: the tile width that minimises (waves over the 148 SMs) x (per-tile cost ~ BN + fixed part).  Matters when
+        // there are only a few waves: the decode-step vocabulary projection (M = 512, N = 9684) is 304 tiles = 3 waves at
+        // BN = 128 but 272 tiles = 2 waves at BN = 144.
+        // With many waves the quantisation loss is small and BN = 128 keeps 3 operand stages in flight: left alone.
+        const int step = b_mn ? 64 : 16;
+        const long tm = ceil_div(M, tc::BM);
+        static const bool auto_bn = [] { const char* e = getenv("CAPHN_TC_BN_AUTO"); return !(e && e[0] == '0'); }();
+        const bool few_waves = auto_bn && tm * ceil_div(N, 128) <= 8L * kNumSMs;
+        long best_cost = -1;
+        p.BN = 128;
+        for (int bn = 128; few_waves && bn <= 256; bn += step) {
+            const long t = tm * ceil_div(N, bn);
+            const long cost = ((t + kNumSMs - 1) / kNumSMs) * (bn + 32);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; p.BN = bn; }
+        }
+    }
     const int tiles = ceil_div(M, tc::BM) * ceil_div(N, p.BN);
     if (splitk <= 0) {
         // smallest split whose unit count fills the 148 SMs to >= 90 % (or the best available), >= 4 k-blocks per unit

@@ -174,5 +174,7 @@ def test_lowrank_head_gradients_give_the_same_training_trajectory(variant):
             continue          # the last generated weights (a function of the parameters, not trained)
         if n.endswith("attention.v_a.bias"):
             continue          # its gradient is analytically zero (softmax shift invariance): Adam normalises rounding noise
-        # updates are lr * O(1) = 1e-2 per step: 1e-5 is 0.1 % of one update (the clip coefficients differ in the last bits)
-        assert (pa[n] - pb[n]).abs().max().item() <= 1e-5 * max(1.0, pa[n].abs().max().item()), n
+        # updates are lr * O(1) = 1e-2 per step: 5e-5 is 0.5 % of one update.  The two runs are not bit-reproducible (the dA
+        # reductions use atomics, so their summation order varies run to run) and Adam's m / sqrt(v) amplifies last-bit
+        # gradient differences of near-cancelling elements: observed spread 0 ... 1.3e-5 between identical runs.
+        assert (pa[n] - pb[n]).abs().max().item() <= 5e-5 * max(1.0, pa[n].abs().max().item()), n
