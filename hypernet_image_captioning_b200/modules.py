@@ -233,14 +233,21 @@ class DecoderGRU(nn.Module):
         x = features.contiguous()
         logits = torch.empty(B, self.vocab_size, device=features.device, dtype=torch.float32)
         xproj, vocab = ops.LinearPlan(W_ih, b_ih), ops.LinearPlan(fc_w, fc_b)   # weight splits made once, not per step
+        # From step 1 on the input is a word embedding, so its projection is a row of  P = Emb W_ih^T + b_ih  [V, 3H]:
+        # one GEMM per call instead of (gather + operand split + GEMM) per step -- same products, same order per element.
+        table = ops.linear(emb, W_ih, b_ih) if ops.use_projection_table(B, max_len, emb.shape[0]) else None
+        words = None
         for t in range(max_len):
-            GI = xproj(x)
+            if t == 0:
+                GI = xproj(x)
+            elif table is not None:
+                GI = ops.gather_rows(table, words)
+            else:
+                GI = xproj(ops.gather_rows(emb, words))
             Hall, _, _, _ = ops.gru_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False)
             h = Hall[1]
             vocab(h, out=logits)
             _, words = ops.softmax_argmax(logits, want_probs=True, probs_out=outputs[:, t, :])
-            if t + 1 < max_len:
-                x = ops.gather_rows(emb, words)
         return outputs
 
 
@@ -286,14 +293,19 @@ class DecoderRNN(DecoderGRU):
         x = features.contiguous()
         logits = torch.empty(B, self.vocab_size, device=features.device, dtype=torch.float32)
         xproj, vocab = ops.LinearPlan(W_ih, b_ih), ops.LinearPlan(fc_w, fc_b)
+        table = ops.linear(emb, W_ih, b_ih) if ops.use_projection_table(B, max_len, emb.shape[0]) else None   # [V, 4H]
+        words = None
         for t in range(max_len):
-            GI = xproj(x)
+            if t == 0:
+                GI = xproj(x)
+            elif table is not None:
+                GI = ops.gather_rows(table, words)
+            else:
+                GI = xproj(ops.gather_rows(emb, words))
             Hall, _, _, _, c = ops.lstm_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False, c0=c, want_c=True)
             h = Hall[1]
             vocab(h, out=logits)
             _, words = ops.softmax_argmax(logits, want_probs=True, probs_out=outputs[:, t, :])
-            if t + 1 < max_len:
-                x = ops.gather_rows(emb, words)
         return outputs
 
 

@@ -77,6 +77,14 @@ def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, f
     else:
         GIw = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
         xproj, vocab = ops.LinearPlan(W_ih_w, b_ih.contiguous()), ops.LinearPlan(fc_w, fc_b)   # split once, reuse per step
+        # Decode without a backward pass: the word half of the input projection is a row of
+        # P = [Emb; 0] W_ih[:, :E]^T + b_ih  [V+1, 3H]  (row V = the zero input of t = 0, 1) -- one GEMM per call instead
+        # of (gather + copy + operand split + GEMM) per step.  Training keeps the per-step path: it needs x_word itself.
+        table = None
+        if not need_grad and ops.use_projection_table(B, T + 1, V):
+            emb_ext = torch.cat([emb_w, emb_w.new_zeros(1, E)], 0)
+            table = ops.linear(emb_ext, W_ih_w.contiguous(), b_ih.contiguous())
+            fed.fill_(V)
         for t in range(T):
             if use_sampling[t]:
                 # :91-96  argmax of log_softmax(logits/0.5) == argmax of logits (lowest index on ties)
@@ -84,9 +92,12 @@ def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, f
                 fed[t].copy_(top)
             elif t >= 2:
                 fed[t].copy_(caps[:, t - 1])
-            xw = ops.gather_rows(emb_w, fed[t])                        # zeros where fed == -1
-            XC[t * B:(t + 1) * B, :E].copy_(xw)
-            xproj(xw, out=GIw[t * B:(t + 1) * B])
+            if table is not None:
+                ops.gather_rows(table, fed[t], out=GIw[t * B:(t + 1) * B])
+            else:
+                xw = ops.gather_rows(emb_w, fed[t])                    # zeros where fed == -1
+                XC[t * B:(t + 1) * B, :E].copy_(xw)
+                xproj(xw, out=GIw[t * B:(t + 1) * B])
             ops.attgru_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, t, t + 1)
             vocab(Hall[t + 1], out=logits[:, t, :])
     sv = (feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih, W_hh, fc_w, Wa_w, Ua_w,

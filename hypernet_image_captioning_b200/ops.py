@@ -382,12 +382,15 @@ def softmax_argmax(X, want_probs=True, probs_out=None, want_argmax=True):
     return Y, am
 
 
-def gather_rows(table, idx):
+def gather_rows(table, idx, out=None):
     _chk(table), _chk(idx, torch.int64)
+    assert table.is_contiguous()
     idx = idx.contiguous()
     n, E = idx.numel(), table.shape[1]
-    out = torch.empty(n, E, device=table.device, dtype=torch.float32)
-    _cabi.call("caphn_gather_rows", table.data_ptr(), idx.data_ptr(), n, E, out.data_ptr(), E, _stream())
+    if out is None:
+        out = torch.empty(n, E, device=table.device, dtype=torch.float32)
+    assert out.shape == (n, E) and out.stride(1) == 1
+    _cabi.call("caphn_gather_rows", table.data_ptr(), idx.data_ptr(), n, E, out.data_ptr(), out.stride(0), _stream())
     return out
 
 
@@ -673,6 +676,13 @@ def gemm_tc(A: SplitOperand, Bm: SplitOperand, bias=None, relu=False, out=None, 
                int(Bm.mn), A.K, out.data_ptr(), out.stride(0), _p(bias), M, N, int(relu), 1 if relu else splitk,
                _stream())
     return out
+
+
+def use_projection_table(B, steps, V):
+    """Greedy decode feeds back word embeddings, so  x_t W^T + b  is a row of the table  Emb W^T + b  [V, N].  Building
+    the table costs one V-row GEMM per decode call (the generated W changes with every style); it replaces a gather, an
+    operand split and a B-row GEMM in each of the remaining steps, and pays off once those rows outnumber V / 2."""
+    return (steps - 1) * B >= V // 2
 
 
 class LinearPlan:

@@ -34,3 +34,25 @@ def grad_close(a, b, rtol, atol=1e-7):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     d = (a - b).abs().max().item()
     return d <= atol or d <= rtol * b.abs().max().item()
+
+
+def same_greedy_paths(a, b, tol=1e-4):
+    """Two greedy decodes a, b [B,T,V] (logits or probabilities) of the same model by two numerically different routes.
+    Greedy feedback amplifies rounding: once a near-tie flips, the trajectories legitimately diverge.  So: wherever the
+    token history is identical so far, the scores must agree within ``tol`` of the score scale, and any first flip must
+    be a near-tie (top-2 margin within 2*tol of the scale); most trajectories must stay identical."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    ta, tb = a.argmax(-1), b.argmax(-1)
+    same = ta == tb
+    hist = torch.cumprod(torch.cat([torch.ones_like(same[:, :1]), same[:, :-1]], 1).long(), 1).bool()
+    scale = a.abs().max().item()
+    diff = (a - b).abs().amax(-1)
+    if not bool((diff[hist] <= tol * scale).all()):
+        return False, f"scores differ by {diff[hist].max().item() / scale:.2e} of scale with identical history"
+    flips = hist & ~same
+    top2 = a.topk(2, -1).values
+    margin = top2[..., 0] - top2[..., 1]
+    if flips.any() and not bool((margin[flips] <= 2 * tol * scale).all()):
+        return False, f"token flip at margin {margin[flips].max().item() / scale:.2e} of scale"
+    frac = hist.double().mean().item()
+    return frac > 0.5, f"identical-history fraction {frac:.3f}, first flips {int(flips.sum())}"

@@ -82,8 +82,14 @@ def test_pooled_golden(name, L, kind, mode):
         assert n >= 12
 
 
+@pytest.mark.parametrize("table", [False, True])
 @pytest.mark.parametrize("name,L,kind", POOLED_CASES)
-def test_pooled_infer_golden_token_exact(name, L, kind):
+def test_pooled_infer_golden_token_exact(name, L, kind, table, monkeypatch):
+    """table = True forces the decode-time projection table (P = Emb W_ih^T + b_ih, one GEMM per call) that large
+    batches use instead of a per-step gather + GEMM; both must reproduce the reference's greedy tokens."""
+    from hypernet_image_captioning_b200 import graphs, ops
+    monkeypatch.setattr(ops, "use_projection_table", lambda B, steps, V: table)
+    graphs.clear()
     c = load_case(name)
     m = _model_from(params_of(c), 8, 6, 9684, L=L, cell=kind)
     with torch.no_grad():
@@ -244,3 +250,31 @@ def test_graphed_step_matches_eager(mode):
     m.zero_grad(set_to_none=True)          # a user dropping .grad between replays gets them back after the next call
     gstep(pooled, caps, h0)
     assert set(grads()) == set(eager[0][1])
+
+
+@pytest.mark.parametrize("kind", ["gru", "lstm"])
+def test_infer_projection_table_equals_per_step_path_at_bench_size(kind, monkeypatch):
+    """B = 512, T = 20, V = 9684 (the size at which the table is chosen automatically): same greedy trajectories as the
+    per-step path up to near-ties, probabilities within fp32 rounding."""
+    import hypernet_image_captioning_b200 as C
+    from hypernet_image_captioning_b200 import graphs, ops
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        m = C.HyperNetPooled(64, 48, 9684, None, type=kind)
+    g = torch.Generator().manual_seed(3)
+    pooled = torch.relu(torch.randn(512, 2048, generator=g)).cuda()
+    h0 = torch.rand(512, 48, generator=g).cuda()
+    assert ops.use_projection_table(512, 20, 9684)
+    outs = []
+    for table in (False, True):
+        monkeypatch.setattr(ops, "use_projection_table", lambda B, steps, V, table=table: table)
+        graphs.clear()
+        with torch.no_grad():
+            cap = m.forward(m.captioner.embed.weight[4:5])
+            outs.append(cap.infer(m.image_encoder(pooled), max_len=20, h0=h0 if kind == "gru" else None).clone())
+    graphs.clear()
+    # the per-step GEMM (M = 512) and the table GEMM (M = 9684) may take different kernels (exact-fp32 SIMT vs bf16x3
+    # tensor cores, ~1e-6 apart): a random-init model has near-tied scores, so tokens are compared up to the first near-tie
+    from golden_util import same_greedy_paths
+    ok, why = same_greedy_paths(outs[0], outs[1])
+    assert ok, why
