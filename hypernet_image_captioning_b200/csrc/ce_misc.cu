@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(CE_THREADS) softmax_argmax_kernel(const float*
     }
     __syncthreads();
     mx = sh[0];
-    if (threadIdx.x == 0 && amax) amax[m] = shi[0];
+    if (threadIdx.x == 0 && amax) amax[m] = shi[0] == 0x7fffffff ? 0 : shi[0];   // all-NaN row: stay in range
     if (!Y) return;
     float s = 0.f;
     for (int i = threadIdx.x; i < V; i += CE_THREADS) s += expf(x[i] - mx);
@@ -261,6 +261,74 @@ __global__ void __launch_bounds__(CE_THREADS) softmax_argmax_kernel(const float*
     const float inv = 1.f / s;
     float* y = Y + m * ldy;
     for (int i = threadIdx.x; i < V; i += CE_THREADS) y[i] = expf(x[i] - mx) * inv;
+}
+
+// Same, for rows that fit in registers (V % 4 == 0, V <= 256 * 4 * SMAX_RV, 16-byte aligned rows): the row is read ONCE
+// with 128-bit loads and kept in registers for the max / argmax, the exp-sum and the normalised write (the generic
+// kernel reads it three times with scalar loads).  One per decode step on [B, 9684] logits.
+constexpr int SMAX_RV = 10;
+__global__ void __launch_bounds__(CE_THREADS) softmax_argmax_vec_kernel(const float* __restrict__ X, long ld, int V,
+                                                                        float* __restrict__ Y, long ldy,
+                                                                        long long* __restrict__ amax) {
+    __shared__ float sh[32];
+    __shared__ int shi[32];
+    const long m = blockIdx.x;
+    const float4* x4 = reinterpret_cast<const float4*>(X + m * ld);
+    const int V4 = V >> 2;
+    float4 r[SMAX_RV];
+    float mx = -INFINITY;
+    int mi = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < SMAX_RV; ++j) {
+        const int q = j * CE_THREADS + threadIdx.x;
+        r[j] = q < V4 ? x4[q] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+#pragma unroll
+    for (int j = 0; j < SMAX_RV; ++j) {      // ascending index within a thread: '>' keeps the lowest index on ties
+        const int i0 = (j * CE_THREADS + threadIdx.x) * 4;
+        if (r[j].x > mx) { mx = r[j].x; mi = i0; }
+        if (r[j].y > mx) { mx = r[j].y; mi = i0 + 1; }
+        if (r[j].z > mx) { mx = r[j].z; mi = i0 + 2; }
+        if (r[j].w > mx) { mx = r[j].w; mi = i0 + 3; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[w] = mx; shi[w] = mi; }
+    __syncthreads();
+    if (w == 0) {
+        float v = l < (CE_THREADS >> 5) ? sh[l] : -INFINITY;
+        int vi = l < (CE_THREADS >> 5) ? shi[l] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+            if (ov > v || (ov == v && oi < vi)) { v = ov; vi = oi; }
+        }
+        if (l == 0) { sh[0] = v; shi[0] = vi; }
+    }
+    __syncthreads();
+    mx = sh[0];
+    if (threadIdx.x == 0 && amax) amax[m] = shi[0] == 0x7fffffff ? 0 : shi[0];   // all-NaN row: stay in range
+    if (!Y) return;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < SMAX_RV; ++j) {      // exp(-inf) = 0 for the padding lanes
+        r[j].x = expf(r[j].x - mx); r[j].y = expf(r[j].y - mx); r[j].z = expf(r[j].z - mx); r[j].w = expf(r[j].w - mx);
+        s += (r[j].x + r[j].y) + (r[j].z + r[j].w);
+    }
+    s = block_reduce_sum(s, sh);
+    const float inv = 1.f / s;
+    float4* y4 = reinterpret_cast<float4*>(Y + m * ldy);
+#pragma unroll
+    for (int j = 0; j < SMAX_RV; ++j) {
+        const int q = j * CE_THREADS + threadIdx.x;
+        if (q < V4) y4[q] = make_float4(r[j].x * inv, r[j].y * inv, r[j].z * inv, r[j].w * inv);
+    }
 }
 
 // out[i,:] = idx[i] >= 0 ? table[idx[i],:] : 0      (i < n, row length E)
@@ -389,7 +457,10 @@ int caphn_ce_bwd_split(const float* X, long ld, const long long* tgt, long M, in
 // Y (optional) = softmax rows of X; amax (optional) = argmax per row (lowest index on ties).
 int caphn_softmax_argmax(const float* X, long ld, long M, int V, float* Y, long ldy, long long* amax, void* stream) {
     if (M <= 0 || V <= 0) return CAPHN_EINVAL;
-    softmax_argmax_kernel<<<(unsigned)M, CE_THREADS, 0, (cudaStream_t)stream>>>(X, ld, V, Y, ldy, amax);
+    const bool vec = (V % 4 == 0) && V <= CE_THREADS * 4 * SMAX_RV && (ld % 4 == 0) && ((uintptr_t)X % 16 == 0) &&
+                     (!Y || ((ldy % 4 == 0) && ((uintptr_t)Y % 16 == 0)));
+    if (vec) softmax_argmax_vec_kernel<<<(unsigned)M, CE_THREADS, 0, (cudaStream_t)stream>>>(X, ld, V, Y, ldy, amax);
+    else softmax_argmax_kernel<<<(unsigned)M, CE_THREADS, 0, (cudaStream_t)stream>>>(X, ld, V, Y, ldy, amax);
     CAPHN_RETURN_LAST();
 }
 

@@ -38,20 +38,23 @@ def grad_close(a, b, rtol, atol=1e-7):
 
 def same_greedy_paths(a, b, tol=1e-4):
     """Two greedy decodes a, b [B,T,V] (logits or probabilities) of the same model by two numerically different routes.
-    Greedy feedback amplifies rounding: once a near-tie flips, the trajectories legitimately diverge.  So: wherever the
-    token history is identical so far, the scores must agree within ``tol`` of the score scale, and any first flip must
-    be a near-tie (top-2 margin within 2*tol of the scale); most trajectories must stay identical."""
+    Greedy feedback amplifies rounding: once a near-tie flips, the trajectories legitimately diverge (and with
+    probabilities the argmax of the output need not even be the token that was fed back when the top two round to the
+    same value).  So a step counts as certainly-identical only if both outputs name the same token AND its top-2 margin
+    exceeds 2*tol of the score scale; wherever all earlier steps are certainly-identical the scores must agree within
+    ``tol`` of the scale, any disagreement there must be a near-tie, and most trajectories must stay identical."""
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     ta, tb = a.argmax(-1), b.argmax(-1)
     same = ta == tb
-    hist = torch.cumprod(torch.cat([torch.ones_like(same[:, :1]), same[:, :-1]], 1).long(), 1).bool()
     scale = a.abs().max().item()
+    top2 = a.topk(2, -1).values
+    margin = top2[..., 0] - top2[..., 1]
+    certain = same & (margin > 2 * tol * scale)
+    hist = torch.cumprod(torch.cat([torch.ones_like(certain[:, :1]), certain[:, :-1]], 1).long(), 1).bool()
     diff = (a - b).abs().amax(-1)
     if not bool((diff[hist] <= tol * scale).all()):
         return False, f"scores differ by {diff[hist].max().item() / scale:.2e} of scale with identical history"
     flips = hist & ~same
-    top2 = a.topk(2, -1).values
-    margin = top2[..., 0] - top2[..., 1]
     if flips.any() and not bool((margin[flips] <= 2 * tol * scale).all()):
         return False, f"token flip at margin {margin[flips].max().item() / scale:.2e} of scale"
     frac = hist.double().mean().item()

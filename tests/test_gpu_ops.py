@@ -163,6 +163,26 @@ def test_softmax_argmax_ties_and_gather():
     assert torch.equal(ops.gather_rows(table, idx), table[idx])
 
 
+@pytest.mark.parametrize("V", [9684, 10240, 10244, 101, 4])
+def test_softmax_argmax_vector_and_generic_paths(V):
+    """V % 4 == 0 and V <= 10240 takes the register-resident 128-bit kernel, anything else the generic one; strided
+    output rows (probs written into outputs[:, t, :]) and ties across threads / vector lanes (lowest index wins)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(V)
+    M, T = 37, 3
+    x = torch.randn(M, V, generator=g).cuda()
+    x[0, V - 1] = 9.0; x[0, V // 2] = 9.0          # tie far apart
+    x[1, 2 % V] = 9.0; x[1, 3 % V] = 9.0           # tie inside one 128-bit vector
+    x[2] = 0.0                                     # all equal -> index 0
+    out = torch.zeros(M, T, V).cuda()
+    probs, am = ops.softmax_argmax(x, want_probs=True, probs_out=out[:, 1, :])
+    ref = torch.softmax(x.double(), 1)
+    assert torch.equal(am.cpu(), x.cpu().argmax(1)) and am[0].item() == V // 2 and am[2].item() == 0
+    assert rel_err(out[:, 1, :], ref) < 2e-6 and float(out[:, 0].abs().max()) == 0.0 and float(out[:, 2].abs().max()) == 0.0
+    _, am2 = ops.softmax_argmax(x, want_probs=False)
+    assert torch.equal(am2, am)
+
+
 @pytest.mark.parametrize("B,T,H", [(3, 5, 6), (9, 4, 150), (21, 3, 33), (16, 6, 200), (5, 2, 301)])
 def test_gru_cluster_matches_streaming_kernel(B, T, H):
     """Weights-resident cluster kernels (W_hh in shared memory, DSMEM state exchange) == L2-streaming kernels."""
