@@ -278,3 +278,63 @@ def test_infer_projection_table_equals_per_step_path_at_bench_size(kind, monkeyp
     from golden_util import same_greedy_paths
     ok, why = same_greedy_paths(outs[0], outs[1])
     assert ok, why
+
+
+def test_pooled_full_size_baseline_config1_matches_oracle():
+    """BASELINE configs[1] at its FULL size -- E=200, H=150, V=9684, L=1, B=512, T=20, 1.62 G hypernet parameters -- on
+    the kernels the benchmark times (weight-streaming heads, tcgen05 GEMMs, cluster GRU, fused decoder+CE node), against
+    the oracle port on the same seeded inputs: logits and loss within 1e-4, gradients within 1e-3 (incl. the 4 GB head
+    gradient, compared on the device), and the graphed step (graphs.GraphedStep) reproduces the eager loss."""
+    from hypernet_image_captioning_b200 import graphs
+    E, H, V, B, T = 200, 150, 9684, 512, 20
+    p = O.init_params_pooled(2048, E, H, V, L=1, seed=5)
+    g = torch.Generator().manual_seed(99)
+    pooled = torch.relu(torch.randn(B, 2048, generator=g))
+    caps = O.synth_captions(B, T, V, g)
+    style = p["captioner.embed.weight"][4:5].clone()
+    h0 = torch.rand(B, H, generator=g)
+    import hypernet_image_captioning_b200 as C
+    with torch.device("cuda"):                               # (initialising 1.6 G parameters on the CPU takes ~20 s)
+        m = C.HyperNetPooled(E, H, V, None, num_layers=1)
+    sd = m.state_dict()
+    sd.update(p)
+    m.load_state_dict(sd)
+    del sd
+    pl = {k: v.requires_grad_(True) for k, v in p.items()}
+    del p
+    logits_ref, _, _ = O.path_pooled(pl, style, pooled, caps, h0, L=1, flow=True)
+    loss_ref = O.caption_loss(logits_ref, caps, None)
+    loss_ref.backward()
+    logits_ref = logits_ref.detach()
+    pooled_d, caps_d, h0_d, style_d = pooled.cuda(), caps.cuda(), h0.cuda(), style.cuda()
+
+    def step(pooled_, caps_, h0_):
+        m.zero_grad(set_to_none=True)
+        captioner = m.forward(style_d)
+        loss, logits = captioner.forward_loss(m.image_encoder(pooled_), caps_, h0=h0_, ignore_index=None)
+        loss.backward()
+        return loss, logits
+
+    loss, logits = step(pooled_d, caps_d, h0_d)
+    assert rel_err(logits, logits_ref) < TOL_LOGITS
+    assert abs(loss.item() - loss_ref.item()) < TOL_LOGITS * abs(loss_ref.item())
+    worst = 0.0
+    for k, v in m.named_parameters():
+        if k.startswith("captioner.lstm_cell."):
+            continue                                        # generated, not trained (flow mode)
+        ref = pl[k].grad.cuda()                             # compared on the device: hn_heads.0.2.weight is 4 GB
+        d = (v.grad - ref).abs().max().item()
+        s = ref.abs().max().item()
+        assert d <= 1e-7 or d <= TOL_GRAD * s, (k, d, s)
+        worst = max(worst, d / s if s > 0 else 0.0)
+        del ref
+        pl[k].grad = None
+    l_eager = loss.item()
+    del loss, logits, pl, logits_ref
+    m.zero_grad(set_to_none=True)
+    torch.cuda.empty_cache()
+    gstep = graphs.GraphedStep(step, (pooled_d, caps_d, h0_d), params=list(m.parameters()), release=m.release_graph)
+    assert gstep.captured
+    l_graph = gstep(pooled_d, caps_d, h0_d)[0].item()
+    assert abs(l_graph - l_eager) <= 1e-6 * abs(l_eager)
+    assert worst < TOL_GRAD
