@@ -186,3 +186,28 @@ def test_metrics_oracle_bleu_known_answers():
     assert MO.bleu_from_counts(m, p, hl, rl, 4) == pytest.approx(math.exp(sum(math.log(x) for x in
                                                                       (8 / 13, 5 / 11, 4 / 9, 3 / 7)) / 4))
     assert MO.compute_bleu([[]], [a], 4) == 0.0
+
+
+def test_metrics_host_arithmetic_matches_oracle():
+    """hypernet_image_captioning_b200.metrics.bleu_from_counts (the host half of the product path: ten integers ->
+    BLEU-n) against the oracle's compute_bleu on random corpora, incl. empty hypotheses and zero-match orders."""
+    import random
+    from hypernet_image_captioning_b200 import metrics
+    from oracle import metrics_oracle as MO
+    rng = random.Random(3)
+    for trial in range(50):
+        B = rng.randint(1, 6)
+        hyps = [[rng.randint(3, 8) for _ in range(rng.randint(0, 9))] for _ in range(B)]
+        refs = [[rng.randint(3, 8) for _ in range(rng.randint(0, 9))] for _ in range(B)]
+        m, p, hl, rl = MO.bleu_counts(hyps, refs, 4)
+        counts = m + p + [hl, rl]
+        for n in (1, 2, 3, 4):
+            assert metrics.bleu_from_counts(counts, n) == pytest.approx(MO.compute_bleu(hyps, refs, n), rel=1e-12, abs=0.0)
+
+
+def test_projection_table_rule():
+    """ops.use_projection_table: the per-call table (V-row GEMM) is chosen once the per-step rows outnumber V / 2."""
+    from hypernet_image_captioning_b200 import ops
+    assert ops.use_projection_table(512, 20, 9684) and ops.use_projection_table(4096, 16, 9684)
+    assert not ops.use_projection_table(1, 20, 9684) and not ops.use_projection_table(64, 20, 9684)
+    assert not ops.use_projection_table(512, 1, 9684)
