@@ -10,10 +10,14 @@ from hypernet_image_captioning_b200.synth import synth_captions  # noqa: E402
 
 B, T, V = 512, 20, 9684
 dev = torch.device("cuda", 0)
+N_TIMED = int(os.environ.get("CAPHN_DECODE_ITERS", "20"))
+if os.environ.get("CAPHN_NO_GRAPH") == "1":      # eager launches (for an ncu launch list: ncu cannot follow stream capture)
+    from hypernet_image_captioning_b200 import graphs
+    graphs.ENABLED = False
 
 
-def timed(fn, n=20):
-    for _ in range(3):
+def timed(fn, n=N_TIMED):
+    for _ in range(3 if n > 2 else 1):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
