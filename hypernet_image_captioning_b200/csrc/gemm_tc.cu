@@ -475,6 +475,11 @@ int caphn_gemm_tc_ex(const void* Ahi, const void* Alo, long a_ld, int a_mn, cons
             const long cost = ((t + kNumSMs - 1) / kNumSMs) * (bn + 32);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; p.BN = bn; }
         }
+        // tuning knob (tools/bench_gemm.py): CAPHN_TC_BN_FORCE=<multiple of 16 (64 for an MN-major B) in 128..256>
+        if (const char* f = getenv("CAPHN_TC_BN_FORCE")) {
+            const int bn = atoi(f);
+            if (bn >= 128 && bn <= 256 && bn % step == 0) p.BN = bn;
+        }
     }
     const int tiles = ceil_div(M, tc::BM) * ceil_div(N, p.BN);
     if (splitk <= 0) {
