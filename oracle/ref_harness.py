@@ -56,17 +56,10 @@ class _TinyResNet(nn.Module):
         self.fc = nn.Linear(2048, 10)
 
 
-_loaded = None
-
-
-def load():
-    """Import the reference; returns a namespace with the hot-path classes."""
-    global _loaded
-    if _loaded is not None:
-        return _loaded
-    if not available():
-        raise RuntimeError(f"reference not found under {REFERENCE_DIR}")
-
+def install_stubs():
+    """Inert stand-ins for the third-party packages the reference imports and this image lacks (no reference code is
+    imported here).  Also used by tests/test_dropin_reference_scripts.py, which imports the reference *scripts* on top of
+    the dropin/ shims."""
     pl = types.ModuleType("pytorch_lightning")
     pl.LightningModule = _FakeLightningModule
     pl.Trainer = MagicMock()
@@ -91,6 +84,20 @@ def load():
     import torchvision
     torchvision.models.resnet152 = _TinyResNet
     torchvision.models.resnet101 = _TinyResNet
+
+
+_loaded = None
+
+
+def load():
+    """Import the reference; returns a namespace with the hot-path classes."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not available():
+        raise RuntimeError(f"reference not found under {REFERENCE_DIR}")
+
+    install_stubs()
 
     os.chdir(REFERENCE_DIR)  # later.py:372 opens the relative path data/vocab.pkl
     if REFERENCE_DIR not in sys.path:
