@@ -187,6 +187,8 @@ def run_ours(args):
     model.grad_mode = "flow"
     model.dp_enabled = world > 1
     shared = parallel.shared_parameters(model)
+    if world > 1:      # the 15 MB shared-gradient bucket is reduced on a side stream while the head backward runs
+        parallel.enable_overlap(shared)
 
     g = torch.Generator().manual_seed(1234 + rank)
     pooled_h = torch.relu(torch.randn(B, c["D"], generator=g)).pin_memory()
@@ -462,6 +464,8 @@ def attention_extras(args, dev, world, timed):
 
     from hypernet_image_captioning_b200 import parallel as par
     shared = par.shared_parameters(model)
+    if world > 1:
+        par.enable_overlap(shared)
 
     def train():
         model.zero_grad(set_to_none=True)
@@ -510,6 +514,8 @@ def lstm_extras(args, dev, world, timed):
         model = C.HyperNetPooled(c["E"], c["H"], V, None, num_layers=c["L"], type="lstm")
     model.dp_enabled = world > 1
     shared = par.shared_parameters(model)
+    if world > 1:
+        par.enable_overlap(shared)
     g = torch.Generator().manual_seed(4321)
     pooled = torch.relu(torch.randn(B, c["D"], generator=g)).to(dev)
     caps = synth_captions(B, T, V, g).to(dev)

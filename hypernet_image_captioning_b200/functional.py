@@ -4,7 +4,7 @@ from typing import List, Optional, Sequence
 import torch
 from torch.autograd import Function
 
-from . import ops
+from . import ops, parallel
 from .ops import ACT_LEAKY, ACT_NONE
 
 
@@ -85,6 +85,7 @@ class HyperNetThetaFn(Function):
                 grads[j] = grads[j].to(params[j].dtype)   # bf16 mode: bias gradients (weights are already bf16)
         if dx is not None and dx.dtype != x.dtype:
             dx = dx.to(x.dtype)
+        parallel.join()   # data parallel: whatever consumes these gradients is ordered after the overlapped bucket all-reduce
         return (dx if need[0] else None, *grads)
 
 

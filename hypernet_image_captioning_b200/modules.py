@@ -77,10 +77,14 @@ class _HyperNetMixin:
         if self.grad_mode == "literal":
             with torch.no_grad():
                 return Fn.hypernet_theta(x2, _hn_params(self))
+        if self.dp_enabled:
+            from . import parallel
+            world = parallel.world_size(self.dp_group)
+            if world > 1 and x2.requires_grad:
+                x2 = parallel.ScaleGradFn.apply(x2, 1.0 / world)   # the style gradient leaves the replicated hypernet already global
         theta = Fn.hypernet_theta(x2, _hn_params(self))
         if self.dp_enabled:
-            from .parallel import allreduce_grad
-            theta = allreduce_grad(theta, self.dp_group)
+            theta = parallel.allreduce_grad(theta, self.dp_group)
         return theta
 
     def regression_loss(self, style_embed: torch.Tensor, target_params):

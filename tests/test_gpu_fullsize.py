@@ -1,0 +1,216 @@
+"""BASELINE.json configs[2], configs[3] and the many-style grouped path at their FULL sizes against the oracle port
+(the pooled configs[1] counterpart is tests/test_gpu_pooled.py::test_pooled_full_size_baseline_config1_matches_oracle).
+
+Tolerances are BASELINE.json's: logits / attention weights / loss within 1e-4 (max|d| / max|ref|), every gradient within
+1e-3, greedy tokens exact wherever the oracle's own top-2 margin is above the numerical noise (margin report printed).
+Reference lines: models/decoderlstm.py:49-120 (AttentionGru.forward), models/attention.py:21-46,
+hypernet_attention.py:111-121, cc_train_hypernet.py:134-153 (one-hot domain vector -> HyperNet.forward -> captioner ->
+cross_entropy(ignore_index=<pad>)), train_cc.py:90-123 (one hypernet call per sample's style = the grouped semantics).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from golden_util import rel_err, grad_close
+from oracle import caption_hn_oracle as O
+
+TOL_LOGITS, TOL_GRAD = 1e-4, 1e-3
+FULL = dict(B=512, T=20, Fo=200, E=200, H=200, V=9684, P=49, D=2048)
+
+
+def _model(p, cc, he, dims=FULL):
+    import hypernet_image_captioning_b200 as C
+    m = C.HyperNetAttention(dims["Fo"], dims["E"], dims["H"], dims["V"], None, cc=cc, hyper_emb=he)
+    sd = m.state_dict()
+    missing = [k for k in p if k not in sd]
+    assert not missing, missing
+    sd.update(p)
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+def _inputs(seed, dims=FULL):
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(dims["B"], dims["P"], dims["D"], generator=g)
+    caps = O.synth_captions(dims["B"], dims["T"], dims["V"], g)
+    return g, feats, caps
+
+
+def _check_grads(m, pl, skip_prefix="captioner.gru."):
+    worst, worst_k = 0.0, None
+    for k, v in m.named_parameters():
+        if k.startswith(skip_prefix):
+            continue                                            # generated, not trained (flow mode)
+        assert v.grad is not None, k
+        assert grad_close(v.grad, pl[k].grad, TOL_GRAD), (k, rel_err(v.grad, pl[k].grad))
+        r = rel_err(v.grad, pl[k].grad)
+        if pl[k].grad.abs().max().item() > 1e-7 and r > worst:
+            worst, worst_k = r, k
+    return worst, worst_k
+
+
+def _greedy_report(gl, gl_ref, tag):
+    """Token-exact wherever the oracle's decision is not a numerical near-tie; prints the margin report."""
+    a, b = gl.detach().double().cpu(), gl_ref.detach().double().cpu()
+    ta, tb = a.argmax(-1), b.argmax(-1)
+    scale = b.abs().max().item()
+    top2 = b.topk(2, -1).values
+    margin = (top2[..., 0] - top2[..., 1]) / scale                 # [B,T] relative top-2 margin of the oracle
+    same = ta == tb
+    # a row is "clean" up to (and including) step t if every earlier fed-back token matched
+    hist = torch.cumprod(torch.cat([torch.ones_like(same[:, :1]), same[:, :-1]], 1).long(), 1).bool()
+    flips = hist & ~same                                           # first divergence of each row
+    n_rows, n_flip = a.shape[0], int(flips.any(1).sum())
+    flip_margin = margin[flips].max().item() if n_flip else 0.0
+    logit_err = ((a - b).abs().amax(-1)[hist]).max().item() / scale
+    print(f"[{tag}] greedy: {int(same.all(1).sum())}/{n_rows} rows token-identical over all {a.shape[1]} steps, "
+          f"token match {same.double().mean().item():.4f}, first flips {n_flip} (largest oracle margin at a flip "
+          f"{flip_margin:.2e} of scale), min oracle margin {margin.min().item():.2e}, "
+          f"logit err on identical histories {logit_err:.2e}")
+    assert logit_err < TOL_LOGITS
+    assert flip_margin <= 2 * TOL_LOGITS, "a token flipped where the oracle's top-2 margin is well above the tolerance"
+    assert same.all(1).double().mean().item() >= 0.97
+    return same
+
+
+def test_attention_full_size_baseline_config2_matches_oracle():
+    """configs[2]: hypernet_attention.HyperNet + AttentionGru, B=512, T=20, F=E=H=200, P=49, D=2048, V=9684 -- the
+    step-split recurrence (forward AND backward) against the oracle's autograd, not against another kernel of ours."""
+    import hypernet_image_captioning_b200 as C
+    d = FULL
+    p = O.init_params_attention(d["D"], d["Fo"], d["E"], d["H"], d["V"], d["E"], seed=11)
+    g, feats, caps = _inputs(21)
+    style = p["captioner.embed.weight"][4:5].clone()             # 'factual' row (hypernet_attention.py:139-142)
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    logits_ref, att_ref, _, _ = O.path_attention(pl, style, feats, caps, 0.0, np.random.RandomState(0), flow=True)
+    loss_ref = O.caption_loss(logits_ref, caps, 0)
+    loss_ref.backward()
+    m = _model(p, False, 10)
+    fd, cd = feats.cuda(), caps.cuda()
+    captioner = m.forward(style.cuda())
+    np.random.seed(0)
+    logits, att = captioner(fd, cd, 0.0)                          # the reference call shape (cc_train_hypernet.py:152-153)
+    loss = C.cross_entropy(logits, cd, 0)
+    loss.backward()
+    assert rel_err(logits, logits_ref) < TOL_LOGITS
+    assert rel_err(att, att_ref) < TOL_LOGITS
+    assert abs(loss.item() - loss_ref.item()) < TOL_LOGITS * abs(loss_ref.item())
+    worst, wk = _check_grads(m, pl)
+    print(f"[configs[2]] logits {rel_err(logits, logits_ref):.2e} attn {rel_err(att, att_ref):.2e} "
+          f"loss {abs(loss.item() - loss_ref.item()) / abs(loss_ref.item()):.2e} worst grad {worst:.2e} ({wk})")
+    # fused decoder+loss node: same loss, same gradients
+    g_unfused = {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}
+    m.zero_grad(set_to_none=True)
+    np.random.seed(0)
+    loss2, logits2, _ = m.forward(style.cuda()).forward_loss(fd, cd, 0.0, ignore_index=0)
+    loss2.backward()
+    assert abs(loss2.item() - loss.item()) <= 1e-6 * abs(loss.item())
+    assert torch.equal(logits2, logits)
+    for k, v in m.named_parameters():
+        if v.grad is not None and k in g_unfused:
+            assert grad_close(v.grad, g_unfused[k], TOL_GRAD), k
+    # greedy decode (sample_prob = 1.0, the test_hn.py / cc_train_hypernet.py:230 path)
+    with torch.no_grad():
+        gl_ref, ga_ref, _, _ = O.path_attention(p, style, feats, caps, 1.0, np.random.RandomState(0))
+        np.random.seed(0)
+        gl, ga = m.forward(style.cuda())(fd, cd, 1.0)
+    same = _greedy_report(gl, gl_ref, "configs[2]")
+    rows = same.all(1)
+    assert rel_err(ga.cpu()[rows], ga_ref[rows]) < TOL_LOGITS
+
+
+@pytest.mark.parametrize("he,B", [(100, 512), (150, 512)])
+def test_cc_onehot_full_size_config3_matches_oracle(he, B):
+    """configs[3] single-domain step exactly as cc_train_hypernet.py:134-153 runs it: cc=True, one-hot domain vector of
+    length he = #domains (100 = the training list, 150 = with the zero-shot domains, :81-89) passed 1-D, F=E=H=200."""
+    import hypernet_image_captioning_b200 as C
+    d = dict(FULL, B=B)
+    p = O.init_params_attention(d["D"], d["Fo"], d["E"], d["H"], d["V"], he, seed=13 + he)
+    g, feats, caps = _inputs(31 + he, d)
+    style = torch.zeros(he)
+    style[he // 3] = 1.0                                          # torch.tensor(self.embed[domain]).float(): 1-D [he]
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    logits_ref, att_ref, _, _ = O.path_attention(pl, style, feats, caps, 0.0, np.random.RandomState(0), flow=True)
+    loss_ref = O.caption_loss(logits_ref, caps, 0)
+    loss_ref.backward()
+    m = _model(p, True, he, d)
+    assert m.hn_base[0].in_features == he and m.hn_heads[0][0].in_features == he
+    captioner = m.forward(style.cuda())
+    np.random.seed(0)
+    loss, logits, att = captioner.forward_loss(feats.cuda(), caps.cuda(), 0.0, ignore_index=0)
+    loss.backward()
+    assert rel_err(logits, logits_ref) < TOL_LOGITS
+    assert rel_err(att, att_ref) < TOL_LOGITS
+    assert abs(loss.item() - loss_ref.item()) < TOL_LOGITS * abs(loss_ref.item())
+    worst, wk = _check_grads(m, pl)
+    print(f"[configs[3] he={he}] logits {rel_err(logits, logits_ref):.2e} worst grad {worst:.2e} ({wk})")
+
+
+def _grouped_oracle(pl, styles, groups, feats, caps):
+    """One reference-semantics call per style group (train_cc.py:90-123 calls the hypernet once per sample's style);
+    rows concatenated back in batch order; loss = CE over the concatenation (SURVEY 8(c) grouped oracle)."""
+    rows = []
+    for gi in range(styles.shape[0]):
+        idx = (groups == gi).nonzero().squeeze(1)
+        if idx.numel() == 0:
+            continue
+        lg, at, _, _ = O.path_attention(pl, styles[gi], feats[idx], caps[idx], 0.0, np.random.RandomState(0))
+        rows.append((idx, lg, at))
+    inv = torch.argsort(torch.cat([i for i, _, _ in rows]))
+    return torch.cat([lg for _, lg, _ in rows], 0)[inv], torch.cat([at for _, _, at in rows], 0)[inv]
+
+
+@pytest.mark.parametrize("G,he", [(3, 100), (100, 100), (150, 150)])
+def test_grouped_full_size_matches_per_group_oracle(G, he):
+    """Many-style batch at B=512: G one-hot domains (cc=True, he = #domains) assigned round-robin, one
+    hypernet pass for all G, grouped decoding; oracle = one call per group."""
+    import hypernet_image_captioning_b200 as C
+    d = FULL
+    p = O.init_params_attention(d["D"], d["Fo"], d["E"], d["H"], d["V"], he, seed=3 + G)
+    g, feats, caps = _inputs(41 + G)
+    styles = torch.eye(he)[:G].contiguous()                       # [G, he] one-hot rows
+    groups = torch.arange(d["B"]) % G
+    groups = groups[torch.randperm(d["B"], generator=g)]          # unsorted on purpose
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    logits_ref, att_ref = _grouped_oracle(pl, styles, groups, feats, caps)
+    loss_ref = O.caption_loss(logits_ref, caps, 0)
+    loss_ref.backward()
+    m = _model(p, True, he)
+    captioner = m.forward_grouped(styles.cuda())
+    np.random.seed(0)
+    logits, att = captioner(feats.cuda(), caps.cuda(), 0.0, groups=groups.cuda())
+    loss = C.cross_entropy(logits, caps.cuda(), 0)
+    loss.backward()
+    assert rel_err(logits, logits_ref) < TOL_LOGITS
+    assert rel_err(att, att_ref) < TOL_LOGITS
+    assert abs(loss.item() - loss_ref.item()) < TOL_LOGITS * abs(loss_ref.item())
+    worst, wk = _check_grads(m, pl)
+    print(f"[grouped G={G}] logits {rel_err(logits, logits_ref):.2e} worst grad {worst:.2e} ({wk})")
+
+
+@pytest.mark.parametrize("B,T,ext", [(70, 5, True), (130, 3, False)])
+def test_step_split_backward_matches_oracle_autograd(B, T, ext):
+    """The step-split BPTT kernels (attgru_step_bwd.cu) against the ORACLE's autograd at ragged batch sizes (B = 70: a
+    full 64-row tile + a 6-row tail; 130: two tiles + 2), incl. an external gradient on the returned attention weights."""
+    import hypernet_image_captioning_b200 as C
+    from hypernet_image_captioning_b200 import ops
+    d = dict(FULL, B=B, T=T, V=300)
+    assert ops._attstep_bwd_bytes(d["H"], d["Fo"], d["P"], B, T)[0] > 0      # the step-split path covers this shape
+    p = O.init_params_attention(d["D"], d["Fo"], d["E"], d["H"], d["V"], d["E"], seed=5)
+    g, feats, caps = _inputs(B, d)
+    style = torch.randn(1, d["E"], generator=g)
+    watt = torch.randn(B, T, d["P"], generator=g) * 0.2
+    pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    logits_ref, att_ref, _, _ = O.path_attention(pl, style, feats, caps, 0.0, np.random.RandomState(0), flow=True)
+    loss_ref = O.caption_loss(logits_ref, caps, 0) + ((att_ref * watt).sum() if ext else 0.0)
+    loss_ref.backward()
+    m = _model(p, False, 10, d)
+    np.random.seed(0)
+    logits, att = m.forward(style.cuda())(feats.cuda(), caps.cuda(), 0.0)
+    loss = C.cross_entropy(logits, caps.cuda(), 0) + ((att * watt.cuda()).sum() if ext else 0.0)
+    loss.backward()
+    assert rel_err(logits, logits_ref) < TOL_LOGITS
+    assert abs(loss.item() - loss_ref.item()) < TOL_LOGITS * abs(loss_ref.item())
+    _check_grads(m, pl)

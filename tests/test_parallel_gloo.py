@@ -105,3 +105,52 @@ def test_dp_masked_loss_weight_reproduces_global_mean(tmp_path):
         ws.append(float(d["w"]))
     n0, n1 = int((caps[:4] != 0).sum()), int((caps[4:] != 0).sum())
     assert ws[0] == pytest.approx(n0 / (n0 + n1)) and ws[1] == pytest.approx(n1 / (n0 + n1)) and n0 != n1
+
+
+def _worker_overlap(rank, world, port, out):
+    """enable_overlap: early gradients are reduced from inside the backward (flush in the d(theta) hook), the late one
+    (a parameter that also feeds the hypernet input, like captioner.embed.weight) by allreduce_shared_grads."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hypernet_image_captioning_b200 import parallel
+    g = torch.Generator().manual_seed(0)
+    emb = torch.nn.Parameter(torch.randn(6, 5, generator=g))      # row 2 is the "style" (hypernet input)
+    W = torch.nn.Parameter(torch.randn(3, 5, generator=g))
+    hn = torch.nn.Parameter(torch.randn(5, generator=g))          # replicated hypernet parameter: never all-reduced
+    x = torch.randn(8, 3, generator=g)
+    idx = torch.randint(0, 6, (8,), generator=g)
+    xb, ib = x[rank * 4:(rank + 1) * 4], idx[rank * 4:(rank + 1) * 4]
+    assert parallel.enable_overlap([emb, W])
+    flushed = {}
+    for it in range(2):                                            # two steps: per-step state must reset
+        emb.grad = W.grad = hn.grad = None
+        style = parallel.ScaleGradFn.apply(emb[2:3], 1.0 / world)
+        theta = parallel.allreduce_grad((style * hn).reshape(-1) ** 2)
+        loss = (1.0 / world) * (((xb @ W) + emb[ib]) * theta).sum()
+        loss.backward()
+        flushed[it] = sorted(id(p) == id(W) for p in parallel._ov.params if id(p) in parallel._ov.done)
+        parallel.allreduce_shared_grads([emb, W])
+    torch.save({"emb": emb.grad, "W": W.grad, "hn": hn.grad, "flushed": flushed}, os.path.join(out, f"o{rank}.pt"))
+    parallel.disable_overlap()
+    dist.destroy_process_group()
+
+
+def test_overlapped_bucket_matches_single_process(tmp_path):
+    world = 2
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_worker_overlap, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(0)
+    emb = torch.nn.Parameter(torch.randn(6, 5, generator=g))
+    W = torch.nn.Parameter(torch.randn(3, 5, generator=g))
+    hn = torch.nn.Parameter(torch.randn(5, generator=g))
+    x = torch.randn(8, 3, generator=g)
+    idx = torch.randint(0, 6, (8,), generator=g)
+    theta = (emb[2:3] * hn).reshape(-1) ** 2
+    ((1.0 / world) * (((x @ W) + emb[idx]) * theta).sum()).backward()
+    for r in range(world):
+        d = torch.load(os.path.join(str(tmp_path), f"o{r}.pt"))
+        assert torch.allclose(d["W"], W.grad, atol=1e-6)
+        assert torch.allclose(d["emb"], emb.grad, atol=1e-6)      # incl. the style row: hypernet-path gradient counted once
+        assert torch.allclose(d["hn"], hn.grad, atol=1e-6)
+        assert d["flushed"][0] == [True] and d["flushed"][1] == [True]   # W went early (inside backward), emb late

@@ -36,7 +36,7 @@ def main():
     B = Bl * world
     pooled = torch.relu(torch.randn(B, 2048, generator=g)).to(dev)
     caps = O.synth_captions(B, T, V, g).to(dev)
-    style = torch.randn(1, E, generator=g).to(dev)
+    style_plain = torch.randn(1, E, generator=g).to(dev)
     h0 = torch.rand(B, H, generator=g).to(dev)
 
     def make():
@@ -44,23 +44,33 @@ def main():
         sd = m.state_dict(); sd.update(p); m.load_state_dict(sd)
         return m.to(dev)
 
-    ref = make()
-    run(ref, style, pooled, caps, h0, 1.0)
-    ref_grads = {k: v.grad.clone() for k, v in ref.named_parameters() if v.grad is not None}
-
-    m = make()
-    m.dp_enabled = True
-    sl = slice(rank * Bl, (rank + 1) * Bl)
-    run(m, style, pooled[sl], caps[sl], h0[sl], 1.0 / world)
-    parallel.allreduce_shared_grads(parallel.shared_parameters(m))
     worst = 0.0
-    for k, v in m.named_parameters():
-        if k.startswith("captioner.lstm_cell."):
-            continue
-        d = (v.grad - ref_grads[k]).abs().max().item()
-        s = ref_grads[k].abs().max().item()
-        rel = d / s if s > 0 else d
-        worst = max(worst, rel if d > 1e-7 else 0.0)
+    # style = a plain tensor, and style = a row of the embedding matrix (the Flickr idiom, hypernet_attention.py:139-142:
+    # that parameter then receives a second, replicated, gradient contribution through the hypernet);
+    # shared-gradient bucket reduced after the backward, and overlapped with the head backward (parallel.enable_overlap)
+    for style_from_embed in (False, True):
+        for overlap in (False, True):
+            ref = make()
+            run(ref, ref.captioner.embed.weight[4:5] if style_from_embed else style_plain, pooled, caps, h0, 1.0)
+            ref_grads = {k: v.grad.clone() for k, v in ref.named_parameters() if v.grad is not None}
+            m = make()
+            m.dp_enabled = True
+            shared = parallel.shared_parameters(m)
+            if overlap:
+                parallel.enable_overlap(shared)
+            sl = slice(rank * Bl, (rank + 1) * Bl)
+            for _ in range(2):                                      # twice: the per-step state of the overlap must reset
+                run(m, m.captioner.embed.weight[4:5] if style_from_embed else style_plain, pooled[sl], caps[sl], h0[sl],
+                    1.0 / world)
+                parallel.allreduce_shared_grads(shared)
+            parallel.disable_overlap()
+            for k, v in m.named_parameters():
+                if k.startswith("captioner.lstm_cell."):
+                    continue
+                d = (v.grad - ref_grads[k]).abs().max().item()
+                s = ref_grads[k].abs().max().item()
+                rel = d / s if s > 0 else d
+                worst = max(worst, rel if d > 1e-7 else 0.0)
     t = torch.tensor([worst], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
