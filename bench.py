@@ -185,6 +185,7 @@ def run_ours(args):
     with torch.device(dev):
         model = C.HyperNetPooled(c["E"], c["H"], c["V"], None, num_layers=c["L"])
     model.grad_mode = "flow"
+    model.async_hypernet = True        # hypernet weight streaming on its own stream (streams.py)
     model.dp_enabled = world > 1
     shared = parallel.shared_parameters(model)
     if world > 1:      # the 15 MB shared-gradient bucket is reduced on a side stream while the head backward runs
@@ -342,12 +343,37 @@ def run_ours(args):
                 "peak_source": "MEASURED_PEAKS.json (burst copy)" if peaks else "fallback 6650 GB/s",
                 "alg_bytes_per_launch": alg_bytes, "ms_per_launch": k_ms}
 
+    # ---- sustained run: >= 2 s of back-to-back headline steps with its own clock samples (power steady state) ----
+    sustained = None
+    if not args.no_extras:
+        n_sus = max(args.steps, int(2200.0 / (ms / args.steps)) + 1)
+        sus_sampler = ClockSampler(local)
+        if rank == 0:
+            sus_sampler.start()
+        ms_sus = timed(lambda: run_step(pooled_d, caps_d, h0_d), n_sus)
+        sus_clocks = sus_sampler.stop() if rank == 0 else None
+        sustained = {"steps": n_sus, "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sus,
+                     "captions_per_s": B * world * n_sus / (ms_sus * 1e-3), "clocks": sus_clocks}
+
     graphed = gstep is not None
     gstep = run_step = None                                   # release the graph's memory pool (gradients + activations)
     model.zero_grad(set_to_none=True)
     torch.cuda.empty_cache()
 
     extras = {}
+    rooflines = {}
+    hn_b = 4.0 * sum(p_.numel() for n_, p_ in model.named_parameters() if n_.startswith("hn_"))
+    sh_b = 4.0 * sum(p_.numel() for n_, p_ in model.named_parameters()
+                     if not n_.startswith("hn_") and not n_.startswith("captioner.lstm_cell"))
+    w2_b = 4.0 * sum(h_[2].weight.numel() for h_ in model.hn_heads)
+    # flow-mode training step, SURVEY 8(d): parameters read once, gradients written once, head second-layer weights read
+    # once more for dA1, per caption: pooled feature + caption + logits written and re-read once
+    step_bytes = 2 * hn_b + w2_b + 2 * sh_b + B * (c["D"] * 4.0 + 8.0 * T + 2.0 * T * c["V"] * 4.0)
+    rooflines["pooled_train_step"] = roofline_block(step_bytes, ms / args.steps, peak,
+                                                    "whole fwd+bwd step (headline `value`), compulsory traffic only")
+    if sustained is not None:
+        rooflines["pooled_train_step_sustained"] = roofline_block(step_bytes, sustained["ms_per_step"], peak,
+                                                                  f"same, {sustained['seconds']:.1f} s back to back")
     if not args.no_extras:
         # literal mode (the reference's actual behaviour: graph cut at utils.py:57, no head backward)
         model.grad_mode = "literal"
@@ -365,6 +391,16 @@ def run_ours(args):
             decode()
         ms_dec = timed(decode, args.steps)
         extras["greedy_decode_captions_per_s"] = B * world * args.steps / (ms_dec * 1e-3)
+        hn_bytes = 4.0 * sum(p_.numel() for n_, p_ in model.named_parameters() if n_.startswith("hn_"))
+        dec_shared = 4.0 * sum(p_.numel() for n_, p_ in model.named_parameters()
+                               if not n_.startswith("hn_") and not n_.startswith("captioner.lstm_cell"))
+        # SURVEY 8(d) compulsory traffic: every parameter read once, pooled feature + int64 caption read, T*V probabilities written
+        dec_bytes = hn_bytes + dec_shared + B * (c["D"] * 4.0 + T * c["V"] * 4.0)
+        rooflines["pooled_greedy_decode"] = roofline_block(dec_bytes, ms_dec / args.steps, peak,
+                                                           "heads + shared params read once, probabilities [B,T,V] written once")
+        lit_bytes = hn_bytes + dec_shared * 2 + B * (c["D"] * 4.0 + 8.0 * T + 2.0 * T * c["V"] * 4.0)
+        rooflines["pooled_train_literal"] = roofline_block(lit_bytes, ms_lit / args.steps, peak,
+                                                           "heads read once (no head backward: graph cut of utils.py:57), decoder as in flow mode")
         # optimizer step: FusedAdam with the global-norm clip folded in, on the gradients of the
         # last training step; Adam moves 28 bytes per parameter (p,g,m,v read; p,m,v written) + 4 for the norm pass
         from hypernet_image_captioning_b200 import FusedAdam
@@ -421,13 +457,24 @@ def run_ours(args):
         ops.set_precision("fp32")
         del model
         torch.cuda.empty_cache()
-        extras.update(attention_extras(args, dev, world, timed))
+        extras.update(attention_extras(args, dev, world, timed, rooflines, peak))
         extras.update(lstm_extras(args, dev, world, timed))
+        extras.update(pooled_l2_extras(args, dev, world, timed, rooflines, peak))
+        if sustained is not None:
+            extras["sustained_headline"] = sustained
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         model = None
         torch.cuda.empty_cache()
+        if not args.no_extras:
+            # third column of SURVEY 8(d): the reference's PyTorch path run by stock torch eager ON THIS GPU (cuBLAS / ATen
+            # kernels; none of ours) -- "the only existing Blackwell path".  Part of the baseline leg: it executes the oracle.
+            try:
+                extras["torch_eager_gpu_captions_per_s"] = torch_eager_gpu_arm(dev, timed, B)
+            except Exception as e:  # noqa: BLE001
+                extras["torch_eager_gpu_captions_per_s"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            torch.cuda.empty_cache()
         cpu = cpu_reference_arm(steps=3, warmup=1)
 
     if rank == 0:
@@ -438,7 +485,7 @@ def run_ours(args):
             "config": dict(workload_config(args, world), cuda_graph=graphed),
             "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
             "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
             "loss": final_loss, "extras": extras,
         }
@@ -447,7 +494,85 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def attention_extras(args, dev, world, timed):
+def roofline_block(alg_bytes, ms, peak, what):
+    """End-to-end HBM roofline of a whole workload: algorithmic (compulsory) bytes / measured time against the measured peak."""
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "alg_bytes": alg_bytes, "ms": ms, "achieved": gbs, "peak": peak, "unit": "GB/s",
+            "frac": gbs / peak, "floor_ms": alg_bytes / (peak * 1e9) * 1e3, "what": what}
+
+
+def torch_eager_gpu_arm(dev, timed, B):
+    """Oracle port (plain torch ops) with every tensor on the GPU: hypernet fwd + fc + DecoderGRU + CE + backward, flow mode."""
+    from oracle import caption_hn_oracle as O
+    c = CFG
+    p = O.init_params_pooled(c["D"], c["E"], c["H"], c["V"], L=c["L"], seed=0)
+    p = {k: v.to(dev).requires_grad_(True) for k, v in p.items()}
+    g = torch.Generator().manual_seed(1234)
+    pooled = torch.relu(torch.randn(B, c["D"], generator=g)).to(dev)
+    caps = O.synth_captions(B, c["T"], c["V"], g).to(dev)
+    h0 = torch.rand(B, c["H"], generator=g).to(dev)
+
+    def step():
+        for v in p.values():
+            v.grad = None
+        logits, _, _ = O.path_pooled(p, p["captioner.embed.weight"][4:5], pooled, caps, h0, L=c["L"], flow=True)
+        O.caption_loss(logits, caps, None).backward()
+
+    for _ in range(3):
+        step()
+    ms = timed(step, 10)
+    return {"pooled_train": B * 10 / (ms * 1e-3), "ms_per_step": ms / 10,
+            "what": "oracle port, torch eager CUDA kernels (cuBLAS/ATen), same workload, fp32 (TF32 off)"}
+
+
+def pooled_l2_extras(args, dev, world, timed, rooflines, peak):
+    """The reference launcher's own operating point (hypernet.py:209): num_layers = 2 -- 2.78 G hypernet parameters
+    (11.1 GB), the second GRU cell reads theta from offset 0 again (utils.py:45,68); L2-streaming multi-layer recurrence."""
+    import hypernet_image_captioning_b200 as C
+    from hypernet_image_captioning_b200 import graphs, parallel as par
+    from hypernet_image_captioning_b200.synth import synth_captions
+    c = CFG
+    B, T, V = args.batch, c["T"], c["V"]
+    torch.manual_seed(0)
+    with torch.device(dev):
+        model = C.HyperNetPooled(c["E"], c["H"], V, None, num_layers=2)
+    model.async_hypernet = True
+    model.dp_enabled = world > 1
+    shared = par.shared_parameters(model)
+    if world > 1:
+        par.enable_overlap(shared)
+    g = torch.Generator().manual_seed(4321)
+    pooled = torch.relu(torch.randn(B, c["D"], generator=g)).to(dev)
+    caps = synth_captions(B, T, V, g).to(dev)
+    h0 = torch.rand(B, c["H"], generator=g).to(dev)
+
+    def train():
+        model.zero_grad(set_to_none=True)
+        cap = model.forward(model.captioner.embed.weight[4:5])
+        loss, _ = cap.forward_loss(model.image_encoder(pooled), caps, h0=h0)
+        ((loss / world) if world > 1 else loss).backward()
+        if world > 1:
+            par.allreduce_shared_grads(shared)
+
+    run = train
+    if os.environ.get("CAPHN_BENCH_GRAPH", "1") != "0":
+        gtrain = graphs.GraphedStep(train, (), params=list(model.parameters()), release=model.release_graph)
+        run = gtrain if gtrain.captured else train
+    for _ in range(3):
+        run()
+    ms = timed(run, args.steps) / args.steps
+    hn_b = 4.0 * sum(p_.numel() for n_, p_ in model.named_parameters() if n_.startswith("hn_"))
+    w2_b = 4.0 * sum(h_[2].weight.numel() for h_ in model.hn_heads)
+    sh_b = 4.0 * sum(p_.numel() for n_, p_ in model.named_parameters()
+                     if not n_.startswith("hn_") and not n_.startswith("captioner.lstm_cell") and not n_.startswith("captioner.layers"))
+    step_bytes = 2 * hn_b + w2_b + 2 * sh_b + B * (c["D"] * 4.0 + 8.0 * T + 2.0 * T * V * 4.0)
+    rooflines["pooled_l2_train_step"] = roofline_block(step_bytes, ms, peak, "num_layers=2 (hypernet.py:209), flow mode fwd+bwd")
+    if world > 1:
+        par.disable_overlap()
+    return {"pooled_l2_train_captions_per_s": B * world / (ms * 1e-3), "pooled_l2_hypernet_params": int(hn_b / 4)}
+
+
+def attention_extras(args, dev, world, timed, rooflines=None, peak=6537.6):
     """BASELINE configs[2]/[1b]: attention variant (hypernet_attention.HyperNet + AttentionGru), F=E=H=200, P=49, D=2048,
     B=512/GPU, T=20: teacher-forced fwd+bwd (flow, ignore_index=<pad>) and greedy decode (sample_prob=1.0, test_hn.py)."""
     import numpy as np
@@ -457,6 +582,7 @@ def attention_extras(args, dev, world, timed):
     torch.manual_seed(0)
     with torch.device(dev):
         model = C.HyperNetAttention(200, 200, 200, V, None)
+    model.async_hypernet = True
     model.dp_enabled = world > 1
     g = torch.Generator().manual_seed(4321)
     feats = torch.randn(B, 49, 2048, generator=g).to(dev)
@@ -498,6 +624,23 @@ def attention_extras(args, dev, world, timed):
             out["attention_train_eager_captions_per_s"] = out["attention_train_captions_per_s"]
             out["attention_train_captions_per_s"] = B * world * args.steps / (ms * 1e-3)
         del gtrain
+    if rooflines is not None:
+        P, D = 49, 2048
+        hn_b = 4.0 * sum(p_.numel() for n_, p_ in model.named_parameters() if n_.startswith("hn_"))
+        w2_b = 4.0 * sum(h_[2].weight.numel() for h_ in model.hn_heads)
+        sh_b = 4.0 * sum(p_.numel() for n_, p_ in model.named_parameters()
+                         if not n_.startswith("hn_") and not n_.startswith("captioner.gru"))
+        per_cap_fwd = P * D * 4.0 + 8.0 * T + T * V * 4.0 + T * P * 4.0          # 1.18 MB
+        tr_bytes = 2 * hn_b + w2_b + 2 * sh_b + B * (per_cap_fwd + T * V * 4.0)  # + logits re-read: 1.95 MB / caption
+        de_bytes = hn_b + sh_b + B * per_cap_fwd
+        rooflines["attention_train_step"] = roofline_block(
+            tr_bytes, B * world / out["attention_train_captions_per_s"] * 1e3, peak,
+            "configs[2] fwd+bwd, flow mode, compulsory traffic (SURVEY 8(d) worked example: 2.78 GB)")
+        rooflines["attention_greedy_decode"] = roofline_block(
+            de_bytes, B * world / out["attention_greedy_decode_captions_per_s"] * 1e3, peak,
+            "configs[2] greedy decode (sample_prob=1.0), compulsory traffic (SURVEY 8(d): 1.20 GB)")
+    if world > 1:
+        par.disable_overlap()
     return out
 
 
@@ -512,6 +655,7 @@ def lstm_extras(args, dev, world, timed):
     torch.manual_seed(0)
     with torch.device(dev):
         model = C.HyperNetPooled(c["E"], c["H"], V, None, num_layers=c["L"], type="lstm")
+    model.async_hypernet = True
     model.dp_enabled = world > 1
     shared = par.shared_parameters(model)
     if world > 1:

@@ -59,7 +59,7 @@ SIGNATURES = {
     "caphn_attstep_bwd": [P] * 22 + [I] * 5 + [P],
     "caphn_attn_df": [P, P, P, I, I, I, I, P],
     "caphn_mean_pos": [P, I, I, I, P, P],
-    "caphn_mean_pos_bwd": [P, I, I, I, P, P],
+    "caphn_mean_pos_bwd": [P, P, I, I, I, P, P],
     "caphn_relu_mask": [P, P, L, P],
     "caphn_sumsq": [P, L, P, P],
     "caphn_clip_coef": [P, F, P, P, P],

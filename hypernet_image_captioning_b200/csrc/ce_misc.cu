@@ -400,11 +400,15 @@ __global__ void mean_pos_kernel(const float* __restrict__ X, int P, int Fd, floa
         out[b * Fd + f] = s / (float)P;
     }
 }
-// dX[b,p,f] += g[b,f] / P
-__global__ void mean_pos_bwd_kernel(const float* __restrict__ g, int P, int Fd, float* __restrict__ dX) {
+// dX[b,p,f] += g[b,f] / P (+ extra[b,p,f])
+__global__ void mean_pos_bwd_kernel(const float* __restrict__ g, const float* __restrict__ extra, int P, int Fd,
+                                    float* __restrict__ dX) {
     const long b = blockIdx.x;
     const float inv = 1.f / (float)P;
-    for (int i = threadIdx.x; i < P * Fd; i += blockDim.x) dX[b * P * Fd + i] += g[b * Fd + (i % Fd)] * inv;
+    for (int i = threadIdx.x; i < P * Fd; i += blockDim.x) {
+        const long o = b * P * Fd + i;
+        dX[o] += g[b * Fd + (i % Fd)] * inv + (extra ? extra[o] : 0.f);
+    }
 }
 
 // y = relu'(ref) * y   (in place on y): y[i] = ref[i] > 0 ? y[i] : 0
@@ -509,9 +513,9 @@ int caphn_mean_pos(const float* X, int B, int P, int Fd, float* out, void* strea
     CAPHN_RETURN_LAST();
 }
 
-int caphn_mean_pos_bwd(const float* g, int B, int P, int Fd, float* dX, void* stream) {
+int caphn_mean_pos_bwd(const float* g, const float* extra, int B, int P, int Fd, float* dX, void* stream) {
     if (B <= 0 || P <= 0 || Fd <= 0) return CAPHN_EINVAL;
-    mean_pos_bwd_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(g, P, Fd, dX);
+    mean_pos_bwd_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(g, extra, P, Fd, dX);
     CAPHN_RETURN_LAST();
 }
 

@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from . import functional as Fn
-from . import ops
+from . import ops, streams
 
 try:  # the reference classes are LightningModules; use the real base when it exists
     import pytorch_lightning as _pl
@@ -57,6 +57,16 @@ class _HyperNetMixin:
     head_grad_mode = "materialize"
     lowrank_min_numel = 1 << 22
 
+    # True: ``forward(x)`` launches the hypernet on a side stream and returns at once; the captioner waits for the generated
+    # weights right before it needs them, so whatever it runs first (feature_fc, the input gather) overlaps with the weight
+    # streaming, and the autograd engine runs the head backward on that stream too (streams.py).  Opt-in, because code that
+    # reads ``captioner.<cell>.weight_*`` directly after ``forward`` must then call ``sync_generated()`` first.
+    async_hypernet = False
+
+    def sync_generated(self):
+        """Order the current stream after an asynchronous hypernet forward (no-op otherwise)."""
+        streams.wait_pending()
+
     def zero_grad(self, set_to_none: bool = True):
         super().zero_grad(set_to_none)
         for p in self.parameters():            # rank-G gradients live beside .grad
@@ -69,6 +79,21 @@ class _HyperNetMixin:
         stay, as in the reference."""
         self.captioner._generated = None
         self.captioner._generated_groups = None
+
+    def _generate_and_inject(self, x: torch.Tensor, grouped: bool = False):
+        """theta (+ its per-cell views, + the copy into the captioner's cell parameters) -- on the hypernet side stream when
+        ``async_hypernet`` is set."""
+        def run():
+            theta = self.generate_theta(x)
+            if grouped:
+                return [self._split_theta(theta[g]) for g in range(theta.shape[0])]
+            return self._split_theta(theta[0], write_params=True)
+        if self.async_hypernet and x.is_cuda and streams.enabled():
+            with streams.fork("hypernet") as s:
+                out = run()
+            streams.defer(s)
+            return out
+        return run()
 
     def generate_theta(self, x: torch.Tensor) -> torch.Tensor:
         x2 = x.reshape(1, -1) if x.dim() == 1 else x
@@ -117,8 +142,7 @@ class _HyperNetMixin:
         One pass over the hypernet weights generates all G weight sets (the reference would stream them G times, one
         ``forward`` per style); the captioner then decodes every batch row with the weights of its group:
         ``captioner(features, captions, ..., groups=group_ids)``.  Oracle = one reference call per group, concatenated."""
-        Theta = self.generate_theta(X)
-        self.captioner._generated_groups = [self._split_theta(Theta[g]) for g in range(Theta.shape[0])]
+        self.captioner._generated_groups = self._generate_and_inject(X, grouped=True)
         return self.captioner
 
 
@@ -189,6 +213,7 @@ class DecoderGRU(nn.Module):
     def forward(self, features, captions, teacher_forcing=True, h0=None, groups=None):
         if not teacher_forcing:
             raise NotImplementedError("multinomial-sampled decoding (later.py:424-434) is outside the hot path")
+        streams.wait_pending()      # an asynchronous hypernet forward (async_hypernet) must have produced the weights
         if groups is not None:
             if h0 is None:
                 h0 = self._h0(features)
@@ -204,6 +229,7 @@ class DecoderGRU(nn.Module):
         but one autograd node whose backward writes the softmax gradient straight into tensor-core operands."""
         if h0 is None:
             h0 = self._h0(features)
+        streams.wait_pending()
         flat = [w for cell in self._cells() for w in cell]
         return Fn.DecoderGRULossFn.apply(ignore_index, features, captions, h0, self.embed.weight, self.fc_out.weight,
                                          self.fc_out.bias, *flat)
@@ -220,6 +246,7 @@ class DecoderGRU(nn.Module):
         """Greedy decode, reference later.py:459-490: argmax feedback, first cell only, returns softmax probs.
         The whole loop (~5 launches per step) is captured into a CUDA graph per (batch, max_len) and replayed."""
         from . import graphs
+        streams.wait_pending()
         W_ih, W_hh, b_ih, b_hh = [t.detach().contiguous() for t in self._cells()[0]]
         if h0 is None:
             h0 = self._h0(features)
@@ -276,6 +303,7 @@ class DecoderRNN(DecoderGRU):
     def forward_loss(self, features, captions, h0=None, ignore_index=None):
         if h0 is None:
             h0 = self._h0(features)
+        streams.wait_pending()
         flat = [w for cell in self._cells() for w in cell]
         return Fn.DecoderRNNLossFn.apply(ignore_index, features, captions, h0, self.embed.weight, self.fc_out.weight,
                                          self.fc_out.bias, *flat)
@@ -348,8 +376,7 @@ class HyperNetPooled(_HyperNetMixin, _Base):
 
     def forward(self, x):
         """theta = heads(base(x)); inject into the captioner's GRU cells; returns self.captioner (hypernet.py:104-114)."""
-        theta = self.generate_theta(x)[0]
-        gen = self._split_theta(theta, write_params=True)
+        gen = self._generate_and_inject(x)
         self.captioner._generated = gen if self.grad_mode == "flow" else None
         self.captioner._generated_groups = None
         return self.captioner

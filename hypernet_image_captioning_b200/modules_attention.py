@@ -12,38 +12,85 @@ from torch import nn
 from torch.autograd import Function
 
 from . import functional as Fn
-from . import ops
+from . import ops, streams
 from .modules import _Base, _HyperNetMixin, _run_grouped
 
 
-def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, fc2_w, fc2_b, emb_w, W_ih, W_hh, b_ih,
-                    b_hh, fc_w, fc_b, Wa_w, Wa_b, Ua_w, Ua_b, va_w, va_b, init_w, init_b):
-    """AttentionGru.forward (models/decoderlstm.py:49-120).  Returns (logits, attn, tensors to save, dims)."""
-    B, P, D = features.shape
+class FeatureFn(Function):
+    """Loop-invariant branch of AttentionGru.forward as its own autograd node: feature_fc (models/decoderlstm.py:61), the
+    attention keys K = W_a f + b_a hoisted out of the time loop (the reference recomputes them every step,
+    models/attention.py:34) and h0 = init_h(mean_p f) (:63, 133-134).  Returns (f [B,P,F], K [B,P,H], h0 [B,H]).
+
+    A separate node so that it can live on its own stream (streams.py): forward next to the hypernet's weight streaming,
+    backward (four tensor-core weight-gradient GEMMs) next to the hypernet head backward."""
+
+    @staticmethod
+    def forward(ctx, features, fc0_w, fc0_b, fc2_w, fc2_b, Wa_w, Wa_b, init_w, init_b):
+        B, P, D = features.shape
+        Fd, H = fc2_w.shape[0], Wa_w.shape[0]
+        feats2 = features.reshape(B * P, D)
+        if not feats2.is_contiguous():
+            feats2 = feats2.contiguous()
+        # the bf16x3 split of the image features (the largest input, 205 MB at B=512) is made once and reused by the
+        # backward as the in-place MN-major operand of dW1 = df1^T . features
+        fsplit = ops.split_bf16(feats2) if ops._tc_ok(B * P, Fd, D) else None
+        if fsplit is not None:
+            f1 = ops.gemm_tc(fsplit, ops.split_bf16(fc0_w.contiguous()), bias=fc0_b, relu=True)   # [B*P, F]
+        else:
+            f1 = ops.linear(feats2, fc0_w, fc0_b, relu=True)
+        f = ops.linear(f1, fc2_w, fc2_b)                                  # [B*P, F]
+        Kp = ops.linear(f, Wa_w, Wa_b)                                    # [B*P, H]
+        fmean = ops.mean_pos(f.view(B, P, Fd))                            # [B, F]
+        h0 = ops.linear(fmean, init_w, init_b)                            # [B, H]
+        if any(ctx.needs_input_grad):
+            ctx.save_for_backward(feats2, f1, f, fmean, fc0_w, fc2_w, Wa_w, init_w,
+                                  fsplit.hi if fsplit is not None else None, fsplit.lo if fsplit is not None else None)
+            ctx.dims = (B, P, D, Fd, H)
+        return f.view(B, P, Fd), Kp.view(B, P, H), h0
+
+    @staticmethod
+    def backward(ctx, df_in, dK, dh0):
+        feats2, f1, f, fmean, fc0_w, fc2_w, Wa_w, init_w, fs_hi, fs_lo = ctx.saved_tensors
+        B, P, D, Fd, H = ctx.dims
+        # attention keys: dW_a = dK^T f, df = dK W_a
+        dK2 = dK.reshape(B * P, H).contiguous()
+        dWa_w = ops.matmul_tn(dK2, f)                                      # [H, F]
+        dWa_b = ops.colsum(dK2)
+        df = ops.matmul_nn(dK2, Wa_w.contiguous())                         # [B*P, F]
+        # init_h; its input gradient and the recurrence's df contribution are added to df in one pass
+        dh0 = dh0.contiguous()
+        dinit_w = ops.matmul_tn(dh0, fmean)                                # [H, F]
+        dinit_b = ops.colsum(dh0)
+        dfmean = ops.matmul_nn(dh0, init_w.contiguous())                   # [B, F]
+        ops.mean_pos_bwd(dfmean, df.view(B, P, Fd), extra=df_in.contiguous() if df_in is not None else None)
+        # feature_fc (no gradient w.r.t. the image features: they are a leaf input)
+        dfc2_w = ops.matmul_tn(df, f1)
+        dfc2_b = ops.colsum(df)
+        df1 = ops.matmul_nn(df, fc2_w.contiguous())
+        ops.relu_mask_(f1, df1)
+        if fs_hi is not None and (fs_lo is not None) == ops.TC_SPLIT:
+            feats_op = ops.SplitOperand(fs_hi, fs_lo, D, B * P, fs_hi.shape[1], True)      # features^T, read in place
+            dfc0_w = ops.gemm_tc(ops.split_bf16(df1, mn=True), feats_op)                   # [F, D]
+        else:
+            dfc0_w = ops.matmul_tn(df1, feats2)                                            # [F, D]
+        dfc0_b = ops.colsum(df1)
+        return (None, dfc0_w, dfc0_b, dfc2_w, dfc2_b, dWa_w, dWa_b, dinit_w, dinit_b)
+
+
+def _attgru_forward(need_grad, f3, K3, h0, captions, use_sampling, emb_w, W_ih, W_hh, b_ih, b_hh, fc_w, fc_b, Ua_w, Ua_b,
+                    va_w, va_b):
+    """The time loop of AttentionGru.forward (models/decoderlstm.py:78-108) + the vocabulary projection, given the
+    loop-invariant tensors of FeatureFn.  Returns (logits, attn, tensors to save, dims)."""
+    B, P, Fd = f3.shape
     T = captions.shape[1]
     E = emb_w.shape[1]
     H = W_hh.shape[1]
-    Fd = fc2_w.shape[0]
     V = fc_w.shape[0]
-    dev = features.device
+    dev = f3.device
     caps = captions.contiguous()
-    feats2 = features.reshape(B * P, D)
-    if not feats2.is_contiguous():
-        feats2 = feats2.contiguous()
+    f3, K3 = f3.contiguous(), K3.contiguous()
     emb_w = emb_w.contiguous()
     W_ih, W_hh = W_ih.contiguous(), W_hh.contiguous()
-    # ---- loop-invariant part: feature_fc (:61), keys W_a f (attention.py:34, hoisted), h0 (:63,133-134) ----
-    # the bf16x3 split of the image features (the largest input, 205 MB at B=512) is made once and reused by the backward
-    # as the in-place MN-major operand of dW1 = df1^T . features
-    fsplit = ops.split_bf16(feats2) if ops._tc_ok(B * P, Fd, D) else None
-    if fsplit is not None:
-        f1 = ops.gemm_tc(fsplit, ops.split_bf16(fc0_w.contiguous()), bias=fc0_b, relu=True)   # [B*P, F]
-    else:
-        f1 = ops.linear(feats2, fc0_w, fc0_b, relu=True)
-    f = ops.linear(f1, fc2_w, fc2_b)                                  # [B*P, F]
-    Kp = ops.linear(f, Wa_w, Wa_b)                                    # [B*P, H]
-    fmean = ops.mean_pos(f.view(B, P, Fd))                            # [B, F]
-    h0 = ops.linear(fmean, init_w, init_b)                            # [B, H]
     lw = ops.AttGruWeights(W_ih, W_hh, Ua_w.contiguous(), E, P)
     va = va_w.reshape(-1).contiguous()
     bv = va_b.reshape(1).contiguous()
@@ -56,7 +103,6 @@ def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, f
     XC = torch.empty(T * B, E + Fd, device=dev, dtype=torch.float32)   # [x_word | ctx] per (t,b)
     saved = torch.empty(5, T, B, H, device=dev, dtype=torch.float32) if need_grad else None
     logits = torch.empty(B, T, V, device=dev, dtype=torch.float32)
-    f3, K3 = f.view(B, P, Fd), Kp.view(B, P, H)
     W_ih_w = W_ih[:, :E]
     fed = torch.full((T, B), -1, device=dev, dtype=torch.int64)        # token whose embedding was fed at (t,b)
 
@@ -100,20 +146,18 @@ def _attgru_forward(need_grad, features, captions, use_sampling, fc0_w, fc0_b, f
                 xproj(xw, out=GIw[t * B:(t + 1) * B])
             ops.attgru_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, t, t + 1)
             vocab(Hall[t + 1], out=logits[:, t, :])
-    sv = (feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih, W_hh, fc_w, Wa_w, Ua_w,
-          va, init_w, fsplit.hi if fsplit is not None else None, fsplit.lo if fsplit is not None else None)
-    return logits, attn, sv, (B, T, P, D, E, H, Fd, V)
+    sv = (f3, K3, XC, Hall, Hbm, attn, saved, fed, emb_w, W_ih, W_hh, fc_w, Ua_w, va)
+    return logits, attn, sv, (B, T, P, E, H, Fd, V)
 
 
 def _attgru_backward(sv, dims, vocab, dattn):
-    """vocab = (dfc_w, dfc_b, dHbm [B*T,H]).  Returns the 19 parameter gradients in AttentionGruFn argument order."""
-    (feats2, f1, f, Kp, fmean, XC, Hall, Hbm, attn, saved, fed, fc0_w, fc2_w, emb_w, W_ih, W_hh, fc_w, Wa_w, Ua_w,
-     va, init_w, fs_hi, fs_lo) = sv
-    B, T, P, D, E, H, Fd, V = dims
+    """vocab = (dfc_w, dfc_b, dHbm [B*T,H]).  Returns the gradients of (f, K, h0) and of the 11 parameters in
+    AttentionGruFn argument order."""
+    f3, K3, XC, Hall, Hbm, attn, saved, fed, emb_w, W_ih, W_hh, fc_w, Ua_w, va = sv
+    B, T, P, E, H, Fd, V = dims
     dfc_w, dfc_b, dHbm = vocab
     if dattn is not None:
         dattn = dattn.contiguous()
-    f3, K3 = f.view(B, P, Fd), Kp.view(B, P, H)
     dGI, dGH, dU, dCTX, dK, dva, dbv, dh0 = ops.attgru_bwd(
         dHbm.view(B, T, H), dattn, K3, f3, attn, saved, Hall, Ua_w.contiguous(), va, W_ih, W_hh, E)
     Hprev = Hall[:-1].reshape(T * B, H)
@@ -127,34 +171,16 @@ def _attgru_backward(sv, dims, vocab, dattn):
     dXw = ops.matmul_nn(dGI, W_ih[:, :E])                              # [T*B, E]
     demb = torch.zeros_like(emb_w)
     ops.scatter_add_rows(dXw, fed.reshape(-1), demb)
-    # attention keys / features
-    dK2 = dK.view(B * P, H)
-    dWa_w = ops.matmul_tn(dK2, f)                                      # [H, F]
-    dWa_b = ops.colsum(dK2)
-    df = ops.matmul_nn(dK2, Wa_w.contiguous())                         # [B*P, F]
-    ops.attn_df(attn, dCTX, df.view(B, P, Fd))
-    # init_h
-    dinit_w = ops.matmul_tn(dh0, fmean)                                # [H, F]
-    dinit_b = ops.colsum(dh0)
-    dfmean = ops.matmul_nn(dh0, init_w.contiguous())                   # [B, F]
-    ops.mean_pos_bwd(dfmean, df.view(B, P, Fd))
-    # feature_fc (no gradient w.r.t. the image features: they are a leaf input)
-    dfc2_w = ops.matmul_tn(df, f1)
-    dfc2_b = ops.colsum(df)
-    df1 = ops.matmul_nn(df, fc2_w.contiguous())
-    ops.relu_mask_(f1, df1)
-    if fs_hi is not None and (fs_lo is not None) == ops.TC_SPLIT:
-        feats_op = ops.SplitOperand(fs_hi, fs_lo, D, B * P, fs_hi.shape[1], True)      # features^T, read in place
-        dfc0_w = ops.gemm_tc(ops.split_bf16(df1, mn=True), feats_op)                   # [F, D]
-    else:
-        dfc0_w = ops.matmul_tn(df1, feats2)                                            # [F, D]
-    dfc0_b = ops.colsum(df1)
-    return (dfc0_w, dfc0_b, dfc2_w, dfc2_b, demb, dW_ih, dW_hh, db_ih, db_hh, dfc_w, dfc_b,
-            dWa_w, dWa_b, dUa_w, dUa_b, dva.view(1, H), dbv.view(1), dinit_w, dinit_b)
+    # features through the context vectors: df[b,p,:] = sum_t alpha[b,t,p] dctx[t,b,:]  (the K / init_h paths are FeatureFn's)
+    df = torch.zeros(B, P, Fd, device=f3.device, dtype=torch.float32)
+    ops.attn_df(attn, dCTX, df)
+    return (df, dK, dh0, demb, dW_ih, dW_hh, db_ih, db_hh, dfc_w, dfc_b, dUa_w, dUa_b, dva.view(1, H), dbv.view(1))
 
 
 class AttentionGruFn(Function):
-    """Whole AttentionGru.forward (models/decoderlstm.py:49-120) as one autograd node.
+    """The time loop of AttentionGru.forward (models/decoderlstm.py:78-108) + vocabulary projection as one autograd node.
+    Inputs: (f, K, h0) from FeatureFn, captions, the scheduled-sampling decisions, then emb_w, the generated
+    (W_ih, W_hh, b_ih, b_hh), fc_w, fc_b, U_a (w, b), v_a (w, b).
 
     ``use_sampling[t]`` are the host-side scheduled-sampling decisions of :79-80 (already drawn by the caller from
     NumPy's global RNG, one per step).  All-False = teacher forcing: one persistent launch covers every step and the
@@ -163,9 +189,9 @@ class AttentionGruFn(Function):
     """
 
     @staticmethod
-    def forward(ctx, features, captions, use_sampling, *params):
+    def forward(ctx, f3, K3, h0, captions, use_sampling, *params):
         need_grad = any(ctx.needs_input_grad)
-        logits, attn, sv, dims = _attgru_forward(need_grad, features, captions, use_sampling, *params)
+        logits, attn, sv, dims = _attgru_forward(need_grad, f3, K3, h0, captions, use_sampling, *params)
         if need_grad:
             ctx.save_for_backward(*sv)
             ctx.dims = dims
@@ -174,19 +200,20 @@ class AttentionGruFn(Function):
     @staticmethod
     def backward(ctx, dlogits, dattn):
         sv = ctx.saved_tensors
-        B, T, P, D, E, H, Fd, V = ctx.dims
+        B, T, P, E, H, Fd, V = ctx.dims
         dl = dlogits.reshape(B * T, V).contiguous()
-        vocab = Fn.vocab_bwd_from_dlogits(dl, sv[7].view(B * T, H), sv[16])
-        return (None, None, None, *_attgru_backward(sv, ctx.dims, vocab, dattn))
+        vocab = Fn.vocab_bwd_from_dlogits(dl, sv[4].view(B * T, H), sv[11])
+        g = _attgru_backward(sv, ctx.dims, vocab, dattn)
+        return (*g[:3], None, None, *g[3:])
 
 
 class AttentionGruLossFn(Function):
-    """AttentionGru.forward + F.cross_entropy(ignore_index) (cc_train_hypernet.py:152-153) as ONE autograd node:
+    """AttentionGruFn + F.cross_entropy(ignore_index) (cc_train_hypernet.py:152-153) as ONE autograd node:
     returns (loss, logits, attn); the CE gradient goes straight into tensor-core operands (no fp32 dlogits)."""
 
     @staticmethod
-    def forward(ctx, ignore_index, features, captions, use_sampling, *params):
-        logits, attn, sv, dims = _attgru_forward(True, features, captions, use_sampling, *params)
+    def forward(ctx, ignore_index, f3, K3, h0, captions, use_sampling, *params):
+        logits, attn, sv, dims = _attgru_forward(True, f3, K3, h0, captions, use_sampling, *params)
         B, T, V = logits.shape
         targets = captions.reshape(-1).contiguous()
         lossbuf, lse = ops.ce_fwd(logits.view(B * T, V), targets, ignore_index)
@@ -201,11 +228,12 @@ class AttentionGruLossFn(Function):
     def backward(ctx, g, _dl, _da):
         allsv = ctx.saved_tensors
         sv, (logits, targets, lse, lossbuf) = allsv[:-4], allsv[-4:]
-        B, T, P, D, E, H, Fd, V = ctx.dims
+        B, T, P, E, H, Fd, V = ctx.dims
         g = g.reshape(1).to(torch.float32).contiguous()
         vocab = Fn.vocab_bwd_fused(logits.view(B * T, V), targets, ctx.ignore_index, lse, lossbuf, g,
-                                   sv[7].view(B * T, H), sv[16])
-        return (None, None, None, None, *_attgru_backward(sv, ctx.dims, vocab, None))
+                                   sv[4].view(B * T, H), sv[11])
+        gr = _attgru_backward(sv, ctx.dims, vocab, None)
+        return (None, *gr[:3], None, None, *gr[3:])
 
 
 class BahdanauAttention(nn.Module):
@@ -261,41 +289,65 @@ class AttentionGru(nn.Module):
             sp = 0.0 if t == 0 else sample_prob
             use.append(bool(np.random.random() < sp))
         if groups is not None:
+            streams.wait_pending()
             return _run_grouped(lambda g, f, c: self._forward_one(f, c, tuple(use), self._gru_weights(g)), groups,
                                 [features, captions], len(self._generated_groups))
         if any(use) and not torch.is_grad_enabled():
             # decode (test_hn.py path, cc_train_hypernet.py:230): ~10 launches per step -> captured into a CUDA graph
             from . import graphs
-            ps = [p.detach() for p in self._params(self._gru_weights())]
-            gen = [ps[5].contiguous(), ps[6].contiguous(), ps[7].contiguous(), ps[8].contiguous()]   # generated weights
+            streams.wait_pending()
+            fp = [p.detach() for p in self._feature_params()]
+            rp = [p.detach() for p in self._recurrence_params(self._gru_weights())]
+            gen = [rp[1].contiguous(), rp[2].contiguous(), rp[3].contiguous(), rp[4].contiguous()]   # generated weights
             key = ("AttentionGru.decode", id(self), tuple(features.shape), tuple(captions.shape), tuple(use),
-                   features.device.index) + tuple(p.data_ptr() for i, p in enumerate(ps) if i not in (5, 6, 7, 8))
+                   features.device.index) + tuple(p.data_ptr() for p in fp) + \
+                tuple(p.data_ptr() for i, p in enumerate(rp) if i not in (1, 2, 3, 4))
 
             def run(f, c, wi, wh, bi, bh):
-                q = list(ps)
-                q[5], q[6], q[7], q[8] = wi, wh, bi, bh
-                return AttentionGruFn.apply(f, c, tuple(use), *q)
+                q = list(rp)
+                q[1], q[2], q[3], q[4] = wi, wh, bi, bh
+                f3, K3, h0 = FeatureFn.apply(f, *fp)
+                return AttentionGruFn.apply(f3, K3, h0, c, tuple(use), *q)
 
             out = graphs.graphed_call(key, run, [features.contiguous().float(), captions.contiguous()] + gen)
             return out[0], out[1]
         return self._forward_one(features, captions, tuple(use), self._gru_weights())
 
-    def _params(self, gru_w):
-        W_ih, W_hh, b_ih, b_hh = gru_w
+    def _feature_params(self):
         a = self.attention
         return (self.feature_fc[0].weight, self.feature_fc[0].bias, self.feature_fc[2].weight, self.feature_fc[2].bias,
-                self.embed.weight, W_ih, W_hh, b_ih, b_hh, self.fc.weight, self.fc.bias, a.W_a.weight, a.W_a.bias,
-                a.U_a.weight, a.U_a.bias, a.v_a.weight, a.v_a.bias, self.init_h.weight, self.init_h.bias)
+                a.W_a.weight, a.W_a.bias, self.init_h.weight, self.init_h.bias)
+
+    def _recurrence_params(self, gru_w):
+        W_ih, W_hh, b_ih, b_hh = gru_w
+        a = self.attention
+        return (self.embed.weight, W_ih, W_hh, b_ih, b_hh, self.fc.weight, self.fc.bias, a.U_a.weight, a.U_a.bias,
+                a.v_a.weight, a.v_a.bias)
+
+    def _features(self, features):
+        """FeatureFn on the "features" side stream: it overlaps with an asynchronous hypernet forward, and its backward
+        node (which the autograd engine runs on the same stream) with the hypernet head backward."""
+        if streams.enabled(features):
+            with streams.fork("features") as s:
+                out = FeatureFn.apply(features, *self._feature_params())
+            torch.cuda.current_stream().wait_stream(s)
+            return out
+        return FeatureFn.apply(features, *self._feature_params())
 
     def _forward_one(self, features, captions, use, gru_w):
-        return AttentionGruFn.apply(features, captions, use, *self._params(gru_w))
+        f3, K3, h0 = self._features(features)
+        streams.wait_pending()                    # generated weights of an asynchronous hypernet forward
+        return AttentionGruFn.apply(f3, K3, h0, captions, use, *self._recurrence_params(gru_w))
 
     def forward_loss(self, features, captions, sample_prob=0.0, ignore_index=0):
         """``forward`` fused with ``F.cross_entropy(outputs.view(-1,V), captions.view(-1), ignore_index=<pad>)``
         (cc_train_hypernet.py:152-153): returns ``(loss, outputs, atten_weights)``; one autograd node."""
         T = captions.size(1)
         use = tuple(bool(np.random.random() < (0.0 if t == 0 else sample_prob)) for t in range(T))
-        return AttentionGruLossFn.apply(ignore_index, features, captions, use, *self._params(self._gru_weights()))
+        f3, K3, h0 = self._features(features)
+        streams.wait_pending()
+        return AttentionGruLossFn.apply(ignore_index, f3, K3, h0, captions, use,
+                                        *self._recurrence_params(self._gru_weights()))
 
     @torch.no_grad()
     def beam_search(self, features, beam_size=3, end_sentence=2, max_steps=50):
@@ -308,6 +360,7 @@ class AttentionGru(nn.Module):
         row's previous word is 0 (:265-266); step 1 ranks ``scores[0]`` only (:274-275); scores are summed
         log-probabilities without length normalisation; finished beams leave the batch (:296-303).
         Each step runs the recurrence kernels on the k live rows; the top-k bookkeeping is host logic as in the reference."""
+        streams.wait_pending()
         feats = features.contiguous().float()
         if feats.dim() != 3 or feats.shape[0] != 1:
             raise ValueError("beam_search expects the features of one image: [1, P, D]")
@@ -384,6 +437,7 @@ class AttentionGru(nn.Module):
         ``feature_fc`` ([1, P, F]); the first input word is index 0; returns (tokens list[int], list of attention
         weights [1, P]).  All ``max_sentence`` steps run on the device without host round trips; the token list is cut
         after the first ``end_sentence`` (the steps after it do not influence the ones before)."""
+        streams.wait_pending()
         f3 = features.contiguous().float()
         B, P, Fd = f3.shape
         W_ih, W_hh, b_ih, b_hh = [w.detach().contiguous() for w in self._gru_weights()]
@@ -463,8 +517,7 @@ class HyperNetAttention(_HyperNetMixin, _Base):
 
     def forward(self, x):
         """theta -> captioner.gru weights; returns self.captioner (hypernet_attention.py:111-121)."""
-        theta = self.generate_theta(x)[0]
-        ws = self._split_theta(theta, write_params=True)
+        ws = self._generate_and_inject(x)
         self.captioner._generated = ws if self.grad_mode == "flow" else None
         self.captioner._generated_groups = None
         return self.captioner

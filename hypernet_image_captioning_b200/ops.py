@@ -429,9 +429,12 @@ def mean_pos(X):
     return out
 
 
-def mean_pos_bwd(g, dX):
+def mean_pos_bwd(g, dX, extra=None):
+    """dX[b,p,:] += g[b,:] / P (+ extra[b,p,:])."""
     B, P, Fd = dX.shape
-    _cabi.call("caphn_mean_pos_bwd", g.data_ptr(), B, P, Fd, dX.data_ptr(), _stream())
+    if extra is not None:
+        assert extra.is_contiguous() and extra.numel() == dX.numel()
+    _cabi.call("caphn_mean_pos_bwd", g.data_ptr(), _p(extra), B, P, Fd, dX.data_ptr(), _stream())
     return dX
 
 

@@ -104,6 +104,7 @@ class _Overlap:
         self.tail_buf = None
         self.inflight = False
         self.handles = []
+        self.src_streams = []
 
 
 _ov = _Overlap()
@@ -141,6 +142,10 @@ def disable_overlap():
 def _on_grad_ready(p):
     if _ov.enabled and id(p) not in _ov.done:
         _ov.ready.append(p)
+        if p.is_cuda:       # the gradient was accumulated on this stream (feature-branch parameters: a side stream)
+            s = torch.cuda.current_stream()
+            if s not in _ov.src_streams:
+                _ov.src_streams.append(s)
 
 
 def flush_ready():
@@ -157,8 +162,10 @@ def flush_ready():
     if _ov.stream is None:
         _ov.buf = _flat_allreduce(grads, _ov.group, _ov.buf)
         return
-    cur = torch.cuda.current_stream()
-    _ov.stream.wait_stream(cur)
+    _ov.stream.wait_stream(torch.cuda.current_stream())
+    for src in _ov.src_streams:
+        _ov.stream.wait_stream(src)
+    _ov.src_streams = []
     with torch.cuda.stream(_ov.stream):
         _ov.buf = _flat_allreduce(grads, _ov.group, _ov.buf)
     _ov.inflight = True
@@ -182,7 +189,7 @@ def allreduce_shared_grads(params: Iterable[torch.nn.Parameter], group=None, ext
         flush_pending = [p for p in _ov.ready]      # ready after the hypernet backward started (or no hypernet backward ran)
         join()
         rest = [p for p in params if id(p) not in _ov.done or id(p) not in _ov.ids]
-        _ov.ready, _ov.done = [], set()
+        _ov.ready, _ov.done, _ov.src_streams = [], set(), []
         del flush_pending
         group = _ov.group if group is None else group
     else:

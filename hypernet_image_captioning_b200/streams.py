@@ -1,0 +1,67 @@
+"""Side streams for the independent branches of a step (capture-safe: plain fork / join with stream waits).
+
+The attention-variant step has three branches that only meet at the recurrence:
+
+    hypernet   x -> theta                       HBM-bound weight streaming        ("hypernet" stream, opt-in)
+    features   feature_fc -> f, K = W_a f, h0   tensor-core GEMMs                 ("features" stream)
+    recurrence + vocabulary projection + loss   everything else                   (the caller's stream)
+
+Each branch is its own autograd node created under its stream, so the autograd engine runs the matching backward nodes
+on the same streams (and inserts the cross-stream waits itself): the head backward (HBM) and the feature_fc backward
+(tensor cores) overlap after the recurrence's BPTT.  Every use of a side stream starts with ``side.wait_stream(current)``,
+so memory handed between streams is never reused early.  ``CAPHN_OVERLAP=0`` keeps everything on the caller's stream.
+"""
+import os
+from typing import Dict, List, Tuple
+
+import torch
+
+ENABLED = os.environ.get("CAPHN_OVERLAP", "1") != "0"
+_streams: Dict[Tuple[str, int], "torch.cuda.Stream"] = {}
+_pending: List["torch.cuda.Stream"] = []
+
+
+def enabled(t: torch.Tensor = None) -> bool:
+    return ENABLED and (t is None or t.is_cuda)
+
+
+def side(name: str, device=None) -> "torch.cuda.Stream":
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    key = (name, idx)
+    if key not in _streams:
+        _streams[key] = torch.cuda.Stream(device=idx)
+    return _streams[key]
+
+
+class fork:
+    """``with fork("features") as s:`` -- run the block on side stream ``s`` after everything queued on the current stream.
+    The caller joins with ``torch.cuda.current_stream().wait_stream(s)`` (or ``defer(s)`` + ``wait_pending()``)."""
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        cur = torch.cuda.current_stream()
+        self.s = side(self.name)
+        self.s.wait_stream(cur)
+        self.ctx = torch.cuda.stream(self.s)
+        self.ctx.__enter__()
+        return self.s
+
+    def __exit__(self, *exc):
+        return self.ctx.__exit__(*exc)
+
+
+def defer(s: "torch.cuda.Stream"):
+    """The current stream must wait for ``s`` before touching what the forked block produced; the wait is issued by the
+    consumer (``wait_pending``), so work queued in between overlaps with the block."""
+    if s not in _pending:
+        _pending.append(s)
+
+
+def wait_pending():
+    if _pending:
+        cur = torch.cuda.current_stream()
+        for s in _pending:
+            cur.wait_stream(s)
+        _pending.clear()

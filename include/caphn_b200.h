@@ -204,9 +204,10 @@ int caphn_embed_scatter_add(const float* dX, const long long* caps, int B, int T
 int caphn_scatter_add_rows(const float* dX, long ldx, const long long* idx, long n, int E, float* table, void* stream);
 /* out[n] += sum_m X[m*ld+n]  (bias gradients). */
 int caphn_colsum(const float* X, long ld, long M, int N, float* out, void* stream);
-/* out[b,f] = mean_p X[b,p,f] (models/decoderlstm.py:133) and its backward dX[b,p,f] += g[b,f]/P. */
+/* out[b,f] = mean_p X[b,p,f] (models/decoderlstm.py:133) and its backward dX[b,p,f] += g[b,f]/P (+ extra[b,p,f] when
+ * extra != NULL: a second gradient contribution to the same tensor folded into the same pass). */
 int caphn_mean_pos(const float* X, int B, int P, int Fd, float* out, void* stream);
-int caphn_mean_pos_bwd(const float* g, int B, int P, int Fd, float* dX, void* stream);
+int caphn_mean_pos_bwd(const float* g, const float* extra, int B, int P, int Fd, float* dX, void* stream);
 /* y[i] = ref[i] > 0 ? y[i] : 0  (ReLU backward, in place). */
 int caphn_relu_mask(const float* ref, float* y, long n, void* stream);
 
