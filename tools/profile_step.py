@@ -57,6 +57,7 @@ def main():
                 m.forward(m.captioner.embed.weight[4:5]).infer(m.image_encoder(pooled), max_len=T, h0=h0)
     if a.mode == "literal":
         m.grad_mode = "literal"
+    m.async_hypernet = os.environ.get("CAPHN_ASYNC_HN", "1") != "0"
     fn = greedy if a.mode == "greedy" else train
     for _ in range(a.warmup):
         fn()
