@@ -357,6 +357,7 @@ def run_ours(args):
 
     graphed = gstep is not None
     gstep = run_step = None                                   # release the graph's memory pool (gradients + activations)
+    model.async_hypernet = False          # the eager extras below run single-stream (the side stream pays off under a graph)
     model.zero_grad(set_to_none=True)
     torch.cuda.empty_cache()
 
@@ -582,7 +583,6 @@ def attention_extras(args, dev, world, timed, rooflines=None, peak=6537.6):
     torch.manual_seed(0)
     with torch.device(dev):
         model = C.HyperNetAttention(200, 200, 200, V, None)
-    model.async_hypernet = True
     model.dp_enabled = world > 1
     g = torch.Generator().manual_seed(4321)
     feats = torch.randn(B, 49, 2048, generator=g).to(dev)
@@ -616,7 +616,9 @@ def attention_extras(args, dev, world, timed, rooflines=None, peak=6537.6):
         out[name] = B * world * args.steps / (ms * 1e-3)
     if os.environ.get("CAPHN_BENCH_GRAPH", "1") != "0":       # the same training step replayed from one CUDA graph
         from hypernet_image_captioning_b200 import graphs
+        model.async_hypernet = True       # hypernet / feature branch / recurrence on three streams inside the graph
         gtrain = graphs.GraphedStep(train, (), params=list(model.parameters()), release=model.release_graph)
+        model.async_hypernet = False
         if gtrain.captured:
             for _ in range(3):
                 gtrain()

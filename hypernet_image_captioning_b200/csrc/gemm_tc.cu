@@ -128,8 +128,32 @@ constexpr int THREADS_V2 = 128 + EPI_WARPS * 32;            // warps 0-3: TMA / 
 constexpr int MAX_STAGES = 6;
 constexpr size_t SMEM_BUDGET = 227 * 1024;
 
+// Grouped mode (caphn_gemm_tc_grouped): every work unit is described by one record instead of being derived from the unit
+// index -- a tile of group g reads A rows / B rows / a K range that belong to that group and writes into that group's
+// slice of C (optionally through a row map).  Ten 32-bit words per unit, built on the host once per batch composition.
+struct GUnit {
+    int a_row;      // first operand row of the A tile (K-major: row index; MN-major: MN column)
+    int b_row;      // same for B
+    int k0;         // first k index (multiple of 64): column offset (K-major) / row offset (MN-major)
+    int nkb;        // 64-wide k blocks to accumulate (>= 1)
+    int m_valid;    // rows of the tile that exist (1..128)
+    int n_valid;    // columns of the tile that exist (1..BN)
+    int bias_off;   // bias[bias_off + col] is added (ignored when bias == NULL)
+    int map0;       // rowmap != NULL: tile row r is written to C row rowmap[map0 + r] (skipped when negative)
+    unsigned c_lo;  // element offset of the tile's (0, 0) inside C (rowmap: column offset only), low / high word
+    int c_hi;
+};
+
+struct UnitInfo {
+    int a0, b0, kb0, nkb, m_valid, n_valid, bias_off, map0, ks;
+    long c_off;
+};
+
 struct TcParams {
     float* C; long ldc; const float* bias;
+    const GUnit* units;   // grouped mode when non-null (num_units records)
+    const int* rowmap;
+    int num_units;
     int M, N, num_kb, relu;
     int BN;          // N tile (multiple of 16, <= 256)
     int splitk;      // K split factor; > 1 => epilogue adds atomically into a zero-initialised C
@@ -138,6 +162,24 @@ struct TcParams {
     uint32_t tmem_cols;
     int a_mn, b_mn;  // operand stored MN-major ([K rows, MN cols] row-major) instead of K-major ([MN rows, K cols])
 };
+
+__device__ __forceinline__ UnitInfo decode_unit(const TcParams& p, int unit, int tiles_m, int BN) {
+    UnitInfo u;
+    if (p.units) {
+        const GUnit g = p.units[unit];
+        u.a0 = g.a_row; u.b0 = g.b_row; u.kb0 = g.k0 / BK; u.nkb = g.nkb; u.m_valid = g.m_valid; u.n_valid = g.n_valid;
+        u.bias_off = g.bias_off; u.map0 = g.map0; u.ks = 0;
+        u.c_off = ((long)g.c_hi << 32) | (long)g.c_lo;
+    } else {
+        const int ks = unit % p.splitk, tile = unit / p.splitk;
+        const int mb = tile % tiles_m, nb = tile / tiles_m;
+        u.a0 = mb * BM; u.b0 = nb * BN; u.kb0 = ks * p.kb_per; u.nkb = min(p.num_kb, u.kb0 + p.kb_per) - u.kb0;
+        u.m_valid = min(BM, p.M - mb * BM); u.n_valid = min(BN, p.N - nb * BN);
+        u.bias_off = nb * BN; u.map0 = 0; u.ks = ks;
+        u.c_off = (long)mb * BM * p.ldc + (long)nb * BN;
+    }
+    return u;
+}
 
 // TMA_STORE (experimental, CAPHN_TC_TMA_STORE=1, off by default -- written at the end of round 1 after the N-tile sweep
 // showed the kernel to be epilogue-bound): full 32-column chunks leave through one cp.async.bulk.tensor store per warp
@@ -161,7 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int BN = p.BN;
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
-    const int num_units = tiles_m * tiles_n * p.splitk;
+    const int num_units = p.units ? p.num_units : tiles_m * tiles_n * p.splitk;
     // operand offsets inside a stage
     const int offAh = 0, offBh = TILE_BYTES;
     const int offAl = TILE_BYTES + p.b_bytes, offBl = 2 * TILE_BYTES + p.b_bytes;
@@ -187,30 +229,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                const int ks = unit % p.splitk, tile = unit / p.splitk;
-                const int mb = tile % tiles_m, nb = tile / tiles_m;
-                const int kb0 = ks * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
+                const UnitInfo u = decode_unit(p, unit, tiles_m, BN);
+                const int kb0 = u.kb0, kb1 = u.kb0 + u.nkb;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty + stage, phase ^ 1);
                     mbar_expect_tx(full + stage, (uint32_t)p.stage_bytes);
                     uint8_t* st = tiles + (size_t)stage * p.stage_bytes;
                     // K-major operand: one box [64 k x rows].  MN-major operand: boxes of [64 mn x 64 k] (8 KiB each).
                     if (!p.a_mn) {
-                        tma_load_2d(st + offAh, &tmAh, full + stage, kb * BK, mb * BM);
-                        if (SPLIT) tma_load_2d(st + offAl, &tmAl, full + stage, kb * BK, mb * BM);
+                        tma_load_2d(st + offAh, &tmAh, full + stage, kb * BK, u.a0);
+                        if (SPLIT) tma_load_2d(st + offAl, &tmAl, full + stage, kb * BK, u.a0);
                     } else {
                         for (int h = 0; h < BM / 64; ++h) {
-                            tma_load_2d(st + offAh + h * 8192, &tmAh, full + stage, mb * BM + h * 64, kb * BK);
-                            if (SPLIT) tma_load_2d(st + offAl + h * 8192, &tmAl, full + stage, mb * BM + h * 64, kb * BK);
+                            tma_load_2d(st + offAh + h * 8192, &tmAh, full + stage, u.a0 + h * 64, kb * BK);
+                            if (SPLIT) tma_load_2d(st + offAl + h * 8192, &tmAl, full + stage, u.a0 + h * 64, kb * BK);
                         }
                     }
                     if (!p.b_mn) {
-                        tma_load_2d(st + offBh, &tmBh, full + stage, kb * BK, nb * BN);
-                        if (SPLIT) tma_load_2d(st + offBl, &tmBl, full + stage, kb * BK, nb * BN);
+                        tma_load_2d(st + offBh, &tmBh, full + stage, kb * BK, u.b0);
+                        if (SPLIT) tma_load_2d(st + offBl, &tmBl, full + stage, kb * BK, u.b0);
                     } else {
                         for (int h = 0; h < BN / 64; ++h) {
-                            tma_load_2d(st + offBh + h * 8192, &tmBh, full + stage, nb * BN + h * 64, kb * BK);
-                            if (SPLIT) tma_load_2d(st + offBl + h * 8192, &tmBl, full + stage, nb * BN + h * 64, kb * BK);
+                            tma_load_2d(st + offBh + h * 8192, &tmBh, full + stage, u.b0 + h * 64, kb * BK);
+                            if (SPLIT) tma_load_2d(st + offBl + h * 8192, &tmBl, full + stage, u.b0 + h * 64, kb * BK);
                         }
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -227,8 +268,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             uint32_t phase = 0;
             int it = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-                const int ks = unit % p.splitk;
-                const int kb0 = ks * p.kb_per, kb1 = min(p.num_kb, kb0 + p.kb_per);
+                const UnitInfo u = decode_unit(p, unit, tiles_m, BN);
+                const int kb0 = u.kb0, kb1 = u.kb0 + u.nkb;
                 const int as = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
                 mbar_wait(tempty + as, aph ^ 1);
@@ -265,14 +306,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         const bool vec = !atomic && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         int it = 0;
         for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-            const int ks = unit % p.splitk, tile = unit / p.splitk;
-            const int mb = tile % tiles_m, nb = tile / tiles_m;
+            const UnitInfo u = decode_unit(p, unit, tiles_m, BN);
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
             mbar_wait(tfull + as, aph);
             tcgen05_fence_after();
-            const int row0 = mb * BM + q * 32;
-            const bool add_bias = p.bias != nullptr && ks == 0;
+            const int row0 = u.a0 + q * 32;           // (non-grouped TMA-store path only: global row of this warp's first row)
+            const int rl0 = q * 32;                   // first tile-local row of this warp
+            const bool add_bias = p.bias != nullptr && u.ks == 0;
+            const float* biasp = p.bias ? p.bias + u.bias_off : nullptr;
+            float* Ct = p.C + u.c_off;
+            const int* rmap = p.rowmap ? p.rowmap + u.map0 : nullptr;
             int last_c = half;
             while (last_c + 2 < nchunks) last_c += 2;
             if (half >= nchunks) {                 // nothing to read for this warp: release the stage immediately
@@ -289,14 +333,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty + as);   // this warp no longer needs the TMEM stage
                 }
-                const int colbase = nb * BN + c * 32;
-                const int cvalid = min(32, min(BN - c * 32, p.N - colbase));   // valid columns of this chunk
+                const int colbase = u.b0 + c * 32;            // (TMA-store path: global column)
+                const int cl0 = c * 32;                       // tile-local column of this chunk
+                const int cvalid = min(32, u.n_valid - cl0);  // valid columns of this chunk (may be <= 0)
                 if constexpr (TMA_STORE) {
                     // chunks that lie fully inside the N tile (TMA clips at the matrix edge, not at the tile edge)
                     if (!atomic && BN - c * 32 >= 32) {
                         if (lane == 0) tma_store_wait_read();          // the previous store has finished reading `st`
                         __syncwarp();
-                        const float bl = (add_bias && lane < cvalid) ? p.bias[colbase + lane] : 0.f;
+                        const float bl = (add_bias && lane < cvalid) ? biasp[cl0 + lane] : 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {                 // lane = row: it needs the bias of all 32 columns
                             float v = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
@@ -329,20 +374,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     const int cl = (lane & 7) * 4;             // 4 consecutive columns per lane, 8 lanes per row
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (add_bias) {
-                        if (cl + 0 < cvalid) bv.x = p.bias[colbase + cl + 0];
-                        if (cl + 1 < cvalid) bv.y = p.bias[colbase + cl + 1];
-                        if (cl + 2 < cvalid) bv.z = p.bias[colbase + cl + 2];
-                        if (cl + 3 < cvalid) bv.w = p.bias[colbase + cl + 3];
+                        if (cl + 0 < cvalid) bv.x = biasp[cl0 + cl + 0];
+                        if (cl + 1 < cvalid) bv.y = biasp[cl0 + cl + 1];
+                        if (cl + 2 < cvalid) bv.z = biasp[cl0 + cl + 2];
+                        if (cl + 3 < cvalid) bv.w = biasp[cl0 + cl + 3];
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int rr = (lane >> 3) + 4 * i;
-                        const int row = row0 + rr;
+                        const int rl = rl0 + rr;
                         float4 v = *reinterpret_cast<const float4*>(st + rr * STG_STRIDE + (((lane & 7) ^ (rr & 7)) << 2));
                         v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                         if (p.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                        if (row < p.M) {
-                            float* o = p.C + (long)row * p.ldc + colbase + cl;
+                        long orow = rl;
+                        if (rmap && rl < u.m_valid) orow = rmap[rl];
+                        if (rl < u.m_valid && orow >= 0) {
+                            float* o = Ct + orow * p.ldc + cl0 + cl;
                             if (cl + 3 < cvalid) {
                                 *reinterpret_cast<float4*>(o) = v;
                             } else {
@@ -354,13 +401,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     }
                 } else {
                     const bool colok = lane < cvalid;
-                    const float bv = (add_bias && colok) ? p.bias[colbase + lane] : 0.f;
+                    const float bv = (add_bias && colok) ? biasp[cl0 + lane] : 0.f;
 #pragma unroll 8
                     for (int rr = 0; rr < 32; ++rr) {
-                        const int row = row0 + rr;
-                        if (row < p.M && colok) {
+                        const int rl = rl0 + rr;
+                        long orow = rl;
+                        if (rmap && rl < u.m_valid) orow = rmap[rl];
+                        if (rl < u.m_valid && orow >= 0 && colok) {
                             float v = st[rr * STG_STRIDE + ((((lane >> 2) ^ (rr & 7)) << 2) | (lane & 3))] + bv;
-                            float* o = p.C + (long)row * p.ldc + colbase + lane;
+                            float* o = Ct + orow * p.ldc + cl0 + lane;
                             if (atomic) {
                                 atomicAdd(o, v);
                             } else {

@@ -38,6 +38,51 @@ def _inputs(seed, dims=FULL):
     return g, feats, caps
 
 
+class _our_relu_decisions:
+    """ReLU is not differentiable at 0, and feature_fc's hidden pre-activation z = W1 x + b1 (K = 2048) has, among the
+    B*P*F = 5 M samples of a full-size batch, a few dozen within rounding distance of the kink.  Two correct fp32
+    implementations then disagree on d relu/dz for those samples, and each such sample moves one row of dW1 by
+    |dz| * |x| -- percent-level against max|dW1| (measured 8e-3 at B=512, against 1e-5 for every other gradient; the
+    forward is continuous there, so logits and loss are unaffected).  The parity test therefore runs the oracle WITH OUR
+    ReLU decisions (mask = f1 > 0 from our kernel) -- after checking that they differ from the oracle's own only where
+    |z_ref| is within 1e-4 of the scale of z, i.e. only at genuine near-ties -- and then holds every row of dW1 to the
+    same 1e-3 as all other gradients."""
+
+    def __init__(self, m, p, feats):
+        from hypernet_image_captioning_b200 import ops
+        B, P, D = feats.shape
+        fc0 = m.captioner.feature_fc[0]
+        with torch.no_grad():
+            f1 = ops.linear(feats.cuda().reshape(B * P, D), fc0.weight.detach(), fc0.bias.detach(), relu=True)
+            z_ref = torch.nn.functional.linear(feats.reshape(B * P, D), p["captioner.feature_fc.0.weight"],
+                                               p["captioner.feature_fc.0.bias"])
+        self.mask = (f1 > 0).cpu()
+        mism = (z_ref > 0) != self.mask
+        scale = z_ref.abs().max().item()
+        worst = z_ref[mism].abs().max().item() / scale if mism.any() else 0.0
+        print(f"[relu] {int(mism.sum())} of {mism.numel()} ReLU decisions differ from the oracle's; largest |z_ref| among "
+              f"them {worst:.2e} of scale")
+        assert worst < 1e-4, "a ReLU decision differs where the oracle's pre-activation is NOT a near-tie"
+        assert mism.sum().item() <= 2e-4 * mism.numel()
+        self.shape3 = (B, P, f1.shape[1])
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self._relu = F.relu
+        mask, shape3 = self.mask, self.shape3
+
+        def relu(x, inplace=False):
+            if x.numel() == mask.numel():
+                return x * mask.view_as(x).to(x.dtype)
+            return self._relu(x, inplace)
+        F.relu = relu
+        return self
+
+    def __exit__(self, *exc):
+        import torch.nn.functional as F
+        F.relu = self._relu
+
+
 def _check_grads(m, pl, skip_prefix="captioner.gru."):
     worst, worst_k = 0.0, None
     for k, v in m.named_parameters():
@@ -84,10 +129,11 @@ def test_attention_full_size_baseline_config2_matches_oracle():
     g, feats, caps = _inputs(21)
     style = p["captioner.embed.weight"][4:5].clone()             # 'factual' row (hypernet_attention.py:139-142)
     pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-    logits_ref, att_ref, _, _ = O.path_attention(pl, style, feats, caps, 0.0, np.random.RandomState(0), flow=True)
-    loss_ref = O.caption_loss(logits_ref, caps, 0)
-    loss_ref.backward()
     m = _model(p, False, 10)
+    with _our_relu_decisions(m, p, feats):
+        logits_ref, att_ref, _, _ = O.path_attention(pl, style, feats, caps, 0.0, np.random.RandomState(0), flow=True)
+        loss_ref = O.caption_loss(logits_ref, caps, 0)
+        loss_ref.backward()
     fd, cd = feats.cuda(), caps.cuda()
     captioner = m.forward(style.cuda())
     np.random.seed(0)
@@ -132,11 +178,12 @@ def test_cc_onehot_full_size_config3_matches_oracle(he, B):
     style = torch.zeros(he)
     style[he // 3] = 1.0                                          # torch.tensor(self.embed[domain]).float(): 1-D [he]
     pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-    logits_ref, att_ref, _, _ = O.path_attention(pl, style, feats, caps, 0.0, np.random.RandomState(0), flow=True)
-    loss_ref = O.caption_loss(logits_ref, caps, 0)
-    loss_ref.backward()
     m = _model(p, True, he, d)
     assert m.hn_base[0].in_features == he and m.hn_heads[0][0].in_features == he
+    with _our_relu_decisions(m, p, feats):
+        logits_ref, att_ref, _, _ = O.path_attention(pl, style, feats, caps, 0.0, np.random.RandomState(0), flow=True)
+        loss_ref = O.caption_loss(logits_ref, caps, 0)
+        loss_ref.backward()
     captioner = m.forward(style.cuda())
     np.random.seed(0)
     loss, logits, att = captioner.forward_loss(feats.cuda(), caps.cuda(), 0.0, ignore_index=0)
@@ -148,15 +195,24 @@ def test_cc_onehot_full_size_config3_matches_oracle(he, B):
     print(f"[configs[3] he={he}] logits {rel_err(logits, logits_ref):.2e} worst grad {worst:.2e} ({wk})")
 
 
-def _grouped_oracle(pl, styles, groups, feats, caps):
+def _grouped_oracle(pl, styles, groups, feats, caps, relu_mask=None):
     """One reference-semantics call per style group (train_cc.py:90-123 calls the hypernet once per sample's style);
-    rows concatenated back in batch order; loss = CE over the concatenation (SURVEY 8(c) grouped oracle)."""
+    rows concatenated back in batch order; loss = CE over the concatenation (SURVEY 8(c) grouped oracle).
+    ``relu_mask`` [B,P,F]: our ReLU decisions for feature_fc's hidden layer (see _our_relu_decisions)."""
+    import torch.nn.functional as F
     rows = []
+    real_relu = F.relu
     for gi in range(styles.shape[0]):
         idx = (groups == gi).nonzero().squeeze(1)
         if idx.numel() == 0:
             continue
-        lg, at, _, _ = O.path_attention(pl, styles[gi], feats[idx], caps[idx], 0.0, np.random.RandomState(0))
+        if relu_mask is not None:
+            mk = relu_mask[idx]
+            F.relu = lambda x, inplace=False, mk=mk: x * mk.to(x.dtype) if x.shape == mk.shape else real_relu(x, inplace)
+        try:
+            lg, at, _, _ = O.path_attention(pl, styles[gi], feats[idx], caps[idx], 0.0, np.random.RandomState(0))
+        finally:
+            F.relu = real_relu
         rows.append((idx, lg, at))
     inv = torch.argsort(torch.cat([i for i, _, _ in rows]))
     return torch.cat([lg for _, lg, _ in rows], 0)[inv], torch.cat([at for _, _, at in rows], 0)[inv]
@@ -174,10 +230,11 @@ def test_grouped_full_size_matches_per_group_oracle(G, he):
     groups = torch.arange(d["B"]) % G
     groups = groups[torch.randperm(d["B"], generator=g)]          # unsorted on purpose
     pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-    logits_ref, att_ref = _grouped_oracle(pl, styles, groups, feats, caps)
+    m = _model(p, True, he)
+    z_mask = _our_relu_decisions(m, p, feats)
+    logits_ref, att_ref = _grouped_oracle(pl, styles, groups, feats, caps, z_mask.mask.view(d["B"], d["P"], -1))
     loss_ref = O.caption_loss(logits_ref, caps, 0)
     loss_ref.backward()
-    m = _model(p, True, he)
     captioner = m.forward_grouped(styles.cuda())
     np.random.seed(0)
     logits, att = captioner(feats.cuda(), caps.cuda(), 0.0, groups=groups.cuda())
@@ -203,10 +260,11 @@ def test_step_split_backward_matches_oracle_autograd(B, T, ext):
     style = torch.randn(1, d["E"], generator=g)
     watt = torch.randn(B, T, d["P"], generator=g) * 0.2
     pl = {k: v.clone().requires_grad_(True) for k, v in p.items()}
-    logits_ref, att_ref, _, _ = O.path_attention(pl, style, feats, caps, 0.0, np.random.RandomState(0), flow=True)
-    loss_ref = O.caption_loss(logits_ref, caps, 0) + ((att_ref * watt).sum() if ext else 0.0)
-    loss_ref.backward()
     m = _model(p, False, 10, d)
+    with _our_relu_decisions(m, p, feats):
+        logits_ref, att_ref, _, _ = O.path_attention(pl, style, feats, caps, 0.0, np.random.RandomState(0), flow=True)
+        loss_ref = O.caption_loss(logits_ref, caps, 0) + ((att_ref * watt).sum() if ext else 0.0)
+        loss_ref.backward()
     np.random.seed(0)
     logits, att = m.forward(style.cuda())(feats.cuda(), caps.cuda(), 0.0)
     loss = C.cross_entropy(logits, caps.cuda(), 0) + ((att * watt.cuda()).sum() if ext else 0.0)
