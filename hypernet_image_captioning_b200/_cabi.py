@@ -58,6 +58,16 @@ SIGNATURES = {
     "caphn_attstep_bwd_pack": [P, P, P, I, I, I, P, P],
     "caphn_attstep_bwd": [P] * 22 + [I] * 5 + [P],
     "caphn_attn_df": [P, P, P, I, I, I, I, P],
+    "caphn_gemm_tc_grouped": [P, P, L, L, L, I, P, P, L, L, L, I, P, L, P, P, P, I, I, P],
+    "caphn_split_bf16_gather": [P, L, P, L, I, P, P, L, P],
+    "caphn_split_bf16_batched": [P, L, L, I, I, I, P, P, L, P],
+    "caphn_group_colsum": [P, L, P, I, I, I, I, P, L, P],
+    "caphn_leaky_relu": [P, L, F, P],
+    "caphn_leaky_relu_bwd": [P, P, L, F, P],
+    "caphn_attstep_pack_grouped": [P, P, P, I, I, I, I, L, P, P],
+    "caphn_attstep_fwd_grouped": [P] * 13 + [L] + [P] * 5 + [I] * 8 + [P, I, P],
+    "caphn_attstep_bwd_pack_grouped": [P, P, P, I, I, I, I, L, P, P],
+    "caphn_attstep_bwd_grouped": [P] * 22 + [I] * 5 + [P, I, P],
     "caphn_mean_pos": [P, I, I, I, P, P],
     "caphn_mean_pos_bwd": [P, P, I, I, I, P, P],
     "caphn_relu_mask": [P, P, L, P],

@@ -27,12 +27,17 @@ namespace caphn {
 //   out[((m * NKT + kt) * 2 + hl) * 32 + lane],   src 0: W_ih[:, E:E+F] (input ctx), src 1: W_hh (input h); after the
 //   6 * NUT gate tiles come NUT tiles of U_a (input h)
 // ------------------------------------------------------------------------------------------------------------------
+// blockIdx.y = style group g: the generated W_ih / W_hh of group g start gstride floats after those of group g - 1 (rows
+// of Theta [G, theta]); U_a is shared.  Pack g starts pstride uint4 after pack g - 1.
 __global__ void attstep_pack_kernel(const float* __restrict__ Wih, const float* __restrict__ Whh,
                                     const float* __restrict__ Ua, int E, int F, int H, int NUT, int NKT,
-                                    uint4* __restrict__ out) {
+                                    uint4* __restrict__ out, long gstride, long pstride) {
     const long total = (long)7 * NUT * NKT * 32;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
+    Wih += (long)blockIdx.y * gstride;
+    Whh += (long)blockIdx.y * gstride;
+    out += (long)blockIdx.y * pstride;
     const int lane = (int)(idx & 31);
     long r = idx >> 5;
     const int kt = (int)(r % NKT);
@@ -349,6 +354,10 @@ struct AttStepY {
     float* Hbm;          // [B,T,H] or null
     float* R; float* Z; float* Nn; float* GHN;   // [B,H] of step t, or null
     int B, T, t, H, NUT, NKT, KP;
+    // many-style batch (rows sorted by style group): tile blockIdx.y covers rows [tiles[y].x, +tiles[y].y) of group
+    // tiles[y].z, whose weight pack / b_hh start pstride uint4 / 3H floats after the previous group's.  null: one group.
+    const int4* tiles;
+    long pstride;
 };
 
 __global__ void __launch_bounds__(YS_THREADS, 1) attstep_gates_kernel(const AttStepY a) {
@@ -361,19 +370,20 @@ __global__ void __launch_bounds__(YS_THREADS, 1) attstep_gates_kernel(const AttS
     float* bhs = hps + YS_NB * 16;                                // [3][16]      b_hh tile
     uint64_t* mbar = reinterpret_cast<uint64_t*>(bhs + 48);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ut = blockIdx.x, r0 = blockIdx.y * YS_NB;
+    const int ut = blockIdx.x;
+    int r0 = blockIdx.y * YS_NB, rows_valid = min(YS_NB, B - r0), grp = 0;
+    if (a.tiles) { const int4 tl = a.tiles[blockIdx.y]; r0 = tl.x; rows_valid = tl.y; grp = tl.z; }
     if (tid == 0) st_mbar_init(mbar, 1);
     if (tid < 48) {
         const int j = ut * 16 + (tid & 15);
-        bhs[tid] = j < H ? a.bhh[(tid >> 4) * H + j] : 0.f;
+        bhs[tid] = j < H ? a.bhh[(long)grp * H3 + (tid >> 4) * H + j] : 0.f;
     }
-    const int rows_valid = min(YS_NB, B - r0);
     const int src = warp / 3;                         // warp tile: gate (warp % 3) of W_ih[:,E:] (src 0) / W_hh (src 1)
     XTS(16);
     // loop-invariant inputs first (they do not depend on the previous kernels): weight fragments, GIw tile
     uint4 ah[ST_MAXKT], al[ST_MAXKT];
     {
-        const uint4* wp = a.Wp + (((long)warp * a.NUT + ut) * NKT) * 64 + lane;
+        const uint4* wp = a.Wp + (long)grp * a.pstride + (((long)warp * a.NUT + ut) * NKT) * 64 + lane;
 #pragma unroll
         for (int kt = 0; kt < ST_MAXKT; ++kt)
             if (kt < NKT) { ah[kt] = st_ldg_u4(wp + (long)kt * 64); al[kt] = st_ldg_u4(wp + (long)kt * 64 + 32); }
@@ -506,7 +516,19 @@ int caphn_attstep_pack(const float* Wih, const float* Whh, const float* Ua, int 
     const int NUT = (H + 15) / 16, NKT = ((H > F ? H : F) + 15) / 16;
     const long total = (long)7 * NUT * NKT * 32;
     attstep_pack_kernel<<<(unsigned)ceil_div(total, 256L), 256, 0, (cudaStream_t)stream>>>(Wih, Whh, Ua, E, F, H, NUT, NKT,
-                                                                                         (uint4*)pack);
+                                                                                         (uint4*)pack, 0, 0);
+    CAPHN_RETURN_LAST();
+}
+
+// Many-style batch: one pack per style group.  Wih / Whh point at group 0's generated weights inside Theta [G, theta];
+// group g's start gstride floats later (gstride = theta).  pack holds G packs of caphn_attstep_pack_size bytes each.
+int caphn_attstep_pack_grouped(const float* Wih, const float* Whh, const float* Ua, int E, int F, int H, int G,
+                               long gstride, void* pack, void* stream) {
+    if (pack_elems(H, F) == 0 || E < 0 || G < 1 || !pack || ((uintptr_t)pack & 15)) return CAPHN_EINVAL;
+    const int NUT = (H + 15) / 16, NKT = ((H > F ? H : F) + 15) / 16;
+    const long total = (long)7 * NUT * NKT * 32;
+    attstep_pack_kernel<<<dim3((unsigned)ceil_div(total, 256L), G), 256, 0, (cudaStream_t)stream>>>(
+        Wih, Whh, Ua, E, F, H, NUT, NKT, (uint4*)pack, gstride, pack_elems(H, F));
     CAPHN_RETURN_LAST();
 }
 
@@ -514,10 +536,11 @@ int caphn_attstep_pack(const float* Wih, const float* Whh, const float* Ua, int 
 // holds h_{t0-1}); pack from caphn_attstep_pack, work a scratch buffer of *work_bytes (256-byte aligned).
 // resume != 0: the workspace still holds the operand rows of Hall[t0] written by the previous call (which ran up to step
 // t0 on the same buffers), so the initial conversion is skipped -- the one-step-per-call decode pattern.
-int caphn_attstep_fwd(const float* Kp, const float* f, const float* GIw, const float* bu, const float* va,
-                      const float* bv, const void* pack, void* work, const float* bhh, float* Hall, float* Hbm,
-                      float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z, float* Nn, float* GHN, int B,
-                      int T, int P, int H, int F, int t0, int t1, int resume, void* stream) {
+static int attstep_fwd_impl(const float* Kp, const float* f, const float* GIw, const float* bu, const float* va,
+                            const float* bv, const void* pack, void* work, const float* bhh, float* Hall, float* Hbm,
+                            float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z, float* Nn, float* GHN,
+                            int B, int T, int P, int H, int F, int t0, int t1, int resume, const int* tiles, int ntiles,
+                            void* stream) {
     long pb = 0, wb = 0;
     if (B <= 0 || T <= 0 || caphn_attstep_pack_size(H, F, P, B, &pb, &wb) != CAPHN_OK || pb == 0 || t0 < 0 || t1 > T ||
         t0 >= t1 || ((uintptr_t)pack & 15) || !work || ((uintptr_t)work & 255) || ((uintptr_t)Kp & 15) ||
@@ -562,11 +585,34 @@ int caphn_attstep_fwd(const float* Kp, const float* f, const float* GIw, const f
         ++caphn_launch_counter;
         AttStepY y{csp, hbuf(t), hbuf(t + 1), Hall + t * BH, GIw + (long)t * B * 3 * H, (const uint4*)pack, bhh,
                    Hall + (t + 1) * BH, Hbm, R ? R + t * BH : nullptr, Z ? Z + t * BH : nullptr,
-                   Nn ? Nn + t * BH : nullptr, GHN ? GHN + t * BH : nullptr, B, T, t, H, NUT, NKT, KP};
-        CAPHN_CHECK(launch_pdl(attstep_gates_kernel, dim3(NUT, ceil_div(B, YS_NB)), dim3(YS_THREADS), ysmem, st, pdl, y));
+                   Nn ? Nn + t * BH : nullptr, GHN ? GHN + t * BH : nullptr, B, T, t, H, NUT, NKT, KP,
+                   (const int4*)tiles, pack_elems(H, F)};
+        CAPHN_CHECK(launch_pdl(attstep_gates_kernel, dim3(NUT, tiles ? ntiles : ceil_div(B, YS_NB)), dim3(YS_THREADS), ysmem,
+                               st, pdl, y));
         ++caphn_launch_counter;
     }
     return (int)cudaGetLastError();
+}
+
+int caphn_attstep_fwd(const float* Kp, const float* f, const float* GIw, const float* bu, const float* va,
+                      const float* bv, const void* pack, void* work, const float* bhh, float* Hall, float* Hbm,
+                      float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z, float* Nn, float* GHN, int B,
+                      int T, int P, int H, int F, int t0, int t1, int resume, void* stream) {
+    return attstep_fwd_impl(Kp, f, GIw, bu, va, bv, pack, work, bhh, Hall, Hbm, attn, ctx, ldctx, Upre, R, Z, Nn, GHN, B, T,
+                            P, H, F, t0, t1, resume, nullptr, 0, stream);
+}
+
+// Many-style batch: rows sorted by style group; `tiles` = ntiles records {first row, rows (<= 64), group, 0} that never
+// straddle a group; `pack` = the G packs of caphn_attstep_pack_grouped, bhh = [G, 3H].  The U and attention kernels use
+// no generated weights and run exactly as in the single-group call (U_a is read from group 0's pack).
+int caphn_attstep_fwd_grouped(const float* Kp, const float* f, const float* GIw, const float* bu, const float* va,
+                              const float* bv, const void* pack, void* work, const float* bhh, float* Hall, float* Hbm,
+                              float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z, float* Nn, float* GHN,
+                              int B, int T, int P, int H, int F, int t0, int t1, int resume, const int* tiles, int ntiles,
+                              void* stream) {
+    if (!tiles || ntiles < 1 || ((uintptr_t)tiles & 15)) return CAPHN_EINVAL;
+    return attstep_fwd_impl(Kp, f, GIw, bu, va, bv, pack, work, bhh, Hall, Hbm, attn, ctx, ldctx, Upre, R, Z, Nn, GHN, B, T,
+                            P, H, F, t0, t1, resume, tiles, ntiles, stream);
 }
 
 #ifdef CAPHN_ATTCL_TIMING

@@ -26,12 +26,16 @@ namespace caphn {
 //   group 1: W_ih[:,E:]^T NFT tiles x NKT3 (rows = feature fi,   K = q over 3H)     A[fi][q] = Wih[q][E+fi]
 //   group 2: W_hh^T     NUT tiles x NKT3  (rows = unit k,        K = q over 3H)     A[k][q]  = Whh[q][k]
 // ------------------------------------------------------------------------------------------------------------------
+// blockIdx.y = style group (see attstep_pack_kernel): W_ih / W_hh advance gstride floats, the pack pstride uint4 per group.
 __global__ void attbwd_pack_kernel(const float* __restrict__ Wih, const float* __restrict__ Whh,
                                    const float* __restrict__ Ua, int E, int F, int H, int NUT, int NFT, int NKT, int NKT3,
-                                   uint4* __restrict__ out) {
+                                   uint4* __restrict__ out, long gstride, long pstride) {
     const long n0 = (long)NUT * NKT, n1 = (long)NFT * NKT3, n2 = (long)NUT * NKT3;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (n0 + n1 + n2) * 32) return;
+    Wih += (long)blockIdx.y * gstride;
+    Whh += (long)blockIdx.y * gstride;
+    out += (long)blockIdx.y * pstride;
     const int lane = (int)(idx & 31);
     const long r = idx >> 5;
     int grp, tile, kt;
@@ -194,6 +198,10 @@ struct BwdG2 {
     float* dctx;                 // [B,F] of step t
     float* dhp;                  // [B,H]
     int B, H, F, NUT, NFT, NKT3, KP3, NG1;   // NG1 = number of dctx tile groups (blockIdx.x < NG1)
+    // many-style batch: row tile blockIdx.y = rows [tiles[y].x, +tiles[y].y) of style group tiles[y].z, whose transposed-weight
+    // pack starts pstride uint4 after the previous group's.  null: one group, tiles of G2_NB consecutive rows.
+    const int4* tiles;
+    long pstride;
 };
 
 __global__ void __launch_bounds__(G2_THREADS) attbwd_gemm_kernel(const BwdG2 a) {
@@ -206,11 +214,11 @@ __global__ void __launch_bounds__(G2_THREADS) attbwd_gemm_kernel(const BwdG2 a) 
     const bool is_ctx = (int)blockIdx.x < a.NG1;
     const int tile = (is_ctx ? blockIdx.x : blockIdx.x - a.NG1) * G2_WARPS + warp;
     const int ntiles = is_ctx ? a.NFT : a.NUT;
-    const int r0 = blockIdx.y * G2_NB;
-    const int rows_valid = min(G2_NB, B - r0);
+    int r0 = blockIdx.y * G2_NB, rows_valid = min(G2_NB, B - r0), grp = 0;
+    if (a.tiles) { const int4 tl = a.tiles[blockIdx.y]; r0 = tl.x; rows_valid = tl.y; grp = tl.z; }
     const bool has_tile = tile < ntiles;
     if (tid == 0) st_mbar_init(mbar, 1);
-    const uint4* wp = (is_ctx ? a.Wc : a.Wh) + ((long)(has_tile ? tile : 0) * NKT3) * 64 + lane;
+    const uint4* wp = (is_ctx ? a.Wc : a.Wh) + (long)grp * a.pstride + ((long)(has_tile ? tile : 0) * NKT3) * 64 + lane;
     uint4 ah[G2_PF], al[G2_PF];
 #pragma unroll
     for (int i = 0; i < G2_PF; ++i)
@@ -591,17 +599,30 @@ int caphn_attstep_bwd_pack(const float* Wih, const float* Whh, const float* Ua, 
     const int NUT = (H + 15) / 16, NFT = (F + 15) / 16, NKT = (H + 15) / 16, NKT3 = (3 * H + 15) / 16;
     const long total = ((long)NUT * NKT + (long)(NFT + NUT) * NKT3) * 32;
     attbwd_pack_kernel<<<(unsigned)ceil_div(total, 256L), 256, 0, (cudaStream_t)stream>>>(Wih, Whh, Ua, E, F, H, NUT, NFT,
-                                                                                         NKT, NKT3, (uint4*)pack);
+                                                                                         NKT, NKT3, (uint4*)pack, 0, 0);
+    CAPHN_RETURN_LAST();
+}
+
+// Many-style batch: G transposed-weight packs (each caphn_attstep_bwd_size bytes); group g's W_ih / W_hh start gstride
+// floats after group g - 1's.
+int caphn_attstep_bwd_pack_grouped(const float* Wih, const float* Whh, const float* Ua, int E, int F, int H, int G,
+                                   long gstride, void* pack, void* stream) {
+    if (H < 1 || F < 1 || H > ST_MAXKT * 16 || F > ST_MAXKT * 16 || E < 0 || G < 1 || !pack || ((uintptr_t)pack & 15))
+        return CAPHN_EINVAL;
+    const int NUT = (H + 15) / 16, NFT = (F + 15) / 16, NKT = (H + 15) / 16, NKT3 = (3 * H + 15) / 16;
+    const long per = ((long)NUT * NKT + (long)(NFT + NUT) * NKT3) * 64;
+    attbwd_pack_kernel<<<dim3((unsigned)ceil_div(per / 2, 256L), G), 256, 0, (cudaStream_t)stream>>>(
+        Wih, Whh, Ua, E, F, H, NUT, NFT, NKT, NKT3, (uint4*)pack, gstride, per);
     CAPHN_RETURN_LAST();
 }
 
 // BPTT of the attention-GRU recurrence over all T steps; same tensors and results as caphn_attgru_seq_bwd, except that
 // dK, dva, dbv need not be zero-initialised by the caller (dK is overwritten, dva / dbv are zeroed here).
-int caphn_attstep_bwd(const float* dHbm, const float* dattn, const float* Kp, const float* f, const float* attn,
-                      const float* Upre, const float* R, const float* Z, const float* Nn, const float* GHN,
-                      const float* Hall, const float* va, const void* pack, void* work, float* dGI, float* dGH,
-                      float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0, int B, int T, int P, int H,
-                      int F, void* stream) {
+static int attstep_bwd_impl(const float* dHbm, const float* dattn, const float* Kp, const float* f, const float* attn,
+                            const float* Upre, const float* R, const float* Z, const float* Nn, const float* GHN,
+                            const float* Hall, const float* va, const void* pack, void* work, float* dGI, float* dGH,
+                            float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0, int B, int T, int P,
+                            int H, int F, const int* tiles, int ntiles, void* stream) {
     if (B <= 0 || T <= 0 || bw_pack_elems(H, F, P, T) == 0 || !pack || ((uintptr_t)pack & 15) || !work ||
         ((uintptr_t)work & 255) || ((uintptr_t)Kp & 15) || ((uintptr_t)f & 15))
         return CAPHN_EINVAL;
@@ -644,8 +665,10 @@ int caphn_attstep_bwd(const float* dHbm, const float* dattn, const float* Kp, co
         CAPHN_CHECK(launch_pdl(attbwd_gate_kernel, dim3(NUT, ceil_div(B, G1_NB)), dim3(G1_THREADS), s1, st,
                                pdl && t != T - 1, g1));
         ++caphn_launch_counter;
-        BwdG2 g2{p1, p2, gisp, ghsp, dCTX + (long)t * B * F, dhp, B, H, F, NUT, NFT, NKT3, KP3, NG1};
-        CAPHN_CHECK(launch_pdl(attbwd_gemm_kernel, dim3(NG1 + NG2, ceil_div(B, G2_NB)), dim3(G2_THREADS), s2, st, pdl, g2));
+        BwdG2 g2{p1, p2, gisp, ghsp, dCTX + (long)t * B * F, dhp, B, H, F, NUT, NFT, NKT3, KP3, NG1, (const int4*)tiles,
+                 pb / 16};
+        CAPHN_CHECK(launch_pdl(attbwd_gemm_kernel, dim3(NG1 + NG2, tiles ? ntiles : ceil_div(B, G2_NB)), dim3(G2_THREADS), s2,
+                               st, pdl, g2));
         ++caphn_launch_counter;
         BwdA ba{Kp, f, va, dCTX + (long)t * B * F, attn, dattn, Upre + t * BH, dS, dU + t * BH, dusp, dbv,
                 B, T, t, P, H, F, KP, rpc, nbuf};
@@ -660,6 +683,28 @@ int caphn_attstep_bwd(const float* dHbm, const float* dattn, const float* Kp, co
     CAPHN_CHECK(launch_pdl(attbwd_dk_kernel, dim3(dgrid), dim3(BD_THREADS), sd, st, pdl, bd));
     ++caphn_launch_counter;
     return (int)cudaGetLastError();
+}
+
+int caphn_attstep_bwd(const float* dHbm, const float* dattn, const float* Kp, const float* f, const float* attn,
+                      const float* Upre, const float* R, const float* Z, const float* Nn, const float* GHN,
+                      const float* Hall, const float* va, const void* pack, void* work, float* dGI, float* dGH,
+                      float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0, int B, int T, int P, int H,
+                      int F, void* stream) {
+    return attstep_bwd_impl(dHbm, dattn, Kp, f, attn, Upre, R, Z, Nn, GHN, Hall, va, pack, work, dGI, dGH, dU, dCTX, dK, dva,
+                            dbv, dh0, B, T, P, H, F, nullptr, 0, stream);
+}
+
+// Many-style batch (rows sorted by style group): `tiles` = ntiles records {first row, rows (<= 32), group, 0} for the
+// transposed-weight GEMM kernel (the only backward kernel that reads generated weights); pack = the G packs of
+// caphn_attstep_bwd_pack_grouped (U_a^T is read from group 0's).
+int caphn_attstep_bwd_grouped(const float* dHbm, const float* dattn, const float* Kp, const float* f, const float* attn,
+                              const float* Upre, const float* R, const float* Z, const float* Nn, const float* GHN,
+                              const float* Hall, const float* va, const void* pack, void* work, float* dGI, float* dGH,
+                              float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0, int B, int T, int P,
+                              int H, int F, const int* tiles, int ntiles, void* stream) {
+    if (!tiles || ntiles < 1 || ((uintptr_t)tiles & 15)) return CAPHN_EINVAL;
+    return attstep_bwd_impl(dHbm, dattn, Kp, f, attn, Upre, R, Z, Nn, GHN, Hall, va, pack, work, dGI, dGH, dU, dCTX, dK, dva,
+                            dbv, dh0, B, T, P, H, F, tiles, ntiles, stream);
 }
 
 }  // extern "C"

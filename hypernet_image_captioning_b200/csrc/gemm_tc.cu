@@ -134,7 +134,8 @@ constexpr size_t SMEM_BUDGET = 227 * 1024;
 struct GUnit {
     int a_row;      // first operand row of the A tile (K-major: row index; MN-major: MN column)
     int b_row;      // same for B
-    int k0;         // first k index (multiple of 64): column offset (K-major) / row offset (MN-major)
+    int ka0;        // first k index of the A operand: column offset (K-major) / row offset (MN-major)
+    int kb0;        // first k index of the B operand (the two operands may keep a group's K range at different places)
     int nkb;        // 64-wide k blocks to accumulate (>= 1)
     int m_valid;    // rows of the tile that exist (1..128)
     int n_valid;    // columns of the tile that exist (1..BN)
@@ -142,10 +143,11 @@ struct GUnit {
     int map0;       // rowmap != NULL: tile row r is written to C row rowmap[map0 + r] (skipped when negative)
     unsigned c_lo;  // element offset of the tile's (0, 0) inside C (rowmap: column offset only), low / high word
     int c_hi;
+    int pad;        // 12 words = 48 bytes per record
 };
 
 struct UnitInfo {
-    int a0, b0, kb0, nkb, m_valid, n_valid, bias_off, map0, ks;
+    int a0, b0, ka0, kb0, nkb, m_valid, n_valid, bias_off, map0, ks;   // ka0 / kb0 in elements
     long c_off;
 };
 
@@ -167,13 +169,14 @@ __device__ __forceinline__ UnitInfo decode_unit(const TcParams& p, int unit, int
     UnitInfo u;
     if (p.units) {
         const GUnit g = p.units[unit];
-        u.a0 = g.a_row; u.b0 = g.b_row; u.kb0 = g.k0 / BK; u.nkb = g.nkb; u.m_valid = g.m_valid; u.n_valid = g.n_valid;
+        u.a0 = g.a_row; u.b0 = g.b_row; u.ka0 = g.ka0; u.kb0 = g.kb0; u.nkb = g.nkb; u.m_valid = g.m_valid; u.n_valid = g.n_valid;
         u.bias_off = g.bias_off; u.map0 = g.map0; u.ks = 0;
         u.c_off = ((long)g.c_hi << 32) | (long)g.c_lo;
     } else {
         const int ks = unit % p.splitk, tile = unit / p.splitk;
         const int mb = tile % tiles_m, nb = tile / tiles_m;
-        u.a0 = mb * BM; u.b0 = nb * BN; u.kb0 = ks * p.kb_per; u.nkb = min(p.num_kb, u.kb0 + p.kb_per) - u.kb0;
+        const int kblk0 = ks * p.kb_per;
+        u.a0 = mb * BM; u.b0 = nb * BN; u.ka0 = u.kb0 = kblk0 * BK; u.nkb = min(p.num_kb, kblk0 + p.kb_per) - kblk0;
         u.m_valid = min(BM, p.M - mb * BM); u.n_valid = min(BN, p.N - nb * BN);
         u.bias_off = nb * BN; u.map0 = 0; u.ks = ks;
         u.c_off = (long)mb * BM * p.ldc + (long)nb * BN;
@@ -230,28 +233,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             uint32_t phase = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
                 const UnitInfo u = decode_unit(p, unit, tiles_m, BN);
-                const int kb0 = u.kb0, kb1 = u.kb0 + u.nkb;
-                for (int kb = kb0; kb < kb1; ++kb) {
+                for (int i = 0; i < u.nkb; ++i) {
+                    const int ka = u.ka0 + i * BK, kbk = u.kb0 + i * BK;
                     mbar_wait(empty + stage, phase ^ 1);
                     mbar_expect_tx(full + stage, (uint32_t)p.stage_bytes);
                     uint8_t* st = tiles + (size_t)stage * p.stage_bytes;
                     // K-major operand: one box [64 k x rows].  MN-major operand: boxes of [64 mn x 64 k] (8 KiB each).
                     if (!p.a_mn) {
-                        tma_load_2d(st + offAh, &tmAh, full + stage, kb * BK, u.a0);
-                        if (SPLIT) tma_load_2d(st + offAl, &tmAl, full + stage, kb * BK, u.a0);
+                        tma_load_2d(st + offAh, &tmAh, full + stage, ka, u.a0);
+                        if (SPLIT) tma_load_2d(st + offAl, &tmAl, full + stage, ka, u.a0);
                     } else {
                         for (int h = 0; h < BM / 64; ++h) {
-                            tma_load_2d(st + offAh + h * 8192, &tmAh, full + stage, u.a0 + h * 64, kb * BK);
-                            if (SPLIT) tma_load_2d(st + offAl + h * 8192, &tmAl, full + stage, u.a0 + h * 64, kb * BK);
+                            tma_load_2d(st + offAh + h * 8192, &tmAh, full + stage, u.a0 + h * 64, ka);
+                            if (SPLIT) tma_load_2d(st + offAl + h * 8192, &tmAl, full + stage, u.a0 + h * 64, ka);
                         }
                     }
                     if (!p.b_mn) {
-                        tma_load_2d(st + offBh, &tmBh, full + stage, kb * BK, u.b0);
-                        if (SPLIT) tma_load_2d(st + offBl, &tmBl, full + stage, kb * BK, u.b0);
+                        tma_load_2d(st + offBh, &tmBh, full + stage, kbk, u.b0);
+                        if (SPLIT) tma_load_2d(st + offBl, &tmBl, full + stage, kbk, u.b0);
                     } else {
                         for (int h = 0; h < BN / 64; ++h) {
-                            tma_load_2d(st + offBh + h * 8192, &tmBh, full + stage, u.b0 + h * 64, kb * BK);
-                            if (SPLIT) tma_load_2d(st + offBl + h * 8192, &tmBl, full + stage, u.b0 + h * 64, kb * BK);
+                            tma_load_2d(st + offBh + h * 8192, &tmBh, full + stage, u.b0 + h * 64, kbk);
+                            if (SPLIT) tma_load_2d(st + offBl + h * 8192, &tmBl, full + stage, u.b0 + h * 64, kbk);
                         }
                     }
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -269,7 +272,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             int it = 0;
             for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
                 const UnitInfo u = decode_unit(p, unit, tiles_m, BN);
-                const int kb0 = u.kb0, kb1 = u.kb0 + u.nkb;
+                const int kb0 = 0, kb1 = u.nkb;
                 const int as = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
                 mbar_wait(tempty + as, aph ^ 1);
@@ -370,7 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                         make_float4(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1]),
                                     __uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3]));
                 __syncwarp();
-                if (vec) {
+                if (vec && ((u.c_off & 3) == 0)) {
                     const int cl = (lane & 7) * 4;             // 4 consecutive columns per lane, 8 lanes per row
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (add_bias) {
@@ -661,6 +664,56 @@ int caphn_gemm_tc_ex(const void* Ahi, const void* Alo, long a_ld, int a_mn, cons
     } else if (tma_store) {
         CAPHN_CHECK(cudaFuncSetAttribute(tc::gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc::gemm_tc_kernel<false, true><<<grid, tc::THREADS_V2, smem, st>>>(mAh, mAl, mBh, mBl, mC, p);
+    } else {
+        CAPHN_CHECK(cudaFuncSetAttribute(tc::gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::gemm_tc_kernel<false><<<grid, tc::THREADS_V2, smem, st>>>(mAh, mAl, mBh, mBl, mC, p);
+    }
+    CAPHN_RETURN_LAST();
+}
+
+// Grouped product (the per-style grouped GEMM of BASELINE.json's north star): `num_units` output tiles, each described by
+// one GUnit record (12 int32 words = 48 bytes, see struct GUnit): which A rows / B rows / K range it multiplies and where it writes.
+// Operands are 2-D bf16 arrays (hi, optional lo) with `*_inner` contiguous elements per row, `*_outer` rows and row pitch
+// `*_ld`: K-major (x_mn = 0: inner = K, outer = operand rows) or MN-major (x_mn = 1: inner = operand rows, outer = K).
+// A tile reads 128 A rows and BN B rows starting at the unit's a_row / b_row (rows beyond m_valid / n_valid are read --
+// TMA zero-fills past the array -- but never written), accumulates nkb 64-wide k blocks from ka0 (in A) and kb0 (in B) (the caller pads each
+// group's K range to a multiple of 64 with zero rows/columns in at least one operand) and writes C + c_off (+ bias), or,
+// with `rowmap`, row r of the tile to C row rowmap[map0 + r] (negative = skip).  BN: multiple of 16 (64 for MN-major B).
+int caphn_gemm_tc_grouped(const void* Ahi, const void* Alo, long a_inner, long a_outer, long a_ld, int a_mn,
+                          const void* Bhi, const void* Blo, long b_inner, long b_outer, long b_ld, int b_mn, float* C,
+                          long ldc, const float* bias, const int* rowmap, const void* units, int num_units, int BN,
+                          void* stream) {
+    if (num_units <= 0 || !units || !Ahi || !Bhi || ((Alo == nullptr) != (Blo == nullptr))) return CAPHN_EINVAL;
+    if (((uintptr_t)Ahi & 15) || ((uintptr_t)Bhi & 15) || ((uintptr_t)Alo & 15) || ((uintptr_t)Blo & 15) || (a_ld & 7) ||
+        (b_ld & 7) || ((uintptr_t)units & 3))
+        return CAPHN_EINVAL;
+    if (BN < 16 || BN > 256 || (BN % (b_mn ? 64 : 16)) != 0) return CAPHN_EINVAL;
+    const bool split = Alo != nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    tc::TcParams p{};
+    p.C = C; p.ldc = ldc; p.bias = bias; p.units = (const tc::GUnit*)units; p.rowmap = rowmap; p.num_units = num_units;
+    p.M = 0; p.N = 0; p.relu = 0; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0; p.num_kb = 0; p.BN = BN;
+    p.splitk = 1; p.kb_per = 0;
+    p.b_bytes = p.BN * tc::BK * 2;
+    p.stage_bytes = (split ? 2 : 1) * (tc::TILE_BYTES + p.b_bytes);
+    const size_t fixed = (size_t)tc::STG_FLOATS_V2 * 4 + (2 * tc::MAX_STAGES + 4) * 8 + 16 + 1024;
+    int stages = (int)((tc::SMEM_BUDGET - fixed) / p.stage_bytes);
+    if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
+    if (stages < 2) return CAPHN_EINVAL;
+    p.stages = stages;
+    p.tmem_cols = (2 * p.BN <= 256) ? 256u : 512u;
+    const size_t smem = (size_t)stages * p.stage_bytes + fixed;
+    CUtensorMap mAh, mAl, mBh, mBl, mC{};
+    int rc;
+    // make_map(map, base, rows = outer extent, Kp = inner extent, box rows, pitch): box = 64 inner x box rows
+    if ((rc = tc::make_map(&mAh, Ahi, a_outer, a_inner, a_mn ? 64 : tc::BM, a_ld))) return rc;
+    if ((rc = tc::make_map(&mAl, split ? Alo : Ahi, a_outer, a_inner, a_mn ? 64 : tc::BM, a_ld))) return rc;
+    if ((rc = tc::make_map(&mBh, Bhi, b_outer, b_inner, b_mn ? 64 : p.BN, b_ld))) return rc;
+    if ((rc = tc::make_map(&mBl, split ? Blo : Bhi, b_outer, b_inner, b_mn ? 64 : p.BN, b_ld))) return rc;
+    const int grid = num_units < kNumSMs ? num_units : kNumSMs;
+    if (split) {
+        CAPHN_CHECK(cudaFuncSetAttribute(tc::gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::gemm_tc_kernel<true><<<grid, tc::THREADS_V2, smem, st>>>(mAh, mAl, mBh, mBl, mC, p);
     } else {
         CAPHN_CHECK(cudaFuncSetAttribute(tc::gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc::gemm_tc_kernel<false><<<grid, tc::THREADS_V2, smem, st>>>(mAh, mAl, mBh, mBl, mC, p);

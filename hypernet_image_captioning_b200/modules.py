@@ -86,6 +86,7 @@ class _HyperNetMixin:
         def run():
             theta = self.generate_theta(x)
             if grouped:
+                self.captioner._theta_groups = theta        # [G, theta]: the grouped kernels take the whole matrix
                 return [self._split_theta(theta[g]) for g in range(theta.shape[0])]
             return self._split_theta(theta[0], write_params=True)
         if self.async_hypernet and x.is_cuda and streams.enabled():
@@ -107,7 +108,13 @@ class _HyperNetMixin:
             world = parallel.world_size(self.dp_group)
             if world > 1 and x2.requires_grad:
                 x2 = parallel.ScaleGradFn.apply(x2, 1.0 / world)   # the style gradient leaves the replicated hypernet already global
-        theta = Fn.hypernet_theta(x2, _hn_params(self))
+        ps = _hn_params(self)
+        if x2.shape[0] > 8 and ps[0].dtype == torch.float32:
+            # many style vectors: the layers as dense tensor-core GEMMs (one pass over the head weights for all G)
+            from .grouped import HyperNetThetaManyFn
+            theta = HyperNetThetaManyFn.apply(x2, *ps)
+        else:
+            theta = Fn.hypernet_theta(x2, ps)
         if self.dp_enabled:
             theta = parallel.allreduce_grad(theta, self.dp_group)
         return theta
@@ -195,6 +202,7 @@ class DecoderGRU(nn.Module):
         self.embed = nn.Embedding(vocab_size, embed_size)
         self._generated = None  # per-cell (W_ih, W_hh, b_ih, b_hh) carrying the hypernet graph (flow mode)
         self._generated_groups = None  # list over style groups of the above (forward_grouped)
+        self._theta_groups = None
 
     def _cells(self, group=None):
         if group is not None:
@@ -379,6 +387,7 @@ class HyperNetPooled(_HyperNetMixin, _Base):
         gen = self._generate_and_inject(x)
         self.captioner._generated = gen if self.grad_mode == "flow" else None
         self.captioner._generated_groups = None
+        self.captioner._theta_groups = None
         return self.captioner
 
     def _split_theta(self, theta, write_params=False):

@@ -269,6 +269,7 @@ class AttentionGru(nn.Module):
         self.init_h = nn.Linear(feature_out, hidden_dim)
         self._generated = None
         self._generated_groups = None
+        self._theta_groups = None
 
     def _gru_weights(self, group=None):
         if group is not None:
@@ -290,6 +291,9 @@ class AttentionGru(nn.Module):
             use.append(bool(np.random.random() < sp))
         if groups is not None:
             streams.wait_pending()
+            if not any(use) and self._grouped_kernels_ok(features):
+                return self._forward_grouped(features, captions, groups, None)
+            # scheduled sampling / decode or a shape the step-split kernels do not cover: one call per group
             return _run_grouped(lambda g, f, c: self._forward_one(f, c, tuple(use), self._gru_weights(g)), groups,
                                 [features, captions], len(self._generated_groups))
         if any(use) and not torch.is_grad_enabled():
@@ -339,11 +343,45 @@ class AttentionGru(nn.Module):
         streams.wait_pending()                    # generated weights of an asynchronous hypernet forward
         return AttentionGruFn.apply(f3, K3, h0, captions, use, *self._recurrence_params(gru_w))
 
-    def forward_loss(self, features, captions, sample_prob=0.0, ignore_index=0):
+    def _grouped_kernels_ok(self, features):
+        """The grouped kernels cover teacher forcing on shapes the step-split recurrence handles (fp32 mode)."""
+        P = features.shape[1]
+        Fd = self.feature_fc[2].out_features
+        return (getattr(self, "_theta_groups", None) is not None and features.is_cuda and ops.ATT_STEP
+                and ops._attstep_bytes(self.hidden_dim, Fd, P, 0)[0] > 0
+                and ops._attstep_bwd_bytes(self.hidden_dim, Fd, P, features.shape[0], 1)[0] > 0)
+
+    def _forward_grouped(self, features, captions, groups, ignore_index):
+        """Many-style batch on the grouped kernels (grouped.py): rows sorted by style group, one grouped tensor-core launch
+        per time-batched product, the step-split recurrence with one weight pack per group.  ``ignore_index`` None:
+        returns (logits, attn); else (loss, logits, attn) with the loss fused."""
+        from . import grouped as Gp
+        Theta = self._theta_groups
+        plan = Gp.GroupPlan.get(groups, Theta.shape[0], captions.shape[1], features.device)
+        f3, K3, h0 = self._features(features)
+        f3s = Gp.RowPermuteFn.apply(f3, plan.order, plan.inv)
+        K3s = Gp.RowPermuteFn.apply(K3, plan.order, plan.inv)
+        h0s = Gp.RowPermuteFn.apply(h0, plan.order, plan.inv)
+        caps_s = captions.index_select(0, plan.order)
+        a = self.attention
+        shared = (self.embed.weight, self.fc.weight, self.fc.bias, a.U_a.weight, a.U_a.bias, a.v_a.weight, a.v_a.bias)
+        if ignore_index is None:
+            return Gp.AttentionGruGroupedFn.apply(plan, f3s, K3s, h0s, caps_s, Theta, *shared)
+        return Gp.AttentionGruGroupedLossFn.apply(ignore_index, plan, captions.contiguous(), f3s, K3s, h0s, caps_s, Theta,
+                                                  *shared)
+
+    def forward_loss(self, features, captions, sample_prob=0.0, ignore_index=0, groups=None):
         """``forward`` fused with ``F.cross_entropy(outputs.view(-1,V), captions.view(-1), ignore_index=<pad>)``
-        (cc_train_hypernet.py:152-153): returns ``(loss, outputs, atten_weights)``; one autograd node."""
+        (cc_train_hypernet.py:152-153): returns ``(loss, outputs, atten_weights)``; one autograd node.
+        ``groups``: many-style batch after ``HyperNet.forward_grouped`` (teacher forcing only)."""
         T = captions.size(1)
         use = tuple(bool(np.random.random() < (0.0 if t == 0 else sample_prob)) for t in range(T))
+        if groups is not None:
+            streams.wait_pending()
+            if any(use) or not self._grouped_kernels_ok(features):
+                raise NotImplementedError("forward_loss(groups=...) covers teacher forcing on step-split shapes; use "
+                                          "forward(..., groups=...) + cross_entropy otherwise")
+            return self._forward_grouped(features, captions, groups, ignore_index)
         f3, K3, h0 = self._features(features)
         streams.wait_pending()
         return AttentionGruLossFn.apply(ignore_index, f3, K3, h0, captions, use,
@@ -520,6 +558,7 @@ class HyperNetAttention(_HyperNetMixin, _Base):
         ws = self._generate_and_inject(x)
         self.captioner._generated = ws if self.grad_mode == "flow" else None
         self.captioner._generated_groups = None
+        self.captioner._theta_groups = None
         return self.captioner
 
     def _split_theta(self, theta, write_params=False):

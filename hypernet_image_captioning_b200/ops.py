@@ -706,3 +706,126 @@ class LinearPlan:
                 self._split = split_bf16(self.W)
             return gemm_tc(split_bf16(X), self._split, bias=self.bias, relu=relu, out=out)
         return _gemm(X, X.stride(0), 1, self.W, self.W.stride(0), 1, M, self.N, self.K, self.bias, relu, out)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# many-style ("grouped") path: operand builders, grouped tensor-core GEMM, per-group recurrence tiles
+# ----------------------------------------------------------------------------------------------------------------------
+def split_bf16_gather(src, rowmap, R, want_lo=None):
+    """K-major operand [R, round64(C)] whose row i is src[rowmap[i]] (zero when rowmap[i] < 0); rowmap int32 [R]."""
+    want_lo = TC_SPLIT if want_lo is None else want_lo
+    _chk(src), _chk(rowmap, torch.int32)
+    assert src.dim() == 2 and src.stride(1) == 1 and rowmap.numel() == R
+    C = src.shape[1]
+    Kp = round64(C)
+    hi = torch.empty(R, Kp, device=src.device, dtype=torch.bfloat16)
+    lo = torch.empty(R, Kp, device=src.device, dtype=torch.bfloat16) if want_lo else None
+    _cabi.call("caphn_split_bf16_gather", src.data_ptr(), src.stride(0), rowmap.data_ptr(), R, C, hi.data_ptr(), _p(lo),
+               Kp, _stream())
+    return SplitOperand(hi, lo, R, C, Kp, False)
+
+
+def split_bf16_batched(src, sstride, lds, nb, R, C, want_lo=None):
+    """nb matrices [R, C] taken from ``src`` (a tensor whose data pointer is matrix 0; matrix b starts sstride floats later,
+    rows lds floats apart) -> one K-major operand [nb*R, round64(C)]."""
+    want_lo = TC_SPLIT if want_lo is None else want_lo
+    _chk(src)
+    Kp = round64(C)
+    hi = torch.empty(nb * R, Kp, device=src.device, dtype=torch.bfloat16)
+    lo = torch.empty(nb * R, Kp, device=src.device, dtype=torch.bfloat16) if want_lo else None
+    _cabi.call("caphn_split_bf16_batched", src.data_ptr(), sstride, lds, nb, R, C, hi.data_ptr(), _p(lo), Kp, _stream())
+    return SplitOperand(hi, lo, nb * R, C, Kp, False)
+
+
+def gemm_tc_grouped(A: SplitOperand, a_mn, Bm: SplitOperand, b_mn, C, ldc, units, BN, bias=None, rowmap=None):
+    """One launch for all the tiles listed in ``units`` (int32 [n, 12], see include/caphn_b200.h).  The operands are the
+    raw 2-D bf16 arrays of ``A`` / ``Bm`` ([rows, ld]); which rows / k range a tile uses is in its unit record."""
+    assert (A.lo is None) == (Bm.lo is None) and units.dtype == torch.int32 and units.is_contiguous()
+    a_outer, b_outer = A.hi.shape[0], Bm.hi.shape[0]
+    _cabi.call("caphn_gemm_tc_grouped", A.hi.data_ptr(), _p(A.lo), A.ld, a_outer, A.ld, int(a_mn), Bm.hi.data_ptr(),
+               _p(Bm.lo), Bm.ld, b_outer, Bm.ld, int(b_mn), C.data_ptr(), ldc, _p(bias), _p(rowmap), units.data_ptr(),
+               units.shape[0], BN, _stream())
+    return C
+
+
+def group_colsum(X, goff, G, B, T, out):
+    """out[g, :] += sum over the rows of group g (time-major X [T*B, N], batch sorted by group, goff int32 [G+1])."""
+    _chk(X), _chk(goff, torch.int32)
+    assert X.stride(1) == 1 and out.stride(1) == 1
+    _cabi.call("caphn_group_colsum", X.data_ptr(), X.stride(0), goff.data_ptr(), G, B, T, X.shape[1], out.data_ptr(),
+               out.stride(0), _stream())
+    return out
+
+
+def leaky_relu_(y, slope=LEAKY_SLOPE):
+    assert y.is_contiguous()
+    _cabi.call("caphn_leaky_relu", y.data_ptr(), y.numel(), slope, _stream())
+    return y
+
+
+def leaky_relu_bwd_(y, dy, slope=LEAKY_SLOPE):
+    assert y.is_contiguous() and dy.is_contiguous() and y.numel() == dy.numel()
+    _cabi.call("caphn_leaky_relu_bwd", y.data_ptr(), dy.data_ptr(), y.numel(), slope, _stream())
+    return dy
+
+
+class AttGruGroupWeights:
+    """Per-group mma-fragment packs of the generated W_ih[:, E:], W_hh (+ the shared U_a) for the step-split kernels.
+    ``Theta`` [G, theta] holds (W_ih [3H, E+F], W_hh [3H, H], b_ih, b_hh) per row."""
+
+    def __init__(self, Theta, U_a, E, Fd, H, P):
+        G, theta = Theta.shape
+        assert Theta.is_contiguous()
+        n = _attstep_bytes(H, Fd, P, 0)[0]
+        if n == 0:
+            raise _cabi.CaphnError(f"the grouped recurrence needs the step-split kernels (H={H}, F={Fd}, P={P} not covered)")
+        self.G, self.pack_bytes = G, n
+        self.pack = torch.empty(G * n, device=Theta.device, dtype=torch.uint8)
+        whh_off = 3 * H * (E + Fd)
+        _cabi.call("caphn_attstep_pack_grouped", Theta.data_ptr(), Theta.data_ptr() + 4 * whh_off, U_a.data_ptr(), E, Fd,
+                   H, G, theta, self.pack.data_ptr(), _stream())
+        self.work = None
+
+
+def attgru_fwd_grouped(Kp, f, GIw, gw: AttGruGroupWeights, bu, va, bv, bhh_g, Hall, Hbm, attn, XC, E, saved, tiles):
+    """All T steps; rows sorted by group; tiles int32 [n, 4] = (first row, rows <= 64, group, 0); bhh_g [G, 3H] contiguous."""
+    B, P, H = Kp.shape
+    Fd = f.shape[2]
+    T = Hall.shape[0] - 1
+    sp = [saved[i].data_ptr() for i in range(5)] if saved is not None else [None] * 5
+    ctx_ptr = XC.data_ptr() + 4 * E
+    wbytes = _attstep_bytes(H, Fd, P, B)[1]
+    if gw.work is None or gw.work.numel() < wbytes:
+        gw.work = torch.empty(wbytes, device=Kp.device, dtype=torch.uint8)
+    assert tiles.dtype == torch.int32 and tiles.is_contiguous() and bhh_g.is_contiguous()
+    _cabi.call("caphn_attstep_fwd_grouped", Kp.data_ptr(), f.data_ptr(), GIw.data_ptr(), bu.data_ptr(), va.data_ptr(),
+               bv.data_ptr(), gw.pack.data_ptr(), gw.work.data_ptr(), bhh_g.data_ptr(), Hall.data_ptr(), _p(Hbm),
+               attn.data_ptr(), ctx_ptr, XC.stride(0), sp[0], sp[1], sp[2], sp[3], sp[4], B, T, P, H, Fd, 0, T, 0,
+               tiles.data_ptr(), tiles.shape[0], _stream())
+
+
+def attgru_bwd_grouped(dHbm, dattn, Kp, f, attn, saved, Hall, Theta, U_a, va, E, tiles):
+    """BPTT of attgru_fwd_grouped.  tiles int32 [n, 4] with <= 32 rows each.  Returns dGI, dGH, dU, dCTX, dK, dva, dbv, dh0."""
+    B, P, H = Kp.shape
+    Fd = f.shape[2]
+    T = Hall.shape[0] - 1
+    G, theta = Theta.shape
+    nbytes, wbytes = _attstep_bwd_bytes(H, Fd, P, B, T)
+    if nbytes == 0:
+        raise _cabi.CaphnError("the grouped BPTT needs the step-split kernels (shape not covered)")
+    dev = Kp.device
+    pack = torch.empty(G * nbytes, device=dev, dtype=torch.uint8)
+    work = torch.empty(wbytes, device=dev, dtype=torch.uint8)
+    whh_off = 3 * H * (E + Fd)
+    _cabi.call("caphn_attstep_bwd_pack_grouped", Theta.data_ptr(), Theta.data_ptr() + 4 * whh_off, U_a.data_ptr(), E, Fd,
+               H, G, theta, pack.data_ptr(), _stream())
+    e = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+    dGI, dGH, dU, dCTX = e(T * B, 3 * H), e(T * B, 3 * H), e(T * B, H), e(T * B, Fd)
+    dK, dva, dbv, dh0 = e(B, P, H), e(H), e(1), e(B, H)
+    assert tiles.dtype == torch.int32 and tiles.is_contiguous()
+    _cabi.call("caphn_attstep_bwd_grouped", dHbm.data_ptr(), _p(dattn), Kp.data_ptr(), f.data_ptr(), attn.data_ptr(),
+               saved[0].data_ptr(), saved[1].data_ptr(), saved[2].data_ptr(), saved[3].data_ptr(), saved[4].data_ptr(),
+               Hall.data_ptr(), va.data_ptr(), pack.data_ptr(), work.data_ptr(), dGI.data_ptr(), dGH.data_ptr(),
+               dU.data_ptr(), dCTX.data_ptr(), dK.data_ptr(), dva.data_ptr(), dbv.data_ptr(), dh0.data_ptr(),
+               B, T, P, H, Fd, tiles.data_ptr(), tiles.shape[0], _stream())
+    return dGI, dGH, dU, dCTX, dK, dva, dbv, dh0

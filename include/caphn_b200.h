@@ -252,6 +252,56 @@ int caphn_launch_count(unsigned long long* out);
 /* *out = 100 (library compiled for sm_100a). */
 int caphn_build_arch(int* out);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Many-style ("grouped") path: one batch whose rows use G different generated weight sets -- BASELINE.json configs[3]
+ * (Conceptual-Captions domains) and the north star's "per-style grouped GEMM".  Reference semantics: one
+ * HyperNet.forward + captioner call per sample's style (train_cc.py:90-123); cc_train_hypernet.py:134-153 is the G = 1
+ * special case.  The batch is sorted by group; the recurrence keeps the time-major layout, the time-batched products
+ * run as ONE grouped tensor-core launch each.
+ *
+ * caphn_gemm_tc_grouped: num_units output tiles, unit i described by 12 int32 words
+ *   {a_row, b_row, ka0, kb0, nkb, m_valid, n_valid, bias_off, map0, c_off_lo, c_off_hi, 0}: the tile multiplies A rows
+ *   a_row.. (128) with B rows b_row.. (BN) over nkb 64-wide k blocks starting at ka0 in A and kb0 in B, and writes
+ *   C + c_off (+ bias[bias_off + col]) or, with rowmap, tile row r to C row rowmap[map0 + r] (negative: skip).
+ *   Operands: 2-D bf16 arrays (hi, optional lo), x_inner contiguous elements per row, x_outer rows, pitch x_ld; K-major
+ *   (x_mn = 0: inner = K) or MN-major (x_mn = 1: inner = operand rows, outer = K).  Replaces, for all groups at once, the
+ *   addmm of nn.GRUCell's input projection (models/decoderlstm.py:100) and its three backward products.
+ * caphn_split_bf16_gather / _batched: build those operands (bf16 hi/lo) while permuting rows between the time-major and
+ *   the group-major order / collecting the W_ih block of every row of Theta [G, theta].
+ * caphn_group_colsum: per-group bias gradients.
+ * caphn_attstep_pack_grouped / caphn_attstep_fwd_grouped / caphn_attstep_bwd_pack_grouped / caphn_attstep_bwd_grouped:
+ *   the step-split recurrence with one weight pack per group; `tiles` = {first row, rows, group, 0} records (int32 x 4,
+ *   16-byte aligned) that never straddle a group (<= 64 rows forward, <= 32 backward).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int caphn_gemm_tc_grouped(const void* Ahi, const void* Alo, long a_inner, long a_outer, long a_ld, int a_mn,
+                          const void* Bhi, const void* Blo, long b_inner, long b_outer, long b_ld, int b_mn, float* C,
+                          long ldc, const float* bias, const int* rowmap, const void* units, int num_units, int BN,
+                          void* stream);
+int caphn_split_bf16_gather(const float* src, long lds, const int* rowmap, long R, int C, void* hi, void* lo, long Kp,
+                            void* stream);
+int caphn_split_bf16_batched(const float* src, long sstride, long lds, int nb, int R, int C, void* hi, void* lo, long Kp,
+                             void* stream);
+int caphn_group_colsum(const float* X, long ldx, const int* goff, int G, int B, int T, int N, float* out, long ldo,
+                       void* stream);
+/* nn.LeakyReLU(slope) forward (in place on y) / backward (in place on dy, y = activation output) for the many-group
+ * hypernet, whose layers run as dense tensor-core GEMMs instead of the weight-streaming kernels. */
+int caphn_leaky_relu(float* y, long n, float slope, void* stream);
+int caphn_leaky_relu_bwd(const float* y, float* dy, long n, float slope, void* stream);
+int caphn_attstep_pack_grouped(const float* Wih, const float* Whh, const float* Ua, int E, int F, int H, int G,
+                               long gstride, void* pack, void* stream);
+int caphn_attstep_fwd_grouped(const float* Kp, const float* f, const float* GIw, const float* bu, const float* va,
+                              const float* bv, const void* pack, void* work, const float* bhh, float* Hall, float* Hbm,
+                              float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z, float* Nn, float* GHN,
+                              int B, int T, int P, int H, int F, int t0, int t1, int resume, const int* tiles, int ntiles,
+                              void* stream);
+int caphn_attstep_bwd_pack_grouped(const float* Wih, const float* Whh, const float* Ua, int E, int F, int H, int G,
+                                   long gstride, void* pack, void* stream);
+int caphn_attstep_bwd_grouped(const float* dHbm, const float* dattn, const float* Kp, const float* f, const float* attn,
+                              const float* Upre, const float* R, const float* Z, const float* Nn, const float* GHN,
+                              const float* Hall, const float* va, const void* pack, void* work, float* dGI, float* dGH,
+                              float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0, int B, int T, int P,
+                              int H, int F, const int* tiles, int ntiles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
