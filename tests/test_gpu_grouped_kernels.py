@@ -28,7 +28,11 @@ def test_grouped_gemms_match_per_group_products(G, B, T, E, Fd, H):
     ops.gemm_tc_grouped(Xgm, False, Wsp, False, GIw, H3, plan.units_xproj(H3, E, 128), 128, bias=b_ih, rowmap=plan.gm2tm)
     W = Theta[:, :o_hh].reshape(G, H3, E + Fd).double().cpu()
     row_g = gs.repeat(T)                                            # group of time-major row t*B + b
-    ref = torch.einsum("re,rne->rn", Xw.double().cpu(), W[row_g][:, :, :E]) + b_ih.double().cpu()[row_g]
+    Xc, bc = Xw.double().cpu(), b_ih.double().cpu()
+    ref = torch.zeros(T * B, H3, dtype=torch.float64)
+    for gi in range(G):
+        rows = (row_g == gi).nonzero().squeeze(1)
+        ref[rows] = Xc[rows] @ W[gi][:, :E].t() + bc[gi]
     assert rel_err(GIw, ref) < 2e-5
     # dX
     dGI = torch.randn(T * B, H3, generator=g).cuda()
@@ -36,7 +40,10 @@ def test_grouped_gemms_match_per_group_products(G, B, T, E, Fd, H):
     dXw = torch.full((T * B, E), float("nan"), device="cuda")
     Wmn = ops.SplitOperand(Wsp.hi, Wsp.lo, E + Fd, G * H3, Wsp.ld, True)
     ops.gemm_tc_grouped(dGI_gm, False, Wmn, True, dXw, E, plan.units_dx(H3, E, 128), 128, rowmap=plan.gm2tm)
-    ref = torch.einsum("rn,rne->re", dGI.double().cpu(), W[row_g][:, :, :E])
+    ref = torch.zeros(T * B, E, dtype=torch.float64)
+    for gi in range(G):
+        rows = (row_g == gi).nonzero().squeeze(1)
+        ref[rows] = dGI.double().cpu()[rows] @ W[gi][:, :E]
     assert rel_err(dXw, ref) < 2e-5
     # dW_ih, dW_hh, bias sums into dTheta
     XC = torch.randn(T * B, E + Fd, generator=g).cuda()
@@ -53,11 +60,13 @@ def test_grouped_gemms_match_per_group_products(G, B, T, E, Fd, H):
     ops.group_colsum(dGH, plan.goff_dev, G, B, T, dTheta[:, o_bh:])
     torch.cuda.synchronize()
     ref = torch.zeros(G, theta, dtype=torch.float64)
-    onehot = torch.nn.functional.one_hot(row_g, G).double()       # [T*B, G]
-    ref[:, :o_hh] = torch.einsum("rg,rn,re->gne", onehot, dGI.double().cpu(), XC.double().cpu()).reshape(G, -1)
-    ref[:, o_hh:o_bi] = torch.einsum("rg,rn,rh->gnh", onehot, dGH.double().cpu(), Hp.double().cpu()).reshape(G, -1)
-    ref[:, o_bi:o_bh] = onehot.t() @ dGI.double().cpu()
-    ref[:, o_bh:] = onehot.t() @ dGH.double().cpu()
+    dGIc, dGHc, XCc, Hpc = dGI.double().cpu(), dGH.double().cpu(), XC.double().cpu(), Hp.double().cpu()
+    for gi in range(G):
+        rows = (row_g == gi).nonzero().squeeze(1)
+        ref[gi, :o_hh] = (dGIc[rows].t() @ XCc[rows]).reshape(-1)
+        ref[gi, o_hh:o_bi] = (dGHc[rows].t() @ Hpc[rows]).reshape(-1)
+        ref[gi, o_bi:o_bh] = dGIc[rows].sum(0)
+        ref[gi, o_bh:] = dGHc[rows].sum(0)
     assert rel_err(dTheta, ref) < 2e-5
 
 
