@@ -459,6 +459,7 @@ def run_ours(args):
         del model
         torch.cuda.empty_cache()
         extras.update(attention_extras(args, dev, world, timed, rooflines, peak))
+        extras.update(cc_extras(args, dev, world, timed, rooflines, peak))
         extras.update(lstm_extras(args, dev, world, timed))
         extras.update(pooled_l2_extras(args, dev, world, timed, rooflines, peak))
         if sustained is not None:
@@ -643,6 +644,76 @@ def attention_extras(args, dev, world, timed, rooflines=None, peak=6537.6):
             "configs[2] greedy decode (sample_prob=1.0), compulsory traffic (SURVEY 8(d): 1.20 GB)")
     if world > 1:
         par.disable_overlap()
+    return out
+
+
+def cc_extras(args, dev, world, timed, rooflines, peak):
+    """BASELINE configs[3]: Conceptual-Captions domain-conditioned hypernet (hypernet_attention.HyperNet(cc=True), one-hot
+    domain vectors, he = #domains = 100 / 150, cc_train_hypernet.py:86-89,134-153), F=E=H=200, B=512/GPU, T=20, teacher-forced
+    fwd+bwd (flow).  G = 1 is the reference's own step (one domain per batch, :136); G = 3 / 100 / 150 put that many domains in
+    ONE batch (rows assigned round-robin) and run the grouped kernels: one hypernet pass for all G, grouped
+    tensor-core x-projection / dX / dW products, per-group weight packs in the recurrence.  Under DP the d(theta) [G, theta]
+    all-reduce (144 MB at G = 100) runs on the hypernet stream next to the feature branch's backward."""
+    import hypernet_image_captioning_b200 as C
+    from hypernet_image_captioning_b200 import graphs, parallel as par
+    from hypernet_image_captioning_b200.synth import synth_captions
+    B, T, V = args.batch, CFG["T"], CFG["V"]
+    g = torch.Generator().manual_seed(777)
+    feats = torch.randn(B, 49, 2048, generator=g).to(dev)
+    caps = synth_captions(B, T, V, g).to(dev)
+    out = {}
+    for he, Gs in ((100, (1, 3, 100)), (150, (150,))):
+        torch.manual_seed(0)
+        with torch.device(dev):
+            model = C.HyperNetAttention(200, 200, 200, V, None, cc=True, hyper_emb=he)
+        model.dp_enabled = world > 1
+        shared = par.shared_parameters(model)
+        if world > 1:
+            par.enable_overlap(shared)
+        eye = torch.eye(he, device=dev)
+        for G in Gs:
+            groups = (torch.arange(B) % G).to(dev)
+            styles = eye[:G].contiguous()
+
+            def train():
+                model.zero_grad(set_to_none=True)
+                if G == 1:
+                    captioner = model.forward(styles[0])                      # 1-D one-hot, as cc_train_hypernet.py:141-143
+                    loss, _, _ = captioner.forward_loss(feats, caps, 0.0, ignore_index=0)
+                else:
+                    captioner = model.forward_grouped(styles)
+                    loss, _, _ = captioner.forward_loss(feats, caps, 0.0, ignore_index=0, groups=groups)
+                if world > 1:
+                    (loss * par.loss_weight(caps, 0)).backward()
+                    par.allreduce_shared_grads(shared)
+                else:
+                    loss.backward()
+
+            run = train
+            if os.environ.get("CAPHN_BENCH_GRAPH", "1") != "0":
+                model.async_hypernet = True
+                gtrain = graphs.GraphedStep(train, (), params=list(model.parameters()), release=model.release_graph)
+                model.async_hypernet = False
+                run = gtrain if gtrain.captured else train
+            for _ in range(3):
+                run()
+            ms = timed(run, args.steps) / args.steps
+            out[f"cc_onehot_he{he}_G{G}_train_captions_per_s"] = B * world / (ms * 1e-3)
+            hn_b = 4.0 * sum(p_.numel() for n_, p_ in model.named_parameters() if n_.startswith("hn_"))
+            w2_b = 4.0 * sum(h_[2].weight.numel() for h_ in model.hn_heads)
+            sh_b = 4.0 * sum(p_.numel() for n_, p_ in model.named_parameters()
+                             if not n_.startswith("hn_") and not n_.startswith("captioner.gru"))
+            theta = sum(p_.numel() for p_ in model.captioner.gru.parameters())
+            per_cap = 49 * 2048 * 4.0 + 8.0 * T + 2.0 * T * V * 4.0 + T * 49 * 4.0
+            alg = 2 * hn_b + w2_b + 2 * sh_b + B * per_cap + 2.0 * G * theta * 4.0      # + theta, d(theta) per group
+            rooflines[f"cc_he{he}_G{G}_train_step"] = roofline_block(
+                alg, ms, peak, f"configs[3], {G} domain(s) in the batch, flow mode fwd+bwd, compulsory traffic")
+            run = None
+            model.zero_grad(set_to_none=True)
+        if world > 1:
+            par.disable_overlap()
+        del model
+        torch.cuda.empty_cache()
     return out
 
 

@@ -89,7 +89,9 @@ def _check_grads(m, pl, skip_prefix="captioner.gru."):
         if k.startswith(skip_prefix):
             continue                                            # generated, not trained (flow mode)
         assert v.grad is not None, k
-        assert grad_close(v.grad, pl[k].grad, TOL_GRAD), (k, rel_err(v.grad, pl[k].grad))
+        # d/d v_a.bias is analytically zero (softmax is shift invariant): both sides are 1e-7-size rounding noise
+        atol = 2e-6 if k.endswith("attention.v_a.bias") else 1e-7
+        assert grad_close(v.grad, pl[k].grad, TOL_GRAD, atol), (k, rel_err(v.grad, pl[k].grad))
         r = rel_err(v.grad, pl[k].grad)
         if pl[k].grad.abs().max().item() > 1e-7 and r > worst:
             worst, worst_k = r, k
