@@ -4,7 +4,7 @@ from typing import List, Optional, Sequence
 import torch
 from torch.autograd import Function
 
-from . import ops, parallel
+from . import ops, parallel, streams
 from .ops import ACT_LEAKY, ACT_NONE
 
 
@@ -250,8 +250,16 @@ def _gru_decoder_backward(saved_tensors, NL, need, vocab):
                  for l in range(1, NL)]
         dGI, dGH, xdGI, xdGH, dh0 = ops.gru_seq_bwd(dHbm.view(B, T, H), saved, Hall, Hmid, Whh_p, extra=extra)
     Hprev = Hall[:-1].reshape(T * B, H)
-    cell_grads = [ops.matmul_tn(dGI, X) if need[6] else None, ops.matmul_tn(dGH, Hprev) if need[7] else None,
-                  ops.colsum(dGI) if need[8] else None, ops.colsum(dGH) if need[9] else None]
+    # independent chains of small launches (operand splits + a weight-gradient GEMM + a bias sum): side by side
+    br = streams.Branches("ptail", like=dGI)
+    br.__enter__()
+    with br.on(0):
+        g_wih = ops.matmul_tn(dGI, X) if need[6] else None
+        g_bih = ops.colsum(dGI) if need[8] else None
+    with br.on(1):
+        g_whh = ops.matmul_tn(dGH, Hprev) if need[7] else None
+        g_bhh = ops.colsum(dGH) if need[9] else None
+    cell_grads = [g_wih, g_whh, g_bih, g_bhh]
     for l in range(1, NL):
         Hin = Hmid[l - 1].reshape(T * B, H)                            # input == state of layer l
         n0 = 6 + 4 * l
@@ -267,6 +275,7 @@ def _gru_decoder_backward(saved_tensors, NL, need, vocab):
         if need[3]:
             demb = torch.zeros_like(emb_w)
             ops.embed_scatter_add(dX, caps, demb, 1)
+    br.__exit__(None, None, None)
     return (dfeats, None, (dh0 if need[2] else None), demb, dfc_w if need[4] else None,
             dfc_b if need[5] else None, *cell_grads)
 

@@ -54,26 +54,30 @@ class FeatureFn(Function):
         B, P, D, Fd, H = ctx.dims
         # attention keys: dW_a = dK^T f, df = dK W_a
         dK2 = dK.reshape(B * P, H).contiguous()
-        dWa_w = ops.matmul_tn(dK2, f)                                      # [H, F]
-        dWa_b = ops.colsum(dK2)
-        df = ops.matmul_nn(dK2, Wa_w.contiguous())                         # [B*P, F]
-        # init_h; its input gradient and the recurrence's df contribution are added to df in one pass
         dh0 = dh0.contiguous()
-        dinit_w = ops.matmul_tn(dh0, fmean)                                # [H, F]
-        dinit_b = ops.colsum(dh0)
-        dfmean = ops.matmul_nn(dh0, init_w.contiguous())                   # [B, F]
-        ops.mean_pos_bwd(dfmean, df.view(B, P, Fd), extra=df_in.contiguous() if df_in is not None else None)
-        # feature_fc (no gradient w.r.t. the image features: they are a leaf input)
-        dfc2_w = ops.matmul_tn(df, f1)
-        dfc2_b = ops.colsum(df)
-        df1 = ops.matmul_nn(df, fc2_w.contiguous())
-        ops.relu_mask_(f1, df1)
-        if fs_hi is not None and (fs_lo is not None) == ops.TC_SPLIT:
-            feats_op = ops.SplitOperand(fs_hi, fs_lo, D, B * P, fs_hi.shape[1], True)      # features^T, read in place
-            dfc0_w = ops.gemm_tc(ops.split_bf16(df1, mn=True), feats_op)                   # [F, D]
-        else:
-            dfc0_w = ops.matmul_tn(df1, feats2)                                            # [F, D]
-        dfc0_b = ops.colsum(df1)
+        with streams.Branches("ftail", like=dK2) as br:
+            with br.on(0):                                                 # off the critical path: only parameter gradients
+                dWa_w = ops.matmul_tn(dK2, f)                              # [H, F]
+                dWa_b = ops.colsum(dK2)
+                dinit_w = ops.matmul_tn(dh0, fmean)                        # [H, F]
+                dinit_b = ops.colsum(dh0)
+            df = ops.matmul_nn(dK2, Wa_w.contiguous())                     # [B*P, F]
+            # init_h's input gradient and the recurrence's df contribution are added to df in one pass
+            dfmean = ops.matmul_nn(dh0, init_w.contiguous())               # [B, F]
+            ops.mean_pos_bwd(dfmean, df.view(B, P, Fd), extra=df_in.contiguous() if df_in is not None else None)
+            # feature_fc (no gradient w.r.t. the image features: they are a leaf input)
+            with br.on(1):                                                 # (df is complete at this point)
+                dfc2_w = ops.matmul_tn(df, f1)
+                dfc2_b = ops.colsum(df)
+            df1 = ops.matmul_nn(df, fc2_w.contiguous())
+            ops.relu_mask_(f1, df1)
+            with br.on(2):                                                 # (df1 is masked at this point)
+                dfc0_b = ops.colsum(df1)
+            if fs_hi is not None and (fs_lo is not None) == ops.TC_SPLIT:
+                feats_op = ops.SplitOperand(fs_hi, fs_lo, D, B * P, fs_hi.shape[1], True)      # features^T, read in place
+                dfc0_w = ops.gemm_tc(ops.split_bf16(df1, mn=True), feats_op)                   # [F, D]
+            else:
+                dfc0_w = ops.matmul_tn(df1, feats2)                                            # [F, D]
         return (None, dfc0_w, dfc0_b, dfc2_w, dfc2_b, dWa_w, dWa_b, dinit_w, dinit_b)
 
 
@@ -161,19 +165,25 @@ def _attgru_backward(sv, dims, vocab, dattn):
     dGI, dGH, dU, dCTX, dK, dva, dbv, dh0 = ops.attgru_bwd(
         dHbm.view(B, T, H), dattn, K3, f3, attn, saved, Hall, Ua_w.contiguous(), va, W_ih, W_hh, E)
     Hprev = Hall[:-1].reshape(T * B, H)
-    dW_ih = ops.matmul_tn(dGI, XC)                                     # [3H, E+F]
-    db_ih = ops.colsum(dGI)
-    dW_hh = ops.matmul_tn(dGH, Hprev)
-    db_hh = ops.colsum(dGH)
-    dUa_w = ops.matmul_tn(dU, Hprev)                                   # [H, H]
-    dUa_b = ops.colsum(dU)
-    # word embeddings (t >= 2 teacher-forced rows, or the fed-back argmax rows)
-    dXw = ops.matmul_nn(dGI, W_ih[:, :E])                              # [T*B, E]
-    demb = torch.zeros_like(emb_w)
-    ops.scatter_add_rows(dXw, fed.reshape(-1), demb)
-    # features through the context vectors: df[b,p,:] = sum_t alpha[b,t,p] dctx[t,b,:]  (the K / init_h paths are FeatureFn's)
-    df = torch.zeros(B, P, Fd, device=f3.device, dtype=torch.float32)
-    ops.attn_df(attn, dCTX, df)
+    # four independent chains of small launches (each: operand splits + a GEMM that fills <= 80 of the 148 SMs + a bias
+    # sum): side by side on branch streams instead of back to back
+    with streams.Branches("atail", like=dGI) as br:
+        with br.on(0):
+            dW_ih = ops.matmul_tn(dGI, XC)                             # [3H, E+F]
+            db_ih = ops.colsum(dGI)
+        with br.on(1):
+            dW_hh = ops.matmul_tn(dGH, Hprev)
+            db_hh = ops.colsum(dGH)
+        with br.on(2):
+            dUa_w = ops.matmul_tn(dU, Hprev)                           # [H, H]
+            dUa_b = ops.colsum(dU)
+            # features through the context vectors: df[b,p,:] = sum_t alpha[b,t,p] dctx[t,b,:]  (the K / init_h paths are FeatureFn's)
+            df = torch.zeros(B, P, Fd, device=f3.device, dtype=torch.float32)
+            ops.attn_df(attn, dCTX, df)
+        # word embeddings (t >= 2 teacher-forced rows, or the fed-back argmax rows)
+        dXw = ops.matmul_nn(dGI, W_ih[:, :E])                          # [T*B, E]
+        demb = torch.zeros_like(emb_w)
+        ops.scatter_add_rows(dXw, fed.reshape(-1), demb)
     return (df, dK, dh0, demb, dW_ih, dW_hh, db_ih, db_hh, dfc_w, dfc_b, dUa_w, dUa_b, dva.view(1, H), dbv.view(1))
 
 

@@ -65,3 +65,44 @@ def wait_pending():
         for s in _pending:
             cur.wait_stream(s)
         _pending.clear()
+
+
+class Branches:
+    """Independent groups of small launches (weight-gradient GEMMs with their operand splits, bias sums, scatter-adds) on
+    side streams, joined at exit.  The backward tails are chains of 5-30 us kernels whose grids do not fill the 148 SMs;
+    run back to back they cost their summed latencies, side by side roughly the longest chain.
+
+        with streams.Branches("tail", like=dGI) as br:
+            with br.on(0): dW_ih = ops.matmul_tn(dGI, XC)
+            with br.on(1): dW_hh = ops.matmul_tn(dGH, Hprev)
+            demb = ...                                   # the caller's stream keeps working meanwhile
+
+    ``on(i)``: the block runs on branch stream i, after everything queued SO FAR on the caller's stream (and after branch
+    i's earlier blocks); the caller's stream waits for all branches at exit.  Disabled (``CAPHN_OVERLAP=0`` or a CPU
+    tensor): the blocks simply run in order."""
+
+    def __init__(self, name: str, like: torch.Tensor = None, enable: bool = True):
+        self.name = name
+        self.active = enable and enabled(like)
+        self.used = {}
+
+    def __enter__(self):
+        if self.active:
+            self.cur = torch.cuda.current_stream()
+        return self
+
+    def on(self, i: int):
+        if not self.active:
+            import contextlib
+            return contextlib.nullcontext()
+        s = self.used.get(i)
+        if s is None:
+            s = self.used[i] = side(f"{self.name}{i}")
+        s.wait_stream(self.cur)
+        return torch.cuda.stream(s)
+
+    def __exit__(self, *exc):
+        if self.active:
+            for s in self.used.values():
+                self.cur.wait_stream(s)
+        return False
