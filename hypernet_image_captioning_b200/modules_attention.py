@@ -480,6 +480,81 @@ class AttentionGru(nn.Module):
         return complete[complete_scores.index(max(complete_scores))]
 
     @torch.no_grad()
+    def beam_search_batched(self, features, beam_size=3, end_sentence=2, max_steps=50, sync_every=8):
+        """Beam search of HyperNet.test_step (hypernet_attention.py:247-326) for a whole batch at once, device-resident:
+        ``features`` [B, P, D] -> list of B results, each the best complete token sequence (leading 0, trailing
+        ``end_sentence``) or ``None`` where the reference computes no beam caption (a beam still open after
+        ``max_steps`` + 1 steps).  Same per-image semantics -- and the same results -- as ``beam_search``.
+
+        All B*k beams go through the decoder step kernels together; between steps ONE kernel per step
+        (csrc/beam.cu, a CTA per image) does the reference's host bookkeeping on the device: log-softmax + running scores,
+        top-k over the k*V candidates, completed beams to the complete list, survivors compacted (history, score, hidden
+        state gathered from the parent beam), next input words.  The host reads the results in one copy at the end; it
+        only peeks at an 'all images finished' flag every ``sync_every`` steps to stop early."""
+        streams.wait_pending()
+        feats = features.contiguous().float()
+        if feats.dim() != 3:
+            raise ValueError("beam_search_batched expects features [B, P, D]")
+        B, P, D = feats.shape
+        k = int(beam_size)
+        W_ih, W_hh, b_ih, b_hh = [w.detach().contiguous() for w in self._gru_weights()]
+        E, H, V = self.embedding_dim, self.hidden_dim, self.vocab_size
+        dev = feats.device
+        a = self.attention
+        emb_w = self.embed.weight.detach()
+        f3, K3, h0 = FeatureFn.apply(feats, *[p.detach() for p in self._feature_params()])
+        Fd = f3.shape[2]
+        rep = lambda x: x.unsqueeze(1).expand(B, k, *x.shape[1:]).reshape(B * k, *x.shape[1:]).contiguous()
+        f3k, K3k = rep(f3), rep(K3)                                   # rows b*k + j: beam j of image b
+        R, L = B * k, int(max_steps) + 3
+        lw = ops.AttGruWeights(W_ih, W_hh, a.U_a.weight.detach().contiguous(), E, P)
+        va, bv = a.v_a.weight.detach().reshape(-1).contiguous(), a.v_a.bias.detach().reshape(1).contiguous()
+        bu = a.U_a.bias.detach().contiguous()
+        xproj, vocab = ops.LinearPlan(W_ih[:, :E], b_ih), ops.LinearPlan(self.fc.weight.detach(), self.fc.bias.detach())
+        i32 = lambda *s: torch.zeros(*s, device=dev, dtype=torch.int32)
+        Hall = torch.empty(2, R, H, device=dev, dtype=torch.float32)
+        Hall[0].copy_(rep(h0))
+        h_next = torch.zeros(R, H, device=dev, dtype=torch.float32)     # rows of finished beams stay finite
+        scores = torch.zeros(R, device=dev, dtype=torch.float32)
+        live = torch.full((B,), k, device=dev, dtype=torch.int32)
+        prev_tok, ncomp, failed = i32(R), i32(B), i32(B)
+        words = torch.full((R,), -1, device=dev, dtype=torch.int64)  # every beam starts from word 0 -> zero embeddings (:265-266)
+        seq = [i32(R, L), i32(R, L)]                                  # histories start with the token 0
+        comp_score = torch.zeros(R, device=dev, dtype=torch.float32)
+        comp_seq, comp_len = i32(R, L), i32(R)
+        attn = torch.empty(R, 1, P, device=dev, dtype=torch.float32)
+        XC = torch.empty(R, E + Fd, device=dev, dtype=torch.float32)
+        GIw = torch.empty(R, 3 * H, device=dev, dtype=torch.float32)
+        logits = torch.empty(R, V, device=dev, dtype=torch.float32)
+        n_steps = int(max_steps) + 1
+        for step in range(1, n_steps + 1):
+            xw = ops.gather_rows(emb_w, words)                        # zeros where words == -1
+            xproj(xw, out=GIw)
+            ops.attgru_fwd(K3k, f3k, GIw, lw, bu, va, bv, b_hh, Hall, None, attn, XC, E, None, 0, 1)
+            lw._resume = None                                         # Hall[0] is rewritten below: re-convert next step
+            vocab(Hall[1], out=logits)
+            _cabi_call = ops._cabi.call
+            _cabi_call("caphn_beam_step", logits.data_ptr(), Hall[1].data_ptr(), h_next.data_ptr(), scores.data_ptr(),
+                       live.data_ptr(), prev_tok.data_ptr(), words.data_ptr(), seq[(step - 1) & 1].data_ptr(),
+                       seq[step & 1].data_ptr(), comp_score.data_ptr(), comp_seq.data_ptr(), comp_len.data_ptr(),
+                       ncomp.data_ptr(), failed.data_ptr(), B, k, V, H, L, step, int(end_sentence),
+                       int(step == n_steps), ops._stream())
+            Hall[0].copy_(h_next)
+            if sync_every and step % sync_every == 0 and step < n_steps and int(live.max()) == 0:
+                break
+        nc, fl = ncomp.cpu().tolist(), failed.cpu().tolist()           # the one read-back of the search
+        cs, cq, cl = comp_score.cpu().view(B, k), comp_seq.cpu().view(B, k, L), comp_len.cpu().view(B, k)
+        out = []
+        for b in range(B):
+            if fl[b] or nc[b] == 0:
+                out.append(None)
+                continue
+            sc = cs[b, :nc[b]].tolist()
+            j = sc.index(max(sc))                                     # first maximum, as list.index does (:319-321)
+            out.append(cq[b, j, :int(cl[b, j])].tolist())
+        return out
+
+    @torch.no_grad()
     def greedy_search(self, features, end_sentence=2, max_sentence=20):
         """B = 1 greedy decoding with EOS stop -- models/decoderlstm.py:138-175.  ``features`` have ALREADY been through
         ``feature_fc`` ([1, P, F]); the first input word is index 0; returns (tokens list[int], list of attention

@@ -302,6 +302,16 @@ int caphn_attstep_bwd_grouped(const float* dHbm, const float* dattn, const float
                               float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0, int B, int T, int P,
                               int H, int F, const int* tiles, int ntiles, void* stream);
 
+/* Batched device-resident beam search bookkeeping (HyperNet.test_step, hypernet_attention.py:247-326): for B images x k
+ * beams (rows b*k.., live beams first) one launch does what the reference does on the host between two decoder steps --
+ * log-softmax + running scores, top-k_live over (live rows x V) (step 1: row 0 only), completed beams moved to the image's
+ * complete list, survivors compacted with their history / score / hidden state, next input words (-1 = zero embedding).
+ * step is 1-based; last != 0: images with beams still open are flagged in failed[] (the reference returns no caption). */
+int caphn_beam_step(const float* logits, const float* h_out, float* h_next, float* scores, int* live, int* prev_tok,
+                    long long* words, const int* seq_in, int* seq_out, float* comp_score, int* comp_seq, int* comp_len,
+                    int* ncomp, int* failed, int B, int k, int V, int H, int L, int step, int end_tok, int last,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -366,3 +366,49 @@ def test_greedy_projection_table_equals_per_step_path_at_bench_size(monkeypatch)
     assert ok, why
     same = (outs[0][0].argmax(-1) == outs[1][0].argmax(-1)).all(1)
     assert same.any() and rel_err(outs[1][1][same], outs[0][1][same]) < 1e-4
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d", "noeos"])
+def test_batched_beam_search_golden(tag):
+    """Device-resident batched beam search (all images of the golden case in ONE call) == the captions the unmodified
+    reference's test_step produced image by image (hypernet_attention.py:247-326)."""
+    c = load_case("attn_flickr")
+    p = params_of(c)
+    p["captioner.fc.bias"] = c[f"beam/{tag}/fc_bias"]
+    p["captioner.fc.weight"] = c[f"beam/{tag}/fc_weight"]
+    m = _model_from(p, 16, 12, 20, 50, False, 10)
+    style = m.captioner.embed.weight.detach()[int(c["beam/style_id"])].reshape(1, -1)
+    captioner = m.forward(style)
+    feats = c["features"].cuda()
+    got = captioner.beam_search_batched(feats, beam_size=3, end_sentence=2, max_steps=50)
+    for bi in range(feats.shape[0]):
+        want = c[f"beam/{tag}/{bi}"].tolist()
+        assert (got[bi] if got[bi] is not None else [-1]) == want, (tag, bi)
+    # a batch with repeated / reordered images gives the same per-image answers (rows of different images never mix)
+    idx = torch.tensor([1, 0, 1, 2, 0][:max(2, feats.shape[0] + 2)]) % feats.shape[0]
+    got2 = captioner.beam_search_batched(feats[idx], beam_size=3, end_sentence=2, max_steps=50, sync_every=1)
+    for j, bi in enumerate(idx.tolist()):
+        assert got2[j] == got[bi]
+
+
+def test_batched_beam_search_matches_oracle_at_scale():
+    """B = 48 images, V = 1500, F = E = H = 200 (step-split kernels), k = 3 and 5: every image's caption equals the oracle's
+    per-image beam search (which restates the reference loop); EOS made likely so that beams finish at different steps."""
+    B, Fo, E, H, V = 48, 200, 200, 200, 1500
+    p = O.init_params_attention(2048, Fo, E, H, V, E, seed=31)
+    p["captioner.fc.bias"][2] += 4.0                                  # </s> competitive: captions of 3-15 tokens
+    g = torch.Generator().manual_seed(5)
+    feats = torch.randn(B, 49, 2048, generator=g)
+    style = torch.randn(1, E, generator=g)
+    m = _model_from(p, Fo, E, H, V, False, 10)
+    captioner = m.forward(style.cuda())
+    theta = O.hypernet_theta(p, style, 4)
+    gw = O.split_theta_attention(theta, E, Fo, H)
+    for k in (3, 5):
+        got = captioner.beam_search_batched(feats.cuda(), beam_size=k, end_sentence=2, max_steps=20)
+        n_none = 0
+        for bi in range(B):
+            want = O.attention_beam_search(p, gw, feats[bi:bi + 1], beam_size=k, end_sentence=2, max_steps=20)
+            assert got[bi] == want, (k, bi, got[bi], want)
+            n_none += want is None
+        print(f"[beam k={k}] {B - n_none}/{B} images with a caption, lengths {sorted(len(x) for x in got if x)[::8]}")
