@@ -392,11 +392,15 @@ def test_batched_beam_search_golden(tag):
 
 
 def test_batched_beam_search_matches_oracle_at_scale():
-    """B = 48 images, V = 1500, F = E = H = 200 (step-split kernels), k = 3 and 5: every image's caption equals the oracle's
-    per-image beam search (which restates the reference loop); EOS made likely so that beams finish at different steps."""
+    """B = 48 images, V = 1500, F = E = H = 200 (step-split kernels, tensor-core GEMMs), k = 3 and 5: every image's caption
+    equals the oracle's per-image beam search (which restates the reference loop).  A beam decision between two candidates
+    whose scores differ by less than the 1e-5-class rounding of the bf16x3 products is numerically ambiguous (about one
+    decision in a thousand on a random-init model); such images are identified by re-running the ORACLE with the vocabulary
+    weights perturbed at 2e-5 relative and are excluded -- all others must match token for token."""
     B, Fo, E, H, V = 48, 200, 200, 200, 1500
     p = O.init_params_attention(2048, Fo, E, H, V, E, seed=31)
-    p["captioner.fc.bias"][2] += 4.0                                  # </s> competitive: captions of 3-15 tokens
+    p["captioner.fc.weight"][2] *= 60.0                               # </s> logit swings with h: beams finish at different steps
+    p["captioner.fc.bias"][2] -= 1.0
     g = torch.Generator().manual_seed(5)
     feats = torch.randn(B, 49, 2048, generator=g)
     style = torch.randn(1, E, generator=g)
@@ -404,11 +408,22 @@ def test_batched_beam_search_matches_oracle_at_scale():
     captioner = m.forward(style.cuda())
     theta = O.hypernet_theta(p, style, 4)
     gw = O.split_theta_attention(theta, E, Fo, H)
+    variants = [p]
+    for i in range(3):
+        q = dict(p)
+        q["captioner.fc.weight"] = p["captioner.fc.weight"] * (1 + 2e-5 * torch.randn(V, H, generator=g))
+        variants.append(q)
     for k in (3, 5):
         got = captioner.beam_search_batched(feats.cuda(), beam_size=k, end_sentence=2, max_steps=20)
-        n_none = 0
+        n_checked = n_none = 0
         for bi in range(B):
-            want = O.attention_beam_search(p, gw, feats[bi:bi + 1], beam_size=k, end_sentence=2, max_steps=20)
-            assert got[bi] == want, (k, bi, got[bi], want)
-            n_none += want is None
-        print(f"[beam k={k}] {B - n_none}/{B} images with a caption, lengths {sorted(len(x) for x in got if x)[::8]}")
+            wants = [O.attention_beam_search(q, gw, feats[bi:bi + 1], beam_size=k, end_sentence=2, max_steps=20)
+                     for q in variants]
+            if any(w != wants[0] for w in wants[1:]):
+                continue                                             # a near-tie somewhere along this image's search
+            assert got[bi] == wants[0], (k, bi, got[bi], wants[0])
+            n_checked += 1
+            n_none += wants[0] is None
+        print(f"[beam k={k}] {n_checked}/{B} images unambiguous and identical ({n_none} without a caption), "
+              f"lengths {sorted(len(x) for x in got if x)[::8]}")
+        assert n_checked >= 0.8 * B
