@@ -75,6 +75,8 @@ SIGNATURES = {
     "caphn_sumsq": [P, L, P, P],
     "caphn_clip_coef": [P, F, P, P, P],
     "caphn_adam_step": [P, P, P, P, L, D, D, D, D, D, I, P, P],
+    "caphn_sumsq_bf16": [P, L, P, P],
+    "caphn_adam_step_bf16": [P, P, P, P, P, L, D, D, D, D, D, I, P, P],
     "caphn_gram": [P, L, I, L, P, P],
     "caphn_sumsq_lowrank": [P, P, I, P, P],
     "caphn_adam_step_lowrank": [P, P, P, P, L, P, L, I, L, L, D, D, D, D, D, I, P, P],

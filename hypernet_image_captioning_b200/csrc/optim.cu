@@ -7,6 +7,7 @@
 // to the gradient on the fly (read from a device scalar: no host synchronisation, the gradients themselves are left
 // untouched), the global norm accumulated in double by a separate read-only pass over the gradients.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <math.h>
 
 namespace caphn {
@@ -253,6 +254,84 @@ static inline int opt_grid(long n4) {
 
 using namespace caphn;
 
+// ---- bf16 parameters with fp32 master weights (bf16 mode: hypernet.set_precision("bf16")) ------------------------------
+// The streaming kernels read bf16 head weights and write bf16 gradients; the optimizer keeps the fp32 master copy and the
+// Adam moments (fp32), reads the bf16 gradient (8 values per 128-bit load) and writes the master weight and its bf16
+// rounding.  30 bytes per parameter: g 2 + master/m/v 12 read, master/m/v 12 + p 2 written (+ 2 for the norm pass).
+__global__ void __launch_bounds__(OPT_THREADS) sumsq_bf16_kernel(const __nv_bfloat16* __restrict__ x, long n,
+                                                                  double* __restrict__ out) {
+    const long n8 = n >> 3;
+    const uint4* x8 = reinterpret_cast<const uint4*>(x);
+    float acc = 0.f;
+    const long stride = (long)gridDim.x * OPT_THREADS;
+    for (long i = (long)blockIdx.x * OPT_THREADS + threadIdx.x; i < n8; i += stride) {
+        const uint4 u = x8[i];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float a = __uint_as_float(w[e] << 16), b = __uint_as_float(w[e] & 0xffff0000u);
+            acc += a * a + b * b;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) { const float t = __bfloat162float(x[(n8 << 3) + threadIdx.x]); acc += t * t; }
+    double s = (double)acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double ws[OPT_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < OPT_THREADS / 32; ++w) t += ws[w];
+        atomicAdd(out, t);
+    }
+}
+
+struct AdamBf16Args {
+    __nv_bfloat16* p; const __nv_bfloat16* g; float* master; float* m; float* v;
+    long n;
+    AdamArgs h;     // hyper-parameters (pointer fields unused)
+};
+
+__global__ void __launch_bounds__(OPT_THREADS) adam_bf16_kernel(const AdamBf16Args a) {
+    const float gs = a.h.gscale ? *a.h.gscale : 1.f;
+    const long n8 = a.n >> 3;
+    const long stride = (long)gridDim.x * OPT_THREADS;
+    for (long i = (long)blockIdx.x * OPT_THREADS + threadIdx.x; i < n8; i += stride) {
+        const uint4 gu = *reinterpret_cast<const uint4*>(a.g + i * 8);
+        float4 w0 = ld_rw4(reinterpret_cast<float4*>(a.master) + 2 * i), w1 = ld_rw4(reinterpret_cast<float4*>(a.master) + 2 * i + 1);
+        float4 m0 = ld_rw4(reinterpret_cast<float4*>(a.m) + 2 * i), m1 = ld_rw4(reinterpret_cast<float4*>(a.m) + 2 * i + 1);
+        float4 v0 = ld_rw4(reinterpret_cast<float4*>(a.v) + 2 * i), v1 = ld_rw4(reinterpret_cast<float4*>(a.v) + 2 * i + 1);
+        const uint32_t gw[4] = {gu.x, gu.y, gu.z, gu.w};
+        float g[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { g[2 * e] = __uint_as_float(gw[e] << 16); g[2 * e + 1] = __uint_as_float(gw[e] & 0xffff0000u); }
+        adam_one(w0.x, g[0], m0.x, v0.x, a.h, gs); adam_one(w0.y, g[1], m0.y, v0.y, a.h, gs);
+        adam_one(w0.z, g[2], m0.z, v0.z, a.h, gs); adam_one(w0.w, g[3], m0.w, v0.w, a.h, gs);
+        adam_one(w1.x, g[4], m1.x, v1.x, a.h, gs); adam_one(w1.y, g[5], m1.y, v1.y, a.h, gs);
+        adam_one(w1.z, g[6], m1.z, v1.z, a.h, gs); adam_one(w1.w, g[7], m1.w, v1.w, a.h, gs);
+        stg_stream4(a.master + 8 * i, w0); stg_stream4(a.master + 8 * i + 4, w1);
+        stg_stream4(a.m + 8 * i, m0); stg_stream4(a.m + 8 * i + 4, m1);
+        stg_stream4(a.v + 8 * i, v0); stg_stream4(a.v + 8 * i + 4, v1);
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        uint4 pu;
+        uint32_t* pw = reinterpret_cast<uint32_t*>(&pu);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat16 lo = __float2bfloat16_rn(w[2 * e]), hi = __float2bfloat16_rn(w[2 * e + 1]);
+            pw[e] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+        }
+        *reinterpret_cast<uint4*>(a.p + i * 8) = pu;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (a.n & 7)) {
+        const long i = (n8 << 3) + threadIdx.x;
+        float w = a.master[i], m = a.m[i], v = a.v[i];
+        adam_one(w, __bfloat162float(a.g[i]), m, v, a.h, gs);
+        a.master[i] = w; a.m[i] = m; a.v[i] = v;
+        a.p[i] = __float2bfloat16_rn(w);
+    }
+}
+
 extern "C" {
 
 // *sumsq (double, device) += sum_i x[i]^2.  x must be 16-byte aligned.
@@ -321,6 +400,29 @@ int caphn_adam_step_lowrank(float* p, float* m, float* v, const float* dP, long 
         case 3: adam_lowrank_kernel<3><<<grid, OPT_THREADS, 0, st>>>(a); break;
         default: adam_lowrank_kernel<4><<<grid, OPT_THREADS, 0, st>>>(a); break;
     }
+    CAPHN_RETURN_LAST();
+}
+
+// bf16 variants (see adam_bf16_kernel): *sumsq += sum x^2 over a bf16 tensor; Adam step on fp32 master / moments with a
+// bf16 gradient, writing the bf16 parameter as the rounding of the updated master weight.
+int caphn_sumsq_bf16(const void* x, long n, double* sumsq, void* stream) {
+    if (n < 0 || !sumsq || ((uintptr_t)x & 15)) return CAPHN_EINVAL;
+    if (n == 0) return CAPHN_OK;
+    sumsq_bf16_kernel<<<opt_grid(n >> 3), OPT_THREADS, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, n, sumsq);
+    CAPHN_RETURN_LAST();
+}
+
+int caphn_adam_step_bf16(void* p, const void* g, float* master, float* m, float* v, long n, double lr, double beta1,
+                         double beta2, double eps, double weight_decay, int step, const float* gscale, void* stream) {
+    if (n < 0 || step < 1 ||
+        (((uintptr_t)p | (uintptr_t)g | (uintptr_t)master | (uintptr_t)m | (uintptr_t)v) & 15))
+        return CAPHN_EINVAL;
+    if (n == 0) return CAPHN_OK;
+    const double bc1 = 1.0 - pow(beta1, step), bc2 = 1.0 - pow(beta2, step);
+    AdamBf16Args a{(__nv_bfloat16*)p, (const __nv_bfloat16*)g, master, m, v, n,
+                   AdamArgs{nullptr, nullptr, nullptr, nullptr, n, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2),
+                            (float)eps, (float)weight_decay, (float)(lr / bc1), (float)sqrt(bc2), gscale}};
+    adam_bf16_kernel<<<opt_grid(n >> 3), OPT_THREADS, 0, (cudaStream_t)stream>>>(a);
     CAPHN_RETURN_LAST();
 }
 

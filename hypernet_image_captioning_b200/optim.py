@@ -45,8 +45,10 @@ class FusedAdam(torch.optim.Optimizer):
         st = self.state[p]
         if not st:
             st["step"] = 0
-            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            st["exp_avg"] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+            if p.dtype == torch.bfloat16:      # bf16 mode: fp32 master weight, the bf16 parameter is its rounding
+                st["master"] = p.detach().to(torch.float32).contiguous()
         st["step"] = int(st["step"]) + 1
         return st
 
@@ -68,9 +70,11 @@ class FusedAdam(torch.optim.Optimizer):
                     continue
                 if p.grad is None:
                     continue
-                if p.dtype != torch.float32 or not p.is_cuda or not p.is_contiguous():
-                    raise _cabi.CaphnError("FusedAdam needs contiguous fp32 CUDA parameters")
+                if p.dtype not in (torch.float32, torch.bfloat16) or not p.is_cuda or not p.is_contiguous():
+                    raise _cabi.CaphnError("FusedAdam needs contiguous fp32 (or bf16, with fp32 master state) CUDA parameters")
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                if g.dtype != p.dtype:
+                    g = g.to(p.dtype)
                 st = self._state_of(p)
                 items.append((group, p, g, st))
         if not items:
@@ -87,6 +91,8 @@ class FusedAdam(torch.optim.Optimizer):
                     _cabi.call("caphn_gram", dP.data_ptr(), dP.stride(0), G, dP.shape[1], gram[0].data_ptr(), _stream())
                     _cabi.call("caphn_gram", a.data_ptr(), a.stride(0), G, a.shape[1], gram[1].data_ptr(), _stream())
                     _cabi.call("caphn_sumsq_lowrank", gram[0].data_ptr(), gram[1].data_ptr(), G, sumsq.data_ptr(), _stream())
+                elif g.dtype == torch.bfloat16:
+                    _cabi.call("caphn_sumsq_bf16", g.data_ptr(), g.numel(), sumsq.data_ptr(), _stream())
                 else:
                     _cabi.call("caphn_sumsq", g.data_ptr(), g.numel(), sumsq.data_ptr(), _stream())
             _cabi.call("caphn_clip_coef", sumsq.data_ptr(), float(self.max_grad_norm), coef.data_ptr(), norm.data_ptr(),
@@ -101,6 +107,11 @@ class FusedAdam(torch.optim.Optimizer):
                            float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
                            st["step"], gscale, _stream())
                 p.grad_lowrank = None         # consumed (zero_grad() does not know about it)
+                continue
+            if p.dtype == torch.bfloat16:
+                _cabi.call("caphn_adam_step_bf16", p.data_ptr(), g.data_ptr(), st["master"].data_ptr(),
+                           st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel(), float(group["lr"]), float(b1),
+                           float(b2), float(group["eps"]), float(group["weight_decay"]), st["step"], gscale, _stream())
                 continue
             _cabi.call("caphn_adam_step", p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                        p.numel(), float(group["lr"]), float(b1), float(b2), float(group["eps"]),

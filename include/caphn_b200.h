@@ -312,6 +312,13 @@ int caphn_beam_step(const float* logits, const float* h_out, float* h_next, floa
                     int* ncomp, int* failed, int B, int k, int V, int H, int L, int step, int end_tok, int last,
                     void* stream);
 
+/* bf16 mode of the optimizer (hypernet.set_precision("bf16")): the parameter and its gradient are bf16 (what the
+ * weight-streaming kernels read and write), the master weight and the Adam moments stay fp32.  caphn_sumsq_bf16 is the
+ * norm pass over a bf16 gradient; caphn_adam_step_bf16 is caphn_adam_step on (master, m, v) with p = bf16(master). */
+int caphn_sumsq_bf16(const void* x, long n, double* sumsq, void* stream);
+int caphn_adam_step_bf16(void* p, const void* g, float* master, float* m, float* v, long n, double lr, double beta1,
+                         double beta2, double eps, double weight_decay, int step, const float* gscale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

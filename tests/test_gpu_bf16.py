@@ -94,3 +94,58 @@ def test_attention_bf16_mode_within_stated_tolerance():
     print(f"attention bf16 mode: logits rel err {e:.2e}, attn rel err {rel_err(att, ar):.2e}")
     assert e < BF16_TOL_LOGITS and rel_err(att, ar) < BF16_TOL_LOGITS
     assert torch.isfinite(dict(m.named_parameters())["hn_heads.0.2.weight"].grad.float()).all()
+
+
+def test_fused_adam_bf16_parameters_with_fp32_master():
+    """bf16 mode is trainable: FusedAdam keeps an fp32 master copy + fp32 moments for bf16 parameters, reads the bf16
+    gradient, writes the master weight and its bf16 rounding.  Reference: torch.optim.Adam + clip_grad_norm_ on fp32 copies
+    fed with the same (bf16-valued) gradients; the bf16 parameter must equal bf16(master) after every step."""
+    import hypernet_image_captioning_b200 as C
+    g = torch.Generator().manual_seed(0)
+    shapes = [(257, 33), (1000,), (64, 128)]
+    ps = [torch.nn.Parameter((torch.randn(*s, generator=g) * 0.1).cuda().to(torch.bfloat16)) for s in shapes]
+    refs = [torch.nn.Parameter(p.detach().float().clone()) for p in ps]
+    opt = C.FusedAdam(ps, lr=1e-2, max_grad_norm=1.0)
+    ref_opt = torch.optim.Adam(refs, lr=1e-2)
+    for step in range(4):
+        for p, r in zip(ps, refs):
+            gr = (torch.randn(*p.shape, generator=g) * (3.0 if step == 1 else 0.3)).cuda().to(torch.bfloat16)
+            p.grad = gr
+            r.grad = gr.float().clone()
+        torch.nn.utils.clip_grad_norm_(refs, 1.0)
+        ref_opt.step()
+        opt.step()
+        for p, r in zip(ps, refs):
+            master = opt.state[p]["master"]
+            assert (master - r.detach()).abs().max().item() <= 2e-6 * max(1.0, r.detach().abs().max().item()), step
+            assert torch.equal(p.detach(), master.to(torch.bfloat16))
+
+
+def test_bf16_mode_training_step_reduces_loss():
+    """End to end in bf16 mode: forward + backward + FusedAdam on the bf16 hypernet parameters lowers the caption loss."""
+    import hypernet_image_captioning_b200 as C
+    from hypernet_image_captioning_b200 import ops
+    from hypernet_image_captioning_b200.synth import synth_captions
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        m = C.HyperNetPooled(48, 40, 500, None)
+    m.set_precision("bf16")
+    try:
+        g = torch.Generator().manual_seed(1)
+        pooled = torch.relu(torch.randn(32, 2048, generator=g)).cuda()
+        caps = synth_captions(32, 8, 500, g).cuda()
+        h0 = torch.rand(32, 40, generator=g).cuda()
+        opt = C.FusedAdam([p for n, p in m.named_parameters() if not n.startswith("captioner.lstm_cell")], lr=2e-3,
+                          max_grad_norm=5.0)
+        losses = []
+        for _ in range(8):
+            m.zero_grad(set_to_none=True)
+            cap = m.forward(m.captioner.embed.weight[4:5])
+            loss, _ = cap.forward_loss(m.image_encoder(pooled), caps, h0=h0)
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        assert all(p.dtype == torch.bfloat16 for p in m.hn_heads.parameters())
+        assert losses[-1] < losses[0] - 0.05, losses
+    finally:
+        ops.set_precision("fp32")
