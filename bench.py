@@ -672,7 +672,7 @@ def cc_extras(args, dev, world, timed, rooflines, peak):
             par.enable_overlap(shared)
         eye = torch.eye(he, device=dev)
         for G in Gs:
-            groups = (torch.arange(B) % G).to(dev)
+            groups = torch.arange(B) % G                     # host tensor: the batch composition is loader (host) data
             styles = eye[:G].contiguous()
 
             def train():

@@ -41,6 +41,9 @@ class GroupPlan:
 
     @classmethod
     def get(cls, groups: torch.Tensor, G: int, T: int, device) -> "GroupPlan":
+        """``groups``: [B] integer group id per batch row.  Pass a CPU tensor (the domain of a sample is host data in the
+        reference's loaders, cc_train_hypernet.py:135-137): a CUDA tensor costs a device->host copy + synchronisation per
+        call and cannot be used while a CUDA graph is being captured."""
         g_host = groups.detach().to("cpu", torch.int64).numpy()
         key = (g_host.tobytes(), G, T, str(device))
         plan = cls._cache.get(key)
@@ -79,6 +82,8 @@ class GroupPlan:
         self.goff_dev = i32(goff)
         self.tiles_fwd = i32(self._tiles(64))
         self.tiles_bwd = i32(self._tiles(32))
+        absent = [g for g in range(G) if cnt[g] == 0]
+        self.absent_dev = i64(absent) if absent else None         # groups without rows: their d(theta) rows are zero
         self._units: Dict[Tuple, torch.Tensor] = {}
 
     def _tiles(self, nb):
@@ -234,9 +239,8 @@ def _grouped_backward(plan: GroupPlan, sv, dims, vocab, dattn_o):
     Hp_gm = ops.split_bf16_gather(Hprev, plan.gm2tm, R)
     dTheta = torch.empty(G, theta, device=dev, dtype=torch.float32)
     dTheta[:, o_bi:].zero_()
-    absent = [g for g in range(G) if g not in set(plan.present)]
-    if absent:
-        dTheta[torch.tensor(absent, device=dev)] = 0.0
+    if plan.absent_dev is not None:
+        dTheta.index_fill_(0, plan.absent_dev, 0.0)
     mn = lambda op: ops.SplitOperand(op.hi, op.lo, op.K, op.rows, op.ld, True)
     ops.gemm_tc_grouped(mn(dGI_gm), True, mn(XC_gm), True, dTheta, E + Fd,
                         plan.units_dw(H3, E + Fd, 128, theta, 0, E + Fd), 128)
