@@ -606,8 +606,11 @@ def attention_extras(args, dev, world, timed, rooflines=None, peak=6537.6):
 
     def greedy():
         with torch.no_grad():
+            model.async_hypernet = True       # the hypernet streams its weights while the feature branch runs
             captioner = model.forward(model.captioner.embed.weight[4:5])
-            return captioner(feats, caps, 1.0)
+            out = captioner(feats, caps, 1.0)
+            model.async_hypernet = False
+            return out
 
     out = {}
     for name, fn in (("attention_train_captions_per_s", train), ("attention_greedy_decode_captions_per_s", greedy)):

@@ -339,6 +339,38 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const long l
     for (int e = threadIdx.x; e < E; e += blockDim.x) out[i * ldo + e] = r >= 0 ? table[r * E + e] : 0.f;
 }
 
+// Greedy feedback after caphn_gemm_tc_amax: finish the row arg-max from the epilogue's partials (ties: lowest column, like
+// torch.argmax / topk(1)), write the token, and gather the row of `table` it selects (the embedding, or the pre-multiplied
+// input projection Emb W_ih^T + b_ih) -- one launch between the vocabulary projection of step t and the recurrence of t+1.
+__global__ void __launch_bounds__(128) argmax_finish_gather_kernel(const float* __restrict__ pval, const int* __restrict__ pidx,
+                                                                    int ld, int nparts, const float* __restrict__ table,
+                                                                    int E, long long* __restrict__ tok,
+                                                                    float* __restrict__ out, long ldo) {
+    __shared__ int s_tok;
+    const long i = blockIdx.x;
+    if (threadIdx.x < 32) {
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int q = threadIdx.x; q < nparts; q += 32) {
+            const float v = pval[i * ld + q];
+            const int c = pidx[i * ld + q];
+            if (v > bv || (v == bv && c < bi)) { bv = v; bi = c; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (threadIdx.x == 0) { s_tok = bi; if (tok) tok[i] = bi; }
+    }
+    __syncthreads();
+    if (table) {
+        const long r = s_tok;
+        for (int e = threadIdx.x; e < E; e += blockDim.x) out[i * ldo + e] = table[r * E + e];
+    }
+}
+
 // Decoder inputs, time-major X[t,b,:]:  mode 0 (DecoderGRU, later.py:411,418): X[0,b] = feat[b], X[t,b] = Emb[caps[b,t-1]]
 //                                       mode 1 (AttentionGru, decoderlstm.py:82-88): X[0] = X[1] = 0, X[t] = Emb[caps[b,t-1]]
 __global__ void build_inputs_kernel(const float* __restrict__ feat, const float* __restrict__ emb,
@@ -471,6 +503,15 @@ int caphn_softmax_argmax(const float* X, long ld, long M, int V, float* Y, long 
 int caphn_gather_rows(const float* table, const long long* idx, long n, int E, float* out, long ldo, void* stream) {
     if (n <= 0 || E <= 0) return CAPHN_EINVAL;
     gather_rows_kernel<<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(table, idx, n, E, out, ldo);
+    CAPHN_RETURN_LAST();
+}
+
+// tok[i] = arg-max over the nparts (value, column) partials of row i (pval / pidx [n, ld], from caphn_gemm_tc_amax);
+// out[i, :] = table[tok[i], :E] when table != NULL.  tok may be NULL.
+int caphn_argmax_finish_gather(const float* pval, const int* pidx, int ld, int nparts, long n, const float* table, int E,
+                               long long* tok, float* out, long ldo, void* stream) {
+    if (n <= 0 || nparts <= 0 || nparts > ld || (table && (E <= 0 || !out))) return CAPHN_EINVAL;
+    argmax_finish_gather_kernel<<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(pval, pidx, ld, nparts, table, E, tok, out, ldo);
     CAPHN_RETURN_LAST();
 }
 

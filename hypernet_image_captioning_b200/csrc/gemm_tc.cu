@@ -156,6 +156,10 @@ struct TcParams {
     const GUnit* units;   // grouped mode when non-null (num_units records)
     const int* rowmap;
     int num_units;
+    // optional row arg-max partials (greedy decode, SURVEY K9: the arg-max of step t feeds step t+1): every epilogue warp
+    // reduces the columns it reads of every row to (max, column) and writes them to amax_val / amax_idx [M, amax_ld],
+    // slot 2 * n-tile + warp half; a tiny kernel finishes the reduction (and gathers the next input row).  null: off.
+    float* amax_val; int* amax_idx; int amax_ld;
     int M, N, num_kb, relu;
     int BN;          // N tile (multiple of 16, <= 256)
     int splitk;      // K split factor; > 1 => epilogue adds atomically into a zero-initialised C
@@ -322,6 +326,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             const int* rmap = p.rowmap ? p.rowmap + u.map0 : nullptr;
             int last_c = half;
             while (last_c + 2 < nchunks) last_c += 2;
+            float am_best = -INFINITY;            // arg-max partial of row (rl0 + lane) over this warp's chunks
+            int am_idx = 0x7fffffff;
             if (half >= nchunks) {                 // nothing to read for this warp: release the stage immediately
                 tcgen05_fence_before();
                 if (lane == 0) mbar_arrive(tempty + as);
@@ -339,6 +345,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 const int colbase = u.b0 + c * 32;            // (TMA-store path: global column)
                 const int cl0 = c * 32;                       // tile-local column of this chunk
                 const int cvalid = min(32, u.n_valid - cl0);  // valid columns of this chunk (may be <= 0)
+                if (p.amax_val) {                             // lane = row: 32 consecutive columns of it are in r[]
+                    const float bl = (add_bias && lane < cvalid) ? biasp[cl0 + lane] : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
+                        if (j < cvalid && v > am_best) { am_best = v; am_idx = colbase + j; }   // ascending columns: first max wins
+                    }
+                }
                 if constexpr (TMA_STORE) {
                     // chunks that lie fully inside the N tile (TMA clips at the matrix edge, not at the tile edge)
                     if (!atomic && BN - c * 32 >= 32) {
@@ -423,6 +437,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     }
                 }
                 __syncwarp();
+            }
+            if (p.amax_val && rl0 + lane < u.m_valid) {
+                const long o = (long)(u.a0 + rl0 + lane) * p.amax_ld + 2 * (u.b0 / BN) + half;
+                p.amax_val[o] = am_best;
+                p.amax_idx[o] = am_idx;
             }
         }
         if constexpr (TMA_STORE) {
@@ -557,10 +576,12 @@ int caphn_split_bf16_t(const float* src, long lds, int R, int C, void* hi, void*
 //   MN-major operand (x_mn = 1): hi/lo [K rows, M or N cols], row pitch x_ld -- i.e. the operand of a TRANSPOSED product
 //                                (dW = dY^T X) read in place, no transposed copy.
 // Alo == Blo == NULL selects plain bf16.  splitk: 0 = automatic, 1 = none, > 1 = split K, partial tiles added atomically.
-int caphn_gemm_tc_ex(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
-                     int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, int relu, int splitk,
-                     void* stream) {
+static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
+                        int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, int relu, int splitk,
+                        float* amax_val, int* amax_idx, int amax_ld, void* stream, int* bn_used = nullptr) {
     if (M <= 0 || N <= 0 || K <= 0 || ((Alo == nullptr) != (Blo == nullptr))) return CAPHN_EINVAL;
+    if (amax_val && (!amax_idx || splitk > 1 || relu)) return CAPHN_EINVAL;
+    if (amax_val) splitk = 1;
     if (((uintptr_t)Ahi & 15) || ((uintptr_t)Bhi & 15) || ((uintptr_t)Alo & 15) || ((uintptr_t)Blo & 15) ||
         (a_ld & 7) || (b_ld & 7))
         return CAPHN_EINVAL;
@@ -621,6 +642,11 @@ int caphn_gemm_tc_ex(const void* Ahi, const void* Alo, long a_ld, int a_mn, cons
     p.stages = stages;
     p.tmem_cols = (2 * p.BN <= 256) ? 256u : 512u;
     const size_t smem = (size_t)stages * p.stage_bytes + fixed;
+    if (bn_used) *bn_used = p.BN;
+    if (amax_val) {
+        if (amax_ld < 2 * ceil_div(N, p.BN)) return CAPHN_EINVAL;
+        p.amax_val = amax_val; p.amax_idx = amax_idx; p.amax_ld = amax_ld;
+    }
     if (p.splitk > 1) {
         if (ldc == N) {
             CAPHN_CHECK(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), st));
@@ -649,10 +675,13 @@ int caphn_gemm_tc_ex(const void* Ahi, const void* Alo, long a_ld, int a_mn, cons
     const int grid = units < kNumSMs ? (int)units : kNumSMs;
     CUtensorMap mC{};
     bool tma_store = false;
-    if (const char* e = getenv("CAPHN_TC_TMA_STORE")) {      // experimental epilogue, see gemm_tc_kernel
-        // N % 4 == 0: with a ragged N (450, 257) the clipped edge box did not match the default epilogue in the one
-        // hardware run this path has had (tests/test_gpu_gemm_tc.py, 4 of 6 shapes bit-identical) -- unresolved.
-        tma_store = e[0] == '1' && p.splitk == 1 && (ldc % 4 == 0) && (N % 4 == 0) && ((uintptr_t)C % 16 == 0);
+    {   // TMA-store epilogue: full 32-column chunks leave through cp.async.bulk.tensor stores.  Bit-identical to the default
+        // epilogue and 2-9 % faster on the logits products (profiles/r02_gemm_tma_store.txt); N % 4 == 0 only (a clipped
+        // edge box of a ragged N did not match in round 1 -- those shapes keep the default epilogue).  CAPHN_TC_TMA_STORE=0
+        // switches it off.
+        const char* e = getenv("CAPHN_TC_TMA_STORE");
+        tma_store = !(e && e[0] == '0') && p.splitk == 1 && (ldc % 4 == 0) && (N % 4 == 0) && ((uintptr_t)C % 16 == 0) &&
+                    !p.amax_val;
         if (tma_store && (rc = tc::make_map_c(&mC, C, M, N, ldc))) return rc;
     }
     if (split && tma_store) {
@@ -719,6 +748,28 @@ int caphn_gemm_tc_grouped(const void* Ahi, const void* Alo, long a_inner, long a
         tc::gemm_tc_kernel<false><<<grid, tc::THREADS_V2, smem, st>>>(mAh, mAl, mBh, mBl, mC, p);
     }
     CAPHN_RETURN_LAST();
+}
+
+int caphn_gemm_tc_ex(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
+                     int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, int relu, int splitk,
+                     void* stream) {
+    return gemm_tc_impl(Ahi, Alo, a_ld, a_mn, Bhi, Blo, b_ld, b_mn, K, C, ldc, bias, M, N, relu, splitk, nullptr, nullptr, 0,
+                        stream);
+}
+
+// caphn_gemm_tc_ex + row arg-max partials in the epilogue (greedy decode: logits_t = h_t W^T + b, next word = arg-max):
+// amax_val / amax_idx [M, amax_ld] receive, per row, one (max, column) pair per (n-tile, epilogue-warp half) in slots
+// 0 .. 2*ceil(N/BN)-1 (slots of halves that read no column hold -inf).  amax_ld >= 2*ceil(N/128) always suffices.
+// *nparts (host int, optional) = number of slots written.  Finish with caphn_argmax_finish_gather.
+int caphn_gemm_tc_amax(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
+                       int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, float* amax_val,
+                       int* amax_idx, int amax_ld, int* nparts, void* stream) {
+    if (!amax_val || !amax_idx) return CAPHN_EINVAL;
+    int bn = 0;
+    const int rc = gemm_tc_impl(Ahi, Alo, a_ld, a_mn, Bhi, Blo, b_ld, b_mn, K, C, ldc, bias, M, N, 0, 1, amax_val, amax_idx,
+                                amax_ld, stream, &bn);
+    if (nparts && bn > 0) *nparts = 2 * ceil_div(N, bn);
+    return rc;
 }
 
 // Both operands K-major with the same padded pitch Kp (Kp % 64 == 0): the original entry point.

@@ -135,21 +135,38 @@ def _attgru_forward(need_grad, f3, K3, h0, captions, use_sampling, emb_w, W_ih, 
             emb_ext = torch.cat([emb_w, emb_w.new_zeros(1, E)], 0)
             table = ops.linear(emb_ext, W_ih_w.contiguous(), b_ih.contiguous())
             fed.fill_(V)
+        # Decode fast path (projection table + step-split kernels + tensor-core vocabulary projection): 5 dependent launches
+        # per step instead of 7 -- the arg-max of the logits comes out of the vocabulary GEMM's epilogue as per-tile partials
+        # and is finished inside the gather of the next step's input row; h_t goes to the GEMM as the bf16 hi/lo rows the
+        # gates kernel has already written for the next step (no separate operand split).
+        fast = table is not None and lw.pack is not None and ops._tc_ok(B, V, H) and ops.DECODE_FUSED_ARGMAX
+        if fast:
+            pv = torch.empty(B, 2 * ((V + 127) // 128), device=dev, dtype=torch.float32)
+            pi = torch.empty(B, 2 * ((V + 127) // 128), device=dev, dtype=torch.int32)
+            nparts = 0
         for t in range(T):
-            if use_sampling[t]:
-                # :91-96  argmax of log_softmax(logits/0.5) == argmax of logits (lowest index on ties)
-                _, top = ops.softmax_argmax(logits[:, t - 1, :], want_probs=False)
-                fed[t].copy_(top)
-            elif t >= 2:
-                fed[t].copy_(caps[:, t - 1])
-            if table is not None:
-                ops.gather_rows(table, fed[t], out=GIw[t * B:(t + 1) * B])
+            if fast and use_sampling[t] and nparts:
+                # tokens of step t-1 from the partials + the table row they select, one launch
+                ops.argmax_finish_gather(pv, pi, nparts, table, fed[t], GIw[t * B:(t + 1) * B])
             else:
-                xw = ops.gather_rows(emb_w, fed[t])                    # zeros where fed == -1
-                XC[t * B:(t + 1) * B, :E].copy_(xw)
-                xproj(xw, out=GIw[t * B:(t + 1) * B])
+                if use_sampling[t]:
+                    # :91-96  argmax of log_softmax(logits/0.5) == argmax of logits (lowest index on ties)
+                    _, top = ops.softmax_argmax(logits[:, t - 1, :], want_probs=False)
+                    fed[t].copy_(top)
+                elif t >= 2:
+                    fed[t].copy_(caps[:, t - 1])
+                if table is not None:
+                    ops.gather_rows(table, fed[t], out=GIw[t * B:(t + 1) * B])
+                else:
+                    xw = ops.gather_rows(emb_w, fed[t])                    # zeros where fed == -1
+                    XC[t * B:(t + 1) * B, :E].copy_(xw)
+                    xproj(xw, out=GIw[t * B:(t + 1) * B])
             ops.attgru_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, t, t + 1)
-            vocab(Hall[t + 1], out=logits[:, t, :])
+            if fast:
+                nparts = ops.gemm_tc_amax(ops.attstep_h_operand(lw, B, H, Fd, t), vocab.operand(), fc_b, logits[:, t, :],
+                                          pv, pi)
+            else:
+                vocab(Hall[t + 1], out=logits[:, t, :])
     sv = (f3, K3, XC, Hall, Hbm, attn, saved, fed, emb_w, W_ih, W_hh, fc_w, Ua_w, va)
     return logits, attn, sv, (B, T, P, E, H, Fd, V)
 
@@ -309,21 +326,21 @@ class AttentionGru(nn.Module):
         if any(use) and not torch.is_grad_enabled():
             # decode (test_hn.py path, cc_train_hypernet.py:230): ~10 launches per step -> captured into a CUDA graph
             from . import graphs
+            # the loop-invariant feature branch runs eagerly on its own stream (next to an asynchronous hypernet forward);
+            # the graph holds only the time loop
+            f3, K3, h0 = self._features(features.contiguous().float())
             streams.wait_pending()
-            fp = [p.detach() for p in self._feature_params()]
             rp = [p.detach() for p in self._recurrence_params(self._gru_weights())]
             gen = [rp[1].contiguous(), rp[2].contiguous(), rp[3].contiguous(), rp[4].contiguous()]   # generated weights
             key = ("AttentionGru.decode", id(self), tuple(features.shape), tuple(captions.shape), tuple(use),
-                   features.device.index) + tuple(p.data_ptr() for p in fp) + \
-                tuple(p.data_ptr() for i, p in enumerate(rp) if i not in (1, 2, 3, 4))
+                   features.device.index) + tuple(p.data_ptr() for i, p in enumerate(rp) if i not in (1, 2, 3, 4))
 
-            def run(f, c, wi, wh, bi, bh):
+            def run(f_, k_, h_, c, wi, wh, bi, bh):
                 q = list(rp)
                 q[1], q[2], q[3], q[4] = wi, wh, bi, bh
-                f3, K3, h0 = FeatureFn.apply(f, *fp)
-                return AttentionGruFn.apply(f3, K3, h0, c, tuple(use), *q)
+                return AttentionGruFn.apply(f_, k_, h_, c, tuple(use), *q)
 
-            out = graphs.graphed_call(key, run, [features.contiguous().float(), captions.contiguous()] + gen)
+            out = graphs.graphed_call(key, run, [f3.detach(), K3.detach(), h0.detach(), captions.contiguous()] + gen)
             return out[0], out[1]
         return self._forward_one(features, captions, tuple(use), self._gru_weights())
 

@@ -443,6 +443,7 @@ def relu_mask_(ref, y):
     return y
 
 
+DECODE_FUSED_ARGMAX = True   # greedy decode: arg-max partials in the vocabulary GEMM's epilogue, finished inside the next gather
 ATT_STEP = True   # two batch-wide kernels per step (attention | tensor-core gates) instead of the persistent streaming kernel
 
 
@@ -681,6 +682,44 @@ def gemm_tc(A: SplitOperand, Bm: SplitOperand, bias=None, relu=False, out=None, 
     return out
 
 
+def gemm_tc_amax(A: SplitOperand, Bm: SplitOperand, bias, out, pval, pidx):
+    """out[M,N] = A B^T + bias on the tensor cores, and per-row arg-max partials of the result written by the epilogue into
+    pval (fp32) / pidx (int32) [M, ld]; returns the number of partial slots per row (finish with argmax_finish_gather)."""
+    import ctypes
+    assert A.K == Bm.K and (A.lo is None) == (Bm.lo is None) and out.stride(1) == 1
+    assert pval.dtype == torch.float32 and pidx.dtype == torch.int32 and pval.stride(0) == pidx.stride(0)
+    M, N = A.rows, Bm.rows
+    n = ctypes.c_int(0)
+    _cabi.call("caphn_gemm_tc_amax", A.hi.data_ptr(), _p(A.lo), A.ld, int(A.mn), Bm.hi.data_ptr(), _p(Bm.lo), Bm.ld,
+               int(Bm.mn), A.K, out.data_ptr(), out.stride(0), _p(bias), M, N, pval.data_ptr(), pidx.data_ptr(),
+               pval.stride(0), ctypes.byref(n), _stream())
+    return int(n.value)
+
+
+def argmax_finish_gather(pval, pidx, nparts, table=None, tok=None, out=None):
+    """tok[i] = arg-max of row i from its ``nparts`` partials (lowest column on ties); out[i] = table[tok[i]] if given."""
+    n = pval.shape[0]
+    E = table.shape[1] if table is not None else 0
+    if table is not None:
+        assert table.is_contiguous() and out is not None and out.stride(1) == 1
+    _cabi.call("caphn_argmax_finish_gather", pval.data_ptr(), pidx.data_ptr(), pval.stride(0), nparts, n, _p(table), E,
+               _p(tok), _p(out), out.stride(0) if out is not None else 0, _stream())
+
+
+def attstep_h_operand(lw, B, H, Fd, t_done):
+    """The hidden state h_{t_done} as the bf16 hi/lo operand rows the step-split gates kernel has just written into its
+    workspace for the next step's U kernel (attgru_step.cu: hsp buffers) -- the A operand of the vocabulary projection,
+    with no separate split pass.  Only for the step-split path (``lw.pack`` set), after ``attgru_fwd(..., t_done, t_done+1)``."""
+    KP = ((max(H, Fd) + 15) // 16) * 16 + 8
+    a256 = lambda v: (v + 255) & ~255
+    plane2 = a256(B * KP * 2)
+    base = a256(B * H * 4) + 2 * plane2 + (2 * plane2 if ((t_done + 1) & 1) else 0)      # hbuf(t_done + 1)
+    w = lw.work
+    hi = w[base: base + B * KP * 2].view(torch.bfloat16).view(B, KP)
+    lo = w[base + B * KP * 2: base + 2 * B * KP * 2].view(torch.bfloat16).view(B, KP) if TC_SPLIT else None
+    return SplitOperand(hi, lo, B, H, KP, False)
+
+
 def use_projection_table(B, steps, V):
     """Greedy decode feeds back word embeddings, so  x_t W^T + b  is a row of the table  Emb W^T + b  [V, N].  Building
     the table costs one V-row GEMM per decode call (the generated W changes with every style); it replaces a gather, an
@@ -699,12 +738,16 @@ class LinearPlan:
         self.N, self.K = W.shape
         self._split = None
 
+    def operand(self):
+        """The cached bf16 hi/lo split of W (the B operand of the tensor-core path)."""
+        if self._split is None or (self._split.lo is None) == TC_SPLIT:
+            self._split = split_bf16(self.W)
+        return self._split
+
     def __call__(self, X, relu=False, out=None):
         M = X.shape[0]
         if _tc_ok(M, self.N, self.K):
-            if self._split is None:
-                self._split = split_bf16(self.W)
-            return gemm_tc(split_bf16(X), self._split, bias=self.bias, relu=relu, out=out)
+            return gemm_tc(split_bf16(X), self.operand(), bias=self.bias, relu=relu, out=out)
         return _gemm(X, X.stride(0), 1, self.W, self.W.stride(0), 1, M, self.N, self.K, self.bias, relu, out)
 
 

@@ -319,6 +319,17 @@ int caphn_sumsq_bf16(const void* x, long n, double* sumsq, void* stream);
 int caphn_adam_step_bf16(void* p, const void* g, float* master, float* m, float* v, long n, double lr, double beta1,
                          double beta2, double eps, double weight_decay, int step, const float* gscale, void* stream);
 
+/* Greedy decode (models/decoderlstm.py:89-96: top_idx = topk(log_softmax(output / 0.5), 1) == arg-max of the logits):
+ * caphn_gemm_tc_amax = caphn_gemm_tc_ex whose epilogue also reduces every row of every output tile to (max, column)
+ * partials [M, amax_ld] (*nparts slots are written; amax_ld >= 2*ceil(N/128) suffices); caphn_argmax_finish_gather
+ * finishes the arg-max (lowest column on ties), writes the token and gathers the row of `table` it selects (embedding, or
+ * the pre-multiplied input projection) -- replacing a full pass over the logits + a separate gather per decode step. */
+int caphn_gemm_tc_amax(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
+                       int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, float* amax_val,
+                       int* amax_idx, int amax_ld, int* nparts, void* stream);
+int caphn_argmax_finish_gather(const float* pval, const int* pidx, int ld, int nparts, long n, const float* table, int E,
+                               long long* tok, float* out, long ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
