@@ -68,9 +68,9 @@ SIGNATURES = {
     "caphn_leaky_relu": [P, L, F, P],
     "caphn_leaky_relu_bwd": [P, P, L, F, P],
     "caphn_attstep_pack_grouped": [P, P, P, I, I, I, I, L, P, P],
-    "caphn_attstep_fwd_grouped": [P] * 13 + [L] + [P] * 5 + [I] * 8 + [P, I, P],
+    "caphn_attstep_fwd_grouped": [P] * 13 + [L] + [P] * 5 + [I] * 8 + [P, I, I, P],
     "caphn_attstep_bwd_pack_grouped": [P, P, P, I, I, I, I, L, P, P],
-    "caphn_attstep_bwd_grouped": [P] * 22 + [I] * 5 + [P, I, P],
+    "caphn_attstep_bwd_grouped": [P] * 22 + [I] * 5 + [P, I, I, P],
     "caphn_mean_pos": [P, I, I, I, P, P],
     "caphn_mean_pos_bwd": [P, P, I, I, I, P, P],
     "caphn_relu_mask": [P, P, L, P],

@@ -337,10 +337,9 @@ __global__ void __launch_bounds__(AS_THREADS, 2) attstep_attn_kernel(const AttSt
 // Y: gi_ctx, gh on the warp tensor cores + gates for step t     CTA = 16 units (6 gate tiles, one warp each) x 64 rows
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int YS_NB = 64;                 // batch rows per CTA (8 n-tiles of 8): the weight tiles are read once per 64 rows
-constexpr int YS_NT = YS_NB / 8;
+constexpr int YS_NB_SMALL = 8;            // many-style batches with <= 8 rows per group: one n-tile, 14 KB of operand rows, many CTAs per SM
 constexpr int YS_WARPS = 6;               // one warp per (source, gate) m-tile of 16 hidden units
 constexpr int YS_THREADS = YS_WARPS * 32;
-constexpr int YS_RP = YS_NB + 1;          // pitch of the result exchange array
 
 struct AttStepY {
     const __nv_bfloat16* csp;   // [2][B][KP] ctx hi, lo        (written by A of this step)
@@ -360,7 +359,10 @@ struct AttStepY {
     long pstride;
 };
 
-__global__ void __launch_bounds__(YS_THREADS, 1) attstep_gates_kernel(const AttStepY a) {
+template <int YS_NB>
+__global__ void __launch_bounds__(YS_THREADS, YS_NB >= 64 ? 1 : 4) attstep_gates_kernel(const AttStepY a) {
+    constexpr int YS_NT = YS_NB / 8;
+    constexpr int YS_RP = YS_NB + 1;          // pitch of the result exchange array
     extern __shared__ __align__(16) uint8_t ysm[];
     const int H = a.H, B = a.B, KP = a.KP, NKT = a.NKT, H3 = 3 * a.H;
     __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(ysm);   // [4][NB][KP]: ctx hi | ctx lo | h hi | h lo
@@ -472,8 +474,8 @@ __global__ void __launch_bounds__(YS_THREADS, 1) attstep_gates_kernel(const AttS
 }
 
 static inline int ys_kp(int H, int F) { return ((((H > F ? H : F) + 15) >> 4) << 4) + 8; }
-static inline size_t ys_smem(int KP) {
-    return (size_t)4 * YS_NB * KP * 2 + ((size_t)6 * 16 * YS_RP + (size_t)YS_NB * 64 + 48) * sizeof(float) + 16;
+static inline size_t ys_smem(int KP, int NB = YS_NB) {
+    return (size_t)4 * NB * KP * 2 + ((size_t)6 * 16 * (NB + 1) + (size_t)NB * 64 + 48) * sizeof(float) + 16;
 }
 static inline size_t as_smem(int P, int H, int F, int rpc, int nbuf = 2) {
     const int KP = ys_kp(H, F);
@@ -540,7 +542,7 @@ static int attstep_fwd_impl(const float* Kp, const float* f, const float* GIw, c
                             const float* bv, const void* pack, void* work, const float* bhh, float* Hall, float* Hbm,
                             float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z, float* Nn, float* GHN,
                             int B, int T, int P, int H, int F, int t0, int t1, int resume, const int* tiles, int ntiles,
-                            void* stream) {
+                            int tile_rows, void* stream) {
     long pb = 0, wb = 0;
     if (B <= 0 || T <= 0 || caphn_attstep_pack_size(H, F, P, B, &pb, &wb) != CAPHN_OK || pb == 0 || t0 < 0 || t1 > T ||
         t0 >= t1 || ((uintptr_t)pack & 15) || !work || ((uintptr_t)work & 255) || ((uintptr_t)Kp & 15) ||
@@ -565,10 +567,14 @@ static int attstep_fwd_impl(const float* Kp, const float* f, const float* GIw, c
     if (2 * (as_smem(P, H, F, rpc, 1) + 1024) > 227 * 1024 || getenv("CAPHN_ATT_DOUBLE_BUFFER")) {
         agrid = as_grid(B, P, H, F); rpc = (B + agrid - 1) / agrid; nbuf = 2;
     }
-    const size_t usmem = (size_t)2 * US_NB * KP * 2 + 16, asmem = as_smem(P, H, F, rpc, nbuf), ysmem = ys_smem(KP);
-    if (asmem > 227 * 1024) return CAPHN_EINVAL;
+    const bool small_tiles = tiles && tile_rows <= YS_NB_SMALL;
+    const size_t usmem = (size_t)2 * US_NB * KP * 2 + 16, asmem = as_smem(P, H, F, rpc, nbuf),
+                 ysmem = ys_smem(KP, small_tiles ? YS_NB_SMALL : YS_NB);
+    if (asmem > 227 * 1024 || (tiles && tile_rows > YS_NB)) return CAPHN_EINVAL;
     CAPHN_CHECK(cudaFuncSetAttribute(attstep_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)asmem));
-    CAPHN_CHECK(cudaFuncSetAttribute(attstep_gates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ysmem));
+    CAPHN_CHECK(cudaFuncSetAttribute(attstep_gates_kernel<YS_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ys_smem(KP)));
+    CAPHN_CHECK(cudaFuncSetAttribute(attstep_gates_kernel<YS_NB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)ys_smem(KP, YS_NB_SMALL)));
     if (!resume) {
         attstep_split_kernel<<<ceil_div(B * (KP / 2), 256), 256, 0, st>>>(Hall + t0 * BH, B, H, KP, hbuf(t0), hbuf(t0 + 1));
         CAPHN_LAUNCH_CHECK();
@@ -587,8 +593,12 @@ static int attstep_fwd_impl(const float* Kp, const float* f, const float* GIw, c
                    Hall + (t + 1) * BH, Hbm, R ? R + t * BH : nullptr, Z ? Z + t * BH : nullptr,
                    Nn ? Nn + t * BH : nullptr, GHN ? GHN + t * BH : nullptr, B, T, t, H, NUT, NKT, KP,
                    (const int4*)tiles, pack_elems(H, F)};
-        CAPHN_CHECK(launch_pdl(attstep_gates_kernel, dim3(NUT, tiles ? ntiles : ceil_div(B, YS_NB)), dim3(YS_THREADS), ysmem,
-                               st, pdl, y));
+        if (small_tiles) {
+            CAPHN_CHECK(launch_pdl(attstep_gates_kernel<YS_NB_SMALL>, dim3(NUT, ntiles), dim3(YS_THREADS), ysmem, st, pdl, y));
+        } else {
+            CAPHN_CHECK(launch_pdl(attstep_gates_kernel<YS_NB>, dim3(NUT, tiles ? ntiles : ceil_div(B, YS_NB)),
+                                   dim3(YS_THREADS), ysmem, st, pdl, y));
+        }
         ++caphn_launch_counter;
     }
     return (int)cudaGetLastError();
@@ -599,20 +609,21 @@ int caphn_attstep_fwd(const float* Kp, const float* f, const float* GIw, const f
                       float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z, float* Nn, float* GHN, int B,
                       int T, int P, int H, int F, int t0, int t1, int resume, void* stream) {
     return attstep_fwd_impl(Kp, f, GIw, bu, va, bv, pack, work, bhh, Hall, Hbm, attn, ctx, ldctx, Upre, R, Z, Nn, GHN, B, T,
-                            P, H, F, t0, t1, resume, nullptr, 0, stream);
+                            P, H, F, t0, t1, resume, nullptr, 0, 0, stream);
 }
 
 // Many-style batch: rows sorted by style group; `tiles` = ntiles records {first row, rows (<= 64), group, 0} that never
-// straddle a group; `pack` = the G packs of caphn_attstep_pack_grouped, bhh = [G, 3H].  The U and attention kernels use
+// straddle a group (tile_rows = the largest row count in the table: <= 8 selects the small-tile gates kernel);
+// `pack` = the G packs of caphn_attstep_pack_grouped, bhh = [G, 3H].  The U and attention kernels use
 // no generated weights and run exactly as in the single-group call (U_a is read from group 0's pack).
 int caphn_attstep_fwd_grouped(const float* Kp, const float* f, const float* GIw, const float* bu, const float* va,
                               const float* bv, const void* pack, void* work, const float* bhh, float* Hall, float* Hbm,
                               float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z, float* Nn, float* GHN,
                               int B, int T, int P, int H, int F, int t0, int t1, int resume, const int* tiles, int ntiles,
-                              void* stream) {
-    if (!tiles || ntiles < 1 || ((uintptr_t)tiles & 15)) return CAPHN_EINVAL;
+                              int tile_rows, void* stream) {
+    if (!tiles || ntiles < 1 || tile_rows < 1 || ((uintptr_t)tiles & 15)) return CAPHN_EINVAL;
     return attstep_fwd_impl(Kp, f, GIw, bu, va, bv, pack, work, bhh, Hall, Hbm, attn, ctx, ldctx, Upre, R, Z, Nn, GHN, B, T,
-                            P, H, F, t0, t1, resume, tiles, ntiles, stream);
+                            P, H, F, t0, t1, resume, tiles, ntiles, tile_rows, stream);
 }
 
 #ifdef CAPHN_ATTCL_TIMING

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(G1_THREADS) attbwd_gate_kernel(const BwdG1 a) 
 // ------------------------------------------------------------------------------------------------------------------
 // G2: dctx_t = dgi_t W_ih[:,E:],  dhp = dgh_t W_hh        CTA = 4 output tiles of one kind (4 warps) x 32 rows
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int G2_NB = 32, G2_NT = G2_NB / 8, G2_WARPS = 4, G2_THREADS = G2_WARPS * 32, G2_PF = 19, G2_RP = G2_NB + 1;
+constexpr int G2_NB = 32, G2_NB_SMALL = 8, G2_WARPS = 4, G2_THREADS = G2_WARPS * 32, G2_PF = 19;
 
 struct BwdG2 {
     const uint4* Wc;             // group 1 tiles (NFT x NKT3)
@@ -204,7 +204,9 @@ struct BwdG2 {
     long pstride;
 };
 
+template <int G2_NB>
 __global__ void __launch_bounds__(G2_THREADS) attbwd_gemm_kernel(const BwdG2 a) {
+    constexpr int G2_NT = G2_NB / 8, G2_RP = G2_NB + 1;
     extern __shared__ __align__(16) uint8_t g2sm[];
     const int B = a.B, KP3 = a.KP3, NKT3 = a.NKT3;
     __nv_bfloat16* act = reinterpret_cast<__nv_bfloat16*>(g2sm);          // [2][NB][KP3]
@@ -548,8 +550,8 @@ static inline int bw_kp3(int H) { return (((3 * H + 15) >> 4) << 4) + 8; }
 static inline size_t g1_smem(int KP) {
     return (size_t)2 * G1_NB * KP * 2 + ((size_t)16 * G1_RP + (size_t)8 * G1_NB * 16) * sizeof(float) + 16;
 }
-static inline size_t g2_smem(int KP3) {
-    return (size_t)2 * G2_NB * KP3 * 2 + ((size_t)4 * 16 * G2_RP + 2) * sizeof(float) + 16;
+static inline size_t g2_smem(int KP3, int NB = G2_NB) {
+    return (size_t)2 * NB * KP3 * 2 + ((size_t)4 * 16 * (NB + 1) + 2) * sizeof(float) + 16;
 }
 static inline size_t ba_smem(int P, int H, int F, int rpc, int nbuf = 2) {
     const int PS = (P + 3) & ~3, H4 = (H + 3) & ~3, F4 = (F + 3) & ~3;
@@ -622,7 +624,7 @@ static int attstep_bwd_impl(const float* dHbm, const float* dattn, const float* 
                             const float* Upre, const float* R, const float* Z, const float* Nn, const float* GHN,
                             const float* Hall, const float* va, const void* pack, void* work, float* dGI, float* dGH,
                             float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0, int B, int T, int P,
-                            int H, int F, const int* tiles, int ntiles, void* stream) {
+                            int H, int F, const int* tiles, int ntiles, int tile_rows, void* stream) {
     if (B <= 0 || T <= 0 || bw_pack_elems(H, F, P, T) == 0 || !pack || ((uintptr_t)pack & 15) || !work ||
         ((uintptr_t)work & 255) || ((uintptr_t)Kp & 15) || ((uintptr_t)f & 15))
         return CAPHN_EINVAL;
@@ -653,7 +655,11 @@ static int attstep_bwd_impl(const float* dHbm, const float* dattn, const float* 
     const size_t s1 = g1_smem(KP), s2 = g2_smem(KP3), sa = ba_smem(P, H, F, rpc, nbuf), sd = bd_smem(P, H, T);
     if (sa > 227 * 1024) return CAPHN_EINVAL;
     CAPHN_CHECK(cudaFuncSetAttribute(attbwd_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
-    CAPHN_CHECK(cudaFuncSetAttribute(attbwd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+    const bool small_tiles = tiles && tile_rows <= G2_NB_SMALL;
+    if (tiles && tile_rows > G2_NB) return CAPHN_EINVAL;
+    const size_t s2s = g2_smem(KP3, G2_NB_SMALL);
+    CAPHN_CHECK(cudaFuncSetAttribute(attbwd_gemm_kernel<G2_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+    CAPHN_CHECK(cudaFuncSetAttribute(attbwd_gemm_kernel<G2_NB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2s));
     CAPHN_CHECK(cudaFuncSetAttribute(attbwd_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa));
     CAPHN_CHECK(cudaFuncSetAttribute(attbwd_dk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd));
     static const bool pdl = []() { const char* e = getenv("CAPHN_PDL"); return !(e && e[0] == '0'); }();
@@ -667,8 +673,12 @@ static int attstep_bwd_impl(const float* dHbm, const float* dattn, const float* 
         ++caphn_launch_counter;
         BwdG2 g2{p1, p2, gisp, ghsp, dCTX + (long)t * B * F, dhp, B, H, F, NUT, NFT, NKT3, KP3, NG1, (const int4*)tiles,
                  pb / 16};
-        CAPHN_CHECK(launch_pdl(attbwd_gemm_kernel, dim3(NG1 + NG2, tiles ? ntiles : ceil_div(B, G2_NB)), dim3(G2_THREADS), s2,
-                               st, pdl, g2));
+        if (small_tiles) {
+            CAPHN_CHECK(launch_pdl(attbwd_gemm_kernel<G2_NB_SMALL>, dim3(NG1 + NG2, ntiles), dim3(G2_THREADS), s2s, st, pdl, g2));
+        } else {
+            CAPHN_CHECK(launch_pdl(attbwd_gemm_kernel<G2_NB>, dim3(NG1 + NG2, tiles ? ntiles : ceil_div(B, G2_NB)),
+                                   dim3(G2_THREADS), s2, st, pdl, g2));
+        }
         ++caphn_launch_counter;
         BwdA ba{Kp, f, va, dCTX + (long)t * B * F, attn, dattn, Upre + t * BH, dS, dU + t * BH, dusp, dbv,
                 B, T, t, P, H, F, KP, rpc, nbuf};
@@ -691,7 +701,7 @@ int caphn_attstep_bwd(const float* dHbm, const float* dattn, const float* Kp, co
                       float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0, int B, int T, int P, int H,
                       int F, void* stream) {
     return attstep_bwd_impl(dHbm, dattn, Kp, f, attn, Upre, R, Z, Nn, GHN, Hall, va, pack, work, dGI, dGH, dU, dCTX, dK, dva,
-                            dbv, dh0, B, T, P, H, F, nullptr, 0, stream);
+                            dbv, dh0, B, T, P, H, F, nullptr, 0, 0, stream);
 }
 
 // Many-style batch (rows sorted by style group): `tiles` = ntiles records {first row, rows (<= 32), group, 0} for the
@@ -701,10 +711,10 @@ int caphn_attstep_bwd_grouped(const float* dHbm, const float* dattn, const float
                               const float* Upre, const float* R, const float* Z, const float* Nn, const float* GHN,
                               const float* Hall, const float* va, const void* pack, void* work, float* dGI, float* dGH,
                               float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0, int B, int T, int P,
-                              int H, int F, const int* tiles, int ntiles, void* stream) {
-    if (!tiles || ntiles < 1 || ((uintptr_t)tiles & 15)) return CAPHN_EINVAL;
+                              int H, int F, const int* tiles, int ntiles, int tile_rows, void* stream) {
+    if (!tiles || ntiles < 1 || tile_rows < 1 || ((uintptr_t)tiles & 15)) return CAPHN_EINVAL;
     return attstep_bwd_impl(dHbm, dattn, Kp, f, attn, Upre, R, Z, Nn, GHN, Hall, va, pack, work, dGI, dGH, dU, dCTX, dK, dva,
-                            dbv, dh0, B, T, P, H, F, tiles, ntiles, stream);
+                            dbv, dh0, B, T, P, H, F, tiles, ntiles, tile_rows, stream);
 }
 
 }  // extern "C"

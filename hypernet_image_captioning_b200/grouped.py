@@ -80,8 +80,11 @@ class GroupPlan:
         self.order, self.inv = i64(order), i64(inv)
         self.gm2tm = i32(gm2tm)
         self.goff_dev = i32(goff)
-        self.tiles_fwd = i32(self._tiles(64))
-        self.tiles_bwd = i32(self._tiles(32))
+        # recurrence row tiles: groups of <= 8 rows (a many-domain batch) take the small-tile kernels
+        small = int(cnt.max()) <= 8
+        self.tile_rows_fwd, self.tile_rows_bwd = (8, 8) if small else (64, 32)
+        self.tiles_fwd = i32(self._tiles(self.tile_rows_fwd))
+        self.tiles_bwd = i32(self._tiles(self.tile_rows_bwd))
         absent = [g for g in range(G) if cnt[g] == 0]
         self.absent_dev = i64(absent) if absent else None         # groups without rows: their d(theta) rows are zero
         self._units: Dict[Tuple, torch.Tensor] = {}
@@ -204,7 +207,7 @@ def _grouped_forward(plan: GroupPlan, f3, K3, h0, caps, Theta, emb_w, fc_w, fc_b
     attn = torch.empty(B, T, P, device=dev, dtype=torch.float32)
     saved = torch.empty(5, T, B, H, device=dev, dtype=torch.float32)
     ops.attgru_fwd_grouped(K3, f3, GIw, gw, Ua_b.contiguous(), va, bv, b_hh_g, Hall, Hbm, attn, XC, E, saved,
-                           plan.tiles_fwd)
+                           plan.tiles_fwd, plan.tile_rows_fwd)
     # back to the caller's batch order before the vocabulary projection: logits [B, T, V] (0.4 GB) are never permuted
     Hbm_o = ops.gather_rows(Hbm.view(B, T * H), plan.inv).view(B, T, H)
     attn_o = ops.gather_rows(attn.view(B, T * P), plan.inv).view(B, T, P)
@@ -226,7 +229,8 @@ def _grouped_backward(plan: GroupPlan, sv, dims, vocab, dattn_o):
     if dattn_o is not None:
         dattn = ops.gather_rows(dattn_o.reshape(B, T * P).contiguous(), plan.order).view(B, T, P)
     dGI, dGH, dU, dCTX, dK, dva, dbv, dh0 = ops.attgru_bwd_grouped(dHbm, dattn, K3, f3, attn, saved, Hall, Theta,
-                                                                    Ua_w.contiguous(), va, E, plan.tiles_bwd)
+                                                                    Ua_w.contiguous(), va, E, plan.tiles_bwd,
+                                                                    plan.tile_rows_bwd)
     Hprev = Hall[:-1].reshape(T * B, H)
     # shared attention parameter U_a: plain products over all rows
     dUa_w = ops.matmul_tn(dU, Hprev)
@@ -312,6 +316,25 @@ class AttentionGruGroupedLossFn(Function):
 # ----------------------------------------------------------------------------------------------------------------------
 # hypernetwork for many style vectors: X [G, he] -> Theta [G, theta] with the layers as dense tensor-core GEMMs
 # ----------------------------------------------------------------------------------------------------------------------
+def _sk(M, N, K):
+    """Split-K factor for a small exact-fp32 product whose output is one or two 128 x 128 tiles: spread K over CTAs."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    return max(1, min(32, K // 64, 64 // tiles))
+
+
+def _small_linear(x, W, b, out=None):
+    """y = x W^T + b for the hypernet's small layers at G <= a few hundred rows (exact fp32, K split over CTAs)."""
+    M, K = x.shape
+    N = W.shape[0]
+    sk = _sk(M, N, K)
+    if sk == 1:
+        return ops._gemm(x, x.stride(0), 1, W, W.stride(0), 1, M, N, K, b, False, out)
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    out.copy_(b.to(torch.float32).reshape(1, N).expand(M, N))          # bias first, then the K chunks accumulate atomically
+    return ops._gemm(x, x.stride(0), 1, W, W.stride(0), 1, M, N, K, None, False, out, splitk=sk, accumulate=True)
+
+
 class HyperNetThetaManyFn(Function):
     """Same function as functional.HyperNetThetaFn (hypernet_attention.py:111-118), for G > 8 style vectors.
 
@@ -325,31 +348,30 @@ class HyperNetThetaManyFn(Function):
     def forward(ctx, x, *params):
         nh = (len(params) - 4) // 4
         act = lambda y: ops.leaky_relu_(y)
-        b0 = act(ops.linear(x.contiguous(), params[0].contiguous(), params[1]))
-        b1 = act(ops.linear(b0, params[2].contiguous(), params[3]))
+        b0 = act(_small_linear(x.contiguous(), params[0].contiguous(), params[1]))
+        b1 = act(_small_linear(b0, params[2].contiguous(), params[3]))
         sizes = [params[4 + 4 * i + 2].shape[0] for i in range(nh)]
         G = x.shape[0]
-        Mp = max(G, 128)                          # the tensor-core tile is 128 rows: Theta is allocated with >= 128 rows
-        theta_full = torch.empty(Mp, sum(sizes), device=x.device, dtype=torch.float32)
+        theta = torch.empty(G, sum(sizes), device=x.device, dtype=torch.float32)
         mids, splits, off = [], [], 0
         for i in range(nh):
             W1, c1, W2, c2 = params[4 + 4 * i: 8 + 4 * i]
-            a = act(ops.linear(b1, W1.contiguous(), c1))
+            a = act(_small_linear(b1, W1.contiguous(), c1))
             W2c = W2.contiguous()
-            if ops._tc_ok(Mp, W2c.shape[0], W2c.shape[1]):
+            if ops._tc_ok(128, W2c.shape[0], W2c.shape[1]):
+                # M = G rows (one partial 128-row tile: TMA zero-fills the missing rows, the epilogue writes only G)
                 sW = ops.split_bf16(W2c)
-                apad = a if G >= 128 else torch.cat([a, a.new_zeros(128 - G, a.shape[1])], 0)
-                ops.gemm_tc(ops.split_bf16(apad), sW, bias=c2, out=theta_full[:, off:off + sizes[i]], splitk=1)
+                ops.gemm_tc(ops.split_bf16(a), sW, bias=c2, out=theta[:, off:off + sizes[i]], splitk=1)
                 splits.append((sW.hi, sW.lo))
             else:
-                ops.linear(a, W2c, c2, out=theta_full[:G, off:off + sizes[i]])
+                _small_linear(a, W2c, c2, out=theta[:, off:off + sizes[i]])
                 splits.append((None, None))
             mids.append(a)
             off += sizes[i]
         flat_splits = [t for pair in splits for t in pair]
         ctx.save_for_backward(x, b0, b1, *mids, *params, *flat_splits)
         ctx.nh, ctx.sizes, ctx.np = nh, sizes, len(params)
-        return theta_full[:G]
+        return theta
 
     @staticmethod
     def backward(ctx, dtheta):
@@ -367,9 +389,14 @@ class HyperNetThetaManyFn(Function):
         off = 0
 
         def layer_bwd(dy, inp, W, leaky_out):
-            """dy [G, N] (already multiplied by the activation derivative) -> dW, db, dinp."""
+            """dy [G, N] (already multiplied by the activation derivative) -> dW, db, dinp (small layers: exact-fp32 SIMT
+            products, K split over several CTAs)."""
             dy = dy.contiguous()
-            return ops.matmul_tn(dy, inp), ops.colsum(dy), ops.matmul_nn(dy, W.contiguous())
+            Wc = W.contiguous()
+            N, K = Wc.shape
+            dW = ops._gemm(dy, dy.stride(0), 0, inp, inp.stride(0), 0, N, K, G, splitk=1)                 # dy^T inp
+            dinp = ops._gemm(dy, dy.stride(0), 1, Wc, Wc.stride(0), 0, G, K, N, splitk=_sk(G, K, N))      # dy W
+            return dW, ops.colsum(dy), dinp
 
         for i in range(nh):
             W1, c1, W2, c2 = params[4 + 4 * i: 8 + 4 * i]
@@ -380,10 +407,10 @@ class HyperNetThetaManyFn(Function):
             N, K = W2.shape
             if s_hi is not None and (s_lo is not None) == ops.TC_SPLIT:
                 # rank-G weight gradient and the input gradient on the tensor cores; W2's forward split read MN-major
-                dW2 = ops.gemm_tc(ops.split_bf16(dth, mn=True), ops.split_bf16(a, mn=True))          # [N, K], K-dim = G
-                dpad = dth if G >= 128 else torch.cat([dth, dth.new_zeros(128 - G, N)], 0)
+                dsp = ops.split_bf16(dth)                                   # one split of dtheta_i serves both products
+                dW2 = ops.gemm_tc(ops.SplitOperand(dsp.hi, dsp.lo, N, G, dsp.ld, True), ops.split_bf16(a, mn=True))   # [N, K], K-dim = G
                 W2t = ops.SplitOperand(s_hi, s_lo, K, N, s_hi.shape[1], True)
-                da = ops.gemm_tc(ops.split_bf16(dpad), W2t)[:G].contiguous()                         # [G, K], K-dim = N
+                da = ops.gemm_tc(dsp, W2t)                                                           # [G, K], K-dim = N
                 dc2 = ops.colsum(dth)
             else:
                 dW2, dc2, da = layer_bwd(dth, a, W2, False)

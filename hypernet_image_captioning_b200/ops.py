@@ -830,8 +830,9 @@ class AttGruGroupWeights:
         self.work = None
 
 
-def attgru_fwd_grouped(Kp, f, GIw, gw: AttGruGroupWeights, bu, va, bv, bhh_g, Hall, Hbm, attn, XC, E, saved, tiles):
-    """All T steps; rows sorted by group; tiles int32 [n, 4] = (first row, rows <= 64, group, 0); bhh_g [G, 3H] contiguous."""
+def attgru_fwd_grouped(Kp, f, GIw, gw: AttGruGroupWeights, bu, va, bv, bhh_g, Hall, Hbm, attn, XC, E, saved, tiles,
+                       tile_rows=64):
+    """All T steps; rows sorted by group; tiles int32 [n, 4] = (first row, rows <= tile_rows <= 64, group, 0); bhh_g [G, 3H]."""
     B, P, H = Kp.shape
     Fd = f.shape[2]
     T = Hall.shape[0] - 1
@@ -844,11 +845,12 @@ def attgru_fwd_grouped(Kp, f, GIw, gw: AttGruGroupWeights, bu, va, bv, bhh_g, Ha
     _cabi.call("caphn_attstep_fwd_grouped", Kp.data_ptr(), f.data_ptr(), GIw.data_ptr(), bu.data_ptr(), va.data_ptr(),
                bv.data_ptr(), gw.pack.data_ptr(), gw.work.data_ptr(), bhh_g.data_ptr(), Hall.data_ptr(), _p(Hbm),
                attn.data_ptr(), ctx_ptr, XC.stride(0), sp[0], sp[1], sp[2], sp[3], sp[4], B, T, P, H, Fd, 0, T, 0,
-               tiles.data_ptr(), tiles.shape[0], _stream())
+               tiles.data_ptr(), tiles.shape[0], int(tile_rows), _stream())
 
 
-def attgru_bwd_grouped(dHbm, dattn, Kp, f, attn, saved, Hall, Theta, U_a, va, E, tiles):
-    """BPTT of attgru_fwd_grouped.  tiles int32 [n, 4] with <= 32 rows each.  Returns dGI, dGH, dU, dCTX, dK, dva, dbv, dh0."""
+def attgru_bwd_grouped(dHbm, dattn, Kp, f, attn, saved, Hall, Theta, U_a, va, E, tiles, tile_rows=32):
+    """BPTT of attgru_fwd_grouped.  tiles int32 [n, 4] with <= tile_rows <= 32 rows each.  Returns dGI, dGH, dU, dCTX, dK, dva,
+    dbv, dh0."""
     B, P, H = Kp.shape
     Fd = f.shape[2]
     T = Hall.shape[0] - 1
@@ -870,5 +872,5 @@ def attgru_bwd_grouped(dHbm, dattn, Kp, f, attn, saved, Hall, Theta, U_a, va, E,
                saved[0].data_ptr(), saved[1].data_ptr(), saved[2].data_ptr(), saved[3].data_ptr(), saved[4].data_ptr(),
                Hall.data_ptr(), va.data_ptr(), pack.data_ptr(), work.data_ptr(), dGI.data_ptr(), dGH.data_ptr(),
                dU.data_ptr(), dCTX.data_ptr(), dK.data_ptr(), dva.data_ptr(), dbv.data_ptr(), dh0.data_ptr(),
-               B, T, P, H, Fd, tiles.data_ptr(), tiles.shape[0], _stream())
+               B, T, P, H, Fd, tiles.data_ptr(), tiles.shape[0], int(tile_rows), _stream())
     return dGI, dGH, dU, dCTX, dK, dva, dbv, dh0

@@ -271,7 +271,8 @@ int caphn_build_arch(int* out);
  * caphn_group_colsum: per-group bias gradients.
  * caphn_attstep_pack_grouped / caphn_attstep_fwd_grouped / caphn_attstep_bwd_pack_grouped / caphn_attstep_bwd_grouped:
  *   the step-split recurrence with one weight pack per group; `tiles` = {first row, rows, group, 0} records (int32 x 4,
- *   16-byte aligned) that never straddle a group (<= 64 rows forward, <= 32 backward).
+ *   16-byte aligned) that never straddle a group (<= 64 rows forward, <= 32 backward); tile_rows = the largest row count in
+ *   the table (<= 8 selects small-tile kernels: many CTAs per SM hide the per-group weight loads of a many-domain batch).
  * ------------------------------------------------------------------------------------------------------------------ */
 int caphn_gemm_tc_grouped(const void* Ahi, const void* Alo, long a_inner, long a_outer, long a_ld, int a_mn,
                           const void* Bhi, const void* Blo, long b_inner, long b_outer, long b_ld, int b_mn, float* C,
@@ -293,14 +294,14 @@ int caphn_attstep_fwd_grouped(const float* Kp, const float* f, const float* GIw,
                               const float* bv, const void* pack, void* work, const float* bhh, float* Hall, float* Hbm,
                               float* attn, float* ctx, long ldctx, float* Upre, float* R, float* Z, float* Nn, float* GHN,
                               int B, int T, int P, int H, int F, int t0, int t1, int resume, const int* tiles, int ntiles,
-                              void* stream);
+                              int tile_rows, void* stream);
 int caphn_attstep_bwd_pack_grouped(const float* Wih, const float* Whh, const float* Ua, int E, int F, int H, int G,
                                    long gstride, void* pack, void* stream);
 int caphn_attstep_bwd_grouped(const float* dHbm, const float* dattn, const float* Kp, const float* f, const float* attn,
                               const float* Upre, const float* R, const float* Z, const float* Nn, const float* GHN,
                               const float* Hall, const float* va, const void* pack, void* work, float* dGI, float* dGH,
                               float* dU, float* dCTX, float* dK, float* dva, float* dbv, float* dh0, int B, int T, int P,
-                              int H, int F, const int* tiles, int ntiles, void* stream);
+                              int H, int F, const int* tiles, int ntiles, int tile_rows, void* stream);
 
 /* Batched device-resident beam search bookkeeping (HyperNet.test_step, hypernet_attention.py:247-326): for B images x k
  * beams (rows b*k.., live beams first) one launch does what the reference does on the host between two decoder steps --
