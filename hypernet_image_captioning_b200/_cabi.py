@@ -36,6 +36,8 @@ SIGNATURES = {
     "caphn_gru_cluster_plan": [I, P],
     "caphn_gru_cluster_fwd": [P, P, P, P, P, P, I, I, I, P],
     "caphn_gru_cluster_bwd": [P, P, P, P, P, P, P, I, I, I, P],
+    "caphn_gru_cluster_fwd_grouped": [P, P, P, P, P, P, I, I, I, P, I, L, L, P],
+    "caphn_gru_cluster_bwd_grouped": [P, P, P, P, P, P, P, I, I, I, P, I, L, P],
     "caphn_ce_fwd": [P, L, P, L, I, I, LL, P, P, P, P],
     "caphn_ce_bwd": [P, L, P, L, I, I, LL, P, P, P, P, L, P],
     "caphn_ce_bwd_split": [P, L, P, L, I, I, LL, P, P, P, P, P, L, P, P, L, P, P],

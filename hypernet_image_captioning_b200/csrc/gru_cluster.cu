@@ -33,6 +33,10 @@ struct GruClArgs {
     float* Hbm;         // [B,T,H] or null
     float* saved;       // [4][T,B,H] or null
     int B, T, H, HS, ldw;   // HS = hidden units per CTA, ldw = smem row stride (odd)
+    // many-style batch (rows sorted by style group): cluster i owns rows [tiles[i].x, +tiles[i].y <= 8) of group tiles[i].z and
+    // keeps THAT group's W_hh slice resident; group g's W_hh / b_hh start wstride / bstride floats after group g-1's.
+    const int4* tiles;
+    long wstride, bstride;
 };
 
 __device__ __forceinline__ void load_w_slice(float* Ws, const float* __restrict__ Whh, int H, int HS, int ldw, int c) {
@@ -58,13 +62,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cluster_fwd_kernel(const Gr
     float* hs = Ws + ((rows * ldw + 3) & ~3);          // [2][H][BT]  double-buffered state (k-major, BT contiguous)
     float* ghs = hs + 2 * H * BT;                      // [3*HS][BT]
     const int tid = threadIdx.x;
-    const int b0 = (blockIdx.x / CS) * BT;
+    int b0 = (blockIdx.x / CS) * BT, nb = min(BT, B - b0), grp = 0;
+    if (a.tiles) { const int4 tl = a.tiles[blockIdx.x / CS]; b0 = tl.x; nb = tl.y; grp = tl.z; }
+    const float* bhh = a.bhh + (long)grp * a.bstride;
     const long TBH = (long)T * B * H;
 
-    load_w_slice(Ws, a.Whh, H, HS, ldw, c);
+    load_w_slice(Ws, a.Whh + (long)grp * a.wstride, H, HS, ldw, c);
     for (int i = tid; i < H * BT; i += CL_THREADS) {
         const int k = i / BT, b = i - k * BT;
-        hs[i] = (b0 + b < B) ? a.Hall[(long)(b0 + b) * H + k] : 0.f;
+        hs[i] = (b < nb) ? a.Hall[(long)(b0 + b) * H + k] : 0.f;
     }
     __syncthreads();
     cluster.sync();
@@ -87,10 +93,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cluster_fwd_kernel(const Gr
         const int jl = i / BT, b = i - jl * BT;
         it_j[q] = c * HS + jl; it_b[q] = b;
         it_ok[q] = (i < HS * BT) && (it_j[q] < H);
-        const bool live = it_ok[q] && (b0 + b < B);
+        const bool live = it_ok[q] && (b < nb);
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
-            bh[q][g] = live ? a.bhh[g * H + it_j[q]] : 0.f;
+            bh[q][g] = live ? bhh[g * H + it_j[q]] : 0.f;
             gi_next[q][g] = live ? a.GI[((long)0 * B + b0 + b) * H3 + g * H + it_j[q]] : 0.f;
         }
     }
@@ -101,7 +107,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cluster_fwd_kernel(const Gr
         float gi_cur[MAXI][3];
 #pragma unroll
         for (int q = 0; q < MAXI; ++q) {
-            const bool live = it_ok[q] && (b0 + it_b[q] < B) && (t + 1 < T);
+            const bool live = it_ok[q] && (it_b[q] < nb) && (t + 1 < T);
 #pragma unroll
             for (int g = 0; g < 3; ++g) {
                 gi_cur[q][g] = gi_next[q][g];
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cluster_fwd_kernel(const Gr
             o_r[q] = o_z[q] = o_n[q] = o_g[q] = o_h[q] = 0.f;
             if (it_ok[q]) {
                 const int j = it_j[q], b = it_b[q], jl = j - c * HS;
-                if (b0 + b < B) {
+                if (b < nb) {
                     float ghr = bh[q][0], ghz = bh[q][1], ghn = bh[q][2];
                     for (int g = 0; g < NG; ++g) {
                         const float* pp = part + (long)g * rows * BT;
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cluster_fwd_kernel(const Gr
 #pragma unroll
         for (int q = 0; q < MAXI; ++q) {
             const int gb = b0 + it_b[q];
-            if (it_ok[q] && gb < B) {
+            if (it_ok[q] && it_b[q] < nb) {
                 const int j = it_j[q];
                 const long o = ((long)t * B + gb) * H + j;
                 a.Hall[o + (long)B * H] = o_h[q];
@@ -182,6 +188,8 @@ struct GruClBwdArgs {
     float* dGI; float* dGH;   // [T,B,3H]
     float* dh0;          // [B,H]
     int B, T, H, HS, ldw;
+    const int4* tiles;   // many-style batch: see GruClArgs
+    long wstride;
 };
 
 __global__ void __launch_bounds__(CL_THREADS, 1) gru_cluster_bwd_kernel(const GruClBwdArgs a) {
@@ -199,10 +207,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cluster_bwd_kernel(const Gr
     float* recv = dhd + HS * BT;                       // [2][CS][HS][BT]  partial dh for own units from every CTA
     float* part = recv + 2 * CS * HS * BT;             // [NG][HP][BT]
     const int tid = threadIdx.x;
-    const int b0 = (blockIdx.x / CS) * BT;
+    int b0 = (blockIdx.x / CS) * BT, nb = min(BT, B - b0), grp = 0;
+    if (a.tiles) { const int4 tl = a.tiles[blockIdx.x / CS]; b0 = tl.x; nb = tl.y; grp = tl.z; }
     const long TBH = (long)T * B * H;
 
-    load_w_slice(Ws, a.Whh, H, HS, ldw, c);
+    load_w_slice(Ws, a.Whh + (long)grp * a.wstride, H, HS, ldw, c);
     for (int i = tid; i < HS * BT; i += CL_THREADS) dhd[i] = 0.f;
     for (int i = tid; i < 2 * CS * HS * BT; i += CL_THREADS) recv[i] = 0.f;
     __syncthreads();
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cluster_bwd_kernel(const Gr
         const int i = tid + q * CL_THREADS;
         const int jl = i / BT, b = i - jl * BT;
         it_j[q] = c * HS + jl; it_b[q] = b;
-        it_live[q] = (i < HS * BT) && (it_j[q] < H) && (b0 + b < B);
+        it_live[q] = (i < HS * BT) && (it_j[q] < H) && (b < nb);
         if (it_live[q]) {
             const long o = ((long)(T - 1) * B + b0 + b) * H + it_j[q];
             nx[q][0] = a.saved[o]; nx[q][1] = a.saved[TBH + o]; nx[q][2] = a.saved[2 * TBH + o];
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cluster_bwd_kernel(const Gr
     for (int i = tid; i < HS * BT; i += CL_THREADS) {
         const int jl = i / BT, b = i - jl * BT;
         const int j = c * HS + jl, gb = b0 + b;
-        if (j < H && gb < B) {
+        if (j < H && b < nb) {
             float v = dhd[i];
             for (int s = 0; s < CS; ++s) v += rc[(s * HS + jl) * BT + b];
             a.dh0[(long)gb * H + j] = v;
@@ -355,10 +364,10 @@ int caphn_gru_cluster_plan(int H, int* cs) {
 
 // Weights-resident single-layer GRU recurrence (see file header).  Same tensors as caphn_gru_seq_fwd with NL = 1, but
 // Whh is the plain row-major [3H,H] generated matrix (no transposed / padded copy).  saved = [4][T,B,H] or NULL.
-int caphn_gru_cluster_fwd(const float* GI, const float* Whh, const float* bhh, float* Hall, float* Hbm, float* saved,
-                          int B, int T, int H, void* stream) {
+static int gru_cluster_fwd_impl(const float* GI, const float* Whh, const float* bhh, float* Hall, float* Hbm, float* saved,
+                                int B, int T, int H, const int* tiles, int ntiles, long wstride, long bstride, void* stream) {
     if (B <= 0 || T <= 0 || H <= 0) return CAPHN_EINVAL;
-    GruClArgs a{GI, Whh, bhh, Hall, Hbm, saved, B, T, H, 0, 0};
+    GruClArgs a{GI, Whh, bhh, Hall, Hbm, saved, B, T, H, 0, 0, (const int4*)tiles, wstride, bstride};
     size_t smem;
     int cs1, cs;
     caphn_gru_cluster_plan(H, &cs);
@@ -371,7 +380,7 @@ int caphn_gru_cluster_fwd(const float* GI, const float* Whh, const float* bhh, f
             (size_t)cl_groups((int)rows) * rows * CL_BT) * sizeof(float);
     CAPHN_CHECK(cudaFuncSetAttribute(gru_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(ceil_div(B, CL_BT) * cs1));
+    cfg.gridDim = dim3((unsigned)((tiles ? ntiles : ceil_div(B, CL_BT)) * cs1));
     cfg.blockDim = dim3(CL_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
@@ -383,20 +392,35 @@ int caphn_gru_cluster_fwd(const float* GI, const float* Whh, const float* bhh, f
     CAPHN_RETURN_LAST();
 }
 
+int caphn_gru_cluster_fwd(const float* GI, const float* Whh, const float* bhh, float* Hall, float* Hbm, float* saved,
+                          int B, int T, int H, void* stream) {
+    return gru_cluster_fwd_impl(GI, Whh, bhh, Hall, Hbm, saved, B, T, H, nullptr, 0, 0, 0, stream);
+}
+
+// Many-style batch (rows sorted by style group): cluster i runs rows [tiles[i].x, +tiles[i].y <= 8) with the W_hh / b_hh of
+// group tiles[i].z resident in its shared memory for all T steps (Whh / bhh point at group 0; strides in floats).
+int caphn_gru_cluster_fwd_grouped(const float* GI, const float* Whh, const float* bhh, float* Hall, float* Hbm,
+                                  float* saved, int B, int T, int H, const int* tiles, int ntiles, long wstride,
+                                  long bstride, void* stream) {
+    if (!tiles || ntiles < 1 || ((uintptr_t)tiles & 15)) return CAPHN_EINVAL;
+    return gru_cluster_fwd_impl(GI, Whh, bhh, Hall, Hbm, saved, B, T, H, tiles, ntiles, wstride, bstride, stream);
+}
+
 // BPTT of caphn_gru_cluster_fwd: dGI, dGH [T,B,3H], dh0 [B,H].
-int caphn_gru_cluster_bwd(const float* dHbm, const float* saved, const float* Hall, const float* Whh, float* dGI,
-                          float* dGH, float* dh0, int B, int T, int H, void* stream) {
+static int gru_cluster_bwd_impl(const float* dHbm, const float* saved, const float* Hall, const float* Whh, float* dGI,
+                                float* dGH, float* dh0, int B, int T, int H, const int* tiles, int ntiles, long wstride,
+                                void* stream) {
     if (B <= 0 || T <= 0 || H <= 0) return CAPHN_EINVAL;
     int cs;
     caphn_gru_cluster_plan(H, &cs);
     if (!cs) return CAPHN_EINVAL;
-    GruClBwdArgs a{dHbm, saved, Hall, Whh, dGI, dGH, dh0, B, T, H, (H + cs - 1) / cs, H | 1};
+    GruClBwdArgs a{dHbm, saved, Hall, Whh, dGI, dGH, dh0, B, T, H, (H + cs - 1) / cs, H | 1, (const int4*)tiles, wstride};
     const size_t rows = 3 * (size_t)a.HS;
     const size_t smem = (((rows * a.ldw + 3) & ~(size_t)3) + rows * CL_BT + (size_t)a.HS * CL_BT +
                          2 * (size_t)cs * a.HS * CL_BT + (size_t)cl_groups(H) * cs * a.HS * CL_BT) * sizeof(float);
     CAPHN_CHECK(cudaFuncSetAttribute(gru_cluster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(ceil_div(B, CL_BT) * cs));
+    cfg.gridDim = dim3((unsigned)((tiles ? ntiles : ceil_div(B, CL_BT)) * cs));
     cfg.blockDim = dim3(CL_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = (cudaStream_t)stream;
@@ -406,6 +430,18 @@ int caphn_gru_cluster_bwd(const float* dHbm, const float* saved, const float* Ha
     cfg.attrs = at; cfg.numAttrs = 1;
     CAPHN_CHECK(cudaLaunchKernelEx(&cfg, gru_cluster_bwd_kernel, a));
     CAPHN_RETURN_LAST();
+}
+
+int caphn_gru_cluster_bwd(const float* dHbm, const float* saved, const float* Hall, const float* Whh, float* dGI,
+                          float* dGH, float* dh0, int B, int T, int H, void* stream) {
+    return gru_cluster_bwd_impl(dHbm, saved, Hall, Whh, dGI, dGH, dh0, B, T, H, nullptr, 0, 0, stream);
+}
+
+int caphn_gru_cluster_bwd_grouped(const float* dHbm, const float* saved, const float* Hall, const float* Whh, float* dGI,
+                                  float* dGH, float* dh0, int B, int T, int H, const int* tiles, int ntiles, long wstride,
+                                  void* stream) {
+    if (!tiles || ntiles < 1 || ((uintptr_t)tiles & 15)) return CAPHN_EINVAL;
+    return gru_cluster_bwd_impl(dHbm, saved, Hall, Whh, dGI, dGH, dh0, B, T, H, tiles, ntiles, wstride, stream);
 }
 
 }  // extern "C"

@@ -85,6 +85,7 @@ class GroupPlan:
         self.tile_rows_fwd, self.tile_rows_bwd = (8, 8) if small else (64, 32)
         self.tiles_fwd = i32(self._tiles(self.tile_rows_fwd))
         self.tiles_bwd = i32(self._tiles(self.tile_rows_bwd))
+        self.tiles8 = i32(self._tiles(8))                           # 8-row tiles: the weights-resident cluster GRU (pooled variant)
         absent = [g for g in range(G) if cnt[g] == 0]
         self.absent_dev = i64(absent) if absent else None         # groups without rows: their d(theta) rows are zero
         self._units: Dict[Tuple, torch.Tensor] = {}
@@ -311,6 +312,108 @@ class AttentionGruGroupedLossFn(Function):
                                    sv[4].view(B * T, H), sv[10])
         gr = _grouped_backward(ctx.plan, sv, ctx.dims, vocab, None)
         return (None, None, None, *gr[:3], None, *gr[3:])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# pooled variant (hypernet.HyperNet + DecoderGRU, single layer): grouped x-projection + weights-resident cluster GRU whose
+# clusters each keep THEIR group's W_hh in shared memory for all T steps
+# ----------------------------------------------------------------------------------------------------------------------
+def _layout_pooled(E, H):
+    """Offsets of (W_ih [3H, E], W_hh [3H, H], b_ih, b_hh) inside one row of Theta (hypernet.py:62-68 parameter order)."""
+    H3 = 3 * H
+    o_hh = H3 * E
+    o_bi = o_hh + H3 * H
+    o_bh = o_bi + H3
+    return H3, o_hh, o_bi, o_bh, o_bh + H3
+
+
+def _pooled_grouped_forward(plan: GroupPlan, feats, caps, h0, Theta, emb_w, fc_w, fc_b):
+    """Teacher-forced DecoderGRU.forward (later.py:389-457, num_layers = 1) for a batch SORTED by style group.  Returns logits
+    in the ORIGINAL batch order."""
+    B, T = caps.shape
+    E, H, V = emb_w.shape[1], fc_w.shape[1], fc_w.shape[0]
+    G, theta = Theta.shape
+    H3, o_hh, o_bi, o_bh, total = _layout_pooled(E, H)
+    assert theta == total and plan.B == B and plan.T == T and plan.G == G
+    dev = feats.device
+    Theta = Theta.contiguous()
+    emb_w = emb_w.contiguous()
+    X = ops.build_inputs(feats.contiguous(), emb_w, caps, 0)                # [T*B, E] time-major: x_0 = feature, x_t = Emb[caps[:, t-1]]
+    b_ih_g = Theta[:, o_bi:o_bh].contiguous()
+    Wsp = ops.split_bf16_batched(Theta, theta, E, G, H3, E)                  # W_ih of every group: [G*3H, Kp]
+    Xgm = ops.split_bf16_gather(X, plan.gm2tm, plan.R_gm)
+    GI = torch.empty(T * B, H3, device=dev, dtype=torch.float32)
+    ops.gemm_tc_grouped(Xgm, False, Wsp, False, GI, H3, plan.units_xproj(H3, E, 128), 128, bias=b_ih_g, rowmap=plan.gm2tm)
+    Hall = torch.empty(T + 1, B, H, device=dev, dtype=torch.float32)
+    Hall[0].copy_(h0)
+    Hbm = torch.empty(B, T, H, device=dev, dtype=torch.float32)
+    saved = torch.empty(1, 4, T, B, H, device=dev, dtype=torch.float32)
+    ops._cabi.call("caphn_gru_cluster_fwd_grouped", GI.data_ptr(), Theta.data_ptr() + 4 * o_hh, Theta.data_ptr() + 4 * o_bh,
+                   Hall.data_ptr(), Hbm.data_ptr(), saved.data_ptr(), B, T, H, plan.tiles8.data_ptr(), plan.tiles8.shape[0],
+                   theta, theta, ops._stream())
+    Hbm_o = ops.gather_rows(Hbm.view(B, T * H), plan.inv).view(B, T, H)
+    logits = ops.linear(Hbm_o.view(B * T, H), fc_w.contiguous(), fc_b).view(B, T, V)
+    sv = (caps, X, Hall, Hbm_o, saved, emb_w, Theta, fc_w, Wsp.hi, Wsp.lo)
+    return logits, sv, (B, T, E, H, V, G)
+
+
+def _pooled_grouped_backward(plan: GroupPlan, sv, dims, vocab, need_feats):
+    caps, X, Hall, Hbm_o, saved, emb_w, Theta, fc_w, Wsp_hi, Wsp_lo = sv
+    B, T, E, H, V, G = dims
+    H3, o_hh, o_bi, o_bh, theta = _layout_pooled(E, H)
+    dfc_w, dfc_b, dHbm_o = vocab
+    dev = X.device
+    dHbm = ops.gather_rows(dHbm_o.reshape(B, T * H).contiguous(), plan.order).view(B, T, H)
+    dGI = torch.empty(T * B, H3, device=dev, dtype=torch.float32)
+    dGH = torch.empty(T * B, H3, device=dev, dtype=torch.float32)
+    dh0 = torch.empty(B, H, device=dev, dtype=torch.float32)
+    ops._cabi.call("caphn_gru_cluster_bwd_grouped", dHbm.data_ptr(), saved.data_ptr(), Hall.data_ptr(),
+                   Theta.data_ptr() + 4 * o_hh, dGI.data_ptr(), dGH.data_ptr(), dh0.data_ptr(), B, T, H,
+                   plan.tiles8.data_ptr(), plan.tiles8.shape[0], theta, ops._stream())
+    Hprev = Hall[:-1].reshape(T * B, H)
+    R = plan.R_gm
+    dGI_gm = ops.split_bf16_gather(dGI, plan.gm2tm, R)
+    dGH_gm = ops.split_bf16_gather(dGH, plan.gm2tm, R)
+    X_gm = ops.split_bf16_gather(X, plan.gm2tm, R)
+    Hp_gm = ops.split_bf16_gather(Hprev, plan.gm2tm, R)
+    dTheta = torch.empty(G, theta, device=dev, dtype=torch.float32)
+    dTheta[:, o_bi:].zero_()
+    if plan.absent_dev is not None:
+        dTheta.index_fill_(0, plan.absent_dev, 0.0)
+    mn = lambda op: ops.SplitOperand(op.hi, op.lo, op.K, op.rows, op.ld, True)
+    ops.gemm_tc_grouped(mn(dGI_gm), True, mn(X_gm), True, dTheta, E, plan.units_dw(H3, E, 128, theta, 0, E), 128)
+    ops.gemm_tc_grouped(mn(dGH_gm), True, mn(Hp_gm), True, dTheta, H, plan.units_dw(H3, H, 128, theta, o_hh, H), 128)
+    ops.group_colsum(dGI, plan.goff_dev, G, B, T, dTheta[:, o_bi:o_bh])
+    ops.group_colsum(dGH, plan.goff_dev, G, B, T, dTheta[:, o_bh:])
+    Wsp = ops.SplitOperand(Wsp_hi, Wsp_lo, E, G * H3, Wsp_hi.shape[1], True)
+    dX = torch.empty(T * B, E, device=dev, dtype=torch.float32)
+    ops.gemm_tc_grouped(dGI_gm, False, Wsp, True, dX, E, plan.units_dx(H3, E, 128), 128, rowmap=plan.gm2tm)
+    dfeats = dX[:B].clone() if need_feats else None                       # rows of t = 0 (sorted order)
+    demb = torch.zeros_like(emb_w)
+    ops.embed_scatter_add(dX, caps, demb, 1)
+    return dfeats, dh0, dTheta, demb, dfc_w, dfc_b
+
+
+class DecoderGRUGroupedFn(Function):
+    """Teacher-forced DecoderGRU.forward (single layer) for a many-style batch.  Inputs: plan, then feats [B,E], captions,
+    h0 (all SORTED by group), Theta [G, theta], emb_w, fc_w, fc_b.  Logits come back in the original batch order."""
+
+    @staticmethod
+    def forward(ctx, plan, feats, caps, h0, Theta, emb_w, fc_w, fc_b):
+        logits, sv, dims = _pooled_grouped_forward(plan, feats, caps, h0, Theta, emb_w, fc_w, fc_b)
+        ctx.save_for_backward(*sv)
+        ctx.plan, ctx.dims = plan, dims
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        sv = ctx.saved_tensors
+        B, T, E, H, V, G = ctx.dims
+        dl = dlogits.reshape(B * T, V).contiguous()
+        vocab = Fn.vocab_bwd_from_dlogits(dl, sv[3].view(B * T, H), sv[7])
+        dfeats, dh0, dTheta, demb, dfc_w, dfc_b = _pooled_grouped_backward(ctx.plan, sv, ctx.dims, vocab,
+                                                                         ctx.needs_input_grad[1])
+        return None, dfeats, None, dh0 if ctx.needs_input_grad[3] else None, dTheta, demb, dfc_w, dfc_b
 
 
 # ----------------------------------------------------------------------------------------------------------------------

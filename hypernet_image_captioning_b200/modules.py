@@ -107,7 +107,11 @@ class _HyperNetMixin:
             from . import parallel
             world = parallel.world_size(self.dp_group)
             if world > 1 and x2.requires_grad:
-                x2 = parallel.ScaleGradFn.apply(x2, 1.0 / world)   # the style gradient leaves the replicated hypernet already global
+                leaf = parallel.route_style_grad(x) if self.grad_mode == "flow" else None
+                if leaf is not None:      # style = a row of a shared parameter: keep that parameter's gradient "early"
+                    x2 = (leaf.reshape(1, -1) if leaf.dim() == 1 else leaf).to(torch.float32).contiguous()
+                else:
+                    x2 = parallel.ScaleGradFn.apply(x2, 1.0 / world)   # the style gradient leaves the replicated hypernet already global
         ps = _hn_params(self)
         if x2.shape[0] > 8 and ps[0].dtype == torch.float32:
             # many style vectors: the layers as dense tensor-core GEMMs (one pass over the head weights for all G)
@@ -225,11 +229,26 @@ class DecoderGRU(nn.Module):
         if groups is not None:
             if h0 is None:
                 h0 = self._h0(features)
+            if self._grouped_kernels_ok(features):
+                # many-style batch on the grouped kernels (grouped.py): batch sorted by group, one grouped tensor-core launch
+                # per time-batched product, clusters that keep THEIR group's W_hh in shared memory for all T steps
+                from . import grouped as Gp
+                Theta = self._theta_groups
+                plan = Gp.GroupPlan.get(groups, Theta.shape[0], captions.shape[1], features.device)
+                fs = Gp.RowPermuteFn.apply(features, plan.order, plan.inv)
+                hs = Gp.RowPermuteFn.apply(h0, plan.order, plan.inv)
+                return Gp.DecoderGRUGroupedFn.apply(plan, fs, captions.index_select(0, plan.order), hs, Theta,
+                                                    self.embed.weight, self.fc_out.weight, self.fc_out.bias)
             return _run_grouped(lambda g, f, c, h: self._forward_one(f, c, h, self._cells(g)), groups,
                                 [features, captions, h0], len(self._generated_groups))[0]
         if h0 is None:
             h0 = self._h0(features)
         return self._forward_one(features, captions, h0, self._cells())
+
+    def _grouped_kernels_ok(self, features):
+        """Grouped kernels: single-layer GRU captioner whose W_hh fits the weights-resident cluster kernel, fp32 mode."""
+        return (type(self) is DecoderGRU and self.num_layers == 1 and getattr(self, "_theta_groups", None) is not None
+                and features.is_cuda and ops.gru_cluster_size(self.hidden_size) > 0 and ops.TC_SPLIT)
 
     def forward_loss(self, features, captions, h0=None, ignore_index=None):
         """Teacher-forced forward fused with the mean cross-entropy of hypernet.py:145 (``ignore_index=None``: no

@@ -105,6 +105,7 @@ class _Overlap:
         self.inflight = False
         self.handles = []
         self.src_streams = []
+        self.routes = []
 
 
 _ov = _Overlap()
@@ -137,6 +138,30 @@ def disable_overlap():
     for h in _ov.handles:
         h.remove()
     _ov.__init__()
+
+
+def route_style_grad(x: torch.Tensor):
+    """Overlap mode only.  When the hypernet input ``x`` is a contiguous view of a shared leaf parameter (the Flickr idiom:
+    the style vector is a row of ``captioner.embed.weight``, hypernet_attention.py:139-142), that parameter would receive a
+    second gradient contribution at the very end of the backward (through the hypernet) and could only be all-reduced after
+    it.  Instead the hypernet runs on a detached leaf copy of ``x``; the parameter's gradient is then final as soon as the
+    decoder's backward has run (so it joins the overlapped bucket), and ``allreduce_shared_grads`` adds the leaf's gradient
+    -- identical on every rank, hence added once, unscaled -- into the reduced gradient.  Returns the leaf, or None."""
+    base = getattr(x, "_base", None)
+    if not _ov.enabled or base is None or not (base.is_leaf and base.requires_grad) or id(base) not in _ov.ids:
+        return None
+    if not (x.is_contiguous() and base.is_contiguous() and x.dtype == base.dtype):
+        return None
+    leaf = x.detach().requires_grad_(True)
+    _ov.routes.append((base, x.storage_offset(), leaf))
+    return leaf
+
+
+def _apply_routes():
+    for base, off, leaf in _ov.routes:
+        if leaf.grad is not None and base.grad is not None:
+            base.grad.view(-1)[off:off + leaf.numel()].add_(leaf.grad.reshape(-1))
+    _ov.routes = []
 
 
 def _on_grad_ready(p):
@@ -197,9 +222,10 @@ def allreduce_shared_grads(params: Iterable[torch.nn.Parameter], group=None, ext
     grads = [p.grad for p in rest if p.grad is not None]
     if extra is not None:
         grads = grads + [extra]
-    if not grads:
-        return
-    _ov.tail_buf = _flat_allreduce(grads, group, _ov.tail_buf)
+    if grads:
+        _ov.tail_buf = _flat_allreduce(grads, group, _ov.tail_buf)
+    if _ov.enabled:
+        _apply_routes()
 
 
 def loss_weight(captions: torch.Tensor, ignore_index: Optional[int] = None, group=None) -> torch.Tensor:

@@ -331,6 +331,17 @@ int caphn_gemm_tc_amax(const void* Ahi, const void* Alo, long a_ld, int a_mn, co
 int caphn_argmax_finish_gather(const float* pval, const int* pidx, int ld, int nparts, long n, const float* table, int E,
                                long long* tok, float* out, long ldo, void* stream);
 
+/* Weights-resident GRU recurrence for a many-style batch (pooled variant; the north star's "keeps each style group's
+ * generated W_hh resident in shared memory across timesteps"): rows sorted by style group, cluster i owns the rows of
+ * tile i = {first row, rows <= 8, group, 0} and loads THAT group's W_hh slice once for all T steps.  Whh / bhh point at
+ * group 0's weights inside Theta [G, theta]; wstride / bstride = theta. */
+int caphn_gru_cluster_fwd_grouped(const float* GI, const float* Whh, const float* bhh, float* Hall, float* Hbm,
+                                  float* saved, int B, int T, int H, const int* tiles, int ntiles, long wstride,
+                                  long bstride, void* stream);
+int caphn_gru_cluster_bwd_grouped(const float* dHbm, const float* saved, const float* Hall, const float* Whh, float* dGI,
+                                  float* dGH, float* dh0, int B, int T, int H, const int* tiles, int ntiles, long wstride,
+                                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

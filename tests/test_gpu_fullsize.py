@@ -340,3 +340,50 @@ def test_async_hypernet_streams_and_graph_match_single_stream(variant, monkeypat
     g_graph = snapshot()
     for k in g_ref:
         assert grad_close(g_graph[k], g_ref[k], 1e-5), k
+
+
+@pytest.mark.parametrize("G,B", [(3, 96), (40, 256)])
+def test_pooled_grouped_full_width_matches_per_group_oracle(G, B):
+    """Pooled variant (hypernet.HyperNet + DecoderGRU) at the launcher's widths E=200, H=150 with G styles in one batch: one
+    hypernet pass for all G (dense tensor-core layers when G > 8), grouped x-projection / dX / dW products, and the
+    weights-resident cluster GRU whose clusters each keep THEIR group's W_hh in shared memory -- against one oracle call per
+    group (later.py:389-457 semantics per call)."""
+    import hypernet_image_captioning_b200 as C
+    E, H, V, T = 200, 150, 2000, 12
+    p = O.init_params_pooled(2048, E, H, V, L=1, seed=5)
+    g = torch.Generator().manual_seed(G)
+    pooled = torch.relu(torch.randn(B, 2048, generator=g))
+    caps = O.synth_captions(B, T, V, g)
+    styles = torch.randn(G, E, generator=g)
+    h0 = torch.rand(B, H, generator=g)
+    groups = torch.randint(0, G, (B,), generator=g)
+    with torch.device("cuda"):
+        m = C.HyperNetPooled(E, H, V, None, num_layers=1)
+    sd = m.state_dict(); sd.update(p); m.load_state_dict(sd)
+    del sd
+    pl = {k: v.requires_grad_(True) for k, v in p.items()}
+    outs, idxs = [], []
+    for gi in range(G):
+        idx = (groups == gi).nonzero().squeeze(1)
+        if idx.numel() == 0:
+            continue
+        lg, _, _ = O.path_pooled(pl, styles[gi:gi + 1], pooled[idx], caps[idx], h0[idx])
+        outs.append(lg); idxs.append(idx)
+    logits_ref = torch.cat(outs, 0)[torch.argsort(torch.cat(idxs))]
+    O.caption_loss(logits_ref, caps, None).backward()
+    captioner = m.forward_grouped(styles.cuda())
+    assert captioner._grouped_kernels_ok(pooled.cuda())
+    logits = captioner(m.image_encoder(pooled.cuda()), caps.cuda(), True, h0=h0.cuda(), groups=groups)
+    C.cross_entropy(logits, caps.cuda(), None).backward()
+    assert rel_err(logits, logits_ref.detach()) < TOL_LOGITS
+    worst = 0.0
+    for k, v in m.named_parameters():
+        if k.startswith("captioner.lstm_cell."):
+            continue
+        ref = pl[k].grad.cuda()
+        d = (v.grad - ref).abs().max().item()
+        s = ref.abs().max().item()
+        assert d <= 1e-7 or d <= TOL_GRAD * s, (k, d, s)
+        worst = max(worst, d / s if s > 0 else 0.0)
+        del ref
+    print(f"[pooled grouped G={G}] logits {rel_err(logits, logits_ref.detach()):.2e} worst grad {worst:.2e}")

@@ -125,7 +125,9 @@ def _worker_overlap(rank, world, port, out):
     flushed = {}
     for it in range(2):                                            # two steps: per-step state must reset
         emb.grad = W.grad = hn.grad = None
-        style = parallel.ScaleGradFn.apply(emb[2:3], 1.0 / world)
+        x = emb[2:3]
+        leaf = parallel.route_style_grad(x) if it == 1 else None          # step 1: routed (style row detached), step 0: scaled
+        style = leaf if leaf is not None else parallel.ScaleGradFn.apply(x, 1.0 / world)
         theta = parallel.allreduce_grad((style * hn).reshape(-1) ** 2)
         loss = (1.0 / world) * (((xb @ W) + emb[ib]) * theta).sum()
         loss.backward()
@@ -153,4 +155,5 @@ def test_overlapped_bucket_matches_single_process(tmp_path):
         assert torch.allclose(d["W"], W.grad, atol=1e-6)
         assert torch.allclose(d["emb"], emb.grad, atol=1e-6)      # incl. the style row: hypernet-path gradient counted once
         assert torch.allclose(d["hn"], hn.grad, atol=1e-6)
-        assert d["flushed"][0] == [True] and d["flushed"][1] == [True]   # W went early (inside backward), emb late
+        # step 0: W went early (inside backward), emb late; step 1 (style row routed): both early
+        assert d["flushed"][0] == [True] and d["flushed"][1] == [False, True]
