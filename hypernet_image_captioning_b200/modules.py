@@ -37,6 +37,21 @@ except Exception:  # noqa: BLE001
             return next(self.parameters()).device
 
 
+class RowsLinear(nn.Linear):
+    """nn.Linear of the hypernet (``hn_base`` / ``hn_heads`` layers; same parameters, same ``state_dict`` keys) whose
+    ``forward`` runs the weight-streaming kernels.  ``HyperNet.forward`` does not go through it (it runs the whole stack as
+    one autograd node); this is for callers that apply the layers themselves -- ``train_init.py:78-91`` calls
+    ``hn_base(style_embed)`` and ``hn_heads[i](base)`` directly in its regression pre-training loop."""
+
+    def forward(self, x):
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.shape[0] > 8 or self.weight.dtype != torch.float32:
+            y = Fn.linear(x2.to(torch.float32), self.weight.to(torch.float32), self.bias.to(torch.float32))
+        else:
+            y = Fn.rows_linear(x2.to(torch.float32).contiguous(), self.weight, self.bias, leaky=False)
+        return y.reshape(*x.shape[:-1], self.out_features)
+
+
 def _hn_params(hn) -> List[torch.Tensor]:
     ps = [hn.hn_base[0].weight, hn.hn_base[0].bias, hn.hn_base[2].weight, hn.hn_base[2].bias]
     for head in hn.hn_heads:
@@ -386,7 +401,7 @@ class HyperNetPooled(_HyperNetMixin, _Base):
         else:
             self.captioner = DecoderRNN(embed_size, hidden_size, vocab_size, num_layers=num_layers)
         E = embed_size
-        self.hn_base = nn.Sequential(nn.Linear(E, 4 * E), nn.LeakyReLU(), nn.Linear(4 * E, 8 * E), nn.LeakyReLU())
+        self.hn_base = nn.Sequential(RowsLinear(E, 4 * E), nn.LeakyReLU(), RowsLinear(4 * E, 8 * E), nn.LeakyReLU())
         heads = []
         for name, W in self.captioner.named_parameters():  # hypernet.py:62-89
             if name in ('embed.weight', 'fc_out.weight', 'fc_out.bias'):
@@ -398,7 +413,7 @@ class HyperNetPooled(_HyperNetMixin, _Base):
                 dims = (8 * E, 8 * E, 8 * E)
             else:
                 dims = (8 * E, w // 8, w // 8)
-            heads.append(nn.Sequential(nn.Linear(dims[0], dims[1]), nn.LeakyReLU(), nn.Linear(dims[2], w)))
+            heads.append(nn.Sequential(RowsLinear(dims[0], dims[1]), nn.LeakyReLU(), RowsLinear(dims[2], w)))
         self.hn_heads = nn.ModuleList(heads)
 
     def forward(self, x):

@@ -13,7 +13,7 @@ from torch.autograd import Function
 
 from . import functional as Fn
 from . import ops, streams
-from .modules import _Base, _HyperNetMixin, _run_grouped
+from .modules import RowsLinear, _Base, _HyperNetMixin, _run_grouped
 
 
 class FeatureFn(Function):
@@ -643,16 +643,16 @@ class HyperNetAttention(_HyperNetMixin, _Base):
         self.captioner = AttentionGru(2048, feature_size, embed_size, hidden_size, vocab_size, p=0.0)
         N, M = 1, 500
         he = hyper_emb if cc else embed_size
-        self.hn_base = nn.Sequential(nn.Linear(he, N * he), nn.LeakyReLU(), nn.Linear(N * he, N * he), nn.LeakyReLU())
+        self.hn_base = nn.Sequential(RowsLinear(he, N * he), nn.LeakyReLU(), RowsLinear(N * he, N * he), nn.LeakyReLU())
         heads = []
         for name, W in self.captioner.gru.named_parameters():  # hypernet_attention.py:69-96
             w = W.numel()
             if w < N * he:
-                heads.append(nn.Sequential(nn.Linear(N * he, N), nn.LeakyReLU(), nn.Linear(w, w)))
+                heads.append(nn.Sequential(RowsLinear(N * he, N), nn.LeakyReLU(), RowsLinear(w, w)))
             elif w // M < N * he:
-                heads.append(nn.Sequential(nn.Linear(N * he, N * he), nn.LeakyReLU(), nn.Linear(N * he, w)))
+                heads.append(nn.Sequential(RowsLinear(N * he, N * he), nn.LeakyReLU(), RowsLinear(N * he, w)))
             else:
-                heads.append(nn.Sequential(nn.Linear(N * he, w // M), nn.LeakyReLU(), nn.Linear(w // M, w)))
+                heads.append(nn.Sequential(RowsLinear(N * he, w // M), nn.LeakyReLU(), RowsLinear(w // M, w)))
         self.hn_heads = nn.ModuleList(heads)
 
     def forward(self, x):

@@ -178,3 +178,37 @@ def test_lowrank_head_gradients_give_the_same_training_trajectory(variant):
         # reductions use atomics, so their summation order varies run to run) and Adam's m / sqrt(v) amplifies last-bit
         # gradient differences of near-cancelling elements: observed spread 0 ... 1.3e-5 between identical runs.
         assert (pa[n] - pb[n]).abs().max().item() <= 5e-5 * max(1.0, pa[n].abs().max().item()), n
+
+
+def test_train_init_regression_loop_runs_on_the_streaming_kernels():
+    """train_init.py:70-123 applies ``hn_base(style_embed)`` and ``hn_heads[i](base)`` itself (plain module calls).  Those
+    modules are RowsLinear layers here, so the unedited loop runs the weight-streaming kernels; loss and gradients equal the
+    torch reference of the same loop."""
+    import torch
+    import hypernet_image_captioning_b200 as C
+    from golden_util import grad_close
+    torch.manual_seed(0)
+    m = C.HyperNetAttention(16, 12, 20, 60, None).cuda()
+    ref = {k: v.detach().clone().requires_grad_(True) for k, v in m.named_parameters() if k.startswith("hn_")}
+    g = torch.Generator().manual_seed(2)
+    style_embed = torch.randn(1, 12, generator=g).cuda()
+    targets = [torch.randn(*p.shape, generator=g).cuda() * 0.1 for p in m.captioner.gru.parameters()]
+    n0 = C._cabi.launches()
+    crit = torch.nn.MSELoss()
+    base = m.hn_base(style_embed)                                   # the reference's own lines (train_init.py:78, 90-91)
+    loss = 0.
+    for i, W in enumerate(targets):
+        loss = loss + crit(m.hn_heads[i](base).flatten(), W.flatten())
+    loss.backward()
+    assert C._cabi.launches() - n0 >= 10                           # 2 base + 8 head layers forward on our kernels
+    lrelu = torch.nn.functional.leaky_relu
+    b = lrelu(lrelu(style_embed @ ref["hn_base.0.weight"].t() + ref["hn_base.0.bias"]) @ ref["hn_base.2.weight"].t() + ref["hn_base.2.bias"])
+    rl = 0.
+    for i, W in enumerate(targets):
+        a = lrelu(b @ ref[f"hn_heads.{i}.0.weight"].t() + ref[f"hn_heads.{i}.0.bias"])
+        rl = rl + crit((a @ ref[f"hn_heads.{i}.2.weight"].t() + ref[f"hn_heads.{i}.2.bias"]).flatten(), W.flatten())
+    rl.backward()
+    assert abs(loss.item() - rl.item()) < 1e-5 * abs(rl.item())
+    for k, v in m.named_parameters():
+        if k.startswith("hn_"):
+            assert grad_close(v.grad, ref[k].grad, 1e-3), k
