@@ -383,6 +383,26 @@ def run_ours(args):
         ms_lit = timed(lambda: step(pooled_d, caps_d, h0_d), args.steps)
         model.grad_mode = "flow"
         extras["literal_mode_captions_per_s"] = B * world * args.steps / (ms_lit * 1e-3)
+        # the reference's own call shape (hypernet.py:139-145): captioner(features, captions, True) returns the logits and the
+        # SCRIPT computes the loss -- with torch's F.cross_entropy (the unedited script) or caphn.cross_entropy (one changed
+        # line); the headline uses the fused decoder + loss node (forward_loss).  Eager launches, flow mode.
+        import torch.nn.functional as F_
+        def step_shape(ce):
+            model.zero_grad(set_to_none=True)
+            captioner = model.forward(model.captioner.embed.weight[4:5])
+            logits = captioner(model.image_encoder(pooled_d), caps_d, True, h0=h0_d)
+            loss = ce(logits)
+            (loss * inv_world if world > 1 else loss).backward()
+            if world > 1:
+                parallel.allreduce_shared_grads(shared)
+        ces = {"torch_F_cross_entropy": lambda lg: F_.cross_entropy(lg.view(-1, c["V"]), caps_d.view(-1)),
+               "caphn_cross_entropy": lambda lg: C.cross_entropy(lg, caps_d, None)}
+        extras["reference_call_shape_captions_per_s"] = {}
+        for name_, ce_ in ces.items():
+            for _ in range(3):
+                step_shape(ce_)
+            ms_s = timed(lambda: step_shape(ce_), args.steps)
+            extras["reference_call_shape_captions_per_s"][name_] = B * world * args.steps / (ms_s * 1e-3)
         # greedy decode (DecoderGRU.infer, max_len = T), hypernet forward included
         def decode():
             with torch.no_grad():
@@ -523,8 +543,32 @@ def torch_eager_gpu_arm(dev, timed, B):
     for _ in range(3):
         step()
     ms = timed(step, 10)
-    return {"pooled_train": B * 10 / (ms * 1e-3), "ms_per_step": ms / 10,
-            "what": "oracle port, torch eager CUDA kernels (cuBLAS/ATen), same workload, fp32 (TF32 off)"}
+    out = {"pooled_train": B * 10 / (ms * 1e-3), "ms_per_step": ms / 10,
+           "what": "oracle port, torch eager CUDA kernels (cuBLAS/ATen), same workloads, fp32 (TF32 off)"}
+    del p
+    torch.cuda.empty_cache()
+    # configs[2]: attention variant, teacher-forced fwd+bwd and greedy decode
+    import numpy as np
+    pa = O.init_params_attention(2048, 200, 200, 200, c["V"], 200, seed=0)
+    pa = {k: v.to(dev).requires_grad_(True) for k, v in pa.items()}
+    feats = torch.randn(B, 49, 2048, generator=g).to(dev)
+
+    def astep():
+        for v in pa.values():
+            v.grad = None
+        logits = O.path_attention(pa, pa["captioner.embed.weight"][4:5], feats, caps, 0.0, np.random.RandomState(0))[0]
+        O.caption_loss(logits, caps, 0).backward()
+
+    def adec():
+        with torch.no_grad():
+            O.path_attention(pa, pa["captioner.embed.weight"][4:5], feats, caps, 1.0, np.random.RandomState(0))
+
+    for name, fn in (("attention_train", astep), ("attention_greedy_decode", adec)):
+        for _ in range(2):
+            fn()
+        ms = timed(fn, 5)
+        out[name] = B * 5 / (ms * 1e-3)
+    return out
 
 
 def pooled_l2_extras(args, dev, world, timed, rooflines, peak):
