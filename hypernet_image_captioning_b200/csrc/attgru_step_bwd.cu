@@ -188,7 +188,9 @@ __global__ void __launch_bounds__(G1_THREADS) attbwd_gate_kernel(const BwdG1 a) 
 // ------------------------------------------------------------------------------------------------------------------
 // G2: dctx_t = dgi_t W_ih[:,E:],  dhp = dgh_t W_hh        CTA = 4 output tiles of one kind (4 warps) x 32 rows
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int G2_NB = 32, G2_NB_SMALL = 8, G2_WARPS = 4, G2_THREADS = G2_WARPS * 32, G2_PF = 19;
+constexpr int G2_NB = 32, G2_NB_SMALL = 8, G2_WARPS = 4, G2_THREADS = G2_WARPS * 32;
+constexpr int G2_PF_BIG = 19;     // register prefetch depth (uint4 pairs) of the weight fragments: 32-row tiles, 2 CTAs per SM
+constexpr int G2_PF_SMALL = 8;    // 8-row tiles of a many-domain batch: shallow prefetch, ~100 registers, 4-5 CTAs per SM hide the loads
 
 struct BwdG2 {
     const uint4* Wc;             // group 1 tiles (NFT x NKT3)
@@ -204,8 +206,8 @@ struct BwdG2 {
     long pstride;
 };
 
-template <int G2_NB>
-__global__ void __launch_bounds__(G2_THREADS) attbwd_gemm_kernel(const BwdG2 a) {
+template <int G2_NB, int G2_PF>
+__global__ void __launch_bounds__(G2_THREADS, G2_NB >= 32 ? 2 : 4) attbwd_gemm_kernel(const BwdG2 a) {
     constexpr int G2_NT = G2_NB / 8, G2_RP = G2_NB + 1;
     extern __shared__ __align__(16) uint8_t g2sm[];
     const int B = a.B, KP3 = a.KP3, NKT3 = a.NKT3;
@@ -658,8 +660,8 @@ static int attstep_bwd_impl(const float* dHbm, const float* dattn, const float* 
     const bool small_tiles = tiles && tile_rows <= G2_NB_SMALL;
     if (tiles && tile_rows > G2_NB) return CAPHN_EINVAL;
     const size_t s2s = g2_smem(KP3, G2_NB_SMALL);
-    CAPHN_CHECK(cudaFuncSetAttribute(attbwd_gemm_kernel<G2_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-    CAPHN_CHECK(cudaFuncSetAttribute(attbwd_gemm_kernel<G2_NB_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2s));
+    CAPHN_CHECK(cudaFuncSetAttribute(attbwd_gemm_kernel<G2_NB, G2_PF_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+    CAPHN_CHECK(cudaFuncSetAttribute(attbwd_gemm_kernel<G2_NB_SMALL, G2_PF_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2s));
     CAPHN_CHECK(cudaFuncSetAttribute(attbwd_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa));
     CAPHN_CHECK(cudaFuncSetAttribute(attbwd_dk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sd));
     static const bool pdl = []() { const char* e = getenv("CAPHN_PDL"); return !(e && e[0] == '0'); }();
@@ -674,9 +676,9 @@ static int attstep_bwd_impl(const float* dHbm, const float* dattn, const float* 
         BwdG2 g2{p1, p2, gisp, ghsp, dCTX + (long)t * B * F, dhp, B, H, F, NUT, NFT, NKT3, KP3, NG1, (const int4*)tiles,
                  pb / 16};
         if (small_tiles) {
-            CAPHN_CHECK(launch_pdl(attbwd_gemm_kernel<G2_NB_SMALL>, dim3(NG1 + NG2, ntiles), dim3(G2_THREADS), s2s, st, pdl, g2));
+            CAPHN_CHECK(launch_pdl(attbwd_gemm_kernel<G2_NB_SMALL, G2_PF_SMALL>, dim3(NG1 + NG2, ntiles), dim3(G2_THREADS), s2s, st, pdl, g2));
         } else {
-            CAPHN_CHECK(launch_pdl(attbwd_gemm_kernel<G2_NB>, dim3(NG1 + NG2, tiles ? ntiles : ceil_div(B, G2_NB)),
+            CAPHN_CHECK(launch_pdl(attbwd_gemm_kernel<G2_NB, G2_PF_BIG>, dim3(NG1 + NG2, tiles ? ntiles : ceil_div(B, G2_NB)),
                                    dim3(G2_THREADS), s2, st, pdl, g2));
         }
         ++caphn_launch_counter;

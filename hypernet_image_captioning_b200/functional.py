@@ -28,13 +28,19 @@ class HyperNetThetaFn(Function):
         b1 = ops.rows_linear_fwd(params[2], params[3], b0, ACT_LEAKY)
         sizes = [params[4 + 4 * i + 2].shape[0] for i in range(nh)]
         theta = torch.empty(x.shape[0], sum(sizes), device=x.device, dtype=torch.float32)
-        mids, off = [], 0
+        mids, offs, off = [None] * nh, [], 0
         for i in range(nh):
-            W1, c1, W2, c2 = params[4 + 4 * i: 8 + 4 * i]
-            a = ops.rows_linear_fwd(W1, c1, b1, ACT_LEAKY)
-            ops.rows_linear_fwd(W2, c2, a, ACT_NONE, out=theta[:, off:off + sizes[i]])
-            mids.append(a)
+            offs.append(off)
             off += sizes[i]
+        # the heads are independent chains (small first layer -> second layer); the two that generate the weight matrices
+        # stream hundreds of MB, the bias heads are a few 4 us launches: side by side instead of back to back
+        with streams.Branches("hnf", like=x, enable=nh > 1) as br:
+            for i in range(nh):
+                W1, c1, W2, c2 = params[4 + 4 * i: 8 + 4 * i]
+                with br.on(i % 4):
+                    a = ops.rows_linear_fwd(W1, c1, b1, ACT_LEAKY)
+                    ops.rows_linear_fwd(W2, c2, a, ACT_NONE, out=theta[:, offs[i]:offs[i] + sizes[i]])
+                    mids[i] = a
         ctx.save_for_backward(x, b0, b1, *mids, *params)
         ctx.lowrank_targets = [params[4 + 4 * i + 2] for i in range(nh)]    # the Parameter objects (saved tensors are views)
         ctx.lowrank_min = LOWRANK_MIN_NUMEL
@@ -53,10 +59,15 @@ class HyperNetThetaFn(Function):
         dtheta = dtheta.contiguous()
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
         db1 = torch.zeros_like(b1)
-        off = 0
+        offs, off = [], 0
         for i in range(nh):
+            offs.append(off)
+            off += sizes[i]
+
+        def head_bwd(i):
             W1, c1, W2, c2 = params[4 + 4 * i: 8 + 4 * i]
             pi = 4 + 4 * i
+            off = offs[i]
             tgt = ctx.lowrank_targets[i]
             prev = getattr(tgt, "grad_lowrank", None)
             lowrank = (ctx.lowrank_min > 0 and need[1 + pi + 2] and W2.numel() >= ctx.lowrank_min
@@ -72,9 +83,14 @@ class HyperNetThetaFn(Function):
             else:
                 dW2, dc2, da = ops.rows_linear_bwd(W2, mids[i], None, dtheta[:, off:off + sizes[i]], ACT_NONE,
                                                    need_dW=need[1 + pi + 2])
-            dW1, dc1, _ = ops.rows_linear_bwd(W1, b1, mids[i], da, ACT_LEAKY, need_dW=need[1 + pi], dA=db1)
+            dW1, dc1, _ = ops.rows_linear_bwd(W1, b1, mids[i], da, ACT_LEAKY, need_dW=need[1 + pi], dA=db1)   # db1 += (atomics)
             grads[pi], grads[pi + 1], grads[pi + 2], grads[pi + 3] = dW1, dc1, dW2, dc2
-            off += sizes[i]
+
+        # independent per-head chains side by side (the bias heads' 6-7 us launches fit next to the big heads' streaming)
+        with streams.Branches("hnb", like=x, enable=nh > 1) as br:
+            for i in range(nh):
+                with br.on(i % 4):
+                    head_bwd(i)
         dWb1, dcb1, db0 = ops.rows_linear_bwd(params[2], b0, b1, db1, ACT_LEAKY, need_dW=need[3])
         dWb0, dcb0, dx = ops.rows_linear_bwd(params[0], x, b0, db0, ACT_LEAKY, need_dW=need[1], need_dA=need[0])
         grads[0], grads[1], grads[2], grads[3] = dWb0, dcb0, dWb1, dcb1

@@ -15,14 +15,16 @@ WANT = [
     ("dram__bytes_write.sum", "wrMB", 1e-6),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%", 1.0),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%", 1.0),
-    ("sm__inst_executed_pipe_tensor.sum", "tensor_inst", 1.0),
+    ("TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "hmma_cyc", 1.0),
+    ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tmem%", 1.0),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%", 1.0),
     ("lts__t_sector_hit_rate.pct", "L2hit%", 1.0),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%", 1.0),
     ("launch__registers_per_thread", "regs", 1.0),
     ("launch__grid_size", "grid", 1.0),
 ]
-UNIT_SCALE = {"nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+UNIT_SCALE = {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9, "nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9,
+              "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
 def load(path):
@@ -38,7 +40,8 @@ def main(paths):
         idx = {h: i for i, h in enumerate(hdr)}
         tens = sorted(h for h in hdr if "tensor" in h)
         print(f"# {path}: {len(data)} profiled launches (ncu --set full --clock-control none; one replay set per launch)")
-        print(f"# tensor-pipe metrics present in this report: {', '.join(tens) if tens else 'none'}")
+        print("# tensor% = sm__pipe_tensor_cycles_active (pct of peak, active cycles); hmma_cyc = tensor-pipe HMMA-subpipe active cycles"
+              " (realtime counter, per TPC = 2 SMs: UTCHMMA / HMMA work shows up here); tmem% = sm__mem_tensor_cycles_active")
         cols = [w for w in WANT if w[0] in idx]
         print(f"{'kernel':44s} " + " ".join(f"{c[1]:>10s}" for c in cols))
         for r in data:
