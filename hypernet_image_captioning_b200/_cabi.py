@@ -64,6 +64,8 @@ SIGNATURES = {
     "caphn_split_bf16_gather": [P, L, P, L, I, P, P, L, P],
     "caphn_split_bf16_batched": [P, L, L, I, I, I, P, P, L, P],
     "caphn_group_colsum": [P, L, P, I, I, I, I, P, L, P],
+    "caphn_gemm_tc_lse": [P, P, L, I, P, P, L, I, L, P, L, P, I, I, P, P, I, P, P],
+    "caphn_ce_fwd_partials": [P, P, I, I, P, L, P, L, I, LL, P, P, P, P],
     "caphn_gemm_tc_amax": [P, P, L, I, P, P, L, I, L, P, L, P, I, I, P, P, I, P, P],
     "caphn_argmax_finish_gather": [P, P, I, I, L, P, I, P, P, L, P],
     "caphn_beam_step": [P] * 14 + [I] * 8 + [P],

@@ -160,6 +160,10 @@ struct TcParams {
     // reduces the columns it reads of every row to (max, column) and writes them to amax_val / amax_idx [M, amax_ld],
     // slot 2 * n-tile + warp half; a tiny kernel finishes the reduction (and gathers the next input row).  null: off.
     float* amax_val; int* amax_idx; int amax_ld;
+    // stat_mode 1: arg-max partials (above).  2: log-sum-exp partials for the fused cross-entropy -- amax_val = running row
+    // max m, amax_idx = the bits of s = sum exp(x - m) over the columns this warp read (SURVEY K7+K8: the loss statistics
+    // come out of the logits GEMM instead of a second pass over the 0.4 GB of logits).
+    int stat_mode;
     int M, N, num_kb, relu;
     int BN;          // N tile (multiple of 16, <= 256)
     int splitk;      // K split factor; > 1 => epilogue adds atomically into a zero-initialised C
@@ -326,8 +330,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             const int* rmap = p.rowmap ? p.rowmap + u.map0 : nullptr;
             int last_c = half;
             while (last_c + 2 < nchunks) last_c += 2;
-            float am_best = -INFINITY;            // arg-max partial of row (rl0 + lane) over this warp's chunks
+            float am_best = -INFINITY;            // arg-max partial (mode 1) / running max (mode 2) of row (rl0 + lane) over this warp's chunks
             int am_idx = 0x7fffffff;
+            float lse_s = 0.f;                    // mode 2: sum exp(x - am_best)
             if (half >= nchunks) {                 // nothing to read for this warp: release the stage immediately
                 tcgen05_fence_before();
                 if (lane == 0) mbar_arrive(tempty + as);
@@ -345,12 +350,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 const int colbase = u.b0 + c * 32;            // (TMA-store path: global column)
                 const int cl0 = c * 32;                       // tile-local column of this chunk
                 const int cvalid = min(32, u.n_valid - cl0);  // valid columns of this chunk (may be <= 0)
+                bool bias_done = false;
                 if (p.amax_val) {                             // lane = row: 32 consecutive columns of it are in r[]
                     const float bl = (add_bias && lane < cvalid) ? biasp[cl0 + lane] : 0.f;
+                    float cm = -INFINITY;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float v = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
-                        if (j < cvalid && v > am_best) { am_best = v; am_idx = colbase + j; }   // ascending columns: first max wins
+                        r[j] = __float_as_uint(v);            // the bias is in: the store paths below must not add it again
+                        if (j < cvalid) {
+                            if (p.stat_mode == 1) { if (v > am_best) { am_best = v; am_idx = colbase + j; } }   // ascending columns: first max wins
+                            else cm = fmaxf(cm, v);
+                        }
+                    }
+                    bias_done = true;
+                    if (p.stat_mode == 2 && cm > -INFINITY) {
+                        const float nm = fmaxf(am_best, cm);
+                        float acc = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (j < cvalid) acc += __expf(__uint_as_float(r[j]) - nm);
+                        lse_s = lse_s * __expf(am_best - nm) + acc;       // exp(-inf) = 0 on the first chunk
+                        am_best = nm;
                     }
                 }
                 if constexpr (TMA_STORE) {
@@ -358,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     if (!atomic && BN - c * 32 >= 32) {
                         if (lane == 0) tma_store_wait_read();          // the previous store has finished reading `st`
                         __syncwarp();
-                        const float bl = (add_bias && lane < cvalid) ? biasp[cl0 + lane] : 0.f;
+                        const float bl = (add_bias && !bias_done && lane < cvalid) ? biasp[cl0 + lane] : 0.f;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {                 // lane = row: it needs the bias of all 32 columns
                             float v = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
@@ -390,7 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 if (vec && ((u.c_off & 3) == 0)) {
                     const int cl = (lane & 7) * 4;             // 4 consecutive columns per lane, 8 lanes per row
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (add_bias) {
+                    if (add_bias && !bias_done) {
                         if (cl + 0 < cvalid) bv.x = biasp[cl0 + cl + 0];
                         if (cl + 1 < cvalid) bv.y = biasp[cl0 + cl + 1];
                         if (cl + 2 < cvalid) bv.z = biasp[cl0 + cl + 2];
@@ -418,7 +439,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     }
                 } else {
                     const bool colok = lane < cvalid;
-                    const float bv = (add_bias && colok) ? biasp[cl0 + lane] : 0.f;
+                    const float bv = (add_bias && !bias_done && colok) ? biasp[cl0 + lane] : 0.f;
 #pragma unroll 8
                     for (int rr = 0; rr < 32; ++rr) {
                         const int rl = rl0 + rr;
@@ -441,7 +462,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             if (p.amax_val && rl0 + lane < u.m_valid) {
                 const long o = (long)(u.a0 + rl0 + lane) * p.amax_ld + 2 * (u.b0 / BN) + half;
                 p.amax_val[o] = am_best;
-                p.amax_idx[o] = am_idx;
+                p.amax_idx[o] = p.stat_mode == 2 ? __float_as_int(lse_s) : am_idx;
             }
         }
         if constexpr (TMA_STORE) {
@@ -578,7 +599,7 @@ int caphn_split_bf16_t(const float* src, long lds, int R, int C, void* hi, void*
 // Alo == Blo == NULL selects plain bf16.  splitk: 0 = automatic, 1 = none, > 1 = split K, partial tiles added atomically.
 static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
                         int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, int relu, int splitk,
-                        float* amax_val, int* amax_idx, int amax_ld, void* stream, int* bn_used = nullptr) {
+                        float* amax_val, int* amax_idx, int amax_ld, void* stream, int* bn_used = nullptr, int stat_mode = 1) {
     if (M <= 0 || N <= 0 || K <= 0 || ((Alo == nullptr) != (Blo == nullptr))) return CAPHN_EINVAL;
     if (amax_val && (!amax_idx || splitk > 1 || relu)) return CAPHN_EINVAL;
     if (amax_val) splitk = 1;
@@ -645,7 +666,7 @@ static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, c
     if (bn_used) *bn_used = p.BN;
     if (amax_val) {
         if (amax_ld < 2 * ceil_div(N, p.BN)) return CAPHN_EINVAL;
-        p.amax_val = amax_val; p.amax_idx = amax_idx; p.amax_ld = amax_ld;
+        p.amax_val = amax_val; p.amax_idx = amax_idx; p.amax_ld = amax_ld; p.stat_mode = stat_mode;
     }
     if (p.splitk > 1) {
         if (ldc == N) {
@@ -680,8 +701,7 @@ static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, c
         // edge box of a ragged N did not match in round 1 -- those shapes keep the default epilogue).  CAPHN_TC_TMA_STORE=0
         // switches it off.
         const char* e = getenv("CAPHN_TC_TMA_STORE");
-        tma_store = !(e && e[0] == '0') && p.splitk == 1 && (ldc % 4 == 0) && (N % 4 == 0) && ((uintptr_t)C % 16 == 0) &&
-                    !p.amax_val;
+        tma_store = !(e && e[0] == '0') && p.splitk == 1 && (ldc % 4 == 0) && (N % 4 == 0) && ((uintptr_t)C % 16 == 0);
         if (tma_store && (rc = tc::make_map_c(&mC, C, M, N, ldc))) return rc;
     }
     if (split && tma_store) {
@@ -768,6 +788,21 @@ int caphn_gemm_tc_amax(const void* Ahi, const void* Alo, long a_ld, int a_mn, co
     int bn = 0;
     const int rc = gemm_tc_impl(Ahi, Alo, a_ld, a_mn, Bhi, Blo, b_ld, b_mn, K, C, ldc, bias, M, N, 0, 1, amax_val, amax_idx,
                                 amax_ld, stream, &bn);
+    if (nparts && bn > 0) *nparts = 2 * ceil_div(N, bn);
+    return rc;
+}
+
+// caphn_gemm_tc_ex + row log-sum-exp partials in the epilogue (training: logits = H W^T + b feed F.cross_entropy,
+// cc_train_hypernet.py:152-153 / hypernet.py:139-145): pm / ps [M, ld] receive, per row and per (n-tile, warp half), the
+// running max m and s = sum exp(x - m) of the columns that warp read (slots without columns: m = -inf, s = 0).
+// *nparts = slots written per row.  Finish with caphn_ce_fwd_partials.
+int caphn_gemm_tc_lse(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
+                      int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, float* pm, float* ps, int ld,
+                      int* nparts, void* stream) {
+    if (!pm || !ps) return CAPHN_EINVAL;
+    int bn = 0;
+    const int rc = gemm_tc_impl(Ahi, Alo, a_ld, a_mn, Bhi, Blo, b_ld, b_mn, K, C, ldc, bias, M, N, 0, 1, pm, (int*)ps, ld,
+                                stream, &bn, 2);
     if (nparts && bn > 0) *nparts = 2 * ceil_div(N, bn);
     return rc;
 }

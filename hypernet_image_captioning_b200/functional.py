@@ -222,7 +222,7 @@ def vocab_bwd_fused(logits2d, targets, ignore_index, lse, lossbuf, gscale, Hbm2,
 # ----------------------------------------------------------------------------------------------------------------------
 # Variant A decoder: teacher-forced DecoderGRU.forward  (reference later.py:389-457)
 # ----------------------------------------------------------------------------------------------------------------------
-def _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells):
+def _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells, want_stats=False):
     B, T = captions.shape
     NL = len(cells) // 4
     W_ih, W_hh, b_ih, b_hh = cells[0:4]
@@ -245,6 +245,9 @@ def _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells):
                           bi.contiguous(), bh.contiguous()))
         Hall, Hbm, saved, Hmid = ops.gru_seq_fwd(GI, WhhT, b_hh.contiguous(), h0.contiguous(), T, save=True,
                                                  extra=extra)
+    if want_stats:      # fused loss node: the cross-entropy statistics come out of this GEMM's epilogue
+        logits, stats = ops.linear_lse(Hbm.view(B * T, H), fc_w.contiguous(), fc_b)
+        return logits.view(B, T, -1), (caps, X, Hall, Hbm, saved, Hmid, emb_w, fc_w), stats
     logits = ops.linear(Hbm.view(B * T, H), fc_w.contiguous(), fc_b)
     return logits.view(B, T, -1), (caps, X, Hall, Hbm, saved, Hmid, emb_w, fc_w)
 
@@ -435,10 +438,10 @@ class DecoderGRULossFn(Function):
 
     @staticmethod
     def forward(ctx, ignore_index, feats, captions, h0, emb_w, fc_w, fc_b, *cells):
-        logits, sv = _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells)
+        logits, sv, stats = _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells, want_stats=True)
         B, T, V = logits.shape
         targets = captions.reshape(-1).contiguous()
-        lossbuf, lse = ops.ce_fwd(logits.view(B * T, V), targets, ignore_index)
+        lossbuf, lse = ops.ce_fwd_stats(logits.view(B * T, V), targets, ignore_index, stats)
         ctx.save_for_backward(*sv, *cells, logits, targets, lse, lossbuf)
         ctx.NL = len(cells) // 4
         ctx.ignore_index = ignore_index

@@ -82,7 +82,7 @@ class FeatureFn(Function):
 
 
 def _attgru_forward(need_grad, f3, K3, h0, captions, use_sampling, emb_w, W_ih, W_hh, b_ih, b_hh, fc_w, fc_b, Ua_w, Ua_b,
-                    va_w, va_b):
+                    va_w, va_b, stats_out=None):
     """The time loop of AttentionGru.forward (models/decoderlstm.py:78-108) + the vocabulary projection, given the
     loop-invariant tensors of FeatureFn.  Returns (logits, attn, tensors to save, dims)."""
     B, P, Fd = f3.shape
@@ -123,7 +123,11 @@ def _attgru_forward(need_grad, f3, K3, h0, captions, use_sampling, emb_w, W_ih, 
                                    E, saved, 0, T)
         else:
             ops.attgru_fwd(K3, f3, GIw, lw, Ua_b, va, bv, b_hh, Hall, Hbm, attn, XC, E, saved, 0, T)
-        ops.linear(Hbm.view(B * T, H), fc_w, fc_b, out=logits.view(B * T, V))
+        if stats_out is not None:       # fused loss node: cross-entropy statistics out of the logits GEMM's epilogue
+            _, st = ops.linear_lse(Hbm.view(B * T, H), fc_w, fc_b, out=logits.view(B * T, V))
+            stats_out.append(st)
+        else:
+            ops.linear(Hbm.view(B * T, H), fc_w, fc_b, out=logits.view(B * T, V))
     else:
         GIw = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
         xproj, vocab = ops.LinearPlan(W_ih_w, b_ih.contiguous()), ops.LinearPlan(fc_w, fc_b)   # split once, reuse per step
@@ -240,10 +244,11 @@ class AttentionGruLossFn(Function):
 
     @staticmethod
     def forward(ctx, ignore_index, f3, K3, h0, captions, use_sampling, *params):
-        logits, attn, sv, dims = _attgru_forward(True, f3, K3, h0, captions, use_sampling, *params)
+        stats = []
+        logits, attn, sv, dims = _attgru_forward(True, f3, K3, h0, captions, use_sampling, *params, stats_out=stats)
         B, T, V = logits.shape
         targets = captions.reshape(-1).contiguous()
-        lossbuf, lse = ops.ce_fwd(logits.view(B * T, V), targets, ignore_index)
+        lossbuf, lse = ops.ce_fwd_stats(logits.view(B * T, V), targets, ignore_index, stats[0] if stats else None)
         ctx.save_for_backward(*sv, logits, targets, lse, lossbuf)
         ctx.dims = dims
         ctx.ignore_index = ignore_index

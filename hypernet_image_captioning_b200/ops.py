@@ -696,6 +696,47 @@ def gemm_tc_amax(A: SplitOperand, Bm: SplitOperand, bias, out, pval, pidx):
     return int(n.value)
 
 
+CE_FUSED_STATS = True   # training: log-sum-exp partials out of the logits GEMM's epilogue instead of a pass over the logits
+
+
+def linear_lse(X, W, bias, out=None):
+    """out = X W^T + bias on the tensor cores + row log-sum-exp partials from the epilogue.  Returns (out, stats) with
+    stats = (pm, ps, nparts), or (out, None) when the product does not take the tensor-core path."""
+    _chk(X), _chk(W)
+    M, K = X.shape
+    N = W.shape[0]
+    if not (CE_FUSED_STATS and _tc_ok(M, N, K)):
+        return linear(X, W, bias, out=out), None
+    import ctypes
+    A, Bm = split_bf16(X), split_bf16(W)
+    if out is None:
+        out = torch.empty(M, N, device=X.device, dtype=torch.float32)
+    ld = 2 * ((N + 127) // 128)
+    pm = torch.empty(M, ld, device=X.device, dtype=torch.float32)
+    ps = torch.empty(M, ld, device=X.device, dtype=torch.float32)
+    n = ctypes.c_int(0)
+    _cabi.call("caphn_gemm_tc_lse", A.hi.data_ptr(), _p(A.lo), A.ld, 0, Bm.hi.data_ptr(), _p(Bm.lo), Bm.ld, 0, A.K,
+               out.data_ptr(), out.stride(0), _p(bias), M, N, pm.data_ptr(), ps.data_ptr(), ld, ctypes.byref(n), _stream())
+    return out, (pm, ps, int(n.value))
+
+
+def ce_fwd_stats(logits2d, targets, ignore_index, stats):
+    """ce_fwd from the epilogue's partials (``stats`` of linear_lse); falls back to the pass over the logits without them."""
+    if stats is None:
+        return ce_fwd(logits2d, targets, ignore_index)
+    pm, ps, nparts = stats
+    M, V = logits2d.shape
+    dev = logits2d.device
+    lse = torch.empty(M, device=dev, dtype=torch.float32)
+    scratch = torch.empty(2 * M, device=dev, dtype=torch.float32)
+    lossbuf = torch.empty(2, device=dev, dtype=torch.float32)
+    has = ignore_index is not None
+    _cabi.call("caphn_ce_fwd_partials", pm.data_ptr(), ps.data_ptr(), pm.stride(0), nparts, logits2d.data_ptr(),
+               logits2d.stride(0), targets.data_ptr(), M, int(has), int(ignore_index) if has else 0, lse.data_ptr(),
+               scratch.data_ptr(), lossbuf.data_ptr(), _stream())
+    return lossbuf, lse
+
+
 def argmax_finish_gather(pval, pidx, nparts, table=None, tok=None, out=None):
     """tok[i] = arg-max of row i from its ``nparts`` partials (lowest column on ties); out[i] = table[tok[i]] if given."""
     n = pval.shape[0]

@@ -342,6 +342,17 @@ int caphn_gru_cluster_bwd_grouped(const float* dHbm, const float* saved, const f
                                   float* dGH, float* dh0, int B, int T, int H, const int* tiles, int ntiles, long wstride,
                                   void* stream);
 
+/* Cross-entropy statistics out of the logits GEMM (SURVEY K7+K8): caphn_gemm_tc_lse = caphn_gemm_tc_ex whose epilogue also
+ * keeps, per row and per (n-tile, epilogue-warp half), the running max m and s = sum exp(x - m) of the columns it wrote
+ * (pm / ps [M, ld], *nparts slots per row); caphn_ce_fwd_partials merges them into lse, reads the one target logit per row
+ * and produces the same (lse, lossbuf) as caphn_ce_fwd -- without re-reading the [M, V] logits (0.4 GB at B=512, T=20). */
+int caphn_gemm_tc_lse(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
+                      int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, float* pm, float* ps, int ld,
+                      int* nparts, void* stream);
+int caphn_ce_fwd_partials(const float* pm, const float* ps, int ldp, int nparts, const float* X, long ld,
+                          const long long* tgt, long M, int has_ignore, long long ignore, float* lse, float* scratch,
+                          float* lossbuf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
