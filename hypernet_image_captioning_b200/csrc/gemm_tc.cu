@@ -351,20 +351,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 const int cl0 = c * 32;                       // tile-local column of this chunk
                 const int cvalid = min(32, u.n_valid - cl0);  // valid columns of this chunk (may be <= 0)
                 bool bias_done = false;
-                if (p.amax_val) {                             // lane = row: 32 consecutive columns of it are in r[]
+                if (p.amax_val && p.stat_mode == 1) {         // lane = row: 32 consecutive columns of it are in r[]
+                    const float bl = (add_bias && lane < cvalid) ? biasp[cl0 + lane] : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
+                        if (j < cvalid && v > am_best) { am_best = v; am_idx = colbase + j; }   // ascending columns: first max wins
+                    }
+                } else if (p.amax_val) {                      // stat_mode 2: running (max, sum exp) of the row
                     const float bl = (add_bias && lane < cvalid) ? biasp[cl0 + lane] : 0.f;
                     float cm = -INFINITY;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float v = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
                         r[j] = __float_as_uint(v);            // the bias is in: the store paths below must not add it again
-                        if (j < cvalid) {
-                            if (p.stat_mode == 1) { if (v > am_best) { am_best = v; am_idx = colbase + j; } }   // ascending columns: first max wins
-                            else cm = fmaxf(cm, v);
-                        }
+                        if (j < cvalid) cm = fmaxf(cm, v);
                     }
                     bias_done = true;
-                    if (p.stat_mode == 2 && cm > -INFINITY) {
+                    if (cm > -INFINITY) {
                         const float nm = fmaxf(am_best, cm);
                         float acc = 0.f;
 #pragma unroll
@@ -701,7 +705,8 @@ static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, c
         // edge box of a ragged N did not match in round 1 -- those shapes keep the default epilogue).  CAPHN_TC_TMA_STORE=0
         // switches it off.
         const char* e = getenv("CAPHN_TC_TMA_STORE");
-        tma_store = !(e && e[0] == '0') && p.splitk == 1 && (ldc % 4 == 0) && (N % 4 == 0) && ((uintptr_t)C % 16 == 0);
+        tma_store = !(e && e[0] == '0') && p.splitk == 1 && (ldc % 4 == 0) && (N % 4 == 0) && ((uintptr_t)C % 16 == 0) &&
+                    !(p.amax_val && p.stat_mode == 1);
         if (tma_store && (rc = tc::make_map_c(&mC, C, M, N, ldc))) return rc;
     }
     if (split && tma_store) {

@@ -696,7 +696,11 @@ def gemm_tc_amax(A: SplitOperand, Bm: SplitOperand, bias, out, pval, pidx):
     return int(n.value)
 
 
-CE_FUSED_STATS = True   # training: log-sum-exp partials out of the logits GEMM's epilogue instead of a pass over the logits
+# Training: log-sum-exp partials out of the logits GEMM's epilogue (caphn_gemm_tc_lse) instead of the ce_fwd pass over the
+# logits.  Correct (tests/test_gpu_ops.py) but OFF: that GEMM is epilogue-bound, and the 32 shuffles + max + exp per 32
+# columns cost more than the 73 us pass they remove -- measured 4.38 -> 4.50 ms (pooled step) and 2.84 -> 2.97 ms
+# (attention step) with it on (profiles/r02_ce_epilogue_fusion_negative.txt).
+CE_FUSED_STATS = False
 
 
 def linear_lse(X, W, bias, out=None):

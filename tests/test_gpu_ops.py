@@ -200,3 +200,30 @@ def test_gru_cluster_matches_streaming_kernel(B, T, H):
     dGI1, dGH1, _, _, dh01 = ops.gru_cluster_bwd(dH, sv1, Hall1, W)
     assert rel_err(Hall1, Hall0) < 2e-6 and rel_err(Hbm1, Hbm0) < 2e-6 and rel_err(sv1, sv0) < 2e-6
     assert rel_err(dGI1, dGI0) < 1e-5 and rel_err(dGH1, dGH0) < 1e-5 and rel_err(dh01, dh00) < 1e-5
+
+
+def test_ce_statistics_from_the_gemm_epilogue_match_the_separate_pass():
+    """caphn_gemm_tc_lse + caphn_ce_fwd_partials (log-sum-exp partials out of the logits GEMM's epilogue; off by default,
+    ops.CE_FUSED_STATS) == gemm_tc + ce_fwd: identical logits, lse / loss within fp32 rounding; ignore_index honoured."""
+    import torch
+    from hypernet_image_captioning_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    M, K, V = 1300, 150, 9684
+    X = (torch.randn(M, K, generator=g) * 0.5).cuda()
+    W = (torch.randn(V, K, generator=g) * 0.2).cuda()
+    b = torch.randn(V, generator=g).cuda()
+    tgt = torch.randint(0, V, (M,), generator=g).cuda()
+    tgt[::7] = 0
+    ref_logits = ops.linear(X, W, b)
+    old = ops.CE_FUSED_STATS
+    ops.CE_FUSED_STATS = True
+    try:
+        logits, stats = ops.linear_lse(X, W, b)
+    finally:
+        ops.CE_FUSED_STATS = old
+    assert stats is not None and torch.equal(logits, ref_logits)
+    for ign in (None, 0):
+        lb_ref, lse_ref = ops.ce_fwd(ref_logits, tgt, ign)
+        lb, lse = ops.ce_fwd_stats(logits, tgt, ign, stats)
+        assert (lse - lse_ref).abs().max().item() < 2e-6 * lse_ref.abs().max().item()
+        assert abs(lb[0].item() - lb_ref[0].item()) < 1e-6 * abs(lb_ref[0].item()) and lb[1].item() == lb_ref[1].item()
