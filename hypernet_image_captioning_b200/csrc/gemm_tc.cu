@@ -482,25 +482,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 }
 
 // hi[r, c] = bf16(src[r, c]);  lo[r, c] = bf16(src - hi);  columns [C, Kp) are zeroed.   (lo may be null)
+// One thread per 8 columns: two 128-bit loads when the source is 16-byte aligned there, one 128-bit store per plane.
 __global__ void split_bf16_kernel(const float* __restrict__ src, long lds, long R, int C, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, long Kp) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per pair of columns
-    const long half = Kp >> 1;
-    if (i >= R * half) return;
-    const long r = i / half;
-    const int c = (int)(i - r * half) * 2;
-    float x0 = 0.f, x1 = 0.f;
-    if (c < C) x0 = src[r * lds + c];
-    if (c + 1 < C) x1 = src[r * lds + c + 1];
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-    __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
-    *reinterpret_cast<__nv_bfloat162*>(hi + r * Kp + c) = hv;
-    if (lo) {
-        __nv_bfloat162 lv;
-        lv.x = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-        lv.y = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-        *reinterpret_cast<__nv_bfloat162*>(lo + r * Kp + c) = lv;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long oct = Kp >> 3;
+    if (i >= R * oct) return;
+    const long r = i / oct;
+    const int c = (int)(i - r * oct) * 8;
+    float x[8];
+    const float* p = src + r * lds + c;
+    if (c + 8 <= C && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        const float4 a = ldg_stream4(p), b = ldg_stream4(p + 4);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = (c + e < C) ? p[e] : 0.f;
     }
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * e]), h1 = __float2bfloat16_rn(x[2 * e + 1]);
+        hw[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * e] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * e + 1] - __bfloat162float(h1));
+        lw[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(hi + r * Kp + c) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo + r * Kp + c) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
 
 // Transposing split: hi/lo [C, Rp] with hi[c, r] = bf16(src[r, c]); columns [R, Rp) zeroed.
@@ -580,7 +589,8 @@ extern "C" {
 // hi/lo [R, Kp] bf16 (Kp % 64 == 0, Kp >= C): the bf16x3 operand format of caphn_gemm_tc.  lo may be NULL (bf16 mode).
 int caphn_split_bf16(const float* src, long lds, long R, int C, void* hi, void* lo, long Kp, void* stream) {
     if (R <= 0 || C <= 0 || Kp < C || (Kp & 63)) return CAPHN_EINVAL;
-    const long n = R * (Kp >> 1);
+    if (((uintptr_t)hi & 15) || ((uintptr_t)lo & 15)) return CAPHN_EINVAL;
+    const long n = R * (Kp >> 3);
     tc::split_bf16_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
         src, lds, R, C, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Kp);
     CAPHN_RETURN_LAST();

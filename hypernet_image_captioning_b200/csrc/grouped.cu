@@ -24,21 +24,31 @@ __device__ __forceinline__ void split_store(float x0, float x1, __nv_bfloat16* h
     }
 }
 
-// one thread per pair of destination columns; columns [C, Kp) and rows with rowmap < 0 are zero
+// one thread per 8 destination columns; columns [C, Kp) and rows with rowmap < 0 are zero
 __global__ void split_gather_kernel(const float* __restrict__ src, long lds, const int* __restrict__ rowmap, long R, int C,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long Kp) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long half = Kp >> 1;
-    if (i >= R * half) return;
-    const long r = i / half;
-    const int c = (int)(i - r * half) * 2;
+    const long oct = Kp >> 3;
+    if (i >= R * oct) return;
+    const long r = i / oct;
+    const int c = (int)(i - r * oct) * 8;
     const long sr = rowmap ? rowmap[r] : r;
-    float x0 = 0.f, x1 = 0.f;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = 0.f;
     if (sr >= 0) {
-        if (c < C) x0 = src[sr * lds + c];
-        if (c + 1 < C) x1 = src[sr * lds + c + 1];
+        const float* p = src + sr * lds + c;
+        if (c + 8 <= C && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+            const float4 a = ldg_stream4(p), b = ldg_stream4(p + 4);
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (c + e < C) x[e] = p[e];
+        }
     }
-    split_store(x0, x1, hi + r * Kp + c, lo ? lo + r * Kp + c : nullptr);
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) split_store(x[e], x[e + 1], hi + r * Kp + c + e, lo ? lo + r * Kp + c + e : nullptr);
 }
 
 // blockIdx.y = batch b: src_b = src + b * sstride (floats), [R, C] with row pitch lds; dst rows b*R .. b*R+R-1
@@ -91,7 +101,7 @@ extern "C" {
 int caphn_split_bf16_gather(const float* src, long lds, const int* rowmap, long R, int C, void* hi, void* lo, long Kp,
                             void* stream) {
     if (R <= 0 || C <= 0 || Kp < C || (Kp & 63)) return CAPHN_EINVAL;
-    const long n = R * (Kp >> 1);
+    const long n = R * (Kp >> 3);
     split_gather_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, rowmap, R, C, (__nv_bfloat16*)hi,
                                                                            (__nv_bfloat16*)lo, Kp);
     CAPHN_RETURN_LAST();
