@@ -365,6 +365,14 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const long l
                                    float* __restrict__ out, long ldo) {
     const long i = blockIdx.x;
     const long long r = idx[i];
+    if (((E | ldo) & 3) == 0 && ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        // 128-bit path (rows of 39 KB when whole [P, F] feature blocks are permuted for a many-style batch)
+        const float4* src = reinterpret_cast<const float4*>(table + (r >= 0 ? r : 0) * E);
+        float4* dst = reinterpret_cast<float4*>(out + i * ldo);
+        for (int e = threadIdx.x; e < (E >> 2); e += blockDim.x)
+            dst[e] = r >= 0 ? src[e] : make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
     for (int e = threadIdx.x; e < E; e += blockDim.x) out[i * ldo + e] = r >= 0 ? table[r * E + e] : 0.f;
 }
 
