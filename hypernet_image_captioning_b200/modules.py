@@ -315,38 +315,43 @@ class DecoderGRU(nn.Module):
         # softmax that produces the RETURNED probabilities (later.py:472) is off the dependency chain: the logits are written
         # straight into outputs[:, t] and normalised in place on a side stream while the next step runs.
         fast = (table is not None and ops.DECODE_FUSED_ARGMAX and ops._tc_ok(B, self.vocab_size, H) and streams.enabled(x))
-        if fast:
-            nslot = 2 * ((self.vocab_size + 127) // 128)
-            pv = torch.empty(B, nslot, device=x.device, dtype=torch.float32)
-            pi = torch.empty(B, nslot, device=x.device, dtype=torch.int32)
-            GIb = torch.empty(B, 3 * H, device=x.device, dtype=torch.float32)
-            nparts = 0
-            cur = torch.cuda.current_stream()
-            side = streams.side("softmax")
-            side.wait_stream(cur)
-        for t in range(max_len):
-            if t == 0:
-                GI = xproj(x)
-            elif fast:
-                ops.argmax_finish_gather(pv, pi, nparts, table, None, GIb)
-                GI = GIb
-            elif table is not None:
-                GI = ops.gather_rows(table, words)
-            else:
-                GI = xproj(ops.gather_rows(emb, words))
-            Hall, _, _, _ = ops.gru_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False)
-            h = Hall[1]
-            if fast:
-                lg = outputs[:, t, :]
-                nparts = ops.gemm_tc_amax(ops.split_bf16(h), vocab.operand(), fc_b, lg, pv, pi)
-                side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    ops.softmax_argmax(lg, want_probs=True, probs_out=lg, want_argmax=False)     # in place
-            else:
+        if not fast:
+            for t in range(max_len):
+                if t == 0:
+                    GI = xproj(x)
+                elif table is not None:
+                    GI = ops.gather_rows(table, words)
+                else:
+                    GI = xproj(ops.gather_rows(emb, words))
+                Hall, _, _, _ = ops.gru_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False)
+                h = Hall[1]
                 vocab(h, out=logits)
                 _, words = ops.softmax_argmax(logits, want_probs=True, probs_out=outputs[:, t, :])
-        if fast:
-            cur.wait_stream(side)
+            return outputs
+        # The dependency chain (gather -> GRU step -> operand split -> vocabulary GEMM) runs on a HIGH-PRIORITY stream; the
+        # in-place softmax of each step's logits follows on the caller's stream, so its 512 CTAs fill the gaps of the chain
+        # instead of delaying it.
+        nslot = 2 * ((self.vocab_size + 127) // 128)
+        pv = torch.empty(B, nslot, device=x.device, dtype=torch.float32)
+        pi = torch.empty(B, nslot, device=x.device, dtype=torch.int32)
+        GIb = torch.empty(B, 3 * H, device=x.device, dtype=torch.float32)
+        nparts = 0
+        cur = torch.cuda.current_stream()
+        chain = streams.side("decode_chain", priority=-1)
+        chain.wait_stream(cur)
+        for t in range(max_len):
+            with torch.cuda.stream(chain):
+                if t == 0:
+                    GI = xproj(x)
+                else:
+                    ops.argmax_finish_gather(pv, pi, nparts, table, None, GIb)
+                    GI = GIb
+                Hall, _, _, _ = ops.gru_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False)
+                h = Hall[1]
+                lg = outputs[:, t, :]
+                nparts = ops.gemm_tc_amax(ops.split_bf16(h), vocab.operand(), fc_b, lg, pv, pi)
+            cur.wait_stream(chain)                                   # (up to this step's GEMM)
+            ops.softmax_argmax(lg, want_probs=True, probs_out=lg, want_argmax=False)     # in place, off the chain
         return outputs
 
 

@@ -25,11 +25,13 @@ def enabled(t: torch.Tensor = None) -> bool:
     return ENABLED and (t is None or t.is_cuda)
 
 
-def side(name: str, device=None) -> "torch.cuda.Stream":
+def side(name: str, device=None, priority: int = 0) -> "torch.cuda.Stream":
+    """Named side stream (one per device).  ``priority`` < 0: a high-priority stream -- its pending CTAs are scheduled before
+    those of default-priority streams (used for the dependency chain of the decode loops)."""
     idx = torch.cuda.current_device() if device is None else torch.device(device).index
     key = (name, idx)
     if key not in _streams:
-        _streams[key] = torch.cuda.Stream(device=idx)
+        _streams[key] = torch.cuda.Stream(device=idx, priority=priority)
     return _streams[key]
 
 
