@@ -104,7 +104,7 @@ class _HyperNetMixin:
                 self.captioner._theta_groups = theta        # [G, theta]: the grouped kernels take the whole matrix
                 return [self._split_theta(theta[g]) for g in range(theta.shape[0])]
             return self._split_theta(theta[0], write_params=True)
-        if self.async_hypernet and x.is_cuda and streams.enabled():
+        if self.async_hypernet and x.is_cuda and streams.ENABLED is not False:      # explicit opt-in: also in eager mode
             with streams.fork("hypernet") as s:
                 out = run()
             streams.defer(s)
@@ -314,7 +314,7 @@ class DecoderGRU(nn.Module):
         # vocabulary GEMM's epilogue as per-tile partials and is finished inside the gather of the next input row, so the
         # softmax that produces the RETURNED probabilities (later.py:472) is off the dependency chain: the logits are written
         # straight into outputs[:, t] and normalised in place on a side stream while the next step runs.
-        fast = (table is not None and ops.DECODE_FUSED_ARGMAX and ops._tc_ok(B, self.vocab_size, H) and streams.enabled(x))
+        fast = table is not None and ops.DECODE_FUSED_ARGMAX and ops._tc_ok(B, self.vocab_size, H)
         if not fast:
             for t in range(max_len):
                 if t == 0:
@@ -336,11 +336,13 @@ class DecoderGRU(nn.Module):
         pi = torch.empty(B, nslot, device=x.device, dtype=torch.int32)
         GIb = torch.empty(B, 3 * H, device=x.device, dtype=torch.float32)
         nparts = 0
+        import contextlib
         cur = torch.cuda.current_stream()
-        chain = streams.side("decode_chain", priority=-1)
-        chain.wait_stream(cur)
+        chain = streams.side("decode_chain", priority=-1) if streams.enabled(x) else None     # None: everything in order
+        if chain is not None:
+            chain.wait_stream(cur)
         for t in range(max_len):
-            with torch.cuda.stream(chain):
+            with (torch.cuda.stream(chain) if chain is not None else contextlib.nullcontext()):
                 if t == 0:
                     GI = xproj(x)
                 else:
@@ -350,7 +352,8 @@ class DecoderGRU(nn.Module):
                 h = Hall[1]
                 lg = outputs[:, t, :]
                 nparts = ops.gemm_tc_amax(ops.split_bf16(h), vocab.operand(), fc_b, lg, pv, pi)
-            cur.wait_stream(chain)                                   # (up to this step's GEMM)
+            if chain is not None:
+                cur.wait_stream(chain)                               # (up to this step's GEMM)
             ops.softmax_argmax(lg, want_probs=True, probs_out=lg, want_argmax=False)     # in place, off the chain
         return outputs
 
