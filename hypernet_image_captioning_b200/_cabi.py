@@ -88,6 +88,9 @@ SIGNATURES = {
     "caphn_adam_step_lowrank": [P, P, P, P, L, P, L, I, L, L, D, D, D, D, D, I, P, P],
     "caphn_caption_compact": [P, L, I, I, LL, LL, LL, P, P, P],
     "caphn_bleu_counts": [P, P, I, P, P, I, I, I, P, P],
+    "caphn_ce_fwd_split": [P, L, P, L, I, I, LL, P, P, P, P, P, L, P],
+    "caphn_gemm_tc_scaled": [P, P, L, I, P, P, L, I, L, P, L, P, I, I, I, P, P, P],
+    "caphn_gemm_tc_prof": [P, P, L, I, P, P, L, I, L, P, L, P, I, I, I, P, P],
     "caphn_launch_count": [P],
     "caphn_build_arch": [P],
 }

@@ -246,6 +246,120 @@ __global__ void __launch_bounds__(256) ce_bwd_split_kernel(
     }
 }
 
+// Cross-entropy forward AND the gradient operand in one pass over the logits (fused loss nodes): one CTA per row, the row
+// is read from HBM once into shared memory; out come lse / row_loss / row_valid exactly as from ce_fwd_kernel plus the
+// bf16 hi/lo split of the UNSCALED gradient  u[m,v] = softmax(x_m)[v] - [v == tgt[m]]  (0 for ignored rows), columns
+// [V, Vp) zeroed.  The scalar the true gradient carries -- grad_output / #valid rows, unknown until backward -- is applied by
+// the epilogues of the two products that consume u (caphn_gemm_tc_scaled); the bias gradient is a column of one of them.
+// Traffic: logits read once + operand written once (0.8 GB at [10240, 9684]) instead of ce_fwd's extra 0.4 GB read.
+__global__ void __launch_bounds__(CE_THREADS) ce_fwd_split_kernel(const float* __restrict__ X, long ld,
+                                                                  const long long* __restrict__ tgt, int V, int has_ignore,
+                                                                  long long ignore, float* __restrict__ lse,
+                                                                  float* __restrict__ row_loss, float* __restrict__ row_valid,
+                                                                  __nv_bfloat16* __restrict__ hi,
+                                                                  __nv_bfloat16* __restrict__ lo, long Vp) {
+    extern __shared__ float4 ce_row4[];
+    float* row = reinterpret_cast<float*>(ce_row4);
+    __shared__ float sh[32];
+    __shared__ uint64_t bar;
+    const long m = blockIdx.x;
+    const float* x = X + m * ld;
+    const bool vec = ((ld & 3) == 0) && ((V & 3) == 0) && (((uintptr_t)X & 15) == 0);
+    float mx = -INFINITY;
+    if (vec) {
+        // the whole row arrives through ONE bulk async copy (no per-thread load chains, nothing held in registers)
+        const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+        const uint32_t bytes = (uint32_t)V * 4u;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(row)), "l"(__cvta_generic_to_global(x)), "r"(bytes), "r"(bar_a)
+                         : "memory");
+        }
+        __syncthreads();                        // the barrier is initialised before anyone polls it
+        uint32_t done = 0;
+        const long long t0 = clock64();
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar_a), "r"(0u)
+                : "memory");
+            if (!done && clock64() - t0 > 4000000000LL) __trap();     // a protocol bug traps instead of hanging the GPU
+        }
+        for (int i = threadIdx.x * 4; i < V; i += CE_THREADS * 4) {
+            const float4 v = *reinterpret_cast<const float4*>(row + i);
+            mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        }
+    } else {
+        for (int i = threadIdx.x; i < V; i += CE_THREADS) {
+            const float v = x[i];
+            row[i] = v;
+            mx = fmaxf(mx, v);
+        }
+    }
+    mx = block_reduce_max(mx, sh);
+    float s = 0.f;
+    if (vec) {          // every thread revisits the elements it wrote itself
+        for (int i = threadIdx.x * 4; i < V; i += CE_THREADS * 4) {
+            float4 v = *reinterpret_cast<const float4*>(row + i);
+            v.x = expf(v.x - mx); v.y = expf(v.y - mx); v.z = expf(v.z - mx); v.w = expf(v.w - mx);
+            *reinterpret_cast<float4*>(row + i) = v;
+            s += (v.x + v.y) + (v.z + v.w);
+        }
+    } else {
+        for (int i = threadIdx.x; i < V; i += CE_THREADS) {
+            const float e = expf(row[i] - mx);
+            row[i] = e;
+            s += e;
+        }
+    }
+    s = block_reduce_sum(s, sh);          // its barriers also publish the exponentials to the whole CTA
+    const long long t = tgt[m];
+    const bool valid = !(has_ignore && t == ignore);
+    if (threadIdx.x == 0) {
+        const float l = mx + logf(s);
+        lse[m] = l;
+        row_valid[m] = valid ? 1.f : 0.f;
+        row_loss[m] = valid ? (l - x[t]) : 0.f;
+    }
+    const float inv = valid ? 1.f / s : 0.f;
+    __nv_bfloat16* hrow = hi + m * Vp;
+    __nv_bfloat16* lrow = lo ? lo + m * Vp : nullptr;
+    const int tcol = valid ? (int)t : -1;
+    for (int i = threadIdx.x * 4; i < Vp; i += CE_THREADS * 4) {      // Vp % 64 == 0; shared row holds round4(V) floats
+        float u[4] = {0.f, 0.f, 0.f, 0.f};
+        if (i < V) {
+            const float4 e = *reinterpret_cast<const float4*>(row + i);
+            u[0] = e.x * inv; u[1] = e.y * inv; u[2] = e.z * inv; u[3] = e.w * inv;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (i + c == tcol) u[c] -= 1.f;
+                if (i + c >= V) u[c] = 0.f;
+            }
+        }
+        uint2 ph, pl;
+        {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(u[0]), h1 = __float2bfloat16_rn(u[1]);
+            const __nv_bfloat16 h2 = __float2bfloat16_rn(u[2]), h3 = __float2bfloat16_rn(u[3]);
+            ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(u[0] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(u[1] - __bfloat162float(h1));
+            const __nv_bfloat16 l2 = __float2bfloat16_rn(u[2] - __bfloat162float(h2));
+            const __nv_bfloat16 l3 = __float2bfloat16_rn(u[3] - __bfloat162float(h3));
+            pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+        }
+        *reinterpret_cast<uint2*>(hrow + i) = ph;
+        if (lrow) *reinterpret_cast<uint2*>(lrow + i) = pl;
+    }
+}
+
 // Row softmax (optional, Y may be null) and first-max argmax (matches torch.argmax / topk(1) tie-breaking: lowest index).
 __global__ void __launch_bounds__(CE_THREADS) softmax_argmax_kernel(const float* __restrict__ X, long ld, int V,
                                                                     float* __restrict__ Y, long ldy,
@@ -499,6 +613,23 @@ int caphn_ce_fwd(const float* X, long ld, const long long* tgt, long M, int V, i
     if (M <= 0 || V <= 0) return CAPHN_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     ce_fwd_kernel<<<(unsigned)M, CE_THREADS, 0, st>>>(X, ld, tgt, V, has_ignore, ignore, lse, scratch, scratch + M);
+    CAPHN_LAUNCH_CHECK();
+    ce_finish_kernel<<<1, 1024, 0, st>>>(scratch, scratch + M, M, lossbuf);
+    CAPHN_RETURN_LAST();
+}
+
+// caphn_ce_fwd + the unscaled gradient u = softmax(X) - onehot(tgt) (0 on ignored rows) as the bf16 hi/lo operand
+// [M, Vp] (Vp % 64 == 0, Vp >= V; lo may be NULL), from ONE read of X (see ce_fwd_split_kernel).  The consumer applies
+// gscale / max(lossbuf[1], 1) (caphn_gemm_tc_scaled).  V is limited by the row having to fit in shared memory (V <= 50000).
+int caphn_ce_fwd_split(const float* X, long ld, const long long* tgt, long M, int V, int has_ignore, long long ignore,
+                       float* lse, float* scratch, float* lossbuf, void* hi, void* lo, long Vp, void* stream) {
+    if (M <= 0 || V <= 0 || V > 50000 || Vp < V || (Vp & 63) || !hi) return CAPHN_EINVAL;
+    if (((uintptr_t)hi & 7) || ((uintptr_t)lo & 7)) return CAPHN_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)((V + 3) / 4) * 16;
+    CAPHN_CHECK(cudaFuncSetAttribute(ce_fwd_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ce_fwd_split_kernel<<<(unsigned)M, CE_THREADS, smem, st>>>(X, ld, tgt, V, has_ignore, ignore, lse, scratch, scratch + M,
+                                                               (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Vp);
     CAPHN_LAUNCH_CHECK();
     ce_finish_kernel<<<1, 1024, 0, st>>>(scratch, scratch + M, M, lossbuf);
     CAPHN_RETURN_LAST();

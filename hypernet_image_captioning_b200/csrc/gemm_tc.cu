@@ -59,6 +59,20 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(x), "r"(y)
         : "memory");
 }
+// One elected lane of a fully converged warp.  The single-thread roles (TMA producer, MMA issuer, bulk stores) run their loops
+// with all 32 lanes converged and only issue under this predicate: the operands of UTMALDG / UTCHMMA / UTMASTG must sit in
+// uniform registers, and a loop under `if (lane == 0)` is divergent code where ptxas cannot use the uniform datapath -- it
+// wrapped EVERY such instruction in an ELECT / 5 x R2UR.BROADCAST / BRA.U.ANY waterfall loop, which made the MMA thread the
+// bottleneck of the kernel (~160 cycles per 128x128x16 MMA issued, against ~64-100 of tensor-pipe time).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 
@@ -116,6 +130,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -171,6 +186,25 @@ struct TcParams {
     int stages, stage_bytes, b_bytes;
     uint32_t tmem_cols;
     int a_mn, b_mn;  // operand stored MN-major ([K rows, MN cols] row-major) instead of K-major ([MN rows, K cols])
+    // optional scalar applied to the accumulators before the bias: scale_num[0] / max(scale_den[0], 1) (den NULL = 1).
+    // The fused cross-entropy nodes hand the UNSCALED gradient operand to the two backward products and let their
+    // epilogues apply grad_output / #valid rows (both device scalars: no host synchronisation).
+    const float* scale_num; const float* scale_den;
+    int K;           // true K (0 in grouped mode): the MMAs of the zero-filled tail of the last k-block are skipped
+    // A-stationary schedule (short K, many N tiles: the vocabulary projection): every CTA owns a contiguous run of tiles in
+    // (m-tile major, n-tile minor) order and keeps the whole [128, K] A slab of its m-tile in shared memory (loaded once per
+    // m-tile, i.e. once or twice per CTA); only B tiles stream through the stage ring.  Halves the L2 -> SM operand traffic
+    // of a product that was bound by it (1.17 GB for 0.4 GB of output at M=10240, N=9684, K=150).
+    int astat;
+    int a_slab_bytes;
+    // staging buffers per epilogue warp (TMA-store epilogue): 2 = the warp fills one 4 KB tile while the bulk store of the
+    // previous one is still reading the other (the wait for that read was the largest epilogue stall in the ncu source view)
+    int stg_bufs;
+    // diagnostics (caphn_gemm_tc_prof; NULL otherwise): 16 cycle counters per CTA -- [0] producer waiting for a free stage,
+    // [1] producer waiting for the A slab to be free, [2] MMA thread waiting for operands, [3] MMA thread waiting for a free
+    // accumulator, [4] MMA thread total, [5] epilogue warp 4 waiting for an accumulator, [6] waiting for bulk-store reads,
+    // [7] epilogue warp 4 total, [8] producer total, [9] units of this CTA
+    long long* prof;
 };
 
 __device__ __forceinline__ UnitInfo decode_unit(const TcParams& p, int unit, int tiles_m, int BN) {
@@ -182,7 +216,13 @@ __device__ __forceinline__ UnitInfo decode_unit(const TcParams& p, int unit, int
         u.c_off = ((long)g.c_hi << 32) | (long)g.c_lo;
     } else {
         const int ks = unit % p.splitk, tile = unit / p.splitk;
-        const int mb = tile % tiles_m, nb = tile / tiles_m;
+        int mb, nb;
+        if (p.astat) {                      // n-tile fastest: consecutive units of a CTA share their A slab
+            const int tiles_n = (p.N + BN - 1) / BN;
+            mb = tile / tiles_n; nb = tile - mb * tiles_n;
+        } else {
+            mb = tile % tiles_m; nb = tile / tiles_m;
+        }
         const int kblk0 = ks * p.kb_per;
         u.a0 = mb * BM; u.b0 = nb * BN; u.ka0 = u.kb0 = kblk0 * BK; u.nkb = min(p.num_kb, kblk0 + p.kb_per) - kblk0;
         u.m_valid = min(BM, p.M - mb * BM); u.n_valid = min(BN, p.N - nb * BN);
@@ -204,24 +244,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;
-    float* stg = reinterpret_cast<float*>(smem + (size_t)p.stages * p.stage_bytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(stg + STG_FLOATS_V2);
+    float* stg = reinterpret_cast<float*>(smem + (size_t)p.a_slab_bytes + (size_t)p.stages * p.stage_bytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(stg + p.stg_bufs * STG_FLOATS_V2);
     uint64_t* empty = full + MAX_STAGES;
     uint64_t* tfull = empty + MAX_STAGES;
     uint64_t* tempty = tfull + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* afull = tempty + 2;            // A-stationary schedule: slab loaded / slab free
+    uint64_t* aempty = afull + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+    const int lane = threadIdx.x & 31;
     const int BN = p.BN;
     const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
     const int num_units = p.units ? p.num_units : tiles_m * tiles_n * p.splitk;
-    // operand offsets inside a stage
-    const int offAh = 0, offBh = TILE_BYTES;
-    const int offAl = TILE_BYTES + p.b_bytes, offBl = 2 * TILE_BYTES + p.b_bytes;
+    // this CTA's units: round-robin over the grid, or (A-stationary) one contiguous, balanced run
+    int u_first, u_step, u_count;
+    if (p.astat) {
+        const int q = num_units / (int)gridDim.x, r = num_units % (int)gridDim.x;
+        u_first = (int)blockIdx.x * q + min((int)blockIdx.x, r);
+        u_count = q + ((int)blockIdx.x < r ? 1 : 0);
+        u_step = 1;
+    } else {
+        u_first = blockIdx.x;
+        u_step = gridDim.x;
+        u_count = (int)blockIdx.x < num_units ? (num_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    }
+    // operand offsets inside a stage (A-stationary: the slab comes first, a stage holds only B_hi, (B_lo))
+    const int offAh = 0, offBh = p.astat ? 0 : TILE_BYTES;
+    const int offAl = TILE_BYTES + p.b_bytes, offBl = p.astat ? p.b_bytes : 2 * TILE_BYTES + p.b_bytes;
+    const int ablk = (SPLIT ? 2 : 1) * TILE_BYTES;       // slab bytes per k-block: A_hi, (A_lo)
+    uint8_t* slab = smem;
+    if (p.astat) tiles = smem + p.a_slab_bytes;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull + s, 1); mbar_init(tempty + s, EPI_WARPS); }
+        mbar_init(afull, 1); mbar_init(aempty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -233,21 +292,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     tcgen05_fence_before();
     __syncthreads();
     tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-                const UnitInfo u = decode_unit(p, unit, tiles_m, BN);
-                for (int i = 0; i < u.nkb; ++i) {
-                    const int ka = u.ka0 + i * BK, kbk = u.kb0 + i * BK;
-                    mbar_wait(empty + stage, phase ^ 1);
+        // TMA producer: all 32 lanes run the loop (converged), one elected lane issues
+        int stage = 0;
+        uint32_t phase = 0;
+        int cur_a0 = -1;
+        uint32_t a_it = 0;
+        long long w_empty = 0, w_aempty = 0;
+        const long long t_start = clock64();
+        for (int ui = 0, unit = u_first; ui < u_count; ++ui, unit += u_step) {
+            const UnitInfo u = decode_unit(p, unit, tiles_m, BN);
+            if (p.astat && u.a0 != cur_a0) {       // new m-tile: (re)load the A slab once the MMAs reading the old one are done
+                const long long tw = clock64();
+                mbar_wait(aempty, (a_it & 1) ^ 1);
+                w_aempty += clock64() - tw;
+                if (elect_one()) {
+                    mbar_expect_tx(afull, (uint32_t)p.a_slab_bytes);
+                    for (int i = 0; i < u.nkb; ++i) {
+                        tma_load_2d(slab + (size_t)i * ablk, &tmAh, afull, u.ka0 + i * BK, u.a0);
+                        if (SPLIT) tma_load_2d(slab + (size_t)i * ablk + TILE_BYTES, &tmAl, afull, u.ka0 + i * BK, u.a0);
+                    }
+                }
+                __syncwarp();
+                cur_a0 = u.a0;
+                ++a_it;
+            }
+            for (int i = 0; i < u.nkb; ++i) {
+                const int ka = u.ka0 + i * BK, kbk = u.kb0 + i * BK;
+                const long long tw = clock64();
+                mbar_wait(empty + stage, phase ^ 1);
+                w_empty += clock64() - tw;
+                uint8_t* st = tiles + (size_t)stage * p.stage_bytes;
+                if (elect_one()) {
                     mbar_expect_tx(full + stage, (uint32_t)p.stage_bytes);
-                    uint8_t* st = tiles + (size_t)stage * p.stage_bytes;
                     // K-major operand: one box [64 k x rows].  MN-major operand: boxes of [64 mn x 64 k] (8 KiB each).
-                    if (!p.a_mn) {
+                    if (p.astat) {
+                        // A is resident in the slab
+                    } else if (!p.a_mn) {
                         tma_load_2d(st + offAh, &tmAh, full + stage, ka, u.a0);
                         if (SPLIT) tma_load_2d(st + offAl, &tmAl, full + stage, ka, u.a0);
                     } else {
@@ -265,62 +348,120 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                             if (SPLIT) tma_load_2d(st + offBl + h * 8192, &tmBl, full + stage, u.b0 + h * 64, kbk);
                         }
                     }
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
+        if (p.prof && lane == 0) {
+            long long* pr = p.prof + (long)blockIdx.x * 16;
+            pr[0] = w_empty; pr[1] = w_aempty; pr[8] = clock64() - t_start; pr[9] = u_count;
+        }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(BM, BN, p.a_mn != 0, p.b_mn != 0);
-            // advance per 16-wide k step: 32 B inside the 128 B swizzle row (K-major) / two 8-row k groups (MN-major)
-            const uint64_t stepA = p.a_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
-            const uint64_t stepB = p.b_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-                const UnitInfo u = decode_unit(p, unit, tiles_m, BN);
-                const int kb0 = 0, kb1 = u.nkb;
-                const int as = it & 1;
-                const uint32_t aph = (it >> 1) & 1;
+        // MMA issuer: converged warp, one elected lane issues the tcgen05.mma / tcgen05.commit instructions
+        const uint32_t idesc = make_idesc(BM, BN, p.a_mn != 0, p.b_mn != 0);
+        // advance per 16-wide k step: 32 B inside the 128 B swizzle row (K-major) / two 8-row k groups (MN-major)
+        const uint64_t stepA = p.a_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
+        const uint64_t stepB = p.b_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        int cur_a0 = -1;
+        uint32_t a_it = 0;
+        const uint32_t slab_base = smem_u32(slab);
+        long long w_full = 0, w_tempty = 0;
+        const long long t_start = clock64();
+        for (int ui = 0, unit = u_first; ui < u_count; ++ui, unit += u_step, ++it) {
+            const UnitInfo u = decode_unit(p, unit, tiles_m, BN);
+            const int kb0 = 0, kb1 = u.nkb;
+            const int as = it & 1;
+            const uint32_t aph = (it >> 1) & 1;
+            {
+                const long long tw = clock64();
                 mbar_wait(tempty + as, aph ^ 1);
+                w_tempty += clock64() - tw;
+            }
+            tcgen05_fence_after();
+            if (p.astat && u.a0 != cur_a0) {
+                mbar_wait(afull, a_it & 1);
                 tcgen05_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-                for (int kb = kb0; kb < kb1; ++kb) {
+                cur_a0 = u.a0;
+                ++a_it;
+            }
+            const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                {
+                    const long long tw = clock64();
                     mbar_wait(full + stage, phase);
-                    tcgen05_fence_after();
-                    const uint32_t sbase = smem_u32(tiles + (size_t)stage * p.stage_bytes);
-                    const uint64_t dAh = make_desc(sbase + offAh, p.a_mn), dBh = make_desc(sbase + offBh, p.b_mn);
-                    const uint64_t dAl = make_desc(sbase + offAl, p.a_mn), dBl = make_desc(sbase + offBl, p.b_mn);
+                    w_full += clock64() - tw;
+                }
+                tcgen05_fence_after();
+                const uint32_t sbase = smem_u32(tiles + (size_t)stage * p.stage_bytes);
+                const uint32_t abase = p.astat ? slab_base + (uint32_t)(kb * ablk) : sbase;
+                const uint64_t dAh = make_desc(abase + offAh, p.a_mn), dBh = make_desc(sbase + offBh, p.b_mn);
+                const uint64_t dAl = make_desc(abase + (p.astat ? TILE_BYTES : offAl), p.a_mn);
+                const uint64_t dBl = make_desc(sbase + offBl, p.b_mn);
+                // last k-block: only the 16-wide steps that hold real columns (TMA zero-filled the rest)
+                int ksteps = BK / 16;
+                if (p.K > 0 && kb == kb1 - 1) {
+                    const int rem = p.K - (u.ka0 + kb * BK);
+                    ksteps = rem >= BK ? BK / 16 : (rem <= 0 ? 1 : (rem + 15) / 16);
+                }
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t ka = stepA * k, kbo = stepB * k;
-                        umma_f16(tmem_d, dAh + ka, dBh + kbo, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                        if (SPLIT) {
-                            umma_f16(tmem_d, dAh + ka, dBl + kbo, idesc, 1u);
-                            umma_f16(tmem_d, dAl + ka, dBh + kbo, idesc, 1u);
+                        if (k < ksteps) {
+                            const uint64_t ka = stepA * k, kbo = stepB * k;
+                            umma_f16(tmem_d, dAh + ka, dBh + kbo, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            if (SPLIT) {
+                                umma_f16(tmem_d, dAh + ka, dBl + kbo, idesc, 1u);
+                                umma_f16(tmem_d, dAl + ka, dBh + kbo, idesc, 1u);
+                            }
                         }
                     }
                     umma_commit(empty + stage);   // frees this smem stage once the MMAs above have read it
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull + as);          // accumulator complete -> epilogue
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
+            bool last_on_slab = false;
+            if (p.astat) {                    // last unit on this A slab: it may be overwritten once these MMAs are done
+                last_on_slab = ui + 1 == u_count;
+                if (!last_on_slab) last_on_slab = decode_unit(p, unit + u_step, tiles_m, BN).a0 != u.a0;
+            }
+            if (elect_one()) {
+                if (last_on_slab) umma_commit(aempty);   // (committed before tfull so that it never outlives the CTA)
+                umma_commit(tfull + as);                 // accumulator complete -> epilogue
+            }
+            __syncwarp();
+        }
+        if (p.prof && lane == 0) {
+            long long* pr = p.prof + (long)blockIdx.x * 16;
+            pr[2] = w_full; pr[3] = w_tempty; pr[4] = clock64() - t_start;
         }
     } else if (warp >= 4) {
         const int ew = warp - 4;
         const int q = warp & 3;                   // TMEM lane quadrant this warp may access (warp id % 4)
         const int half = ew >> 2;                 // two warps per quadrant split the 32-column chunks
-        float* st = stg + ew * (32 * STG_STRIDE);
+        float* const st0 = stg + ew * (p.stg_bufs * 32 * STG_STRIDE);
+        float* st = st0;
+        int sti = 0;                              // TMA-store items issued by this warp (selects the staging buffer)
         const int nchunks = (BN + 31) / 32;
         const bool atomic = p.splitk > 1;
         const bool vec = !atomic && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         int it = 0;
-        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const float alpha = p.scale_num ? p.scale_num[0] / fmaxf(p.scale_den ? p.scale_den[0] : 1.f, 1.f) : 1.f;
+        long long w_tfull = 0, w_store = 0;
+        const long long t_start = clock64();
+        for (int ui = 0, unit = u_first; ui < u_count; ++ui, unit += u_step, ++it) {
             const UnitInfo u = decode_unit(p, unit, tiles_m, BN);
             const int as = it & 1;
             const uint32_t aph = (it >> 1) & 1;
-            mbar_wait(tfull + as, aph);
+            {
+                const long long tw = clock64();
+                mbar_wait(tfull + as, aph);
+                w_tfull += clock64() - tw;
+            }
             tcgen05_fence_after();
             const int row0 = u.a0 + q * 32;           // (non-grouped TMA-store path only: global row of this warp's first row)
             const int rl0 = q * 32;                   // first tile-local row of this warp
@@ -346,6 +487,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty + as);   // this warp no longer needs the TMEM stage
+                }
+                if (p.scale_num) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * alpha);
                 }
                 const int colbase = u.b0 + c * 32;            // (TMA-store path: global column)
                 const int cl0 = c * 32;                       // tile-local column of this chunk
@@ -381,7 +526,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 if constexpr (TMA_STORE) {
                     // chunks that lie fully inside the N tile (TMA clips at the matrix edge, not at the tile edge)
                     if (!atomic && BN - c * 32 >= 32) {
-                        if (lane == 0) tma_store_wait_read();          // the previous store has finished reading `st`
+                        const long long tw = clock64();
+                        if (p.stg_bufs == 2) {
+                            st = st0 + (sti & 1) * (32 * STG_STRIDE);
+                            if (lane == 0) tma_store_wait_read1();     // the store before the previous one has read `st`
+                        } else {
+                            if (lane == 0) tma_store_wait_read();      // the previous store has finished reading `st`
+                        }
+                        w_store += clock64() - tw;
+                        ++sti;
                         __syncwarp();
                         const float bl = (add_bias && !bias_done && lane < cvalid) ? biasp[cl0 + lane] : 0.f;
 #pragma unroll
@@ -403,8 +556,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                         }
                         continue;
                     }
-                    if (lane == 0) tma_store_wait_read();              // legacy path below reuses `st`
+                    if (lane == 0) tma_store_wait_read();              // legacy path below reuses the staging tile
                     __syncwarp();
+                    st = st0;
                 }
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4)   // row = lane; float4 slot j4 lives at (j4 ^ (row & 7)): conflict-free
@@ -471,6 +625,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
         }
         if constexpr (TMA_STORE) {
             if (lane == 0) tma_store_wait_all();       // shared memory must outlive the bulk stores that read it
+        }
+        if (p.prof && ew == 0 && lane == 0) {
+            long long* pr = p.prof + (long)blockIdx.x * 16;
+            pr[5] = w_tfull; pr[6] = w_store; pr[7] = clock64() - t_start;
         }
     }
     tcgen05_fence_before();
@@ -613,8 +771,10 @@ int caphn_split_bf16_t(const float* src, long lds, int R, int C, void* hi, void*
 // Alo == Blo == NULL selects plain bf16.  splitk: 0 = automatic, 1 = none, > 1 = split K, partial tiles added atomically.
 static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
                         int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, int relu, int splitk,
-                        float* amax_val, int* amax_idx, int amax_ld, void* stream, int* bn_used = nullptr, int stat_mode = 1) {
+                        float* amax_val, int* amax_idx, int amax_ld, void* stream, int* bn_used = nullptr, int stat_mode = 1,
+                        const float* scale_num = nullptr, const float* scale_den = nullptr, long long* prof = nullptr) {
     if (M <= 0 || N <= 0 || K <= 0 || ((Alo == nullptr) != (Blo == nullptr))) return CAPHN_EINVAL;
+    if (scale_den && !scale_num) return CAPHN_EINVAL;
     if (amax_val && (!amax_idx || splitk > 1 || relu)) return CAPHN_EINVAL;
     if (amax_val) splitk = 1;
     if (((uintptr_t)Ahi & 15) || ((uintptr_t)Bhi & 15) || ((uintptr_t)Alo & 15) || ((uintptr_t)Blo & 15) ||
@@ -625,6 +785,8 @@ static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, c
     tc::TcParams p{};
     p.C = C; p.ldc = ldc; p.bias = bias; p.M = M; p.N = N; p.relu = relu; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
     p.num_kb = (int)((K + tc::BK - 1) / tc::BK);
+    p.K = (int)K;
+    p.scale_num = scale_num; p.scale_den = scale_den; p.prof = prof;
     // N tile: one tile when N <= 256 (rounded up to 16, or to 64 for an MN-major B whose boxes are 64 wide), else 128
     if (N <= 256) {
         p.BN = b_mn ? ((N + 63) / 64) * 64 : ((N + 15) / 16) * 16;
@@ -670,13 +832,52 @@ static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, c
     p.splitk = (p.num_kb + p.kb_per - 1) / p.kb_per;
     p.b_bytes = p.BN * tc::BK * 2;
     p.stage_bytes = (split ? 2 : 1) * (tc::TILE_BYTES + p.b_bytes);
-    const size_t fixed = (size_t)tc::STG_FLOATS_V2 * 4 + (2 * tc::MAX_STAGES + 4) * 8 + 16 + 1024;
-    int stages = (int)((tc::SMEM_BUDGET - fixed) / p.stage_bytes);
-    if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
-    if (stages < 2) return CAPHN_EINVAL;
+    if (amax_val) { p.amax_val = amax_val; p.stat_mode = stat_mode; }
+    bool tma_store = false;
+    {   // TMA-store epilogue: full 32-column chunks leave through cp.async.bulk.tensor stores.  Bit-identical to the default
+        // epilogue and 2-9 % faster on the logits products (profiles/r02_gemm_tma_store.txt); N % 4 == 0 only (a clipped
+        // edge box of a ragged N did not match in round 1 -- those shapes keep the default epilogue).  CAPHN_TC_TMA_STORE=0
+        // switches it off.
+        const char* e = getenv("CAPHN_TC_TMA_STORE");
+        tma_store = !(e && e[0] == '0') && p.splitk == 1 && (ldc % 4 == 0) && (N % 4 == 0) && ((uintptr_t)C % 16 == 0) &&
+                    !(p.amax_val && p.stat_mode == 1);
+    }
+    const char* ae = getenv("CAPHN_TC_ASTAT");
+    const int astat_mode = ae ? atoi(ae) : 1;
+    const char* se = getenv("CAPHN_TC_STG2");
+    const int stg2_mode = se ? atoi(se) : 0;
+    const size_t slab = (size_t)p.num_kb * (split ? 2 : 1) * tc::TILE_BYTES;
+    const size_t bstage = (size_t)(split ? 2 : 1) * p.b_bytes;
+    // A-stationary schedule (see TcParams::astat): K-major operands, no split-K, >= 4 tiles per CTA, >= 4 n-tiles, the A slab
+    // and enough B stages fit in shared memory.  CAPHN_TC_ASTAT=0 switches it off, =2 accepts 2 B stages instead of 3.
+    const bool astat_shape = astat_mode > 0 && !a_mn && !b_mn && p.splitk == 1 && ceil_div(N, p.BN) >= 4 &&
+                             tiles >= 4 * kNumSMs;
+    size_t fixed = 0;
+    int stages = 0;
+    // plan(bufs): shared-memory plan with `bufs` staging tiles per epilogue warp; false when fewer than 2 stages fit
+    auto plan = [&](int bufs) -> bool {
+        fixed = (size_t)bufs * tc::STG_FLOATS_V2 * 4 + (2 * tc::MAX_STAGES + 6) * 8 + 16 + 1024;
+        p.stg_bufs = bufs;
+        p.astat = 0; p.a_slab_bytes = 0;
+        p.stage_bytes = (split ? 2 : 1) * (tc::TILE_BYTES + p.b_bytes);
+        const int min_st = astat_mode >= 2 ? 2 : 3;
+        if (astat_shape && slab + fixed + (size_t)min_st * bstage <= tc::SMEM_BUDGET) {
+            p.astat = 1;
+            p.a_slab_bytes = (int)slab;
+            p.stage_bytes = (int)bstage;
+            stages = (int)((tc::SMEM_BUDGET - fixed - slab) / bstage);
+        } else {
+            if (fixed + 2 * (size_t)p.stage_bytes > tc::SMEM_BUDGET) return false;
+            stages = (int)((tc::SMEM_BUDGET - fixed) / p.stage_bytes);
+        }
+        if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
+        return stages >= 2;
+    };
+    // two staging tiles per epilogue warp (CAPHN_TC_STG2=1) only with the TMA-store epilogue and when the stages still fit
+    if (!(tma_store && stg2_mode > 0 && plan(2)) && !plan(1)) return CAPHN_EINVAL;
     p.stages = stages;
     p.tmem_cols = (2 * p.BN <= 256) ? 256u : 512u;
-    const size_t smem = (size_t)stages * p.stage_bytes + fixed;
+    const size_t smem = (size_t)p.a_slab_bytes + (size_t)stages * p.stage_bytes + fixed;
     if (bn_used) *bn_used = p.BN;
     if (amax_val) {
         if (amax_ld < 2 * ceil_div(N, p.BN)) return CAPHN_EINVAL;
@@ -709,16 +910,7 @@ static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, c
     const long units = (long)tiles * p.splitk;
     const int grid = units < kNumSMs ? (int)units : kNumSMs;
     CUtensorMap mC{};
-    bool tma_store = false;
-    {   // TMA-store epilogue: full 32-column chunks leave through cp.async.bulk.tensor stores.  Bit-identical to the default
-        // epilogue and 2-9 % faster on the logits products (profiles/r02_gemm_tma_store.txt); N % 4 == 0 only (a clipped
-        // edge box of a ragged N did not match in round 1 -- those shapes keep the default epilogue).  CAPHN_TC_TMA_STORE=0
-        // switches it off.
-        const char* e = getenv("CAPHN_TC_TMA_STORE");
-        tma_store = !(e && e[0] == '0') && p.splitk == 1 && (ldc % 4 == 0) && (N % 4 == 0) && ((uintptr_t)C % 16 == 0) &&
-                    !(p.amax_val && p.stat_mode == 1);
-        if (tma_store && (rc = tc::make_map_c(&mC, C, M, N, ldc))) return rc;
-    }
+    if (tma_store && (rc = tc::make_map_c(&mC, C, M, N, ldc))) return rc;
     if (split && tma_store) {
         CAPHN_CHECK(cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc::gemm_tc_kernel<true, true><<<grid, tc::THREADS_V2, smem, st>>>(mAh, mAl, mBh, mBl, mC, p);
@@ -757,10 +949,10 @@ int caphn_gemm_tc_grouped(const void* Ahi, const void* Alo, long a_inner, long a
     tc::TcParams p{};
     p.C = C; p.ldc = ldc; p.bias = bias; p.units = (const tc::GUnit*)units; p.rowmap = rowmap; p.num_units = num_units;
     p.M = 0; p.N = 0; p.relu = 0; p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0; p.num_kb = 0; p.BN = BN;
-    p.splitk = 1; p.kb_per = 0;
+    p.splitk = 1; p.kb_per = 0; p.stg_bufs = 1;
     p.b_bytes = p.BN * tc::BK * 2;
     p.stage_bytes = (split ? 2 : 1) * (tc::TILE_BYTES + p.b_bytes);
-    const size_t fixed = (size_t)tc::STG_FLOATS_V2 * 4 + (2 * tc::MAX_STAGES + 4) * 8 + 16 + 1024;
+    const size_t fixed = (size_t)tc::STG_FLOATS_V2 * 4 + (2 * tc::MAX_STAGES + 6) * 8 + 16 + 1024;
     int stages = (int)((tc::SMEM_BUDGET - fixed) / p.stage_bytes);
     if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
     if (stages < 2) return CAPHN_EINVAL;
@@ -790,6 +982,27 @@ int caphn_gemm_tc_ex(const void* Ahi, const void* Alo, long a_ld, int a_mn, cons
                      void* stream) {
     return gemm_tc_impl(Ahi, Alo, a_ld, a_mn, Bhi, Blo, b_ld, b_mn, K, C, ldc, bias, M, N, relu, splitk, nullptr, nullptr, 0,
                         stream);
+}
+
+// caphn_gemm_tc_ex with a device-side scalar on the product: C = (scale_num[0] / max(scale_den[0], 1)) * A B^T (+bias).
+// scale_den may be NULL (= 1).  Used by the fused cross-entropy nodes: A or B is the unscaled gradient operand written by
+// caphn_ce_fwd_split, scale_num = grad_output of the loss, scale_den = number of valid rows (lossbuf + 1).
+int caphn_gemm_tc_scaled(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
+                         int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, int splitk,
+                         const float* scale_num, const float* scale_den, void* stream) {
+    if (!scale_num) return CAPHN_EINVAL;
+    return gemm_tc_impl(Ahi, Alo, a_ld, a_mn, Bhi, Blo, b_ld, b_mn, K, C, ldc, bias, M, N, 0, splitk, nullptr, nullptr, 0,
+                        stream, nullptr, 1, scale_num, scale_den);
+}
+
+// Diagnostics: caphn_gemm_tc_ex that also fills prof [148, 16] (int64 cycle counters per CTA, see TcParams::prof): where
+// the producer, the MMA thread and one epilogue warp spend their time waiting.  tools/bench_vocab.py prints them.
+int caphn_gemm_tc_prof(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
+                       int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, int splitk, long long* prof,
+                       void* stream) {
+    if (!prof) return CAPHN_EINVAL;
+    return gemm_tc_impl(Ahi, Alo, a_ld, a_mn, Bhi, Blo, b_ld, b_mn, K, C, ldc, bias, M, N, 0, splitk, nullptr, nullptr, 0,
+                        stream, nullptr, 1, nullptr, nullptr, prof);
 }
 
 // caphn_gemm_tc_ex + row arg-max partials in the epilogue (greedy decode: logits_t = h_t W^T + b, next word = arg-max):

@@ -295,8 +295,9 @@ class AttentionGruGroupedLossFn(Function):
         logits, attn_o, sv, dims = _grouped_forward(plan, f3, K3, h0, caps, *params)
         B, T, V = logits.shape
         targets = caps_o.reshape(-1).contiguous()
-        lossbuf, lse = ops.ce_fwd(logits.view(B * T, V), targets, ignore_index)
-        ctx.save_for_backward(*sv, logits, targets, lse, lossbuf)
+        lossbuf, lse, dhi, dlo = Fn.ce_fwd_for_loss(logits.view(B * T, V), targets, ignore_index, dims[4],
+                                                    any(ctx.needs_input_grad))
+        ctx.save_for_backward(*sv, logits, targets, lse, lossbuf, dhi, dlo)
         ctx.plan, ctx.dims, ctx.ignore_index = plan, dims, ignore_index
         ctx.mark_non_differentiable(logits, attn_o)
         ctx.set_materialize_grads(False)
@@ -305,11 +306,11 @@ class AttentionGruGroupedLossFn(Function):
     @staticmethod
     def backward(ctx, g, _dl, _da):
         allsv = ctx.saved_tensors
-        sv, (logits, targets, lse, lossbuf) = allsv[:-4], allsv[-4:]
+        sv, (logits, targets, lse, lossbuf, dhi, dlo) = allsv[:-6], allsv[-6:]
         B, T, P, E, H, Fd, V, G = ctx.dims
         g = g.reshape(1).to(torch.float32).contiguous()
         vocab = Fn.vocab_bwd_fused(logits.view(B * T, V), targets, ctx.ignore_index, lse, lossbuf, g,
-                                   sv[4].view(B * T, H), sv[10])
+                                   sv[4].view(B * T, H), sv[10], dhi, dlo)
         gr = _grouped_backward(ctx.plan, sv, ctx.dims, vocab, None)
         return (None, None, None, *gr[:3], None, *gr[3:])
 

@@ -248,8 +248,9 @@ class AttentionGruLossFn(Function):
         logits, attn, sv, dims = _attgru_forward(True, f3, K3, h0, captions, use_sampling, *params, stats_out=stats)
         B, T, V = logits.shape
         targets = captions.reshape(-1).contiguous()
-        lossbuf, lse = ops.ce_fwd_stats(logits.view(B * T, V), targets, ignore_index, stats[0] if stats else None)
-        ctx.save_for_backward(*sv, logits, targets, lse, lossbuf)
+        lossbuf, lse, dhi, dlo = Fn.ce_fwd_for_loss(logits.view(B * T, V), targets, ignore_index, dims[4],
+                                                    any(ctx.needs_input_grad), stats[0] if stats else None)
+        ctx.save_for_backward(*sv, logits, targets, lse, lossbuf, dhi, dlo)
         ctx.dims = dims
         ctx.ignore_index = ignore_index
         ctx.mark_non_differentiable(logits, attn)
@@ -259,11 +260,11 @@ class AttentionGruLossFn(Function):
     @staticmethod
     def backward(ctx, g, _dl, _da):
         allsv = ctx.saved_tensors
-        sv, (logits, targets, lse, lossbuf) = allsv[:-4], allsv[-4:]
+        sv, (logits, targets, lse, lossbuf, dhi, dlo) = allsv[:-6], allsv[-6:]
         B, T, P, E, H, Fd, V = ctx.dims
         g = g.reshape(1).to(torch.float32).contiguous()
         vocab = Fn.vocab_bwd_fused(logits.view(B * T, V), targets, ctx.ignore_index, lse, lossbuf, g,
-                                   sv[4].view(B * T, H), sv[11])
+                                   sv[4].view(B * T, H), sv[11], dhi, dlo)
         gr = _attgru_backward(sv, ctx.dims, vocab, None)
         return (None, *gr[:3], None, None, *gr[3:])
 

@@ -368,6 +368,31 @@ def ce_bwd_split(logits2d, targets, ignore_index, lse, lossbuf, gscale):
     return SplitOperand(hi, lo, M, V, Vp), SplitOperand(hi, lo, V, M, Vp, True), dbias
 
 
+CE_FWD_SPLIT_MAX_V = 50000   # the fused kernel stages one row of logits in shared memory
+
+
+def ce_fwd_split(logits2d, targets, ignore_index):
+    """ce_fwd + the UNSCALED CE gradient u = softmax - onehot (0 on ignored rows) as a tensor-core operand, from one read of
+    the logits.  Returns (lossbuf, lse, hi, lo): hi / lo [M, round64(V)] bf16 (lo None in bf16 mode), to be viewed as the
+    K-major operand of u or the MN-major operand of u^T.  The products that consume them apply grad_output / #valid rows
+    (``gemm_tc(..., scale=...)``)."""
+    _chk(logits2d), _chk(targets, torch.int64)
+    M, V = logits2d.shape
+    assert logits2d.stride(1) == 1 and targets.is_contiguous() and targets.numel() == M and V <= CE_FWD_SPLIT_MAX_V
+    dev = logits2d.device
+    Vp = round64(V)
+    lse = torch.empty(M, device=dev, dtype=torch.float32)
+    scratch = torch.empty(2 * M, device=dev, dtype=torch.float32)
+    lossbuf = torch.empty(2, device=dev, dtype=torch.float32)
+    hi = torch.empty(M, Vp, device=dev, dtype=torch.bfloat16)
+    lo = torch.empty(M, Vp, device=dev, dtype=torch.bfloat16) if TC_SPLIT else None
+    has = ignore_index is not None
+    _cabi.call("caphn_ce_fwd_split", logits2d.data_ptr(), logits2d.stride(0), targets.data_ptr(), M, V, int(has),
+               int(ignore_index) if has else 0, lse.data_ptr(), scratch.data_ptr(), lossbuf.data_ptr(), hi.data_ptr(),
+               _p(lo), Vp, _stream())
+    return lossbuf, lse, hi, lo
+
+
 def softmax_argmax(X, want_probs=True, probs_out=None, want_argmax=True):
     _chk(X)
     M, V = X.shape
@@ -656,26 +681,41 @@ def split_bf16(src, want_lo=None, mn=False):
     return SplitOperand(hi, lo, R, C, Kp, False)
 
 
-def split_bf16_t(src, want_lo=None):
-    """src [R, C] -> operand for src^T: hi, lo [C, Rp]."""
+def split_bf16_t(src, want_lo=None, ones_row=False):
+    """src [R, C] -> operand for src^T: hi, lo [C, Rp].  ones_row: one more operand row of ones (hi = 1, lo = 0), so that
+    a product X^T [src | 1] also delivers the column sums of X (the bias gradient) from the tensor cores."""
     want_lo = TC_SPLIT if want_lo is None else want_lo
     _chk(src)
     assert src.dim() == 2 and src.stride(1) == 1
     R, C = src.shape
     Rp = round64(R)
-    hi = torch.empty(C, Rp, device=src.device, dtype=torch.bfloat16)
-    lo = torch.empty(C, Rp, device=src.device, dtype=torch.bfloat16) if want_lo else None
+    Cx = C + (1 if ones_row else 0)
+    hi = torch.empty(Cx, Rp, device=src.device, dtype=torch.bfloat16)
+    lo = torch.empty(Cx, Rp, device=src.device, dtype=torch.bfloat16) if want_lo else None
     _cabi.call("caphn_split_bf16_t", src.data_ptr(), src.stride(0), R, C, hi.data_ptr(), _p(lo), Rp, _stream())
-    return SplitOperand(hi, lo, C, R, Rp, False)
+    if ones_row:
+        hi[C].fill_(1.0)
+        if lo is not None:
+            lo[C].zero_()
+    return SplitOperand(hi, lo, Cx, R, Rp, False)
 
 
-def gemm_tc(A: SplitOperand, Bm: SplitOperand, bias=None, relu=False, out=None, splitk=0):
-    """out[M,N] = A B^T (+bias) on the tensor cores; operands K-major or MN-major (see SplitOperand), equal K."""
+def gemm_tc(A: SplitOperand, Bm: SplitOperand, bias=None, relu=False, out=None, splitk=0, scale=None):
+    """out[M,N] = A B^T (+bias) on the tensor cores; operands K-major or MN-major (see SplitOperand), equal K.
+    scale = (num, den): device scalars, the product is multiplied by num[0] / max(den[0], 1) in the epilogue (den may be
+    None)."""
     assert A.K == Bm.K and (A.lo is None) == (Bm.lo is None)
     M, N = A.rows, Bm.rows
     if out is None:
         out = torch.empty(M, N, device=A.hi.device, dtype=torch.float32)
     assert out.stride(1) == 1
+    if scale is not None:
+        assert not relu
+        num, den = scale
+        _cabi.call("caphn_gemm_tc_scaled", A.hi.data_ptr(), _p(A.lo), A.ld, int(A.mn), Bm.hi.data_ptr(), _p(Bm.lo),
+                   Bm.ld, int(Bm.mn), A.K, out.data_ptr(), out.stride(0), _p(bias), M, N, splitk, num.data_ptr(), _p(den),
+                   _stream())
+        return out
     _cabi.call("caphn_gemm_tc_ex", A.hi.data_ptr(), _p(A.lo), A.ld, int(A.mn), Bm.hi.data_ptr(), _p(Bm.lo), Bm.ld,
                int(Bm.mn), A.K, out.data_ptr(), out.stride(0), _p(bias), M, N, int(relu), 1 if relu else splitk,
                _stream())

@@ -353,6 +353,25 @@ int caphn_ce_fwd_partials(const float* pm, const float* ps, int ldp, int nparts,
                           const long long* tgt, long M, int has_ignore, long long ignore, float* lse, float* scratch,
                           float* lossbuf, void* stream);
 
+/* Cross-entropy forward and gradient operand in ONE pass over the logits (the fused loss nodes; F.cross_entropy +
+ * its backward at cc_train_hypernet.py:152-153 / hypernet.py:139-145): caphn_ce_fwd's outputs plus the bf16 hi/lo split of
+ * the UNSCALED gradient u = softmax(X) - onehot(tgt) (0 on ignored rows) as a tensor-core operand [M, Vp] (Vp % 64 == 0;
+ * lo may be NULL in bf16 mode).  Logits read once, operand written once.  V <= 50000 (the row is staged in shared memory). */
+int caphn_ce_fwd_split(const float* X, long ld, const long long* tgt, long M, int V, int has_ignore, long long ignore,
+                       float* lse, float* scratch, float* lossbuf, void* hi, void* lo, long Vp, void* stream);
+/* caphn_gemm_tc_ex (no ReLU) with a device-side scalar: C = scale_num[0] / max(scale_den[0], 1) * A B^T (+ bias);
+ * scale_den may be NULL.  The products that consume caphn_ce_fwd_split's operand pass scale_num = grad_output of the loss
+ * and scale_den = lossbuf + 1 (number of valid rows): dH = s * u W_out, [dW_out | db] = s * u^T [H | 1]. */
+int caphn_gemm_tc_scaled(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
+                         int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, int splitk,
+                         const float* scale_num, const float* scale_den, void* stream);
+
+/* Diagnostics: caphn_gemm_tc_ex (no ReLU) that also writes 16 int64 cycle counters per CTA into prof [148, 16] -- the time
+ * the TMA producer, the MMA thread and one epilogue warp spend waiting on each of their barriers (gemm_tc.cu TcParams::prof). */
+int caphn_gemm_tc_prof(const void* Ahi, const void* Alo, long a_ld, int a_mn, const void* Bhi, const void* Blo, long b_ld,
+                       int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, int splitk, long long* prof,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -227,3 +227,72 @@ def test_ce_statistics_from_the_gemm_epilogue_match_the_separate_pass():
         lb, lse = ops.ce_fwd_stats(logits, tgt, ign, stats)
         assert (lse - lse_ref).abs().max().item() < 2e-6 * lse_ref.abs().max().item()
         assert abs(lb[0].item() - lb_ref[0].item()) < 1e-6 * abs(lb_ref[0].item()) and lb[1].item() == lb_ref[1].item()
+
+
+@pytest.mark.parametrize("M,V,ignore", [(1300, 9684, 0), (1300, 9684, None), (257, 1502, 0), (130, 9685, 0)])
+def test_ce_forward_with_gradient_operand_in_one_pass(M, V, ignore):
+    """caphn_ce_fwd_split (loss + UNSCALED gradient operand from one read of the logits) followed by the scaled products
+    (caphn_gemm_tc_scaled: grad_output / #valid rows applied in the epilogue, bias gradient as the ones column) ==
+    torch's cross_entropy backward through the vocabulary projection, F.cross_entropy at cc_train_hypernet.py:153."""
+    import torch
+    import torch.nn.functional as F
+    from hypernet_image_captioning_b200 import functional as Fn
+    from hypernet_image_captioning_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    H = 150
+    logits = (torch.randn(M, V, generator=g) * 2.0).cuda()
+    Hbm = torch.randn(M, H, generator=g).cuda()
+    fc_w = (torch.randn(V, H, generator=g) * 0.2).cuda()
+    tgt = torch.randint(0, V, (M,), generator=g).cuda()
+    if ignore is not None:
+        tgt[::5] = ignore
+    gscale = torch.tensor([0.37], device="cuda")
+    # the separate passes
+    lb_ref, lse_ref = ops.ce_fwd(logits, tgt, ignore)
+    lb, lse, hi, lo = Fn.ce_fwd_for_loss(logits, tgt, ignore, H, True)
+    assert hi is not None, "the one-pass kernel must be selected at this size"
+    assert torch.equal(lse, lse_ref) or (lse - lse_ref).abs().max().item() < 2e-6 * lse_ref.abs().max().item()
+    assert abs(lb[0].item() - lb_ref[0].item()) < 1e-6 * abs(lb_ref[0].item()) and lb[1].item() == lb_ref[1].item()
+    # the operand is softmax - onehot (0 on ignored rows), hi + lo to 2^-16
+    u = torch.softmax(logits.double(), dim=1)
+    u[torch.arange(M), tgt] -= 1.0
+    if ignore is not None:
+        u[tgt == ignore] = 0.0
+    got = hi[:, :V].double() + lo[:, :V].double()
+    assert (got - u).abs().max().item() < 3e-5
+    assert hi[:, V:].abs().max().item() == 0 if hi.shape[1] > V else True
+    # gradients of gscale * mean CE through logits = Hbm fc_w^T
+    Hd, Wd = Hbm.double().requires_grad_(True), fc_w.double().requires_grad_(True)
+    bd = torch.zeros(V, device="cuda", dtype=torch.double, requires_grad=True)
+    ld = logits.double().requires_grad_(True)
+    loss = F.cross_entropy(ld, tgt, ignore_index=-100 if ignore is None else ignore)
+    (dl,) = torch.autograd.grad(loss * 0.37, ld)
+    dfc_w, dfc_b, dHbm = Fn.vocab_bwd_fused(logits, tgt, ignore, lse, lb, gscale, Hbm, fc_w, hi, lo)
+    ref_dH, ref_dW, ref_db = dl @ fc_w.double(), dl.t() @ Hbm.double(), dl.sum(0)
+    for got_t, ref_t in ((dHbm, ref_dH), (dfc_w, ref_dW), (dfc_b, ref_db)):
+        assert got_t.shape == ref_t.shape and got_t.is_contiguous()
+        assert (got_t.double() - ref_t).abs().max().item() < 3e-5 * ref_t.abs().max().item()
+    # and it agrees with the two-pass path (ce_fwd + ce_bwd_split + unscaled products)
+    dfc_w2, dfc_b2, dHbm2 = Fn.vocab_bwd_fused(logits, tgt, ignore, lse_ref, lb_ref, gscale, Hbm, fc_w)
+    for a, b in ((dHbm, dHbm2), (dfc_w, dfc_w2), (dfc_b, dfc_b2)):
+        assert (a - b).abs().max().item() < 3e-5 * b.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K", [(10240, 9684, 150), (4096, 9684, 200), (2048, 1100, 64), (5000, 777, 130)])
+def test_gemm_tc_a_stationary_schedule_is_bit_identical(M, N, K, monkeypatch):
+    """The A-stationary schedule of the tensor-core GEMM (A slab resident per m-tile, contiguous tile runs per CTA; the
+    vocabulary projection) only reorders tiles: bit-identical to the round-robin schedule, bias / ragged N / ragged K
+    included (CAPHN_TC_ASTAT=0 switches it off, =2 also accepts two B stages, e.g. K = 200)."""
+    import torch
+    from hypernet_image_captioning_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    X = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) * 0.3).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    outs = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("CAPHN_TC_ASTAT", mode)
+        outs[mode] = ops.linear(X, W, b).clone()
+    ref = X.double() @ W.double().t() + b.double()
+    assert (outs["0"].double() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
+    assert torch.equal(outs["0"], outs["1"]) and torch.equal(outs["0"], outs["2"])
