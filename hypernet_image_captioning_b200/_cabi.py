@@ -91,6 +91,7 @@ SIGNATURES = {
     "caphn_ce_fwd_split": [P, L, P, L, I, I, LL, P, P, P, P, P, L, P],
     "caphn_gemm_tc_scaled": [P, P, L, I, P, P, L, I, L, P, L, P, I, I, I, P, P, P],
     "caphn_gemm_tc_prof": [P, P, L, I, P, P, L, I, L, P, L, P, I, I, I, P, P],
+    "caphn_gru_decode_step": [P, P, P, I, I, P, P, P, P, P, P, P, L, P, I, I, P],
     "caphn_launch_count": [P],
     "caphn_build_arch": [P],
 }

@@ -132,6 +132,12 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Shared-memory plan (dynamic, 1024-byte aligned): [stage 0 | stage 1 | ...][epilogue staging][mbarriers][tmem slot].
@@ -496,6 +502,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 const int cl0 = c * 32;                       // tile-local column of this chunk
                 const int cvalid = min(32, u.n_valid - cl0);  // valid columns of this chunk (may be <= 0)
                 bool bias_done = false;
+                if (atomic) {
+                    // split-K: partial tiles are added into a zero-initialised C straight from the registers -- lane = row,
+                    // its 32 consecutive columns leave as vector reductions (red.global.add.v4 / .v2.f32 by row alignment: the same
+                    // four 32-byte sectors per row as a coalesced warp-wide atomicAdd, a quarter / half the instructions of the scalar
+                    // form) -- so this mode needs no staging tile and the 32 KiB go to a third operand stage.
+                    const int rl = rl0 + lane;
+                    long orow = rl;
+                    if (rmap && rl < u.m_valid) orow = rmap[rl];
+                    if (rl < u.m_valid && orow >= 0 && cvalid > 0) {
+                        float* o = Ct + orow * p.ldc + cl0;
+                        if (add_bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < cvalid) r[j] = __float_as_uint(__uint_as_float(r[j]) + biasp[cl0 + j]);
+                        }
+                        if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                if (j + 3 < cvalid) {
+                                    red_add_v4(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        if (j + e < cvalid) atomicAdd(o + j + e, __uint_as_float(r[j + e]));
+                                }
+                            }
+                        } else if ((reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 2) {
+                                if (j + 1 < cvalid) red_add_v2(o + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]));
+                                else if (j < cvalid) atomicAdd(o + j, __uint_as_float(r[j]));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < cvalid) atomicAdd(o + j, __uint_as_float(r[j]));
+                        }
+                    }
+                    continue;
+                }
                 if (p.amax_val && p.stat_mode == 1) {         // lane = row: 32 consecutive columns of it are in r[]
                     const float bl = (add_bias && lane < cvalid) ? biasp[cl0 + lane] : 0.f;
 #pragma unroll
@@ -855,7 +902,7 @@ static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, c
     size_t fixed = 0;
     int stages = 0;
     // plan(bufs): shared-memory plan with `bufs` staging tiles per epilogue warp; false when fewer than 2 stages fit
-    auto plan = [&](int bufs) -> bool {
+    auto plan = [&](int bufs) -> bool {     // bufs == 0: split-K, the epilogue adds from registers (no staging tile)
         fixed = (size_t)bufs * tc::STG_FLOATS_V2 * 4 + (2 * tc::MAX_STAGES + 6) * 8 + 16 + 1024;
         p.stg_bufs = bufs;
         p.astat = 0; p.a_slab_bytes = 0;
@@ -874,7 +921,11 @@ static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, c
         return stages >= 2;
     };
     // two staging tiles per epilogue warp (CAPHN_TC_STG2=1) only with the TMA-store epilogue and when the stages still fit
-    if (!(tma_store && stg2_mode > 0 && plan(2)) && !plan(1)) return CAPHN_EINVAL;
+    if (p.splitk > 1) {
+        if (!plan(0)) return CAPHN_EINVAL;
+    } else if (!(tma_store && stg2_mode > 0 && plan(2)) && !plan(1)) {
+        return CAPHN_EINVAL;
+    }
     p.stages = stages;
     p.tmem_cols = (2 * p.BN <= 256) ? 256u : 512u;
     const size_t smem = (size_t)p.a_slab_bytes + (size_t)stages * p.stage_bytes + fixed;

@@ -234,7 +234,9 @@ def vocab_bwd_fused(logits2d, targets, ignore_index, lse, lossbuf, gscale, Hbm2,
         d, dT = ops.SplitOperand(hi, lo, M, V, Vp), ops.SplitOperand(hi, lo, V, M, Vp, True)
         scale = (gscale, lossbuf[1:])
         dHbm = ops.gemm_tc(d, ops.split_bf16_t(fc_w.contiguous(), want_lo=lo is not None), scale=scale)   # [B*T, H]
-        wb = ops.gemm_tc(dT, ops.split_bf16_t(Hbm2, want_lo=lo is not None, ones_row=True), scale=scale)  # [V, H+1]
+        # [V, H+1] with a row pitch that is a multiple of 4 floats: the split-K epilogue adds 16-byte vectors per row
+        wb = torch.empty(V, ops.round4(H + 1), device=Hbm2.device, dtype=torch.float32)[:, :H + 1]
+        ops.gemm_tc(dT, ops.split_bf16_t(Hbm2, want_lo=lo is not None, ones_row=True), scale=scale, out=wb)
         return wb[:, :H].contiguous(), wb[:, H].contiguous(), dHbm
     if not (ops._tc_ok(M, H, V) and ops._tc_ok(V, H, M)):
         dl = ops.ce_bwd(logits2d, targets, ignore_index, lse, lossbuf, gscale)

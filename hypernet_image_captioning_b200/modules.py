@@ -328,13 +328,20 @@ class DecoderGRU(nn.Module):
                 vocab(h, out=logits)
                 _, words = ops.softmax_argmax(logits, want_probs=True, probs_out=outputs[:, t, :])
             return outputs
-        # The dependency chain (gather -> GRU step -> operand split -> vocabulary GEMM) runs on a HIGH-PRIORITY stream; the
-        # in-place softmax of each step's logits follows on the caller's stream, so its 512 CTAs fill the gaps of the chain
-        # instead of delaying it.
+        # The dependency chain -- ONE fused launch per step for (arg-max finish, table gather, GRU cell, bf16 operand rows of
+        # the new state: ops.gru_decode_step) followed by the vocabulary GEMM -- runs on a HIGH-PRIORITY stream; the in-place
+        # softmax of each step's logits follows on the caller's stream, so its 512 CTAs fill the gaps of the chain instead of
+        # delaying it.
         nslot = 2 * ((self.vocab_size + 127) // 128)
         pv = torch.empty(B, nslot, device=x.device, dtype=torch.float32)
         pi = torch.empty(B, nslot, device=x.device, dtype=torch.int32)
+        Kp = ops.round64(H)
+        hhi = torch.empty(B, Kp, device=x.device, dtype=torch.bfloat16)
+        hlo = torch.empty(B, Kp, device=x.device, dtype=torch.bfloat16) if ops.TC_SPLIT else None
+        hop = ops.SplitOperand(hhi, hlo, B, H, Kp)
+        hbuf = [torch.empty(B, H, device=x.device, dtype=torch.float32) for _ in range(2)]
         GIb = torch.empty(B, 3 * H, device=x.device, dtype=torch.float32)
+        fused_step = ops.gru_decode_step_ok(H)      # else: arg-max finish + gather, GRU step, operand split as three launches
         nparts = 0
         import contextlib
         cur = torch.cuda.current_stream()
@@ -343,15 +350,20 @@ class DecoderGRU(nn.Module):
             chain.wait_stream(cur)
         for t in range(max_len):
             with (torch.cuda.stream(chain) if chain is not None else contextlib.nullcontext()):
-                if t == 0:
-                    GI = xproj(x)
-                else:
-                    ops.argmax_finish_gather(pv, pi, nparts, table, None, GIb)
-                    GI = GIb
-                Hall, _, _, _ = ops.gru_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False)
-                h = Hall[1]
                 lg = outputs[:, t, :]
-                nparts = ops.gemm_tc_amax(ops.split_bf16(h), vocab.operand(), fc_b, lg, pv, pi)
+                if fused_step:
+                    hn = hbuf[t & 1]
+                    ops.gru_decode_step(xproj(x) if t == 0 else None, pv, pi, nparts, table, W_hh, b_hh, h, hn, hhi, hlo)
+                    h = hn
+                    nparts = ops.gemm_tc_amax(hop, vocab.operand(), fc_b, lg, pv, pi)
+                else:
+                    if t == 0:
+                        GI = xproj(x)
+                    else:
+                        ops.argmax_finish_gather(pv, pi, nparts, table, None, GIb)
+                        GI = GIb
+                    h = ops.gru_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False)[0][1]
+                    nparts = ops.gemm_tc_amax(ops.split_bf16(h), vocab.operand(), fc_b, lg, pv, pi)
             if chain is not None:
                 cur.wait_stream(chain)                               # (up to this step's GEMM)
             ops.softmax_argmax(lg, want_probs=True, probs_out=lg, want_argmax=False)     # in place, off the chain

@@ -791,6 +791,26 @@ def argmax_finish_gather(pval, pidx, nparts, table=None, tok=None, out=None):
                _p(tok), _p(out), out.stride(0) if out is not None else 0, _stream())
 
 
+def gru_decode_step_ok(H):
+    """The fused decode-step kernel keeps 96 rows of W_hh and up to 32 states in shared memory as float2: H even, <= ~390."""
+    return H % 2 == 0 and (96 * (H + 2) + 32 * H) * 4 <= 200 * 1024
+
+
+def gru_decode_step(GI, pval, pidx, nparts, table, W_hh, b_hh, hprev, hnew, hi=None, lo=None, tok=None):
+    """One greedy-decode step of the pooled captioner in one launch (csrc/gru_decode.cu): arg-max finish + projection-table
+    gather (GI None) or the given input projection, GRU cell, new state as fp32 and as bf16 hi / lo operand rows."""
+    B, H = hprev.shape
+    assert W_hh.is_contiguous() and hprev.is_contiguous() and hnew.is_contiguous() and hnew.data_ptr() != hprev.data_ptr()
+    if GI is not None:
+        assert GI.is_contiguous() and GI.shape == (B, 3 * H)
+    else:
+        assert table.is_contiguous() and table.shape[1] == 3 * H and pval.stride(0) == pidx.stride(0)
+    _cabi.call("caphn_gru_decode_step", _p(GI), _p(pval), _p(pidx), pval.stride(0) if pval is not None else 0, nparts,
+               _p(table), W_hh.data_ptr(), b_hh.data_ptr(), hprev.data_ptr(), hnew.data_ptr(), _p(hi), _p(lo),
+               hi.stride(0) if hi is not None else 0, _p(tok), B, H, _stream())
+    return hnew
+
+
 def attstep_h_operand(lw, B, H, Fd, t_done):
     """The hidden state h_{t_done} as the bf16 hi/lo operand rows the step-split gates kernel has just written into its
     workspace for the next step's U kernel (attgru_step.cu: hsp buffers) -- the A operand of the vocabulary projection,

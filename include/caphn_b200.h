@@ -372,6 +372,15 @@ int caphn_gemm_tc_prof(const void* Ahi, const void* Alo, long a_ld, int a_mn, co
                        int b_mn, long K, float* C, long ldc, const float* bias, int M, int N, int splitk, long long* prof,
                        void* stream);
 
+/* One greedy-decode step of the pooled captioner (later.py:459-490: argmax feedback -> embedding -> nn.GRUCell) as one
+ * launch: finishes the arg-max of the previous vocabulary projection from the partials of caphn_gemm_tc_amax (GI == NULL; the
+ * token goes to tok if non-NULL), takes the input projection from row tok of table [V, 3H] (= Emb W_ih^T + b_ih) -- or uses
+ * GI [B, 3H] directly (step 0) --, applies the GRU cell with W_hh [3H, H] / b_hh and writes hnew [B, H] plus, if hi != NULL, its
+ * bf16 hi / lo operand rows [B, Kp] for the next vocabulary projection.  hnew must not alias hprev. */
+int caphn_gru_decode_step(const float* GI, const float* pval, const int* pidx, int ldp, int nparts, const float* table,
+                          const float* Whh, const float* bhh, const float* hprev, float* hnew, void* hi, void* lo, long Kp,
+                          long long* tok, int B, int H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

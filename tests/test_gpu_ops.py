@@ -296,3 +296,43 @@ def test_gemm_tc_a_stationary_schedule_is_bit_identical(M, N, K, monkeypatch):
     ref = X.double() @ W.double().t() + b.double()
     assert (outs["0"].double() - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
     assert torch.equal(outs["0"], outs["1"]) and torch.equal(outs["0"], outs["2"])
+
+
+@pytest.mark.parametrize("B,H,V", [(512, 150, 9684), (37, 34, 301), (16, 200, 1000), (5, 6, 40), (300, 256, 500)])
+def test_fused_decode_step_matches_the_three_launch_chain(B, H, V):
+    """caphn_gru_decode_step (arg-max finish + projection-table gather + GRU cell + bf16 operand rows in one launch) ==
+    argmax_finish_gather -> gru_seq_fwd(T = 1) -> split_bf16, the chain it replaces in DecoderGRU.infer (later.py:459-490)."""
+    import torch
+    from hypernet_image_captioning_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    nslot, nparts = 2 * ((V + 127) // 128), 2 * ((V + 127) // 128) - 1
+    table = torch.randn(V, 3 * H, generator=g).cuda()
+    W_hh = (torch.randn(3 * H, H, generator=g) * 0.2).cuda()
+    b_hh = torch.randn(3 * H, generator=g).cuda()
+    h = torch.rand(B, H, generator=g).cuda()
+    pv = torch.randn(B, nslot, generator=g).cuda()
+    pi = torch.randint(0, V, (B, nslot), generator=g, dtype=torch.int32).cuda()
+    pv[::3, nparts - 1] = pv[::3, 0] = 9.0              # ties: the lower column must win
+    WhhT = ops.transpose_pad(W_hh, ops.round4(3 * H))
+    # reference chain
+    GI = torch.empty(B, 3 * H, device="cuda")
+    tok_ref = torch.empty(B, device="cuda", dtype=torch.int64)
+    ops.argmax_finish_gather(pv, pi, nparts, table, tok_ref, GI)
+    h_ref = ops.gru_seq_fwd(GI, WhhT, b_hh, h, 1, save=False, want_bm=False)[0][1]
+    sp = ops.split_bf16(h_ref)
+    # fused
+    Kp = ops.round64(H)
+    hn = torch.empty(B, H, device="cuda")
+    hi = torch.zeros(B, Kp, device="cuda", dtype=torch.bfloat16)
+    lo = torch.zeros(B, Kp, device="cuda", dtype=torch.bfloat16)
+    tok = torch.empty(B, device="cuda", dtype=torch.int64)
+    ops.gru_decode_step(None, pv, pi, nparts, table, W_hh, b_hh, h, hn, hi, lo, tok)
+    assert torch.equal(tok, tok_ref)
+    assert (hn - h_ref).abs().max().item() < 2e-6
+    assert (hi[:, :H].float() + lo[:, :H].float() - hn).abs().max().item() < 1e-5 * max(1.0, hn.abs().max().item())
+    assert torch.equal(hi[:, :H], hn.to(torch.bfloat16))
+    # step 0: the input projection is given
+    hn0 = torch.empty(B, H, device="cuda")
+    ops.gru_decode_step(GI, None, None, 0, None, W_hh, b_hh, h, hn0)
+    assert (hn0 - h_ref).abs().max().item() < 2e-6
+    del sp
