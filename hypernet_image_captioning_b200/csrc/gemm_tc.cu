@@ -548,8 +548,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float v = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bl, j);
+                        r[j] = __float_as_uint(v);            // the bias is in: the store paths below must not add it again
                         if (j < cvalid && v > am_best) { am_best = v; am_idx = colbase + j; }   // ascending columns: first max wins
                     }
+                    bias_done = true;
                 } else if (p.amax_val) {                      // stat_mode 2: running (max, sum exp) of the row
                     const float bl = (add_bias && lane < cvalid) ? biasp[cl0 + lane] : 0.f;
                     float cm = -INFINITY;
@@ -886,8 +888,7 @@ static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, c
         // edge box of a ragged N did not match in round 1 -- those shapes keep the default epilogue).  CAPHN_TC_TMA_STORE=0
         // switches it off.
         const char* e = getenv("CAPHN_TC_TMA_STORE");
-        tma_store = !(e && e[0] == '0') && p.splitk == 1 && (ldc % 4 == 0) && (N % 4 == 0) && ((uintptr_t)C % 16 == 0) &&
-                    !(p.amax_val && p.stat_mode == 1);
+        tma_store = !(e && e[0] == '0') && p.splitk == 1 && (ldc % 4 == 0) && (N % 4 == 0) && ((uintptr_t)C % 16 == 0);
     }
     const char* ae = getenv("CAPHN_TC_ASTAT");
     const int astat_mode = ae ? atoi(ae) : 1;

@@ -260,7 +260,10 @@ def _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells, want_sta
     emb_w = emb_w.contiguous()
     X = ops.build_inputs(feats, emb_w, caps, 0)                       # [T*B, E]
     GI = ops.linear(X, W_ih.contiguous(), b_ih.contiguous())          # [T*B, 3H]
-    if NL == 1 and ops.gru_cluster_size(H):
+    if NL == 1 and ops.gru_resident_ok(H):
+        # weights-resident path: the whole W_hh lives in ONE CTA (shared memory + registers) for all T steps, 4 rows per CTA
+        Hall, Hbm, saved, Hmid = ops.gru_resident_fwd(GI, W_hh.contiguous(), b_hh.contiguous(), h0.contiguous(), T)
+    elif NL == 1 and ops.gru_cluster_size(H):
         # weights-resident path: W_hh stays in shared memory (cluster-split) for all T steps
         Hall, Hbm, saved, Hmid = ops.gru_cluster_fwd(GI, W_hh.contiguous(), b_hh.contiguous(), h0.contiguous(), T)
     else:
@@ -288,7 +291,9 @@ def _gru_decoder_backward(saved_tensors, NL, need, vocab):
     B, T = caps.shape
     H = W_hh.shape[1]
     dfc_w, dfc_b, dHbm = vocab
-    if NL == 1 and ops.gru_cluster_size(H):
+    if NL == 1 and ops.gru_resident_ok(H):
+        dGI, dGH, xdGI, xdGH, dh0 = ops.gru_resident_bwd(dHbm.view(B, T, H), saved, Hall, W_hh.contiguous())
+    elif NL == 1 and ops.gru_cluster_size(H):
         dGI, dGH, xdGI, xdGH, dh0 = ops.gru_cluster_bwd(dHbm.view(B, T, H), saved, Hall, W_hh.contiguous())
     else:
         ldh = ops.round4(H)

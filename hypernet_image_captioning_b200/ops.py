@@ -277,6 +277,48 @@ def gru_cluster_size(H):
     return _cluster_plan_cache[H]
 
 
+RESIDENT_RECURRENCE = True   # CTA-resident W_hh (smem + registers, no cluster) where it fits; else the cluster kernels
+_resident_plan_cache = {}
+
+
+def gru_resident_ok(H):
+    """True when the CTA-resident GRU kernels (csrc/gru_resident.cu) apply to hidden size H."""
+    if not RESIDENT_RECURRENCE:
+        return False
+    if H not in _resident_plan_cache:
+        import ctypes
+        ok = ctypes.c_int(0)
+        _cabi.call("caphn_gru_resident_plan", H, ctypes.byref(ok))
+        _resident_plan_cache[H] = bool(ok.value)
+    return _resident_plan_cache[H]
+
+
+def gru_resident_fwd(GI, W_hh, bhh, h0, T, save=True, want_bm=True):
+    """Single-layer recurrence with the whole W_hh resident in one CTA per 4 rows.  Same returns as gru_seq_fwd."""
+    B, H = h0.shape
+    dev = GI.device
+    Hall = torch.empty(T + 1, B, H, device=dev, dtype=torch.float32)
+    Hall[0].copy_(h0)
+    Hbm = torch.empty(B, T, H, device=dev, dtype=torch.float32) if want_bm else None
+    saved = torch.empty(1, 4, T, B, H, device=dev, dtype=torch.float32) if save else None
+    _cabi.call("caphn_gru_resident_fwd", GI.data_ptr(), W_hh.data_ptr(), bhh.data_ptr(), Hall.data_ptr(), _p(Hbm),
+               _p(saved), B, T, H, _stream())
+    return Hall, Hbm, saved, None
+
+
+def gru_resident_bwd(dHbm, saved, Hall, W_hh):
+    Tp1, B, H = Hall.shape
+    T = Tp1 - 1
+    dev = Hall.device
+    dGI = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+    dGH = torch.empty(T * B, 3 * H, device=dev, dtype=torch.float32)
+    dh0 = torch.empty(B, H, device=dev, dtype=torch.float32)
+    assert dHbm.is_contiguous()
+    _cabi.call("caphn_gru_resident_bwd", dHbm.data_ptr(), saved.data_ptr(), Hall.data_ptr(), W_hh.data_ptr(),
+               dGI.data_ptr(), dGH.data_ptr(), dh0.data_ptr(), B, T, H, _stream())
+    return dGI, dGH, None, None, dh0
+
+
 def gru_cluster_fwd(GI, W_hh, bhh, h0, T, save=True, want_bm=True):
     """Single-layer recurrence with W_hh resident in shared memory (cluster + DSMEM).  Same returns as gru_seq_fwd."""
     B, H = h0.shape

@@ -381,6 +381,15 @@ int caphn_gru_decode_step(const float* GI, const float* pval, const int* pidx, i
                           const float* Whh, const float* bhh, const float* hprev, float* hnew, void* hi, void* lo, long Kp,
                           long long* tok, int B, int H, void* stream);
 
+/* Weights-resident GRU recurrence without a cluster (csrc/gru_resident.cu): one CTA per 4 batch rows keeps the whole generated
+ * W_hh as thread-private weight vectors (shared memory + registers), so every step is CTA-local.  Same contract as
+ * caphn_gru_cluster_fwd / _bwd (nn.GRUCell per step + BPTT, later.py:411,418); *ok of the plan call says whether H fits. */
+int caphn_gru_resident_plan(int H, int* ok);
+int caphn_gru_resident_fwd(const float* GI, const float* Whh, const float* bhh, float* Hall, float* Hbm, float* saved, int B,
+                           int T, int H, void* stream);
+int caphn_gru_resident_bwd(const float* dHbm, const float* saved, const float* Hall, const float* Whh, float* dGI,
+                           float* dGH, float* dh0, int B, int T, int H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

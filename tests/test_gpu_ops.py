@@ -336,3 +336,29 @@ def test_fused_decode_step_matches_the_three_launch_chain(B, H, V):
     ops.gru_decode_step(GI, None, None, 0, None, W_hh, b_hh, h, hn0)
     assert (hn0 - h_ref).abs().max().item() < 2e-6
     del sp
+
+
+@pytest.mark.parametrize("B,T,H", [(3, 5, 6), (9, 4, 150), (21, 3, 33), (16, 6, 160), (512, 20, 150), (6, 2, 100)])
+def test_gru_resident_matches_streaming_kernel(B, T, H):
+    """CTA-resident W_hh (csrc/gru_resident.cu: shared memory + registers, no cluster) == the L2-streaming recurrence
+    (gru_seq.cu), forward outputs / saved gates and the BPTT gradients (nn.GRUCell + autograd, later.py:411,418)."""
+    import torch
+    from hypernet_image_captioning_b200 import ops
+    from golden_util import rel_err
+    if not ops.gru_resident_ok(H):
+        pytest.skip("hidden size outside the resident kernels' range")
+    g = torch.Generator().manual_seed(5)
+    GI = torch.randn(T * B, 3 * H, generator=g).cuda()
+    W = (torch.randn(3 * H, H, generator=g) * 0.2).cuda()
+    b = torch.randn(3 * H, generator=g).cuda()
+    h0 = torch.rand(B, H, generator=g).cuda()
+    dH = torch.randn(B, T, H, generator=g).cuda()
+    Hall0, Hbm0, sv0, _ = ops.gru_seq_fwd(GI, ops.transpose_pad(W, ops.round4(3 * H)), b, h0, T)
+    dGI0, dGH0, _, _, dh00 = ops.gru_seq_bwd(dH, sv0, Hall0, None, ops.copy_pad(W, ops.round4(H)))
+    Hall1, Hbm1, sv1, _ = ops.gru_resident_fwd(GI, W, b, h0, T)
+    dGI1, dGH1, _, _, dh01 = ops.gru_resident_bwd(dH, sv1, Hall1, W)
+    assert rel_err(Hall1, Hall0) < 2e-6 and rel_err(Hbm1, Hbm0) < 2e-6 and rel_err(sv1, sv0) < 2e-6
+    assert rel_err(dGI1, dGI0) < 1e-5 and rel_err(dGH1, dGH0) < 1e-5 and rel_err(dh01, dh00) < 1e-5
+    # inference form (no saved gates, no batch-major copy)
+    Hall2, Hbm2, sv2, _ = ops.gru_resident_fwd(GI, W, b, h0, T, save=False, want_bm=False)
+    assert Hbm2 is None and sv2 is None and torch.equal(Hall2, Hall1)
