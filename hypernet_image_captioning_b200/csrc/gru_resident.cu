@@ -13,6 +13,7 @@
 //   backward: thread (g, k) owns column k of gate block g; part[g][row][k] = sum_jj dgh[row][gH + jj] W[gH + jj][k]
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace caphn {
 
@@ -49,9 +50,6 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_res_fwd_kernel(const GruRes
     float* hs = Ws + (((long)H3 * ldw + 3) & ~3L);         // [2][HP][4]  state, k-major, 4 rows contiguous; tail zero
     float* gps = hs + 2 * HP * GR_RB;                      // [3 (ks)][3H][4]  partial gh
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#ifdef GR_PROF
-    const long long tp0 = clock64();
-#endif
     const int b0 = blockIdx.x * GR_RB, nb = min(GR_RB, B - b0);
     const long TBH = (long)T * B * H;
     const int ks = warp / UB, u_own = (warp - ks * UB) * 32 + lane;
@@ -125,14 +123,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_res_fwd_kernel(const GruRes
         }
     }
     const float* wv = Ws + (long)(owner ? vrow : 0) * ldw;
-#ifdef GR_PROF
-    long long pc[4] = {0, 0, 0, 0};
-    const long long tp1 = clock64();
-#endif
     for (int t = 0; t < T; ++t) {
-#ifdef GR_PROF
-        const long long c0 = clock64();
-#endif
         const float* hc = hs + (t & 1) * HP * GR_RB;
         float* hn = hs + ((t + 1) & 1) * HP * GR_RB;
         float gi_cur[MAXI][3];
@@ -169,13 +160,7 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_res_fwd_kernel(const GruRes
             *reinterpret_cast<float4*>(gp + (H + u_own) * GR_RB) = make_float4(az[0], az[1], az[2], az[3]);
             *reinterpret_cast<float4*>(gp + (2 * H + u_own) * GR_RB) = make_float4(an[0], an[1], an[2], an[3]);
         }
-#ifdef GR_PROF
-        const long long c1 = clock64();
-#endif
         __syncthreads();
-#ifdef GR_PROF
-        const long long c2 = clock64();
-#endif
 #pragma unroll
         for (int q = 0; q < MAXI; ++q) {
             const int i = tid + q * GR_THREADS, u = i >> 2, r = i & 3;
@@ -204,19 +189,8 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_res_fwd_kernel(const GruRes
                 hn[u * GR_RB + r] = hnew;
             }
         }
-#ifdef GR_PROF
-        const long long c3 = clock64();
-#endif
         __syncthreads();
-#ifdef GR_PROF
-        pc[0] += c1 - c0; pc[1] += c2 - c1; pc[2] += c3 - c2; pc[3] += clock64() - c3;
-#endif
     }
-#ifdef GR_PROF
-    if (blockIdx.x == 3 && (tid == 0 || tid == 200 || tid == 500))
-        printf("fwd tid %d: prologue %lld | per step: matvec %lld sync %lld gates %lld sync %lld cycles\n", tid, tp1 - tp0, pc[0] / T,
-               pc[1] / T, pc[2] / T, pc[3] / T);
-#endif
 }
 
 template <int KR>
@@ -327,6 +301,171 @@ __global__ void __launch_bounds__(GR_THREADS, 1) gru_res_bwd_kernel(const GruRes
     }
 }
 
+// Backward, column-blocked (H >= ~100): warp jg owns the RJ = ceil(3H / 15) rows [jg RJ, (jg + 1) RJ) of W_hh, lane kc the C columns
+// 5 kc .. 5 kc + C - 1 -- a private vector of RJ x C weights (row-major), the last 60 in registers.  Per row it reads C private
+// weights and ONE broadcast float4 of dgh (4 batch rows) for 4 C FMAs (the one-column-per-thread kernel above does 4 FMAs per
+// broadcast and is bound by those reads); the 15 row-group partials per (column, batch row) are summed by the next step's
+// gate-gradient items.
+constexpr int GB_KR = 60;
+constexpr int GB_JG = 15;
+template <int C>
+__global__ void __launch_bounds__(GR_THREADS, 1) gru_res_bwdc_kernel(const GruResArgs a) {
+    extern __shared__ __align__(16) float gr_smem[];
+    const int H = a.H, H3 = 3 * a.H, KS = a.KS, ldw = a.ldw, B = a.B, T = a.T;
+    const int RJ = (H3 + GB_JG - 1) / GB_JG;               // rows per warp
+    const int LN = (H + C - 1) / C;                        // lanes in use
+    const int KSR = KS / C, RR = GB_KR / C;                // rows of a vector in shared memory / in registers (KSR + RR = RJ)
+    float* Ws = gr_smem;                                   // [15][LN][ldw]
+    float* dgs = Ws + (((long)GB_JG * LN * ldw + 3) & ~3L);   // [15 RJ][4]  dgh (rows >= 3H zero)
+    float* dhz = dgs + GB_JG * RJ * GR_RB;                 // [H][4]   direct term dh_t * z
+    float* part = dhz + H * GR_RB;                         // [15][H][4]  partial dh per row group
+    const int tid = threadIdx.x, lane = tid & 31, jg = tid >> 5;
+    const int b0 = blockIdx.x * GR_RB, nb = min(GR_RB, B - b0);
+    const long TBH = (long)T * B * H;
+    const bool owner = jg < GB_JG && lane < LN;
+    const int k0 = lane * C;
+
+    float wr[GB_KR];
+    {
+        float* dst = Ws + (long)(jg * LN + lane) * ldw;
+        if (owner) {
+            for (int jl = 0; jl < KSR; ++jl) {
+                const int j = jg * RJ + jl;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    if (j < H3 && k0 + c < H) gr_cp_async4(dst + jl * C + c, a.Whh + (long)j * H + k0 + c);
+                    else dst[jl * C + c] = 0.f;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < GB_KR; ++q) {
+            const int jl = KSR + q / C, c = q % C, j = jg * RJ + jl;
+            wr[q] = (owner && jl < RJ && j < H3 && k0 + c < H) ? a.Whh[(long)j * H + k0 + c] : 0.f;
+        }
+    }
+    for (int i = tid; i < GB_JG * RJ * GR_RB + H * GR_RB + GB_JG * H * GR_RB; i += GR_THREADS) dgs[i] = 0.f;   // dgs, dhz, part
+    gr_cp_async_wait_all();
+    __syncthreads();
+
+    constexpr int MAXI = 2;
+    bool live[MAXI];
+    float nx[MAXI][6];   // prefetched r, z, n, gh_n, h_prev, dHbm of the step about to be processed
+#pragma unroll
+    for (int q = 0; q < MAXI; ++q) {
+        const int i = tid + q * GR_THREADS, u = i >> 2, r = i & 3;
+        live[q] = (u < H) && (r < nb);
+        if (live[q]) {
+            const long o = ((long)(T - 1) * B + b0 + r) * H + u;
+            nx[q][0] = a.saved[o]; nx[q][1] = a.saved[TBH + o]; nx[q][2] = a.saved[2 * TBH + o];
+            nx[q][3] = a.saved[3 * TBH + o]; nx[q][4] = a.Hall[o];
+            nx[q][5] = a.dHbm[((long)(b0 + r) * T + (T - 1)) * H + u];
+        }
+    }
+    const float* wv = Ws + (long)(owner ? jg * LN + lane : 0) * ldw;
+    const float* dg = dgs + (long)(jg < GB_JG ? jg : 0) * RJ * GR_RB;
+    for (int t = T - 1; t >= 0; --t) {
+        // ---- gate gradients of (unit u, row r) ----
+#pragma unroll
+        for (int q = 0; q < MAXI; ++q) {
+            const int i = tid + q * GR_THREADS, u = i >> 2, r = i & 3;
+            if (u < H) {
+                float dar = 0.f, daz = 0.f, danr = 0.f, keep = 0.f;
+                if (live[q]) {
+                    float ps = 0.f;
+#pragma unroll
+                    for (int w = 0; w < GB_JG; ++w) ps += part[(w * H + u) * GR_RB + r];
+                    const float dht = dhz[i] + nx[q][5] + ps;
+                    const float rg = nx[q][0], z = nx[q][1], n = nx[q][2], ghn = nx[q][3], hp = nx[q][4];
+                    const float dn = dht * (1.f - z);
+                    const float dz = dht * (hp - n);
+                    const float dan = dn * (1.f - n * n);
+                    dar = dan * ghn * rg * (1.f - rg);
+                    daz = dz * z * (1.f - z);
+                    danr = dan * rg;
+                    keep = dht * z;
+                    const int gb = b0 + r;
+                    float* gi = a.dGI + ((long)t * B + gb) * H3;
+                    float* gh = a.dGH + ((long)t * B + gb) * H3;
+                    gi[u] = dar; gi[H + u] = daz; gi[2 * H + u] = dan;
+                    gh[u] = dar; gh[H + u] = daz; gh[2 * H + u] = danr;
+                    if (t > 0) {   // prefetch the next (earlier) step while the product below runs
+                        const long o = ((long)(t - 1) * B + gb) * H + u;
+                        nx[q][0] = a.saved[o]; nx[q][1] = a.saved[TBH + o]; nx[q][2] = a.saved[2 * TBH + o];
+                        nx[q][3] = a.saved[3 * TBH + o]; nx[q][4] = a.Hall[o];
+                        nx[q][5] = a.dHbm[((long)gb * T + (t - 1)) * H + u];
+                    }
+                }
+                dhz[i] = keep;
+                dgs[u * GR_RB + r] = dar;
+                dgs[(H + u) * GR_RB + r] = daz;
+                dgs[(2 * H + u) * GR_RB + r] = danr;
+            }
+        }
+        __syncthreads();
+        // ---- part[jg][k][row] = sum over this warp's rows j of dgh[row][j] * W[j][k] ----
+        if (owner) {
+            float acc[C][4];
+#pragma unroll
+            for (int c = 0; c < C; ++c) { acc[c][0] = acc[c][1] = acc[c][2] = acc[c][3] = 0.f; }
+#pragma unroll 2
+            for (int jl = 0; jl < KSR; ++jl) {
+                const float4 d4 = *reinterpret_cast<const float4*>(dg + jl * GR_RB);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float w = wv[jl * C + c];
+                    acc[c][0] = fmaf(w, d4.x, acc[c][0]); acc[c][1] = fmaf(w, d4.y, acc[c][1]);
+                    acc[c][2] = fmaf(w, d4.z, acc[c][2]); acc[c][3] = fmaf(w, d4.w, acc[c][3]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < GB_KR / C; ++q) {
+                if (KSR + q < RJ) {
+                    const float4 d4 = *reinterpret_cast<const float4*>(dg + (KSR + q) * GR_RB);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float w = wr[q * C + c];
+                        acc[c][0] = fmaf(w, d4.x, acc[c][0]); acc[c][1] = fmaf(w, d4.y, acc[c][1]);
+                        acc[c][2] = fmaf(w, d4.z, acc[c][2]); acc[c][3] = fmaf(w, d4.w, acc[c][3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (k0 + c < H)
+                    *reinterpret_cast<float4*>(part + ((long)jg * H + k0 + c) * GR_RB) =
+                        make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < MAXI; ++q) {
+        const int i = tid + q * GR_THREADS, u = i >> 2, r = i & 3;
+        if (live[q]) {
+            float ps = 0.f;
+#pragma unroll
+            for (int w = 0; w < GB_JG; ++w) ps += part[(w * H + u) * GR_RB + r];
+            a.dh0[(long)(b0 + r) * H + u] = dhz[i] + ps;
+        }
+    }
+}
+
+// plan of the column-blocked backward: C columns per lane, 60 register weights; 0 when it does not apply
+static int gr_plan_bwdc(int H, int* C, int* KS, int* ldw, size_t* smem) {
+    if (H <= 0 || 3 * H > GR_THREADS) return 0;
+    const int c = (H + 31) / 32;                           // columns per lane
+    if (c < 1 || c > 5 || GB_KR % c) return 0;
+    const int RJ = (3 * H + GB_JG - 1) / GB_JG, LN = (H + c - 1) / c, VL = RJ * c;
+    const int ks = VL - GB_KR;
+    if (ks < 0 || (ks % c)) return 0;
+    const int l = ks | 1;
+    const size_t w = (((size_t)GB_JG * LN * l + 3) & ~(size_t)3);
+    const size_t tot = (w + (size_t)GB_JG * RJ * GR_RB + (size_t)H * GR_RB + (size_t)GB_JG * H * GR_RB) * sizeof(float);
+    if (tot > 226 * 1024) return 0;
+    *C = c; *KS = ks; *ldw = l; *smem = tot;
+    return 1;
+}
+
 // Registers per private weight vector: the largest multiple of 12 (<= 60, no spills at 512 threads) with which the rest fits
 // in shared memory.
 //   forward : 3H vectors of 3 ceil(H/3) weights (+ 2 x padded state + 3 x partial gh)
@@ -363,9 +502,30 @@ static int gr_launch(bool bwd, const GruResArgs& a, size_t smem, cudaStream_t st
     CAPHN_RETURN_LAST();
 }
 
+template <int C>
+static int gr_launch_bwdc(const GruResArgs& a, size_t smem, cudaStream_t st) {
+    CAPHN_CHECK(cudaFuncSetAttribute(gru_res_bwdc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gru_res_bwdc_kernel<C><<<(unsigned)ceil_div(a.B, GR_RB), GR_THREADS, smem, st>>>(a);
+    CAPHN_RETURN_LAST();
+}
+
 static int gr_dispatch(bool bwd, GruResArgs& a, cudaStream_t st) {
     int KR = 0, ldw = 0;
     size_t smem = 0;
+    if (bwd) {
+        static const bool colblk = [] { const char* e = getenv("CAPHN_GRU_BWD_COLBLK"); return !(e && e[0] == '0'); }();
+        int C = 0, KS = 0;
+        if (colblk && gr_plan_bwdc(a.H, &C, &KS, &ldw, &smem)) {
+            a.KS = KS; a.ldw = ldw;
+            switch (C) {
+                case 1: return gr_launch_bwdc<1>(a, smem, st);
+                case 2: return gr_launch_bwdc<2>(a, smem, st);
+                case 3: return gr_launch_bwdc<3>(a, smem, st);
+                case 4: return gr_launch_bwdc<4>(a, smem, st);
+                default: return gr_launch_bwdc<5>(a, smem, st);
+            }
+        }
+    }
     if (!gr_plan(a.H, bwd, &KR, &ldw, &smem)) return CAPHN_EINVAL;
     a.KS = (bwd ? a.H : 3 * ((a.H + 2) / 3)) - KR; a.ldw = ldw;
     switch (KR) {
