@@ -73,6 +73,13 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// L2 prefetch of one TMA box (no shared memory involved): turns the DRAM latency of a streamed operand into L2 latency for the
+// load that follows a few k-blocks later
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tmap, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y)
+                 : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 
@@ -206,6 +213,9 @@ struct TcParams {
     // staging buffers per epilogue warp (TMA-store epilogue): 2 = the warp fills one 4 KB tile while the bulk store of the
     // previous one is still reading the other (the wait for that read was the largest epilogue stall in the ncu source view)
     int stg_bufs;
+    // k-blocks by which an L2 prefetch of the A operand runs ahead of its load (0 = off; long-K products whose A streams
+    // from DRAM through a 2-3 stage ring)
+    int pf_dist;
     // diagnostics (caphn_gemm_tc_prof; NULL otherwise): 16 cycle counters per CTA -- [0] producer waiting for a free stage,
     // [1] producer waiting for the A slab to be free, [2] MMA thread waiting for operands, [3] MMA thread waiting for a free
     // accumulator, [4] MMA thread total, [5] epilogue warp 4 waiting for an accumulator, [6] waiting for bulk-store reads,
@@ -332,6 +342,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 w_empty += clock64() - tw;
                 uint8_t* st = tiles + (size_t)stage * p.stage_bytes;
                 if (elect_one()) {
+                    if (p.pf_dist > 0 && i + p.pf_dist < u.nkb) {      // A tiles of a later k-block -> L2
+                        const int kp = ka + p.pf_dist * BK;
+                        if (!p.a_mn) {
+                            tma_prefetch_2d(&tmAh, kp, u.a0);
+                            if (SPLIT) tma_prefetch_2d(&tmAl, kp, u.a0);
+                        } else {
+                            for (int h = 0; h < BM / 64; ++h) {
+                                tma_prefetch_2d(&tmAh, u.a0 + h * 64, kp);
+                                if (SPLIT) tma_prefetch_2d(&tmAl, u.a0 + h * 64, kp);
+                            }
+                        }
+                    }
                     mbar_expect_tx(full + stage, (uint32_t)p.stage_bytes);
                     // K-major operand: one box [64 k x rows].  MN-major operand: boxes of [64 mn x 64 k] (8 KiB each).
                     if (p.astat) {
@@ -855,6 +877,19 @@ static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, c
             const long cost = ((t + kNumSMs - 1) / kNumSMs) * (bn + 32);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; p.BN = bn; }
         }
+        if (!few_waves && auto_bn) {
+            // many waves: the kernel is bound by the MMA's operand fetch from shared memory (a cta_group::1 MMA reads
+            // 4 KB of A + 32 BN bytes of B per 64 BN / 128 cycles of math), so either A stays resident and BN = 128 keeps three
+            // B stages (A-stationary schedule, short K), or the tile is as wide as it gets: BN = 256 moves 25 % fewer operand
+            // bytes per flop (K = 200: 159 -> 144 us at M = 10240, N = 9684, with two 96 KB stages).
+            const char* ae0 = getenv("CAPHN_TC_ASTAT");
+            const bool astat_on = !(ae0 && atoi(ae0) == 0);
+            const size_t slab0 = (size_t)p.num_kb * (split ? 2 : 1) * tc::TILE_BYTES;
+            const size_t fixed0 = (size_t)tc::STG_FLOATS_V2 * 4 + (2 * tc::MAX_STAGES + 6) * 8 + 16 + 1024;
+            const size_t bst0 = (size_t)(split ? 2 : 1) * 128 * tc::BK * 2;
+            const bool astat_fits = astat_on && !a_mn && !b_mn && slab0 + fixed0 + 3 * bst0 <= tc::SMEM_BUDGET;
+            if (!astat_fits) p.BN = 256;
+        }
         // tuning knob (tools/bench_gemm.py): CAPHN_TC_BN_FORCE=<multiple of 16 (64 for an MN-major B) in 128..256>
         if (const char* f = getenv("CAPHN_TC_BN_FORCE")) {
             const int bn = atoi(f);
@@ -928,6 +963,11 @@ static int gemm_tc_impl(const void* Ahi, const void* Alo, long a_ld, int a_mn, c
         return CAPHN_EINVAL;
     }
     p.stages = stages;
+    {   // L2 prefetch distance for the A operand of long-K products (CAPHN_TC_PREFETCH=<k-blocks>, 0 = off)
+        const char* pe = getenv("CAPHN_TC_PREFETCH");
+        const int pf = pe ? atoi(pe) : 0;
+        p.pf_dist = (!p.astat && p.kb_per >= 16 && pf > 0) ? pf : 0;
+    }
     p.tmem_cols = (2 * p.BN <= 256) ? 256u : 512u;
     const size_t smem = (size_t)p.a_slab_bytes + (size_t)stages * p.stage_bytes + fixed;
     if (bn_used) *bn_used = p.BN;

@@ -34,13 +34,20 @@ class HyperNetThetaFn(Function):
             off += sizes[i]
         # the heads are independent chains (small first layer -> second layer); the two that generate the weight matrices
         # stream hundreds of MB, the bias heads are a few 4 us launches: side by side instead of back to back
+        streams.clear_ranges()
         with streams.Branches("hnf", like=x, enable=nh > 1) as br:
-            for i in range(nh):
+            # tiny (bias) heads first, the matrix heads after them in parameter order (W_ih before W_hh: the input projection
+            # starts when W_ih and b_ih are there): the big heads' persistent CTAs fill every SM for hundreds of microseconds,
+            # and a bias head queued behind them (12 us of work) would only run when they drain
+            for i in sorted(range(nh), key=lambda q: (sizes[q] >= 4096, q)):
                 W1, c1, W2, c2 = params[4 + 4 * i: 8 + 4 * i]
                 with br.on(i % 4):
                     a = ops.rows_linear_fwd(W1, c1, b1, ACT_LEAKY)
-                    ops.rows_linear_fwd(W2, c2, a, ACT_NONE, out=theta[:, offs[i]:offs[i] + sizes[i]])
+                    seg = theta[:, offs[i]:offs[i] + sizes[i]]
+                    ops.rows_linear_fwd(W2, c2, a, ACT_NONE, out=seg)
                     mids[i] = a
+                    if x.shape[0] == 1:
+                        streams.mark_range(seg)      # consumers of this slice alone need not wait for the other heads
         ctx.save_for_backward(x, b0, b1, *mids, *params)
         ctx.lowrank_targets = [params[4 + 4 * i + 2] for i in range(nh)]    # the Parameter objects (saved tensors are views)
         ctx.lowrank_min = LOWRANK_MIN_NUMEL
@@ -103,6 +110,47 @@ class HyperNetThetaFn(Function):
             dx = dx.to(x.dtype)
         parallel.join()   # data parallel: whatever consumes these gradients is ordered after the overlapped bucket all-reduce
         return (dx if need[0] else None, *grads)
+
+
+class ThetaSplitFn(Function):
+    """theta [1, n] -> the generated parameter tensors of every cell, as views (the injection of utils.py:24-69: cell c's
+    (weight_ih, weight_hh, bias_ih, bias_hh) are consecutive slices that start again at offset 0 for every extra cell,
+    utils.py:45).  One autograd node whose backward assembles d(theta) with ONE concatenation per cell, instead of autograd's
+    select + slice + view chain (a zero fill, a copy and an add per slice, all in front of the head backward)."""
+
+    @staticmethod
+    def forward(ctx, theta, shapes):
+        ctx.shapes, ctx.n = shapes, theta.shape[1]
+        outs = []
+        for cell in shapes:
+            a = 0
+            for shp in cell:
+                n = 1
+                for d in shp:
+                    n *= d
+                outs.append(theta[0, a:a + n].view(shp))
+                a += n
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        out, i = None, 0
+        ref = next(g for g in grads if g is not None)
+        for cell in ctx.shapes:
+            parts = []
+            for shp in cell:
+                n = 1
+                for d in shp:
+                    n *= d
+                g = grads[i]
+                i += 1
+                parts.append(g.reshape(-1) if g is not None else ref.new_zeros(n))
+            used = sum(p.numel() for p in parts)
+            if used < ctx.n:
+                parts.append(ref.new_zeros(ctx.n - used))
+            flat = torch.cat(parts)
+            out = flat if out is None else out + flat
+        return out.view(1, ctx.n), None
 
 
 def hypernet_theta(x2d: torch.Tensor, params: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -223,7 +271,51 @@ def ce_fwd_for_loss(logits2d, targets, ignore_index, H, need_grad, stats=None):
     return lossbuf, lse, None, None
 
 
-def vocab_bwd_fused(logits2d, targets, ignore_index, lse, lossbuf, gscale, Hbm2, fc_w, hi=None, lo=None):
+def CE_FUSED_STATS_ON():
+    return ops.CE_FUSED_STATS
+
+
+class VocabPrep:
+    """Operand preparation of the vocabulary projection moved off the step's dependency chain (fused loss nodes, while a CUDA
+    graph is captured -- eagerly the same launches simply run in order): the two bf16 splits of the projection weight do not
+    depend on the step's activations, so they run on a branch stream from the start of the decoder forward (next to the input
+    projection and the recurrence); the transposed split of the hidden states [H | 1] that only the BACKWARD needs runs on a
+    second branch next to the logits product instead of in front of the dW product."""
+
+    def __init__(self, M, V, H, need_grad, like):
+        self.on = bool(CE_FUSED_FWD and need_grad and V <= ops.CE_FWD_SPLIT_MAX_V and ops._tc_ok(M, H, V)
+                       and ops._tc_ok(V, H + 1, M) and ops._tc_ok(M, V, H))
+        self.w = self.wt = self.ht = None
+        self.br = streams.Branches("vprep", like=like) if self.on else None
+
+    def start(self, fc_w):
+        if not self.on:
+            return
+        self.br.__enter__()
+        with self.br.on(0):
+            wc = fc_w.contiguous()
+            self.w = ops.split_bf16(wc)                    # B operand of the logits product
+            self.wt = ops.split_bf16_t(wc)                 # B operand of dH = d W_out
+
+    def logits(self, Hbm2, fc_b):
+        """Called right after the recurrence: logits = Hbm2 W^T + b with the prepared weight operand."""
+        with self.br.on(1):                                # after the recurrence (queued so far on the caller's stream)
+            self.ht = ops.split_bf16_t(Hbm2, ones_row=True)    # B operand of [dW_out | db] = d^T [H | 1]
+        self.br.join(0)
+        return ops.gemm_tc(ops.split_bf16(Hbm2), self.w, bias=fc_b)
+
+    def finish(self):
+        if self.on:
+            self.br.__exit__(None, None, None)
+
+    def saved(self):
+        """Tensors for save_for_backward (None entries when the preparation is off)."""
+        if not self.on:
+            return (None, None, None, None)
+        return (self.wt.hi, self.wt.lo, self.ht.hi, self.ht.lo)
+
+
+def vocab_bwd_fused(logits2d, targets, ignore_index, lse, lossbuf, gscale, Hbm2, fc_w, hi=None, lo=None, pre=None):
     """Loss fused with the projection: the cross-entropy gradient is written directly as bf16x3 tensor-core operands
     (row-major for dH = d W_out, transposed for dW_out = d^T H) and the bias gradient is reduced in the same pass, so
     the fp32 dlogits tensor never exists.  hi / lo: the unscaled operand ce_fwd_for_loss produced in the forward."""
@@ -233,10 +325,17 @@ def vocab_bwd_fused(logits2d, targets, ignore_index, lse, lossbuf, gscale, Hbm2,
         Vp = hi.shape[1]
         d, dT = ops.SplitOperand(hi, lo, M, V, Vp), ops.SplitOperand(hi, lo, V, M, Vp, True)
         scale = (gscale, lossbuf[1:])
-        dHbm = ops.gemm_tc(d, ops.split_bf16_t(fc_w.contiguous(), want_lo=lo is not None), scale=scale)   # [B*T, H]
+        if pre is not None and pre[0] is not None:         # operands prepared in the forward (VocabPrep)
+            Mp = pre[2].shape[1]
+            wt = ops.SplitOperand(pre[0], pre[1], H, V, pre[0].shape[1])
+            ht = ops.SplitOperand(pre[2], pre[3], H + 1, M, Mp)
+        else:
+            wt = ops.split_bf16_t(fc_w.contiguous(), want_lo=lo is not None)
+            ht = ops.split_bf16_t(Hbm2, want_lo=lo is not None, ones_row=True)
+        dHbm = ops.gemm_tc(d, wt, scale=scale)             # [B*T, H]
         # [V, H+1] with a row pitch that is a multiple of 4 floats: the split-K epilogue adds 16-byte vectors per row
         wb = torch.empty(V, ops.round4(H + 1), device=Hbm2.device, dtype=torch.float32)[:, :H + 1]
-        ops.gemm_tc(dT, ops.split_bf16_t(Hbm2, want_lo=lo is not None, ones_row=True), scale=scale, out=wb)
+        ops.gemm_tc(dT, ht, scale=scale, out=wb)
         return wb[:, :H].contiguous(), wb[:, H].contiguous(), dHbm
     if not (ops._tc_ok(M, H, V) and ops._tc_ok(V, H, M)):
         dl = ops.ce_bwd(logits2d, targets, ignore_index, lse, lossbuf, gscale)
@@ -250,16 +349,25 @@ def vocab_bwd_fused(logits2d, targets, ignore_index, lse, lossbuf, gscale, Hbm2,
 # ----------------------------------------------------------------------------------------------------------------------
 # Variant A decoder: teacher-forced DecoderGRU.forward  (reference later.py:389-457)
 # ----------------------------------------------------------------------------------------------------------------------
-def _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells, want_stats=False):
+def _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells, want_stats=False, prep=None):
     B, T = captions.shape
     NL = len(cells) // 4
     W_ih, W_hh, b_ih, b_hh = cells[0:4]
     H = W_hh.shape[1]
+    if prep is not None:
+        prep.start(fc_w)
     caps = captions.contiguous()
     feats = feats.contiguous()
     emb_w = emb_w.contiguous()
     X = ops.build_inputs(feats, emb_w, caps, 0)                       # [T*B, E]
+    # the input projection needs only the W_ih / b_ih slices of the generated weights: with an asynchronous hypernet forward
+    # (modules.py async_hypernet) it runs while the head that generates W_hh is still streaming
+    if not streams.wait_ranges((W_ih, b_ih)):
+        streams.wait_pending()
     GI = ops.linear(X, W_ih.contiguous(), b_ih.contiguous())          # [T*B, 3H]
+    late_join = streams.wait_ranges(tuple(cells))                    # every generated slice (not the parameter injection copies)
+    if not late_join:
+        streams.wait_pending()
     if NL == 1 and ops.gru_resident_ok(H):
         # weights-resident path: the whole W_hh lives in ONE CTA (shared memory + registers) for all T steps, 4 rows per CTA
         Hall, Hbm, saved, Hmid = ops.gru_resident_fwd(GI, W_hh.contiguous(), b_hh.contiguous(), h0.contiguous(), T)
@@ -276,6 +384,11 @@ def _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells, want_sta
                           bi.contiguous(), bh.contiguous()))
         Hall, Hbm, saved, Hmid = ops.gru_seq_fwd(GI, WhhT, b_hh.contiguous(), h0.contiguous(), T, save=True,
                                                  extra=extra)
+    if late_join:
+        streams.wait_pending()      # (whatever else the forked hypernet computation queued; done long before this point)
+    if prep is not None and prep.on:
+        logits = prep.logits(Hbm.view(B * T, H), fc_b)
+        return logits.view(B, T, -1), (caps, X, Hall, Hbm, saved, Hmid, emb_w, fc_w), None
     if want_stats:      # fused loss node: the cross-entropy statistics come out of this GEMM's epilogue
         logits, stats = ops.linear_lse(Hbm.view(B * T, H), fc_w.contiguous(), fc_b)
         return logits.view(B, T, -1), (caps, X, Hall, Hbm, saved, Hmid, emb_w, fc_w), stats
@@ -307,9 +420,10 @@ def _gru_decoder_backward(saved_tensors, NL, need, vocab):
     br.__enter__()
     with br.on(0):
         g_wih = ops.matmul_tn(dGI, X) if need[6] else None
-        g_bih = ops.colsum(dGI) if need[8] else None
     with br.on(1):
         g_whh = ops.matmul_tn(dGH, Hprev) if need[7] else None
+    with br.on(2):      # the bias sums only read dGI / dGH: on their own branch they are done long before the GEMM chains
+        g_bih = ops.colsum(dGI) if need[8] else None
         g_bhh = ops.colsum(dGH) if need[9] else None
     cell_grads = [g_wih, g_whh, g_bih, g_bhh]
     for l in range(1, NL):
@@ -472,12 +586,17 @@ class DecoderGRULossFn(Function):
 
     @staticmethod
     def forward(ctx, ignore_index, feats, captions, h0, emb_w, fc_w, fc_b, *cells):
-        logits, sv, stats = _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells, want_stats=True)
+        Bc, Tc = captions.shape
+        prep = VocabPrep(Bc * Tc, fc_w.shape[0], cells[1].shape[1], any(ctx.needs_input_grad), feats)
+        if CE_FUSED_STATS_ON():
+            prep.on = False
+        logits, sv, stats = _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells, want_stats=True, prep=prep)
         B, T, V = logits.shape
         targets = captions.reshape(-1).contiguous()
         lossbuf, lse, dhi, dlo = ce_fwd_for_loss(logits.view(B * T, V), targets, ignore_index, sv[3].shape[-1],
                                                  any(ctx.needs_input_grad), stats)
-        ctx.save_for_backward(*sv, *cells, logits, targets, lse, lossbuf, dhi, dlo)
+        prep.finish()
+        ctx.save_for_backward(*sv, *cells, logits, targets, lse, lossbuf, dhi, dlo, *prep.saved())
         ctx.NL = len(cells) // 4
         ctx.ignore_index = ignore_index
         ctx.mark_non_differentiable(logits)
@@ -487,11 +606,11 @@ class DecoderGRULossFn(Function):
     @staticmethod
     def backward(ctx, g, _unused):
         allsv = ctx.saved_tensors
-        sv, (logits, targets, lse, lossbuf, dhi, dlo) = allsv[:-6], allsv[-6:]
+        sv, (logits, targets, lse, lossbuf, dhi, dlo), pre = allsv[:-10], allsv[-10:-4], allsv[-4:]
         Hbm, fc_w = sv[3], sv[7]
         B, T, H = Hbm.shape
         need = ctx.needs_input_grad[1:]
         g = g.reshape(1).to(torch.float32).contiguous()
         vocab = vocab_bwd_fused(logits.view(B * T, -1), targets, ctx.ignore_index, lse, lossbuf, g,
-                                Hbm.view(B * T, H), fc_w, dhi, dlo)
+                                Hbm.view(B * T, H), fc_w, dhi, dlo, pre)
         return (None, *_gru_decoder_backward(sv, ctx.NL, need, vocab))

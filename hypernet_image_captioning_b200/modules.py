@@ -100,11 +100,14 @@ class _HyperNetMixin:
     def _generate_and_inject(self, x: torch.Tensor, grouped: bool = False):
         """theta (+ its per-cell views, + the copy into the captioner's cell parameters) -- on the hypernet side stream when
         ``async_hypernet`` is set."""
+        streams.clear_ranges()      # readiness marks of an earlier forward must not be mistaken for this one's
         def run():
             theta = self.generate_theta(x)
             if grouped:
                 self.captioner._theta_groups = theta        # [G, theta]: the grouped kernels take the whole matrix
                 return [self._split_theta(theta[g]) for g in range(theta.shape[0])]
+            if hasattr(self, "_split_theta_node"):
+                return self._split_theta_node(theta)
             return self._split_theta(theta[0], write_params=True)
         if self.async_hypernet and x.is_cuda and streams.ENABLED is not False:      # explicit opt-in: also in eager mode
             with streams.fork("hypernet") as s:
@@ -279,7 +282,7 @@ class DecoderGRU(nn.Module):
         but one autograd node whose backward writes the softmax gradient straight into tensor-core operands."""
         if h0 is None:
             h0 = self._h0(features)
-        streams.wait_pending()
+        # (no wait_pending here: the fused node waits for the generated weights slice by slice, Fn._gru_decoder_forward)
         flat = [w for cell in self._cells() for w in cell]
         return Fn.DecoderGRULossFn.apply(ignore_index, features, captions, h0, self.embed.weight, self.fc_out.weight,
                                          self.fc_out.bias, *flat)
@@ -485,6 +488,19 @@ class HyperNetPooled(_HyperNetMixin, _Base):
         self.captioner._generated_groups = None
         self.captioner._theta_groups = None
         return self.captioner
+
+    def _split_theta_node(self, theta):
+        """Single-style form of ``_split_theta(theta[0], write_params=True)`` as one autograd node (Fn.ThetaSplitFn)."""
+        cells_mod = [self.captioner.lstm_cell] + (list(self.captioner.layers) if self.captioner.layers else [])
+        names = ("weight_ih", "weight_hh", "bias_ih", "bias_hh")
+        shapes = tuple(tuple(tuple(getattr(c, n).shape) for n in names) for c in cells_mod)
+        flat = Fn.ThetaSplitFn.apply(theta, shapes)
+        gen = [tuple(flat[4 * ci: 4 * ci + 4]) for ci in range(len(cells_mod))]
+        with torch.no_grad():
+            for cell, ws in zip(cells_mod, gen):
+                for n, w in zip(names, ws):
+                    getattr(cell, n).copy_(w)  # state_dict keeps the last generated weights, as the reference does
+        return gen
 
     def _split_theta(self, theta, write_params=False):
         cells_mod = [self.captioner.lstm_cell] + (list(self.captioner.layers) if self.captioner.layers else [])

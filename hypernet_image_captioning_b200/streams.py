@@ -70,6 +70,43 @@ def defer(s: "torch.cuda.Stream"):
         _pending.append(s)
 
 
+# Partial readiness of a tensor that several streams are still writing (the generated weight vector theta: every hypernet head
+# writes its own slice on its own branch stream).  The producer marks each slice when it is complete; a consumer that needs
+# only some slices waits for exactly those instead of for the whole forked computation (``wait_pending``).
+_ranges: List[Tuple[int, int, "torch.cuda.Event"]] = []
+
+
+def clear_ranges():
+    _ranges.clear()
+
+
+def mark_range(t: torch.Tensor):
+    """The bytes of ``t`` (a contiguous view) are complete once everything queued so far on the current stream has run."""
+    if not t.is_cuda:
+        return
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    _ranges.append((t.data_ptr(), t.data_ptr() + t.numel() * t.element_size(), ev))
+
+
+def wait_ranges(tensors) -> bool:
+    """Make the current stream wait for the marks that cover ``tensors``; False (nothing waited for) unless every tensor
+    is fully covered by marked ranges."""
+    todo = []
+    for t in tensors:
+        if not t.is_cuda:
+            return False
+        a, b = t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()
+        hit = [r for r in _ranges if r[0] < b and a < r[1]]
+        if not hit or min(r[0] for r in hit) > a or max(r[1] for r in hit) < b:
+            return False
+        todo += hit
+    cur = torch.cuda.current_stream()
+    for r in todo:
+        cur.wait_event(r[2])
+    return True
+
+
 def wait_pending():
     if _pending:
         cur = torch.cuda.current_stream()
@@ -111,6 +148,11 @@ class Branches:
             s = self.used[i] = side(f"{self.name}{i}")
         s.wait_stream(self.cur)
         return torch.cuda.stream(s)
+
+    def join(self, i: int):
+        """The caller's stream waits for what branch i has been given so far (a partial join before __exit__)."""
+        if self.active and i in self.used:
+            self.cur.wait_stream(self.used[i])
 
     def __exit__(self, *exc):
         if self.active:

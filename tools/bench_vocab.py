@@ -77,6 +77,11 @@ for H in (150, 200):
     wt = ops.split_bf16_t(W)
     ht = ops.split_bf16_t(X, ones_row=True)
     wbuf = torch.empty(V, ops.round4(H + 1), device="cuda")[:, :H + 1]
+    for pf in ("0", "2", "4", "8"):
+        os.environ["CAPHN_TC_PREFETCH"] = pf
+        print(f"H={H} L2 prefetch distance {pf}: dH {timed(lambda: ops.gemm_tc(d, wt, scale=(gs, lb1[1:]))):6.1f} us, "
+              f"[dW | db] {timed(lambda: ops.gemm_tc(dT, ht, scale=(gs, lb1[1:]), out=wbuf)):6.1f} us", flush=True)
+    os.environ.pop("CAPHN_TC_PREFETCH", None)
     print(f"H={H} dH product alone {timed(lambda: ops.gemm_tc(d, wt, scale=(gs, lb1[1:]))):6.1f} us, "
           f"[dW | db] product alone {timed(lambda: ops.gemm_tc(dT, ht, scale=(gs, lb1[1:]), out=wbuf)):6.1f} us", flush=True)
 
