@@ -198,7 +198,9 @@ def _attgru_backward(sv, dims, vocab, dattn):
         with br.on(2):
             dUa_w = ops.matmul_tn(dU, Hprev)                           # [H, H]
             dUa_b = ops.colsum(dU)
-            # features through the context vectors: df[b,p,:] = sum_t alpha[b,t,p] dctx[t,b,:]  (the K / init_h paths are FeatureFn's)
+        with br.on(3):
+            # features through the context vectors: df[b,p,:] = sum_t alpha[b,t,p] dctx[t,b,:]  (the K / init_h paths are
+            # FeatureFn's); 72 us of fill + kernel that only need the BPTT's dctx: on their own branch, not behind a GEMM chain
             df = torch.zeros(B, P, Fd, device=f3.device, dtype=torch.float32)
             ops.attn_df(attn, dCTX, df)
         # word embeddings (t >= 2 teacher-forced rows, or the fed-back argmax rows)
@@ -365,7 +367,10 @@ class AttentionGru(nn.Module):
         """FeatureFn on the "features" side stream: it overlaps with an asynchronous hypernet forward, and its backward
         node (which the autograd engine runs on the same stream) with the hypernet head backward."""
         if streams.enabled(features):
-            with streams.fork("features") as s:
+            # high priority: the backward of this branch (tensor-core GEMMs, the long feature_fc weight gradient last) runs
+            # next to the hypernet head backward, whose thousands of short CTAs otherwise fill every SM slot first and push
+            # the branch -- the end of the step -- behind them (tools/timeline_step.py attention)
+            with streams.fork("features_hp", priority=-1) as s:
                 out = FeatureFn.apply(features, *self._feature_params())
             torch.cuda.current_stream().wait_stream(s)
             return out

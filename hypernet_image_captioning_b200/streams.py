@@ -48,12 +48,12 @@ class fork:
     """``with fork("features") as s:`` -- run the block on side stream ``s`` after everything queued on the current stream.
     The caller joins with ``torch.cuda.current_stream().wait_stream(s)`` (or ``defer(s)`` + ``wait_pending()``)."""
 
-    def __init__(self, name: str):
-        self.name = name
+    def __init__(self, name: str, priority: int = 0):
+        self.name, self.priority = name, priority
 
     def __enter__(self):
         cur = torch.cuda.current_stream()
-        self.s = side(self.name)
+        self.s = side(self.name, priority=self.priority)
         self.s.wait_stream(cur)
         self.ctx = torch.cuda.stream(self.s)
         self.ctx.__enter__()
