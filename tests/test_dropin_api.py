@@ -69,3 +69,48 @@ def test_dropin_shims_resolve_reference_import_names():
         sys.path.remove(d)
         for mod in ("hypernet_attention", "hypernet", "models.decoderlstm", "models.attention", "models"):
             sys.modules.pop(mod, None)
+
+
+def test_theta_split_node_equals_autograd_slicing():
+    """Fn.ThetaSplitFn (the generated-parameter views of utils.py:24-69 as ONE autograd node, incl. the offset-0 aliasing of
+    extra cells, utils.py:45) == plain slicing + autograd: same views, same d(theta).  Pure torch: runs without a GPU."""
+    import torch
+    from hypernet_image_captioning_b200 import functional as Fn
+    torch.manual_seed(0)
+    for shapes in ((((6, 4), (6, 2), (6,), (6,)),),
+                   (((6, 4), (6, 2), (6,), (6,)), ((6, 2), (6, 2), (6,), (6,))),
+                   (((8, 3), (8, 2), (8,), (8,)), ((8, 2), (8, 2), (8,), (8,)), ((8, 2), (8, 2), (8,), (8,)))):
+        n = sum(torch.Size(s).numel() for s in shapes[0]) + 5            # theta may be longer than what the cells use
+        th = torch.randn(1, n, requires_grad=True)
+        outs = Fn.ThetaSplitFn.apply(th, shapes)
+        ws = [torch.randn_like(o) for o in outs]
+        sum((o * w).sum() for o, w in zip(outs, ws)).backward()
+        g1, th.grad = th.grad.clone(), None
+        ref = []
+        for cell in shapes:
+            a = 0
+            for shp in cell:
+                k = torch.Size(shp).numel()
+                ref.append(th[0][a:a + k].reshape(shp))
+                a += k
+        sum((o * w).sum() for o, w in zip(ref, ws)).backward()
+        assert all(torch.equal(a, b) for a, b in zip(outs, ref))
+        assert torch.allclose(g1, th.grad, rtol=0, atol=1e-6)
+        # a missing gradient (an unused generated tensor) counts as zero
+        th.grad = None
+        outs = Fn.ThetaSplitFn.apply(th, shapes)
+        (outs[0] * ws[0]).sum().backward()
+        want = torch.zeros_like(th)
+        want[0, :ws[0].numel()] = ws[0].reshape(-1)
+        assert torch.allclose(th.grad, want)
+
+
+def test_slice_readiness_marks_never_claim_cpu_tensors():
+    """streams.wait_ranges (the partial wait of the fused decoder node for the generated W_ih / b_ih slices) must report
+    'not covered' -- so the caller falls back to the full join -- for anything it holds no marks for."""
+    import torch
+    from hypernet_image_captioning_b200 import streams
+    streams.clear_ranges()
+    assert streams.wait_ranges((torch.zeros(4),)) is False
+    streams.mark_range(torch.zeros(4))            # CPU tensors are not marked
+    assert streams.wait_ranges((torch.zeros(4),)) is False
