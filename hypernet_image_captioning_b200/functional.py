@@ -271,10 +271,6 @@ def ce_fwd_for_loss(logits2d, targets, ignore_index, H, need_grad, stats=None):
     return lossbuf, lse, None, None
 
 
-def CE_FUSED_STATS_ON():
-    return ops.CE_FUSED_STATS
-
-
 class VocabPrep:
     """Operand preparation of the vocabulary projection moved off the step's dependency chain (fused loss nodes, while a CUDA
     graph is captured -- eagerly the same launches simply run in order): the two bf16 splits of the projection weight do not
@@ -588,7 +584,7 @@ class DecoderGRULossFn(Function):
     def forward(ctx, ignore_index, feats, captions, h0, emb_w, fc_w, fc_b, *cells):
         Bc, Tc = captions.shape
         prep = VocabPrep(Bc * Tc, fc_w.shape[0], cells[1].shape[1], any(ctx.needs_input_grad), feats)
-        if CE_FUSED_STATS_ON():
+        if ops.CE_FUSED_STATS:             # (the epilogue-statistics experiment takes the logits product itself)
             prep.on = False
         logits, sv, stats = _gru_decoder_forward(feats, captions, h0, emb_w, fc_w, fc_b, cells, want_stats=True, prep=prep)
         B, T, V = logits.shape
