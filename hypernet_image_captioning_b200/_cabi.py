@@ -118,7 +118,10 @@ def load():
             _build.build()
         except Exception as e:  # no silent fallback: the product path needs the CUDA library
             raise CaphnError(f"libcaphn_b200.so is missing and could not be built: {e}") from e
-    lib = ctypes.CDLL(LIB_PATH)
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:
+        raise CaphnError(f"cannot load {LIB_PATH}: {e}") from e
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = header / library mismatch; must be loud
         fn.argtypes = argtypes

@@ -211,11 +211,11 @@ def allreduce_shared_grads(params: Iterable[torch.nn.Parameter], group=None, ext
         return
     params = list(params)
     if _ov.enabled:
-        flush_pending = [p for p in _ov.ready]      # ready after the hypernet backward started (or no hypernet backward ran)
         join()
-        rest = [p for p in params if id(p) not in _ov.done or id(p) not in _ov.ids]
+        # whatever became ready after the hypernet backward started (or when no hypernet backward ran) was never
+        # flushed: it is reduced here together with the parameters that are not in the overlapped set at all
+        rest = [p for p in params if id(p) not in _ov.done]
         _ov.ready, _ov.done, _ov.src_streams = [], set(), []
-        del flush_pending
         group = _ov.group if group is None else group
     else:
         rest = params
