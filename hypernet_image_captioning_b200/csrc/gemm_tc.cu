@@ -129,7 +129,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// TMA store of one [32 rows x 32 fp32] SWIZZLE_128B box from shared memory (experimental epilogue, TMA_STORE = true)
+// TMA store of one [32 rows x 32 fp32] SWIZZLE_128B box from shared memory (TMA_STORE = true epilogue)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int x, int y) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(x), "r"(y)
@@ -248,10 +248,10 @@ __device__ __forceinline__ UnitInfo decode_unit(const TcParams& p, int unit, int
     return u;
 }
 
-// TMA_STORE (experimental, CAPHN_TC_TMA_STORE=1, off by default -- written at the end of round 1 after the N-tile sweep
-// showed the kernel to be epilogue-bound): full 32-column chunks leave through one cp.async.bulk.tensor store per warp
-// from the swizzled staging tile instead of 8 x (ld.shared + st.global) per lane.  State: bit-identical to the default
-// epilogue on the shapes with N % 4 == 0 (incl. the 10240 x 9684 x 150 logits product); its speed has NOT been measured.
+// TMA_STORE (the default epilogue for N % 4 == 0 without split-K since round 2; CAPHN_TC_TMA_STORE=0 switches it off): full
+// 32-column chunks leave through one cp.async.bulk.tensor store per warp from the swizzled staging tile instead of
+// 8 x (ld.shared + st.global) per lane.  Bit-identical to the register-store epilogue (tests/test_gpu_gemm_tc.py) and 2-9 %
+// faster on the logits products (profiles/r02_gemm_tma_store.txt); ragged N keeps the register-store epilogue.
 template <bool SPLIT, bool TMA_STORE = false>
 __global__ void __launch_bounds__(THREADS_V2, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
@@ -794,7 +794,7 @@ static int make_map(CUtensorMap* m, const void* base, long rows, long Kp, int bo
 }
 
 // 2-D map over the fp32 output [M, N] (row pitch ldc): box = 32 columns (128 bytes) x 32 rows, 128-byte swizzle -- the
-// layout of one epilogue warp's staging tile.  Only used by the experimental TMA_STORE epilogue.
+// layout of one epilogue warp's staging tile.  Only used by the TMA_STORE epilogue.
 static int make_map_c(CUtensorMap* m, const float* C, long M, long N, long ldc) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return CAPHN_EINVAL;
