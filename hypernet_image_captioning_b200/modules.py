@@ -13,7 +13,6 @@ generated weights become leaves and their gradient lands on ``captioner.<cell>.w
 """
 from typing import List
 
-import numpy as np
 import os
 
 import torch

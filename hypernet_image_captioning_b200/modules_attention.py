@@ -4,8 +4,6 @@ Reference: hypernet_attention.py:32-131 (HyperNet), models/decoderlstm.py:11-135
 models/attention.py:5-46 (BahdanauAttention).  The CNN trunk (models/encoder.py EncoderCNN) is out of scope: features are
 the precomputed 7x7x2048 ResNet maps ``[B, 49, 2048]``.
 """
-from typing import Optional
-
 import numpy as np
 import torch
 from torch import nn

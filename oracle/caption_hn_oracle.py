@@ -17,7 +17,7 @@ Each function cites the reference lines it restates (paths relative to the refer
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
